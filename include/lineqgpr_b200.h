@@ -1,0 +1,180 @@
+/* lineqgpr_b200 — C ABI of the B200-native constrained-posterior simulation path.
+ *
+ * This header is the drop-in boundary.  Plain C: pointers, sizes and
+ * status codes only; no torch / C++ types.  All matrices are FP64, COLUMN-major, exactly
+ * as R lays them out.  Reference citations:
+ *   R/...   = /root/reference/dev/lineqGPR/R/...
+ *   tmg:... = file inside /root/reference/dependecies/tmg_0.3.tar.gz
+ *
+ * Every entry point returns an lqg status code and never throws / exits across the ABI
+ * (tmg's C++ has no error path at all and can loop forever, tmg:src/HmcSampler.cpp:51).
+ * There is NO CPU fallback: without a CUDA device every compute entry point returns
+ * LQG_ERR_CUDA.
+ */
+#ifndef LINEQGPR_B200_H
+#define LINEQGPR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes ------------------------------------------------------------------- */
+#define LQG_OK                   0
+#define LQG_ERR_INVALID          1   /* bad argument (sizes, NULL, l >= u ...)                 */
+#define LQG_ERR_UNSUPPORTED      2   /* quadratic constraints (numquad > 0): dead path in
+                                        lineqGPR (R/lineqGPsamplers.R:140-141 passes q=NULL)  */
+#define LQG_ERR_INIT_INFEASIBLE  3   /* tmg:R/tmg.R:44-47 "initial point violates ..."        */
+#define LQG_ERR_CUDA             4   /* no device / CUDA runtime error (see lqg_last_error)   */
+#define LQG_ERR_RESTART_CAP      5   /* a chain exceeded max_restarts in one transition        */
+#define LQG_ERR_DRAWS_EXHAUSTED  6   /* injected Gaussian stream too short                     */
+#define LQG_ERR_BUDGET           7   /* RSM: proposal budget exhausted before nsim accepts     */
+
+/* where the caller's pointers live */
+#define LQG_MEM_HOST    0
+#define LQG_MEM_DEVICE  1
+
+/* ---- options shared by the samplers ------------------------------------------------- */
+typedef struct lqg_opts {
+  int32_t  mem;            /* LQG_MEM_HOST: all pointers are host memory, the call copies in/out
+                              (this is what the .Call shim uses); LQG_MEM_DEVICE: all array
+                              pointers are device memory on the current device                */
+  int32_t  reserved0;
+  void*    stream;         /* cudaStream_t to launch on (NULL = legacy default stream)         */
+  uint64_t seed;           /* Philox key; replaces sample(1:1e7,1) of tmg:R/tmg.R:102          */
+  int32_t  n_chains;       /* HMC: independent chains. 1 = the reference's single serial chain */
+  int32_t  max_restarts;   /* HMC: cap on velocity/feasibility restarts per transition
+                              (0 -> 100000); the reference loops forever                        */
+  int64_t  chain_offset;   /* HMC: global id of this call's first chain. RNG streams are keyed
+                              by (seed, global chain id), so a job sharded over GPUs gives the
+                              same samples as the unsharded job                                 */
+  const double* injected;  /* nullable. HMC: [n_chains][n_injected] N(0,1) draws consumed in
+                              order, d per (re)start, exactly like nd(eng1) at
+                              tmg:src/HmcSampler.cpp:54-55.  RSM: d x n_injected normals,
+                              one column per proposal                                           */
+  int64_t  n_injected;     /* HMC: draws available per chain; RSM: number of proposal columns  */
+  const double* injected_u;/* RSM only, nullable: uniforms, one per IN-BOX proposal
+                              (R/lineqGPsamplers.R:55)                                          */
+  int64_t  n_injected_u;
+  int32_t  prepass;        /* HMC box: 1 = batch the fresh momenta U*a of all transitions as one
+                              FP64 tensor-core GEMM before the chain kernel, 0 = per-chain
+                              in-kernel product, -1 = auto                                      */
+  int32_t  reserved1;
+} lqg_opts;
+
+typedef struct lqg_hmc_stats {
+  int64_t transitions;     /* completed transitions, burn-in included                          */
+  int64_t bounces;         /* wall reflections (tmg:src/HmcSampler.cpp:90-112 executions)      */
+  int64_t hit_searches;    /* _getNextLinearHitTime calls (tmg:src/HmcSampler.cpp:152)         */
+  int64_t vel_restarts;    /* velsign < 0 restarts (tmg:src/HmcSampler.cpp:112,117)            */
+  int64_t chk_restarts;    /* end-point infeasible restarts (tmg:src/HmcSampler.cpp:121-130)   */
+  int64_t exact_evals;     /* constraints whose hit time was evaluated with sqrt/atan2/acos    */
+  int64_t violations;      /* emitted samples outside the constraints: always 0                */
+  int64_t failed_chains;   /* chains stopped by max_restarts / exhausted injected draws        */
+  double  chain_ms;        /* device time of the chain kernel(s)                               */
+  double  prepass_ms;      /* device time of the momentum GEMM pre-pass (0 when off)           */
+} lqg_hmc_stats;
+
+typedef struct lqg_rsm_stats {
+  int64_t proposals;       /* mvrnorm draws consumed (R/lineqGPsamplers.R:50,52)               */
+  int64_t in_box;          /* proposals inside [lb,ub] (R/lineqGPsamplers.R:51)                */
+  int64_t accepted;        /* u <= t accepts (R/lineqGPsamplers.R:56)                          */
+  int64_t rounds;          /* kernel rounds                                                    */
+  double  kernel_ms;
+} lqg_rsm_stats;
+
+/* ---- HMC ---------------------------------------------------------------------------- */
+
+/* Replaces the native entry of tmg:
+ *   RcppExport SEXP rtmg(SEXP n_, SEXP seed_, SEXP initial_, SEXP numlin_, SEXP F_, SEXP g_,
+ *                        SEXP numquad_, SEXP quadratics_)      tmg:src/rtmg.h:6, rtmg.cpp:14-66
+ * called as .Call("rtmg", n+burn.in, seed, initial2, numlin, f2, g2, numquad, quads)
+ *                                                              tmg:R/tmg.R:104
+ * Same contract: canonical (whitened) frame, one chain, HOST pointers, F is numlin x d
+ * column-major, out is n x d column-major with ROW = sample (all n rows returned, the
+ * caller drops burn-in, tmg:R/tmg.R:105).  numquad must be 0.
+ * Momentum draws are Philox-4x32-10 keyed by `seed` (not libstdc++'s knuth_b): the chain is
+ * statistically, not bitwise, the reference's chain. */
+int lqg_rtmg(int32_t n, int32_t seed, const double* initial, int32_t d, int32_t numlin,
+             const double* F, const double* g, int32_t numquad, const double* quadratics,
+             double* out);
+
+/* General dense constraints F z + g >= 0 in the canonical frame, many chains.
+ * Transition = tmg:src/HmcSampler.cpp:43-133 (sampleNext), hit search :152-189,
+ * feasibility :244-265.
+ *   F        c x d column-major; g[c]
+ *   initial  d x n_chains column-major when initial_ld >= d, one shared d-vector when
+ *            initial_ld == 0 (tmg:src/rtmg.cpp:55 setInitialValue)
+ *   out      d x (n_chains * n_per_chain) column-major, COLUMN = sample, chain-major:
+ *            column chain*n_per_chain + s is the (burn_in + s)-th transition of `chain`
+ *   state_out nullable, d x n_chains: last state of every chain (to continue a run)
+ */
+int lqg_hmc_canonical(int32_t d, int32_t c, const double* F, const double* g,
+                      const double* initial, int64_t initial_ld,
+                      int32_t n_per_chain, int32_t burn_in, const lqg_opts* opts,
+                      double* out, double* state_out, lqg_hmc_stats* stats);
+
+/* Box-constrained form: what tmvrnorm.HMC always builds (R/lineqGPsamplers.R:128-141:
+ * f = [I; -I] rows with finite bounds, g = c(-lb, ub)), sampled directly in the eta frame.
+ * With U = Ri of tmg:R/tmg.R:27 (so U U' = Sigma) the chain is algebraically the reference's
+ * whitened chain: x_a = U a, a bounce on coordinate j reflects with
+ * column j of Sigma, the emitted sample is mu + x_b and needs no un-whitening
+ * (tmg:R/tmg.R:106).
+ *   mu[d], lb[d], ub[d] (+-Inf allowed), init[d] or d x n_chains (init_ld as above): the
+ *   clamped start of R/lineqGPsamplers.R:133-135 in the ORIGINAL eta frame
+ *   U d x d column-major; u_upper != 0 promises U is upper triangular (tmg's Ri is)
+ *   Sigma d x d column-major
+ *   out d x (n_chains*n_per_chain), COLUMN = sample (the d x nsim layout tmvrnorm returns,
+ *   R/lineqGPsamplers.R:142)
+ * Returns LQG_ERR_INIT_INFEASIBLE unless lb < init < ub strictly (tmg:R/tmg.R:44-47).
+ */
+int lqg_hmc_box(int32_t d, const double* mu, const double* U, int32_t u_upper,
+                const double* Sigma, const double* lb, const double* ub,
+                const double* init, int64_t init_ld,
+                int32_t n_per_chain, int32_t burn_in, const lqg_opts* opts,
+                double* out, double* state_out, lqg_hmc_stats* stats);
+
+/* ---- RSM ---------------------------------------------------------------------------- */
+
+/* Rejection sampling from the mode, R/lineqGPsamplers.R:36-61.
+ *   map[d]; factor d x d column-major with x = map + factor z (MASS::mvrnorm's eigen factor,
+ *   R/lineqGPsamplers.R:50); w[d] = Sigma^-1 map (R/lineqGPsamplers.R:42-43); lb, ub [d]
+ *   out d x nsim, the first nsim accepted proposals in proposal order
+ *   max_proposals: budget (0 -> 2^40)
+ */
+int lqg_rsm(int32_t d, const double* map, const double* factor, const double* w,
+            const double* lb, const double* ub, int64_t nsim, int64_t max_proposals,
+            const lqg_opts* opts, double* out, lqg_rsm_stats* stats);
+
+/* ---- sample paths and bands --------------------------------------------------------- */
+
+/* C (m x n) = A (m x k) * B (k x n), all column-major FP64, on the FP64 tensor cores.
+ * This is xi.sim = Lambda^+ eta and ysim = Phi.test %*% xi.sim of R/lineqGP.R:639-640 and the
+ * user-side PhiAll.test %*% xiAll.sim of R/lineqAGP.R:509-512.
+ * row_sum nullable [m]: when given, sum_j C[i,j] is accumulated (band mean numerator);
+ * C nullable when only row sums are wanted (config 5: ysim does not fit anywhere). */
+int lqg_dgemm(int32_t m, int32_t n, int32_t k, const double* A, int64_t lda,
+              const double* B, int64_t ldb, double* C, int64_t ldc, double* row_sum,
+              const lqg_opts* opts, double* kernel_ms);
+
+/* Row-wise mean and R type-7 quantiles of ysim (n_t x N, column-major):
+ * apply(ysim, 1, mean); apply(ysim, 1, quantile, probs)   R/lineqGPutils.R:422-423, :294-296
+ *   mean[n_t]; qtls nprobs x n_t column-major (the layout apply() returns) */
+int lqg_bands(int32_t n_t, int64_t N, const double* ysim, int64_t ld,
+              const double* probs, int32_t nprobs, double* mean, double* qtls,
+              const lqg_opts* opts, double* kernel_ms);
+
+/* ---- misc --------------------------------------------------------------------------- */
+const char* lqg_version(void);
+const char* lqg_last_error(void);        /* thread-local text of the last non-OK status       */
+int lqg_device_count(void);              /* number of CUDA devices, 0 when none               */
+/* measured peaks used as roofline denominators: DFMA and DMMA micro-benchmarks (Tflop/s) */
+int lqg_measure_fp64_peaks(double* dfma_tflops, double* dmma_tflops, const lqg_opts* opts);
+/* counts kernel launches made by this library since the last reset (bench gpu_launches) */
+int64_t lqg_launch_count(int32_t reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LINEQGPR_B200_H */

@@ -1,0 +1,136 @@
+"""ctypes binding of the C ABI declared in include/lineqgpr_b200.h.
+
+There is no fallback: if liblineqgpr_b200.so is missing or a call reports LQG_ERR_CUDA the
+error is raised to the caller."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "liblineqgpr_b200.so"
+
+LQG_OK = 0
+STATUS = {0: "LQG_OK", 1: "LQG_ERR_INVALID", 2: "LQG_ERR_UNSUPPORTED", 3: "LQG_ERR_INIT_INFEASIBLE",
+          4: "LQG_ERR_CUDA", 5: "LQG_ERR_RESTART_CAP", 6: "LQG_ERR_DRAWS_EXHAUSTED", 7: "LQG_ERR_BUDGET"}
+MEM_HOST, MEM_DEVICE = 0, 1
+
+# every symbol include/lineqgpr_b200.h declares
+SYMBOLS = ["lqg_rtmg", "lqg_hmc_canonical", "lqg_hmc_box", "lqg_rsm", "lqg_dgemm", "lqg_bands",
+           "lqg_version", "lqg_last_error", "lqg_device_count", "lqg_measure_fp64_peaks",
+           "lqg_launch_count"]
+
+_dp = C.POINTER(C.c_double)
+
+
+class LqgError(RuntimeError):
+    def __init__(self, status: int, where: str, text: str):
+        self.status = status
+        super().__init__(f"{where}: {STATUS.get(status, status)}: {text}")
+
+
+class Opts(C.Structure):
+    _fields_ = [("mem", C.c_int32), ("reserved0", C.c_int32), ("stream", C.c_void_p),
+                ("seed", C.c_uint64), ("n_chains", C.c_int32), ("max_restarts", C.c_int32),
+                ("chain_offset", C.c_int64), ("injected", C.c_void_p), ("n_injected", C.c_int64),
+                ("injected_u", C.c_void_p), ("n_injected_u", C.c_int64), ("prepass", C.c_int32),
+                ("reserved1", C.c_int32)]
+
+
+class HmcStats(C.Structure):
+    _fields_ = [("transitions", C.c_int64), ("bounces", C.c_int64), ("hit_searches", C.c_int64),
+                ("vel_restarts", C.c_int64), ("chk_restarts", C.c_int64), ("exact_evals", C.c_int64),
+                ("violations", C.c_int64), ("failed_chains", C.c_int64), ("chain_ms", C.c_double),
+                ("prepass_ms", C.c_double)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class RsmStats(C.Structure):
+    _fields_ = [("proposals", C.c_int64), ("in_box", C.c_int64), ("accepted", C.c_int64),
+                ("rounds", C.c_int64), ("kernel_ms", C.c_double)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+_lib = None
+
+
+def lib():
+    """Loads the shared library (building nothing: see lineqgpr_b200.build / __graft_entry__.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m lineqgpr_b200.build` "
+            "(nvcc, sm_100a). lineqgpr_b200 has no CPU fallback.")
+    L = C.CDLL(str(LIB_PATH))
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    L.lqg_rtmg.restype = C.c_int
+    L.lqg_rtmg.argtypes = [i32, i32, vp, i32, i32, vp, vp, i32, vp, vp]
+    L.lqg_hmc_canonical.restype = C.c_int
+    L.lqg_hmc_canonical.argtypes = [i32, i32, vp, vp, vp, i64, i32, i32, C.POINTER(Opts), vp, vp,
+                                    C.POINTER(HmcStats)]
+    L.lqg_hmc_box.restype = C.c_int
+    L.lqg_hmc_box.argtypes = [i32, vp, vp, i32, vp, vp, vp, vp, i64, i32, i32, C.POINTER(Opts), vp, vp,
+                              C.POINTER(HmcStats)]
+    L.lqg_rsm.restype = C.c_int
+    L.lqg_rsm.argtypes = [i32, vp, vp, vp, vp, vp, i64, i64, C.POINTER(Opts), vp, C.POINTER(RsmStats)]
+    L.lqg_dgemm.restype = C.c_int
+    L.lqg_dgemm.argtypes = [i32, i32, i32, vp, i64, vp, i64, vp, i64, vp, C.POINTER(Opts), _dp]
+    L.lqg_bands.restype = C.c_int
+    L.lqg_bands.argtypes = [i32, i64, vp, i64, vp, i32, vp, vp, C.POINTER(Opts), _dp]
+    L.lqg_version.restype = C.c_char_p
+    L.lqg_last_error.restype = C.c_char_p
+    L.lqg_device_count.restype = C.c_int
+    L.lqg_measure_fp64_peaks.restype = C.c_int
+    L.lqg_measure_fp64_peaks.argtypes = [_dp, _dp, C.POINTER(Opts)]
+    L.lqg_launch_count.restype = i64
+    L.lqg_launch_count.argtypes = [i32]
+    _lib = L
+    return L
+
+
+def check(rc: int, where: str):
+    if rc != LQG_OK:
+        raise LqgError(rc, where, lib().lqg_last_error().decode())
+
+
+def last_error() -> str:
+    return lib().lqg_last_error().decode()
+
+
+def f64(a, order="F"):
+    """FP64 array in R (column-major) layout."""
+    return np.require(np.asarray(a, dtype=np.float64), dtype=np.float64, requirements=[order.upper() + "_CONTIGUOUS", "ALIGNED"]) \
+        if np.ndim(a) > 1 else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return int(a)          # raw device pointer (e.g. torch tensor.data_ptr())
+
+
+def make_opts(mem=MEM_HOST, stream=None, seed=0, n_chains=1, max_restarts=0, chain_offset=0,
+              injected=None, n_injected=0, injected_u=None, n_injected_u=0, prepass=-1) -> Opts:
+    o = Opts()
+    o.mem = mem
+    o.stream = stream
+    o.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    o.n_chains = int(n_chains)
+    o.max_restarts = int(max_restarts)
+    o.chain_offset = int(chain_offset)
+    o.injected = ptr(injected)
+    o.n_injected = int(n_injected)
+    o.injected_u = ptr(injected_u)
+    o.n_injected_u = int(n_injected_u)
+    o.prepass = int(prepass)
+    return o

@@ -1,0 +1,590 @@
+// C-ABI layer of lineqgpr_b200 (see include/lineqgpr_b200.h): argument validation, staging
+// of host buffers, launch orchestration, status codes.  No compute happens on the host.
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+#include <cmath>
+#include <vector>
+
+#include "lqg_common.cuh"
+#include "lqg_kernels.h"
+
+namespace lqg {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+static std::atomic<int64_t> g_launches{0};
+static thread_local int64_t g_launch_tls = 0;
+int64_t& launch_counter() {
+  // kernels are launched from the calling thread; fold the thread-local count into the
+  // global one lazily (see lqg_launch_count)
+  return g_launch_tls;
+}
+static void fold_launches() {
+  g_launches += g_launch_tls;
+  g_launch_tls = 0;
+}
+
+// owning device allocation
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t n) {
+    if (p) { cudaFree(p); p = nullptr; }
+    bytes = n ? n : 16;
+    return cudaMalloc(&p, bytes);
+  }
+  template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+// A read-only input that is either already on the device or staged from the host.
+struct Input {
+  DevBuf buf;
+  const double* dev = nullptr;
+  int stage(const double* src, size_t n, int mem, cudaStream_t st, size_t pad_to = 0) {
+    if (mem == LQG_MEM_DEVICE && pad_to == 0) { dev = src; return LQG_OK; }
+    const size_t n_alloc = pad_to > n ? pad_to : n;
+    LQG_CUDA_TRY(buf.alloc(n_alloc * sizeof(double)));
+    if (n_alloc > n) LQG_CUDA_TRY(cudaMemsetAsync(buf.p, 0, n_alloc * sizeof(double), st));
+    LQG_CUDA_TRY(cudaMemcpyAsync(buf.p, src, n * sizeof(double),
+                                 mem == LQG_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    dev = buf.as<double>();
+    return LQG_OK;
+  }
+};
+
+static int have_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    set_error("no CUDA device available (%s); lineqgpr_b200 has no CPU fallback",
+              e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    return 0;
+  }
+  return n;
+}
+
+static int fetch_host(std::vector<double>& dst, const double* src, size_t n, int mem, cudaStream_t st) {
+  dst.resize(n);
+  if (mem == LQG_MEM_DEVICE) {
+    LQG_CUDA_TRY(cudaMemcpyAsync(dst.data(), src, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    LQG_CUDA_TRY(cudaStreamSynchronize(st));
+  } else {
+    memcpy(dst.data(), src, n * sizeof(double));
+  }
+  return LQG_OK;
+}
+
+static void fill_stats(lqg_hmc_stats* s, const unsigned long long* h, double chain_ms, double pre_ms) {
+  if (!s) return;
+  s->transitions = (int64_t)h[0]; s->bounces = (int64_t)h[1]; s->hit_searches = (int64_t)h[2];
+  s->vel_restarts = (int64_t)h[3]; s->chk_restarts = (int64_t)h[4]; s->exact_evals = (int64_t)h[5];
+  s->violations = (int64_t)h[6]; s->failed_chains = (int64_t)h[7];
+  s->chain_ms = chain_ms; s->prepass_ms = pre_ms;
+}
+
+struct Timer {
+  cudaEvent_t a = nullptr, b = nullptr;
+  cudaStream_t st;
+  explicit Timer(cudaStream_t s) : st(s) { cudaEventCreate(&a); cudaEventCreate(&b); }
+  ~Timer() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+  void start() { cudaEventRecord(a, st); }
+  void stop() { cudaEventRecord(b, st); }
+  double ms() { float f = 0; cudaEventSynchronize(b); cudaEventElapsedTime(&f, a, b); return f; }
+};
+
+static lqg_opts default_opts() {
+  lqg_opts o;
+  memset(&o, 0, sizeof(o));
+  o.mem = LQG_MEM_HOST; o.n_chains = 1; o.prepass = -1;
+  return o;
+}
+
+// summarise per-chain status words into a return code
+static int chain_status_rc(const std::vector<int>& st, unsigned long long* failed) {
+  int rc = LQG_OK;
+  unsigned long long f = 0;
+  for (int v : st) if (v != 0) { ++f; if (rc == LQG_OK) rc = v; }
+  *failed = f;
+  return rc;
+}
+
+}  // namespace lqg
+
+using namespace lqg;
+
+// ===========================================================================================
+extern "C" int lqg_hmc_box(int32_t d, const double* mu, const double* U, int32_t u_upper,
+                           const double* Sigma, const double* lb, const double* ub,
+                           const double* init, int64_t init_ld, int32_t n_per_chain,
+                           int32_t burn_in, const lqg_opts* opts_, double* out,
+                           double* state_out, lqg_hmc_stats* stats) {
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (!have_device()) return LQG_ERR_CUDA;
+  const lqg_opts o = opts_ ? *opts_ : default_opts();
+  const int n_chains = o.n_chains > 0 ? o.n_chains : 1;
+  if (d <= 0 || d > 8192 || !mu || !U || !Sigma || !lb || !ub || !init || !out || n_per_chain <= 0 ||
+      burn_in < 0 || (init_ld != 0 && init_ld < d)) {
+    set_error("lqg_hmc_box: invalid argument (d=%d, n_per_chain=%d, burn_in=%d, init_ld=%lld)", d,
+              n_per_chain, burn_in, (long long)init_ld);
+    return LQG_ERR_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)o.stream;
+  const int mem = o.mem;
+  const size_t dd = (size_t)d * d;
+  const size_t n_init = init_ld == 0 ? (size_t)d : (size_t)init_ld * (n_chains - 1) + d;
+
+  // ---- host-side validation, as the R layers do it ----
+  std::vector<double> h_lb, h_ub, h_init;
+  int rc;
+  if ((rc = fetch_host(h_lb, lb, d, mem, st)) || (rc = fetch_host(h_ub, ub, d, mem, st)) ||
+      (rc = fetch_host(h_init, init, n_init, mem, st)))
+    return rc;
+  for (int i = 0; i < d; ++i)
+    if (!(h_lb[i] < h_ub[i])) {                            // R/lineqGPutils.R:359-360
+      set_error("The elements from \"u\" has to be greater than the elements from \"l\" (i=%d)", i);
+      return LQG_ERR_INVALID;
+    }
+  for (int ch = 0; ch < (init_ld == 0 ? 1 : n_chains); ++ch)
+    for (int i = 0; i < d; ++i) {
+      const double x = h_init[(size_t)ch * init_ld + i];
+      if (!(x - h_lb[i] > 0.0) || !(h_ub[i] - x > 0.0)) {  // tmg:R/tmg.R:44-47
+        set_error("Error: initial point violates linear constraints. (chain %d, coordinate %d)", ch, i);
+        return LQG_ERR_INIT_INFEASIBLE;
+      }
+    }
+
+  // ---- stage inputs ----
+  Input i_mu, i_U, i_S, i_lb, i_ub, i_init, i_inj;
+  if ((rc = i_mu.stage(mu, d, mem, st)) || (rc = i_U.stage(U, dd, mem, st)) ||
+      (rc = i_S.stage(Sigma, dd, mem, st)) || (rc = i_lb.stage(lb, d, mem, st)) ||
+      (rc = i_ub.stage(ub, d, mem, st)) || (rc = i_init.stage(init, n_init, mem, st)))
+    return rc;
+  if (o.injected && (rc = i_inj.stage(o.injected, (size_t)n_chains * o.n_injected, mem, st))) return rc;
+
+  const size_t n_cols = (size_t)n_chains * n_per_chain;
+  DevBuf b_out, b_state, b_glo, b_ghi, b_sd, b_misc, b_status, b_injpos;
+  double* d_out = out;
+  if (mem == LQG_MEM_HOST) { LQG_CUDA_TRY(b_out.alloc(n_cols * d * sizeof(double))); d_out = b_out.as<double>(); }
+  LQG_CUDA_TRY(b_state.alloc((size_t)d * n_chains * sizeof(double)));
+  LQG_CUDA_TRY(b_glo.alloc(d * sizeof(double)));
+  LQG_CUDA_TRY(b_ghi.alloc(d * sizeof(double)));
+  LQG_CUDA_TRY(b_sd.alloc(d * sizeof(double)));
+  LQG_CUDA_TRY(b_misc.alloc(16 * sizeof(unsigned long long)));      // [0..7] stats, [8] queue head
+  LQG_CUDA_TRY(b_status.alloc((size_t)n_chains * sizeof(int)));
+  LQG_CUDA_TRY(b_injpos.alloc((size_t)n_chains * sizeof(int64_t)));
+  LQG_CUDA_TRY(cudaMemsetAsync(b_misc.p, 0, b_misc.bytes, st));
+  LQG_CUDA_TRY(cudaMemsetAsync(b_status.p, 0, b_status.bytes, st));
+  LQG_CUDA_TRY(cudaMemsetAsync(b_injpos.p, 0, b_injpos.bytes, st));
+
+  LQG_CUDA_TRY(launch_box_prep(d, i_mu.dev, i_lb.dev, i_ub.dev, i_S.dev, b_glo.as<double>(),
+                               b_ghi.as<double>(), b_sd.as<double>(), st));
+  // x_b(0) = init - mu for every chain (init_ld == 0 broadcasts one shared start)
+  LQG_CUDA_TRY(launch_box_init_state(d, n_chains, i_init.dev, init_ld, i_mu.dev, b_state.as<double>(), st));
+  std::vector<double> h_sd(d);
+  LQG_CUDA_TRY(cudaMemcpyAsync(h_sd.data(), b_sd.p, d * sizeof(double), cudaMemcpyDeviceToHost, st));
+  LQG_CUDA_TRY(cudaStreamSynchronize(st));
+  double sd_max = 0.0;
+  for (int i = 0; i < d; ++i) {
+    if (!(h_sd[i] > 0.0)) { set_error("lqg_hmc_box: Sigma[%d,%d] = %g is not positive", i, i, h_sd[i]); return LQG_ERR_INVALID; }
+    sd_max = std::max(sd_max, h_sd[i]);
+  }
+
+  BoxParams p;
+  memset(&p, 0, sizeof(p));
+  p.d = d; p.mu = i_mu.dev; p.lb = i_lb.dev; p.ub = i_ub.dev; p.U = i_U.dev; p.u_upper = u_upper;
+  p.Sigma = i_S.dev; p.glo = b_glo.as<double>(); p.ghi = b_ghi.as<double>(); p.sdiag = b_sd.as<double>();
+  p.abs_eps = kFilterRel * std::sqrt(sd_max);
+  p.state = b_state.as<double>(); p.xa_pre = nullptr; p.n_chains = n_chains;
+  p.burn_in = burn_in; p.n_per_chain = n_per_chain; p.out = d_out; p.seed = o.seed;
+  p.chain_offset = o.chain_offset; p.injected = o.injected ? i_inj.dev : nullptr;
+  p.n_injected = o.n_injected; p.inj_pos = b_injpos.as<int64_t>();
+  p.max_restarts = o.max_restarts > 0 ? o.max_restarts : 100000;
+  p.stats = b_misc.as<unsigned long long>();
+  p.next_chain = reinterpret_cast<int*>(b_misc.as<unsigned long long>() + 8);
+  p.chain_status = b_status.as<int>();
+
+  const int total = burn_in + n_per_chain;
+  // ---- momentum pre-pass: X_a = U A for the first draw of every transition, as ONE GEMM ----
+  const bool use_pre = !o.injected && (o.prepass == 1 || (o.prepass == -1 && d >= 256));
+  double chain_ms = 0.0, pre_ms = 0.0;
+  Timer t_chain(st), t_pre(st);
+  if (!use_pre) {
+    p.s_begin = 0; p.s_end = total;
+    t_chain.start();
+    LQG_CUDA_TRY(launch_hmc_box(p, 0, st));
+    t_chain.stop();
+    chain_ms = t_chain.ms();
+  } else {
+    // rounds sized so that the momentum scratch stays below ~6 GB
+    const size_t budget = (size_t)4 << 30;   // per buffer (draws + momenta)
+    int round_len = (int)std::max<size_t>(1, std::min<size_t>(total, budget / ((size_t)d * n_chains * sizeof(double))));
+    DevBuf b_xa, b_a;
+    LQG_CUDA_TRY(b_xa.alloc((size_t)d * n_chains * round_len * sizeof(double)));
+    LQG_CUDA_TRY(b_a.alloc((size_t)d * n_chains * round_len * sizeof(double)));
+    for (int s0 = 0; s0 < total; s0 += round_len) {
+      const int s1 = std::min(total, s0 + round_len);
+      const int len = s1 - s0;
+      NormalGen gen{o.seed, o.chain_offset, len, s0};
+      t_pre.start();
+      LQG_CUDA_TRY(launch_fill_normals(d, (size_t)n_chains * len, b_a.as<double>(), gen, st));
+      LQG_CUDA_TRY(launch_dgemm(d, n_chains * len, d, i_U.dev, d, b_a.as<double>(), d,
+                                b_xa.as<double>(), d, nullptr, u_upper, st));
+      t_pre.stop();
+      p.xa_pre = b_xa.as<double>();
+      p.s_begin = s0; p.s_end = s1;
+      LQG_CUDA_TRY(cudaMemsetAsync(p.next_chain, 0, sizeof(int), st));
+      t_chain.start();
+      LQG_CUDA_TRY(launch_hmc_box(p, 0, st));
+      t_chain.stop();
+      pre_ms += t_pre.ms();
+      chain_ms += t_chain.ms();
+    }
+  }
+
+  // ---- audit, stats, results ----
+  LQG_CUDA_TRY(launch_box_violations(d, n_cols, d_out, i_lb.dev, i_ub.dev, p.stats + 6, st));
+  unsigned long long h_stats[8];
+  std::vector<int> h_status(n_chains);
+  LQG_CUDA_TRY(cudaMemcpyAsync(h_stats, p.stats, sizeof(h_stats), cudaMemcpyDeviceToHost, st));
+  LQG_CUDA_TRY(cudaMemcpyAsync(h_status.data(), b_status.p, n_chains * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (mem == LQG_MEM_HOST)
+    LQG_CUDA_TRY(cudaMemcpyAsync(out, d_out, n_cols * d * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (state_out) {
+    // state_out holds positions in the ORIGINAL frame: mu + x_b, chain by chain
+    std::vector<double> h_state((size_t)d * n_chains), h_mu;
+    LQG_CUDA_TRY(cudaMemcpyAsync(h_state.data(), b_state.p, h_state.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if ((rc = fetch_host(h_mu, mu, d, mem, st))) return rc;
+    LQG_CUDA_TRY(cudaStreamSynchronize(st));
+    for (int ch = 0; ch < n_chains; ++ch)
+      for (int i = 0; i < d; ++i) h_state[(size_t)ch * d + i] += h_mu[i];
+    if (mem == LQG_MEM_HOST) memcpy(state_out, h_state.data(), h_state.size() * sizeof(double));
+    else LQG_CUDA_TRY(cudaMemcpyAsync(state_out, h_state.data(), h_state.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
+  LQG_CUDA_TRY(cudaStreamSynchronize(st));
+  rc = chain_status_rc(h_status, &h_stats[7]);
+  fill_stats(stats, h_stats, chain_ms, pre_ms);
+  fold_launches();
+  if (rc == LQG_ERR_RESTART_CAP) set_error("lqg_hmc_box: %llu chain(s) exceeded max_restarts=%d in one transition", h_stats[7], p.max_restarts);
+  if (rc == LQG_ERR_DRAWS_EXHAUSTED) set_error("lqg_hmc_box: injected Gaussian stream too short for %llu chain(s)", h_stats[7]);
+  if (rc == LQG_OK && h_stats[6] != 0) { set_error("lqg_hmc_box: %llu emitted values violate the bounds", h_stats[6]); }
+  return rc;
+}
+
+// ===========================================================================================
+extern "C" int lqg_hmc_canonical(int32_t d, int32_t c, const double* F, const double* g,
+                                 const double* initial, int64_t initial_ld, int32_t n_per_chain,
+                                 int32_t burn_in, const lqg_opts* opts_, double* out,
+                                 double* state_out, lqg_hmc_stats* stats) {
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (!have_device()) return LQG_ERR_CUDA;
+  const lqg_opts o = opts_ ? *opts_ : default_opts();
+  const int n_chains = o.n_chains > 0 ? o.n_chains : 1;
+  if (d <= 0 || d > 8192 || c < 0 || (c > 0 && (!F || !g)) || !initial || !out || n_per_chain <= 0 ||
+      burn_in < 0 || (initial_ld != 0 && initial_ld < d)) {
+    set_error("lqg_hmc_canonical: invalid argument (d=%d, c=%d, n_per_chain=%d)", d, c, n_per_chain);
+    return LQG_ERR_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)o.stream;
+  const int mem = o.mem;
+  const size_t n_init = initial_ld == 0 ? (size_t)d : (size_t)initial_ld * (n_chains - 1) + d;
+  const size_t n_F = (size_t)c * d;
+  int rc;
+
+  Input i_F, i_g, i_init, i_inj;
+  // F is always copied: the bulk copy into shared memory needs a 16-byte multiple
+  if ((rc = i_F.stage(F, n_F, mem, st, ((n_F + 1) & ~(size_t)1) + 2)) || (rc = i_g.stage(g, c, mem, st, c + 2)) ||
+      (rc = i_init.stage(initial, n_init, mem, st)))
+    return rc;
+  if (o.injected && (rc = i_inj.stage(o.injected, (size_t)n_chains * o.n_injected, mem, st))) return rc;
+
+  const size_t n_cols = (size_t)n_chains * n_per_chain;
+  DevBuf b_out, b_state, b_f2, b_fn, b_misc, b_status, b_injpos;
+  double* d_out = out;
+  if (mem == LQG_MEM_HOST) { LQG_CUDA_TRY(b_out.alloc(n_cols * d * sizeof(double))); d_out = b_out.as<double>(); }
+  LQG_CUDA_TRY(b_state.alloc((size_t)d * n_chains * sizeof(double)));
+  LQG_CUDA_TRY(b_f2.alloc((c + 1) * sizeof(double)));
+  LQG_CUDA_TRY(b_fn.alloc((c + 1) * sizeof(double)));
+  LQG_CUDA_TRY(b_misc.alloc(16 * sizeof(unsigned long long)));
+  LQG_CUDA_TRY(b_status.alloc((size_t)n_chains * sizeof(int)));
+  LQG_CUDA_TRY(b_injpos.alloc((size_t)n_chains * sizeof(int64_t)));
+  LQG_CUDA_TRY(cudaMemsetAsync(b_misc.p, 0, b_misc.bytes, st));
+  LQG_CUDA_TRY(cudaMemsetAsync(b_status.p, 0, b_status.bytes, st));
+  LQG_CUDA_TRY(cudaMemsetAsync(b_injpos.p, 0, b_injpos.bytes, st));
+  if (c > 0) LQG_CUDA_TRY(launch_canon_rownorms(d, c, i_F.dev, b_f2.as<double>(), b_fn.as<double>(), st));
+  // state = initial (canonical frame): reuse the box helper with mu = 0
+  {
+    DevBuf zero;
+    LQG_CUDA_TRY(zero.alloc(d * sizeof(double)));
+    LQG_CUDA_TRY(cudaMemsetAsync(zero.p, 0, d * sizeof(double), st));
+    LQG_CUDA_TRY(launch_box_init_state(d, n_chains, i_init.dev, initial_ld, zero.as<double>(), b_state.as<double>(), st));
+    LQG_CUDA_TRY(cudaStreamSynchronize(st));
+  }
+
+  CanonParams p;
+  memset(&p, 0, sizeof(p));
+  p.d = d; p.c = c; p.F = i_F.dev; p.g = i_g.dev; p.frow2 = b_f2.as<double>(); p.fnorm = b_fn.as<double>();
+  p.state = b_state.as<double>(); p.n_chains = n_chains; p.s_begin = 0; p.s_end = burn_in + n_per_chain;
+  p.burn_in = burn_in; p.n_per_chain = n_per_chain; p.out = d_out; p.seed = o.seed;
+  p.chain_offset = o.chain_offset; p.injected = o.injected ? i_inj.dev : nullptr;
+  p.n_injected = o.n_injected; p.inj_pos = b_injpos.as<int64_t>();
+  p.max_restarts = o.max_restarts > 0 ? o.max_restarts : 100000;
+  p.f_in_smem = (c > 0 && canon_f_fits_smem(d, c)) ? 1 : 0;
+  p.stats = b_misc.as<unsigned long long>();
+  p.next_chain = reinterpret_cast<int*>(b_misc.as<unsigned long long>() + 8);
+  p.chain_status = b_status.as<int>();
+
+  Timer t_chain(st);
+  t_chain.start();
+  LQG_CUDA_TRY(launch_hmc_canonical(p, 0, st));
+  t_chain.stop();
+  const double chain_ms = t_chain.ms();
+
+  if (c > 0)
+    LQG_CUDA_TRY(launch_canon_violations(d, c, n_cols, i_F.dev, i_g.dev, b_fn.as<double>(), d_out, p.stats + 6, st));
+  unsigned long long h_stats[8];
+  std::vector<int> h_status(n_chains);
+  LQG_CUDA_TRY(cudaMemcpyAsync(h_stats, p.stats, sizeof(h_stats), cudaMemcpyDeviceToHost, st));
+  LQG_CUDA_TRY(cudaMemcpyAsync(h_status.data(), b_status.p, n_chains * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (mem == LQG_MEM_HOST)
+    LQG_CUDA_TRY(cudaMemcpyAsync(out, d_out, n_cols * d * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (state_out)
+    LQG_CUDA_TRY(cudaMemcpyAsync(state_out, b_state.p, (size_t)d * n_chains * sizeof(double),
+                                 mem == LQG_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
+  LQG_CUDA_TRY(cudaStreamSynchronize(st));
+  rc = chain_status_rc(h_status, &h_stats[7]);
+  fill_stats(stats, h_stats, chain_ms, 0.0);
+  fold_launches();
+  if (rc == LQG_ERR_RESTART_CAP) set_error("lqg_hmc_canonical: %llu chain(s) exceeded max_restarts=%d", h_stats[7], p.max_restarts);
+  if (rc == LQG_ERR_DRAWS_EXHAUSTED) set_error("lqg_hmc_canonical: injected Gaussian stream too short for %llu chain(s)", h_stats[7]);
+  return rc;
+}
+
+// ===========================================================================================
+extern "C" int lqg_rtmg(int32_t n, int32_t seed, const double* initial, int32_t d, int32_t numlin,
+                        const double* F, const double* g, int32_t numquad, const double* quadratics,
+                        double* out) {
+  (void)quadratics;
+  if (numquad != 0) {
+    set_error("lqg_rtmg: quadratic constraints are not supported (lineqGPR always passes q=NULL)");
+    return LQG_ERR_UNSUPPORTED;
+  }
+  if (n <= 0 || d <= 0 || !initial || !out) { set_error("lqg_rtmg: invalid argument"); return LQG_ERR_INVALID; }
+  lqg_opts o = default_opts();
+  o.seed = (uint64_t)(uint32_t)seed;
+  o.n_chains = 1;
+  std::vector<double> cols((size_t)n * d);
+  int rc = lqg_hmc_canonical(d, numlin, F, g, initial, 0, n, 0, &o, cols.data(), nullptr, nullptr);
+  if (rc != LQG_OK) return rc;
+  for (int i = 0; i < n; ++i)                    // d x n (column = sample) -> n x d (row = sample)
+    for (int j = 0; j < d; ++j) out[(size_t)i + (size_t)j * n] = cols[(size_t)i * d + j];
+  return LQG_OK;
+}
+
+// ===========================================================================================
+extern "C" const char* lqg_version(void) { return "lineqgpr_b200 0.1.0 (sm_100a)"; }
+extern "C" const char* lqg_last_error(void) { return g_err; }
+extern "C" int lqg_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+extern "C" int64_t lqg_launch_count(int32_t reset) {
+  fold_launches();
+  int64_t v = g_launches.load();
+  if (reset) g_launches = 0;
+  return v;
+}
+extern "C" int lqg_measure_fp64_peaks(double* dfma_tflops, double* dmma_tflops, const lqg_opts* opts) {
+  if (!have_device()) return LQG_ERR_CUDA;
+  cudaStream_t st = opts ? (cudaStream_t)opts->stream : nullptr;
+  LQG_CUDA_TRY(measure_fp64_peaks(dfma_tflops, dmma_tflops, st));
+  fold_launches();
+  return LQG_OK;
+}
+
+// ===========================================================================================
+extern "C" int lqg_rsm(int32_t d, const double* map, const double* factor, const double* w,
+                       const double* lb, const double* ub, int64_t nsim, int64_t max_proposals,
+                       const lqg_opts* opts_, double* out, lqg_rsm_stats* stats) {
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (!have_device()) return LQG_ERR_CUDA;
+  const lqg_opts o = opts_ ? *opts_ : default_opts();
+  if (d <= 0 || d > 4096 || !map || !factor || !w || !lb || !ub || !out || nsim <= 0) {
+    set_error("lqg_rsm: invalid argument (d=%d, nsim=%lld)", d, (long long)nsim);
+    return LQG_ERR_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)o.stream;
+  const int mem = o.mem;
+  int rc;
+  Input i_map, i_fac, i_w, i_lb, i_ub, i_z, i_u;
+  if ((rc = i_map.stage(map, d, mem, st)) || (rc = i_fac.stage(factor, (size_t)d * d, mem, st)) ||
+      (rc = i_w.stage(w, d, mem, st)) || (rc = i_lb.stage(lb, d, mem, st)) || (rc = i_ub.stage(ub, d, mem, st)))
+    return rc;
+  const bool inj = o.injected != nullptr;
+  if (inj && (rc = i_z.stage(o.injected, (size_t)d * o.n_injected, mem, st))) return rc;
+  if (o.injected_u && (rc = i_u.stage(o.injected_u, (size_t)o.n_injected_u, mem, st))) return rc;
+
+  int64_t budget = max_proposals > 0 ? max_proposals : ((int64_t)1 << 40);
+  if (inj && o.n_injected < budget) budget = o.n_injected;
+  const int64_t kMaxRound = (int64_t)1 << 22;
+  int64_t round = std::min<int64_t>(kMaxRound, std::max<int64_t>(4096, 4 * nsim));
+  round = std::min(round, budget);
+  if (round <= 0) { set_error("lqg_rsm: empty proposal budget"); return LQG_ERR_BUDGET; }
+
+  DevBuf b_out, b_flags, b_t, b_cnt, b_ioff, b_aoff, b_ctr;
+  double* d_out = out;
+  if (mem == LQG_MEM_HOST) { LQG_CUDA_TRY(b_out.alloc((size_t)nsim * d * sizeof(double))); d_out = b_out.as<double>(); }
+  const int nb_max = rsm_blocks(kMaxRound);
+  LQG_CUDA_TRY(b_flags.alloc((size_t)kMaxRound));
+  LQG_CUDA_TRY(b_t.alloc((size_t)kMaxRound * sizeof(double)));
+  LQG_CUDA_TRY(b_cnt.alloc((size_t)nb_max * sizeof(int)));
+  LQG_CUDA_TRY(b_ioff.alloc((size_t)(nb_max + 1) * sizeof(int64_t)));
+  LQG_CUDA_TRY(b_aoff.alloc((size_t)(nb_max + 1) * sizeof(int64_t)));
+  LQG_CUDA_TRY(b_ctr.alloc(2 * sizeof(unsigned long long)));
+  LQG_CUDA_TRY(cudaMemsetAsync(b_ctr.p, 0, 2 * sizeof(unsigned long long), st));
+
+  RsmParams q;
+  memset(&q, 0, sizeof(q));
+  q.d = d; q.map = i_map.dev; q.factor = i_fac.dev; q.w = i_w.dev; q.lb = i_lb.dev; q.ub = i_ub.dev;
+  q.seed = o.seed; q.inj_z = inj ? i_z.dev : nullptr; q.inj_u = o.injected_u ? i_u.dev : nullptr;
+  q.n_inj_u = o.n_injected_u; q.flags = b_flags.as<unsigned char>(); q.tval = b_t.as<double>();
+
+  int64_t got = 0, first = 0, inbox = 0, rounds = 0;
+  Timer tm(st);
+  tm.start();
+  while (got < nsim) {
+    if (first >= budget) break;
+    const int64_t P = std::min(round, budget - first);
+    q.first_proposal = first; q.n_proposals = P; q.inbox_before = inbox;
+    LQG_CUDA_TRY(launch_rsm_round(q, b_cnt.as<int>(), b_ioff.as<int64_t>(), b_aoff.as<int64_t>(), got, nsim,
+                                  d_out, b_ctr.as<unsigned long long>(), st));
+    const int nb = rsm_blocks(P);
+    int64_t tot_in = 0, tot_acc = 0;
+    LQG_CUDA_TRY(cudaMemcpyAsync(&tot_in, b_ioff.as<int64_t>() + nb, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    LQG_CUDA_TRY(cudaMemcpyAsync(&tot_acc, b_aoff.as<int64_t>() + nb, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    LQG_CUDA_TRY(cudaStreamSynchronize(st));
+    got += tot_acc; inbox += tot_in; first += P; ++rounds;
+    if (q.inj_u && inbox > q.n_inj_u && got < nsim) break;     // uniforms ran out
+    const double rate = (double)std::max<int64_t>(got, 1) / (double)first;
+    round = (int64_t)std::min<double>((double)kMaxRound, std::max<double>(4096.0, (double)(nsim - got) / rate * 1.3 + 1024.0));
+  }
+  tm.stop();
+  const double ms = tm.ms();
+  unsigned long long ctr[2] = {0, 0};
+  LQG_CUDA_TRY(cudaMemcpyAsync(ctr, b_ctr.p, sizeof(ctr), cudaMemcpyDeviceToHost, st));
+  const int64_t n_emit = std::min(got, nsim);
+  if (mem == LQG_MEM_HOST && n_emit > 0)
+    LQG_CUDA_TRY(cudaMemcpyAsync(out, d_out, (size_t)n_emit * d * sizeof(double), cudaMemcpyDeviceToHost, st));
+  LQG_CUDA_TRY(cudaStreamSynchronize(st));
+  if (stats) {
+    stats->proposals = got >= nsim ? (int64_t)ctr[0] : first;
+    stats->in_box = got >= nsim ? (int64_t)ctr[1] : inbox;
+    stats->accepted = n_emit; stats->rounds = rounds; stats->kernel_ms = ms;
+  }
+  fold_launches();
+  if (got < nsim) {
+    if (inj || o.injected_u) {
+      set_error("lqg_rsm: injected draws exhausted after %lld proposals (%lld of %lld accepted)",
+                (long long)first, (long long)got, (long long)nsim);
+      return LQG_ERR_DRAWS_EXHAUSTED;
+    }
+    set_error("lqg_rsm: proposal budget %lld exhausted (%lld of %lld accepted, %lld in box): "
+              "the box has negligible mass under N(map, Sigma)", (long long)budget, (long long)got,
+              (long long)nsim, (long long)inbox);
+    return LQG_ERR_BUDGET;
+  }
+  return LQG_OK;
+}
+
+// ===========================================================================================
+extern "C" int lqg_dgemm(int32_t m, int32_t n, int32_t k, const double* A, int64_t lda,
+                         const double* B, int64_t ldb, double* C, int64_t ldc, double* row_sum,
+                         const lqg_opts* opts_, double* kernel_ms) {
+  if (!have_device()) return LQG_ERR_CUDA;
+  const lqg_opts o = opts_ ? *opts_ : default_opts();
+  if (m <= 0 || n <= 0 || k <= 0 || !A || !B || (!C && !row_sum) || lda < m || ldb < k || (C && ldc < m)) {
+    set_error("lqg_dgemm: invalid argument (m=%d n=%d k=%d lda=%lld ldb=%lld ldc=%lld)", m, n, k,
+              (long long)lda, (long long)ldb, (long long)ldc);
+    return LQG_ERR_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)o.stream;
+  const int mem = o.mem;
+  int rc;
+  Input i_A, i_B;
+  if ((rc = i_A.stage(A, (size_t)lda * (k - 1) + m, mem, st)) || (rc = i_B.stage(B, (size_t)ldb * (n - 1) + k, mem, st)))
+    return rc;
+  DevBuf b_C, b_rs;
+  double* d_C = C; double* d_rs = row_sum;
+  if (mem == LQG_MEM_HOST) {
+    if (C) { LQG_CUDA_TRY(b_C.alloc(((size_t)ldc * (n - 1) + m) * sizeof(double))); d_C = b_C.as<double>(); }
+    if (row_sum) { LQG_CUDA_TRY(b_rs.alloc(m * sizeof(double))); d_rs = b_rs.as<double>(); }
+  }
+  if (d_rs) LQG_CUDA_TRY(cudaMemsetAsync(d_rs, 0, m * sizeof(double), st));
+  Timer tm(st);
+  tm.start();
+  LQG_CUDA_TRY(launch_dgemm(m, n, k, i_A.dev, lda, i_B.dev, ldb, d_C, ldc, d_rs, 0, st));
+  tm.stop();
+  if (kernel_ms) *kernel_ms = tm.ms();
+  if (mem == LQG_MEM_HOST) {
+    if (C) {
+      if (ldc == m) LQG_CUDA_TRY(cudaMemcpyAsync(C, d_C, (size_t)m * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+      else LQG_CUDA_TRY(cudaMemcpy2DAsync(C, ldc * sizeof(double), d_C, ldc * sizeof(double), m * sizeof(double), n, cudaMemcpyDeviceToHost, st));
+    }
+    if (row_sum) LQG_CUDA_TRY(cudaMemcpyAsync(row_sum, d_rs, m * sizeof(double), cudaMemcpyDeviceToHost, st));
+  }
+  LQG_CUDA_TRY(cudaStreamSynchronize(st));
+  fold_launches();
+  return LQG_OK;
+}
+
+// ===========================================================================================
+extern "C" int lqg_bands(int32_t n_t, int64_t N, const double* ysim, int64_t ld, const double* probs,
+                         int32_t nprobs, double* mean, double* qtls, const lqg_opts* opts_,
+                         double* kernel_ms) {
+  if (!have_device()) return LQG_ERR_CUDA;
+  const lqg_opts o = opts_ ? *opts_ : default_opts();
+  if (n_t <= 0 || N <= 0 || !ysim || ld < n_t || nprobs < 0 || nprobs > 8 || (nprobs > 0 && (!probs || !qtls)) || !mean) {
+    set_error("lqg_bands: invalid argument (n_t=%d N=%lld nprobs=%d; at most 8 probabilities)", n_t, (long long)N, nprobs);
+    return LQG_ERR_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)o.stream;
+  const int mem = o.mem;
+  int rc;
+  std::vector<double> h_probs;
+  if (nprobs > 0 && (rc = fetch_host(h_probs, probs, nprobs, mem, st))) return rc;
+  for (int k = 0; k < nprobs; ++k)
+    if (!(h_probs[k] >= 0.0 && h_probs[k] <= 1.0)) { set_error("'probs' outside [0,1]"); return LQG_ERR_INVALID; }
+  Input i_y;
+  if ((rc = i_y.stage(ysim, (size_t)ld * (N - 1) + n_t, mem, st))) return rc;
+  DevBuf b_scr, b_mean, b_q;
+  LQG_CUDA_TRY(b_scr.alloc((size_t)n_t * N * sizeof(double)));
+  double* d_mean = mean; double* d_q = qtls;
+  if (mem == LQG_MEM_HOST) {
+    LQG_CUDA_TRY(b_mean.alloc(n_t * sizeof(double))); d_mean = b_mean.as<double>();
+    LQG_CUDA_TRY(b_q.alloc((size_t)std::max(1, nprobs) * n_t * sizeof(double))); d_q = b_q.as<double>();
+  }
+  Timer tm(st);
+  tm.start();
+  LQG_CUDA_TRY(launch_bands(n_t, N, i_y.dev, ld, h_probs.data(), nprobs, d_mean, d_q, b_scr.as<double>(), st));
+  tm.stop();
+  if (kernel_ms) *kernel_ms = tm.ms();
+  if (mem == LQG_MEM_HOST) {
+    LQG_CUDA_TRY(cudaMemcpyAsync(mean, d_mean, n_t * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (nprobs > 0) LQG_CUDA_TRY(cudaMemcpyAsync(qtls, d_q, (size_t)nprobs * n_t * sizeof(double), cudaMemcpyDeviceToHost, st));
+  }
+  LQG_CUDA_TRY(cudaStreamSynchronize(st));
+  fold_launches();
+  return LQG_OK;
+}

@@ -1,0 +1,149 @@
+// Shared device/host helpers for the lineqgpr_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/lineqgpr_b200.h"
+
+namespace lqg {
+
+constexpr double kMinT   = 0.00001;                 // tmg:src/HmcSampler.cpp:21
+constexpr double kPi     = 3.14159265358979323846;  // M_PI
+constexpr double kTwoPi  = 2 * kPi;                 // 2*M_PI as the reference writes it
+constexpr double kHalfPi = kPi / 2;                 // T = M_PI/2, tmg:src/HmcSampler.cpp:47
+constexpr double kBigG   = 1.0e300;                 // stands in for a dropped (infinite) bound
+constexpr double kFilterRel = 1.0e-9;               // safety margin of the hit-time filter
+
+// ---------------------------------------------------------------------------------------
+// error plumbing (host)
+void set_error(const char* fmt, ...);
+int64_t& launch_counter();
+#define LQG_CUDA_TRY(expr)                                                              \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      lqg::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,               \
+                     cudaGetErrorString(_e));                                           \
+      return LQG_ERR_CUDA;                                                              \
+    }                                                                                   \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------
+// Philox-4x32-10 (Salmon et al. 2011), counter-based: any draw is addressable, so the
+// pre-pass GEMM and the in-kernel restart path generate the same N(0,1) for the same
+// (chain, transition, restart, coordinate).
+struct Philox {
+  static constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+  static constexpr uint32_t W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+  __host__ __device__ static inline void round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#ifdef __CUDA_ARCH__
+    uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
+    uint32_t hi1 = __umulhi(M1, c[2]), lo1 = M1 * c[2];
+#else
+    uint64_t p0 = (uint64_t)M0 * c[0], p1 = (uint64_t)M1 * c[2];
+    uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+    uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+#endif
+    uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+  }
+  __host__ __device__ static inline void gen(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                             uint32_t k0, uint32_t k1, uint32_t (&out)[4]) {
+    uint32_t c[4] = {c0, c1, c2, c3};
+#pragma unroll
+    for (int i = 0; i < 10; ++i) { round(c, k0, k1); k0 += W0; k1 += W1; }
+    out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+  }
+};
+
+// 53-bit uniform strictly inside (0,1)
+__host__ __device__ inline double u01(uint32_t hi, uint32_t lo) {
+  uint64_t b = (((uint64_t)hi << 32) | lo) >> 11;                  // 53 bits
+  return ((double)b + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+// Two N(0,1) for the coordinate pair (2p, 2p+1) of momentum draw (chain, transition, restart).
+// Box-Muller in FP64.
+__device__ inline void normal_pair(uint64_t seed, uint64_t chain, uint32_t transition,
+                                   uint32_t restart, uint32_t pair, double& n0, double& n1) {
+  uint32_t r[4];
+  Philox::gen(pair, transition, restart, (uint32_t)chain,
+              (uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(chain >> 32) * 0x85EBCA6Bu, r);
+  double u1 = u01(r[0], r[1]), u2 = u01(r[2], r[3]);
+  double rad = sqrt(-2.0 * log(u1));
+  double s, c;
+  sincospi(2.0 * u2, &s, &c);
+  n0 = rad * c; n1 = rad * s;
+}
+
+// ---------------------------------------------------------------------------------------
+// One constraint's hit time, tmg:src/HmcSampler.cpp:157-181, operation for operation.
+// fa = f.a, fb = f.b.  Returns the candidate t, or 0 when the constraint offers no hit
+// (u <= |g|, or t <= min_t).  No FMA contraction here on purpose: the CPU reference is
+// compiled without it and these few flops decide discrete events.
+// Deliberately NOT inlined: it runs for the few survivors of the filter only, and keeping its
+// atan2/acos/sqrt temporaries out of the callers' register budget buys occupancy.
+static __device__ __noinline__ double hit_time_exact(double fa, double fb, double g) {
+  double u = sqrt(__dadd_rn(__dmul_rn(fa, fa), __dmul_rn(fb, fb)));     // :159
+  if (!(u > g && u > -g)) return 0.0;                                   // :160
+  double phi = atan2(-fa, fb);                                          // :161
+  double t1 = acos(-g / u) - phi;                                       // :162
+  if (t1 < 0) t1 += kTwoPi;                                             // :165
+  if (fabs(t1) < kMinT) t1 = 0;                                         // :166
+  else if (fabs(t1 - kTwoPi) < kMinT) t1 = 0;                           // :167
+  double t2 = __dsub_rn(-t1, __dmul_rn(2.0, phi));                      // :170
+  if (t2 < 0) t2 += kTwoPi;                                             // :171
+  if (t2 < 0) t2 += kTwoPi;                                             // :172
+  if (fabs(t2) < kMinT) t2 = 0;                                         // :174
+  else if (fabs(t2 - kTwoPi) < kMinT) t2 = 0;                           // :175
+  double t = t1;                                                        // :178
+  if (t1 == 0) t = t2;                                                  // :179
+  else if (t2 == 0) t = t1;                                             // :180
+  else t = (t1 < t2 ? t1 : t2);                                         // :181
+  return t > kMinT ? t : 0.0;                                           // :183 (first half)
+}
+
+// Conservative filter in front of hit_time_exact.  y(t) = fa sin t + fb cos t + g is the
+// constraint value along the trajectory; only hits with t <= tt can matter to sampleNext
+// (tmg:src/HmcSampler.cpp:82 breaks when tt < t), and such a hit needs a zero of y on [0,tt].
+// On an interval no longer than pi/2, y has at most one interior extremum; it is a minimum
+// iff y'(0) = fa < 0 and y'(tt) = fa cos tt - fb sin tt > 0.  Otherwise min y = min(y(0), y(tt)).
+// A constraint is skipped only when that minimum is above a margin far larger than any
+// rounding difference, so every constraint that can win the arg-min is still evaluated by
+// hit_time_exact and tie/threshold semantics are untouched.
+//   S = sin tt, C = cos tt; scale >= |fa|+|fb|+|g|
+__device__ __forceinline__ bool may_hit(double fa, double fb, double g, double S, double C,
+                                        double margin) {
+  double y0 = fb + g;
+  double y1 = fma(fa, S, fma(fb, C, g));
+  double d1 = fma(fa, C, -fb * S);
+  bool interior_min = (fa < 0.0) && (d1 > 0.0);
+  return !(y0 > margin && y1 > margin) || interior_min;
+}
+
+// (t, key) lexicographic min with t == 0 meaning "none": lowest key wins ties, which is the
+// reference's "first index wins" (strict < at tmg:src/HmcSampler.cpp:183).
+struct Hit {
+  double t; int key;
+};
+__device__ __forceinline__ bool hit_better(double t, int key, double bt, int bkey) {
+  return t > 0.0 && (bt == 0.0 || t < bt || (t == bt && key < bkey));
+}
+__device__ __forceinline__ Hit warp_min_hit(Hit h) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    double ot = __shfl_xor_sync(0xffffffffu, h.t, off);
+    int ok = __shfl_xor_sync(0xffffffffu, h.key, off);
+    if (hit_better(ot, ok, h.t, h.key)) { h.t = ot; h.key = ok; }
+  }
+  return h;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
+}  // namespace lqg

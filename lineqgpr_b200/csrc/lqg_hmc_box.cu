@@ -1,0 +1,383 @@
+// Exact bouncing HMC for box constraints lb <= eta <= ub, run in the eta frame.
+//
+// What it replaces: tmvrnorm.HMC -> tmg::rtmg -> HmcSampler::sampleNext
+//   R/lineqGPsamplers.R:99-143, tmg:R/tmg.R:1-108, tmg:src/HmcSampler.cpp:43-133,152-189,244-265
+//
+// tmvrnorm.HMC only ever builds f = [I;-I] (finite rows), g = c(-lb, ub)
+// (R/lineqGPsamplers.R:128-136), so every whitened constraint row is +-Ri[i,:] with
+// Ri Ri' = Sigma (tmg:R/tmg.R:25-27,50).  Carrying x_a = Ri a and x_b = Ri b instead of (a, b):
+//   f_k.a = s x_a[i],  f_k.b = s x_b[i],  f_k.f_k = Sigma[i,i],  g2_k = s(mu_i - bound_i)
+//   bounce on coordinate j:  x_b <- sin t x_a + cos t x_b ;  v <- cos t x_a - sin t x_b
+//                            x_a <- v - 2 (v_j / Sigma_jj) Sigma[:,j] ;  velsign = s x_a[j]
+//   emitted sample = mu + x_b  (no un-whitening GEMM, tmg:R/tmg.R:106)
+// so the hit search is O(c) and the reflection O(d) instead of O(c d).
+//
+// Mapping: one chain per CTA of G warps; every thread keeps CPT coordinates of (x_a, x_b)
+// and their two bound offsets in REGISTERS (coordinate i = tid + k*32G, so the Sigma column
+// and the output are read/written coalesced).  The bounce-time search is: register-only
+// filter (may_hit) -> exact tmg formula for the survivors -> warp-shuffle arg-min ->
+// one shared-memory slot per warp -> one barrier.  CTAs are persistent and pull chains from
+// an atomic queue, so chains with very different bounce counts do not stall an SM.
+#include <limits.h>
+
+#include "lqg_common.cuh"
+#include "lqg_kernels.h"
+
+namespace lqg {
+
+struct RedSlot {
+  double t; double xa; double xb; int key; int ok;
+};
+
+// fresh momentum x_a = U a for this chain, computed by the CTA itself (restarts, injected
+// draws, or when the GEMM pre-pass is off).  a ~ N(0, I_d) drawn like tmg:src/HmcSampler.cpp:54-55.
+template <int G, int CPT>
+__device__ __forceinline__ bool draw_momentum(const BoxParams& p, int chain, uint32_t s,
+                                              uint32_t restart, int64_t& inj_pos,
+                                              double* a_sm, double (&xa)[CPT]) {
+  constexpr int T = 32 * G;
+  const int tid = threadIdx.x;
+  const int d = p.d;
+  if (p.injected) {
+    if (inj_pos + d > p.n_injected) return false;                 // uniform across the CTA
+    const double* src = p.injected + (size_t)chain * p.n_injected + inj_pos;
+    for (int i = tid; i < d; i += T) a_sm[i] = src[i];
+    inj_pos += d;
+  } else {
+    const uint64_t gchain = (uint64_t)(p.chain_offset + chain);
+    for (int pr = tid; 2 * pr < d; pr += T) {
+      double n0, n1;
+      normal_pair(p.seed, gchain, s, restart, (uint32_t)pr, n0, n1);
+      a_sm[2 * pr] = n0;
+      if (2 * pr + 1 < d) a_sm[2 * pr + 1] = n1;
+    }
+  }
+  __syncthreads();
+  double acc[CPT];
+#pragma unroll
+  for (int k = 0; k < CPT; ++k) acc[k] = 0.0;
+  const double* U = p.U;
+  // x_a[i] = sum_col U[i,col] a[col]; U column-major so a warp reads 256 contiguous bytes
+#pragma unroll 2
+  for (int col = 0; col < d; ++col) {
+    const double av = a_sm[col];
+    const double* ucol = U + (size_t)col * d;
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+      const int i = tid + k * T;
+      if (i < d && (!p.u_upper || i <= col)) acc[k] = fma(__ldg(ucol + i), av, acc[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < CPT; ++k) xa[k] = acc[k];
+  __syncthreads();                                                 // a_sm is reused
+  return true;
+}
+
+template <int G, int CPT, bool GSM, int MINB>
+__global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p) {
+  constexpr int T = 32 * G;
+  extern __shared__ double a_sm[];                 // d doubles: staging of a fresh draw
+                                                   // (+ 2d doubles of bound offsets when GSM)
+  __shared__ RedSlot red[2][G];
+  __shared__ int chain_sm;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int d = p.d;
+
+  // per-coordinate bound offsets: registers for small CPT, shared memory (padded to CPT*T
+  // entries, read conflict-free) when the register budget is better spent on occupancy
+  constexpr int NG = GSM ? 1 : CPT;
+  double glo_r[NG], ghi_r[NG];
+  double* glo_s = a_sm + d;
+  double* ghi_s = glo_s + CPT * T;
+  if (GSM) {
+    for (int i = tid; i < CPT * T; i += T) {
+      glo_s[i] = i < d ? p.glo[i] : kBigG;
+      ghi_s[i] = i < d ? p.ghi[i] : kBigG;
+    }
+    __syncthreads();
+  } else {
+#pragma unroll
+    for (int k = 0; k < NG; ++k) {
+      const int i = tid + k * T;
+      glo_r[k] = i < d ? p.glo[i] : kBigG;
+      ghi_r[k] = i < d ? p.ghi[i] : kBigG;
+    }
+  }
+  const double abs_eps = p.abs_eps;
+
+  for (;;) {
+    if (tid == 0) chain_sm = atomicAdd(p.next_chain, 1);
+    __syncthreads();
+    const int chain = chain_sm;
+    __syncthreads();
+    if (chain >= p.n_chains) break;
+
+    double xa[CPT], xb[CPT];
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+      const int i = tid + k * T;
+      xb[k] = i < d ? p.state[(size_t)chain * d + i] : 0.0;
+      xa[k] = 0.0;
+    }
+    int64_t inj_pos = p.inj_pos ? p.inj_pos[chain] : 0;
+    int status = p.chain_status[chain];
+    unsigned long long n_bounce = 0, n_search = 0, n_vel = 0, n_chk = 0, n_exact = 0, n_trans = 0;
+    int parity = 0;
+
+    for (int s = p.s_begin; s < p.s_end && status == 0; ++s) {
+      uint32_t restart = 0;
+      for (;;) {                                                   // while(2), HmcSampler.cpp:51
+        if (restart == 0 && p.xa_pre != nullptr) {
+          const double* src = p.xa_pre + ((size_t)chain * (p.s_end - p.s_begin) + (s - p.s_begin)) * d;
+#pragma unroll
+          for (int k = 0; k < CPT; ++k) {
+            const int i = tid + k * T;
+            xa[k] = i < d ? src[i] : 0.0;
+          }
+        } else if (!draw_momentum<G, CPT>(p, chain, (uint32_t)s, restart, inj_pos, a_sm, xa)) {
+          status = LQG_ERR_DRAWS_EXHAUSTED;
+          break;
+        }
+        double tt = kHalfPi;                                       // :57
+        double velsign = 0.0;                                      // :53
+        bool end_ok = false;
+        double S = 1.0, C = 0.0;
+        for (;;) {                                                 // while(1), :64
+          sincos(tt, &S, &C);
+          // ---- hit search over this thread's coordinates (both sides) ----
+          double bt = 0.0, bxa = 0.0, bxb = 0.0; int bkey = INT_MAX; bool ok = true;
+#pragma unroll
+          for (int k = 0; k < CPT; ++k) {
+            const int i = tid + k * T;
+            const double a_ = xa[k], b_ = xb[k];
+            const double y = fma(a_, S, b_ * C);                   // position at time tt (:119)
+            const double dy = fma(a_, C, -b_ * S);
+            const double base = fabs(a_) + fabs(b_);
+            {                                                      // lower bound row: f = +e_i
+              const double g = GSM ? glo_s[i] : glo_r[GSM ? 0 : k];
+              const double m = fma(kFilterRel, base + fabs(g), abs_eps);
+              const double y0 = b_ + g, y1 = y + g;
+              ok = ok && (y1 >= 0.0);
+              if (!(y0 > m && y1 > m) || (a_ < 0.0 && dy > 0.0)) {
+                const double t = hit_time_exact(a_, b_, g);
+                ++n_exact;
+                if (hit_better(t, i, bt, bkey)) { bt = t; bkey = i; bxa = a_; bxb = b_; }
+              }
+            }
+            {                                                      // upper bound row: f = -e_i
+              const double g = GSM ? ghi_s[i] : ghi_r[GSM ? 0 : k];
+              const double m = fma(kFilterRel, base + fabs(g), abs_eps);
+              const double y0 = g - b_, y1 = g - y;
+              ok = ok && (y1 >= 0.0);
+              if (!(y0 > m && y1 > m) || (a_ > 0.0 && dy < 0.0)) {
+                const double t = hit_time_exact(-a_, -b_, g);
+                ++n_exact;
+                if (hit_better(t, d + i, bt, bkey)) { bt = t; bkey = d + i; bxa = a_; bxb = b_; }
+              }
+            }
+          }
+          // ---- arg-min: warp shuffle, then one slot per warp ----
+          Hit w = warp_min_hit(Hit{bt, bkey});
+          const bool wok = __all_sync(0xffffffffu, ok);
+          const unsigned owner = __ballot_sync(0xffffffffu, bt == w.t && bkey == w.key);
+          const int src = __ffs(owner) - 1;
+          double wxa = __shfl_sync(0xffffffffu, bxa, src);
+          double wxb = __shfl_sync(0xffffffffu, bxb, src);
+          bool all_ok = wok;
+          if (G > 1) {
+            if (lane == 0) {
+              RedSlot& r = red[parity][warp];
+              r.t = w.t; r.key = w.key; r.xa = wxa; r.xb = wxb; r.ok = wok;
+            }
+            __syncthreads();
+            w.t = 0.0; w.key = INT_MAX; all_ok = true;
+#pragma unroll
+            for (int g2 = 0; g2 < G; ++g2) {
+              const RedSlot r = red[parity][g2];
+              all_ok = all_ok && r.ok;
+              if (hit_better(r.t, r.key, w.t, w.key)) { w.t = r.t; w.key = r.key; wxa = r.xa; wxb = r.xb; }
+            }
+            parity ^= 1;
+          }
+          ++n_search;
+          const double t = w.t;
+          if (t == 0.0 || tt < t) { end_ok = all_ok; break; }      // :82
+          // ---- bounce: rotate to the wall, reflect (:90-110) ----
+          ++n_bounce;
+          tt = tt - t;                                             // :90
+          double st, ct;
+          sincos(t, &st, &ct);
+          const int j = w.key < d ? w.key : w.key - d;
+          const double side = w.key < d ? 1.0 : -1.0;
+          const double sjj = __ldg(p.sdiag + j);
+          const double vj = __dsub_rn(__dmul_rn(ct, wxa), __dmul_rn(st, wxb));   // hit_vel[j]
+          const double alpha2 = 2.0 * (vj / sjj);                  // 2*alpha, alpha = f.v / f.f
+          const double* scol = p.Sigma + (size_t)j * d;
+#pragma unroll
+          for (int k = 0; k < CPT; ++k) {
+            const int i = tid + k * T;
+            const double sc = i < d ? __ldg(scol + i) : 0.0;
+            const double a_ = xa[k], b_ = xb[k];
+            xb[k] = fma(st, a_, ct * b_);                          // new_b  (:91)
+            const double v = fma(ct, a_, -st * b_);                // hit_vel (:92)
+            xa[k] = fma(-alpha2, sc, v);                           // reflected velocity (:109)
+          }
+          velsign = side * __dsub_rn(vj, __dmul_rn(alpha2, sjj));  // a.f (:110)
+          if (velsign < 0.0) break;                                // :112
+        }
+        if (velsign < 0.0) {                                       // :117
+          ++n_vel;
+          if (++restart > (uint32_t)p.max_restarts) { status = LQG_ERR_RESTART_CAP; break; }
+          continue;
+        }
+        // ---- end point: reference check (:121) and exact check of the emitted value ----
+        // (S, C) are still sin/cos of the final tt: bb = sin(tt) a + cos(tt) b  (:119)
+        bool fine = end_ok;
+        if (fine) {
+#pragma unroll
+          for (int k = 0; k < CPT; ++k) {
+            const int i = tid + k * T;
+            if (i < d) {
+              const double e = __ldg(p.mu + i) + fma(xa[k], S, xb[k] * C);
+              fine = fine && (e >= __ldg(p.lb + i)) && (e <= __ldg(p.ub + i));
+            }
+          }
+        }
+        fine = (G > 1) ? (__syncthreads_and(fine) != 0) : __all_sync(0xffffffffu, fine);
+        if (fine) {
+#pragma unroll
+          for (int k = 0; k < CPT; ++k) xb[k] = fma(xa[k], S, xb[k] * C);   // lastSample = bb (:123)
+          break;
+        }
+        ++n_chk;                                                   // :130
+        if (++restart > (uint32_t)p.max_restarts) { status = LQG_ERR_RESTART_CAP; break; }
+      }
+      if (status != 0) break;
+      ++n_trans;
+      if (s >= p.burn_in) {                                        // tmg:R/tmg.R:105 drops burn-in
+        double* dst = p.out + ((size_t)chain * p.n_per_chain + (s - p.burn_in)) * d;
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) {
+          const int i = tid + k * T;
+          if (i < d) dst[i] = __ldg(p.mu + i) + xb[k];             // tmg:R/tmg.R:106
+        }
+      }
+    }
+
+    // ---- persist chain state and counters ----
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+      const int i = tid + k * T;
+      if (i < d) p.state[(size_t)chain * d + i] = xb[k];
+    }
+    n_exact = (unsigned long long)warp_sum((double)n_exact);
+    if (lane == 0) atomicAdd(p.stats + 5, n_exact);
+    if (tid == 0) {
+      if (p.inj_pos) p.inj_pos[chain] = inj_pos;
+      p.chain_status[chain] = status;
+      atomicAdd(p.stats + 0, n_trans);
+      atomicAdd(p.stats + 1, n_bounce);
+      atomicAdd(p.stats + 2, n_search);
+      atomicAdd(p.stats + 3, n_vel);
+      atomicAdd(p.stats + 4, n_chk);
+    }
+  }
+}
+
+// glo = mu - lb, ghi = ub - mu (kBigG for infinite bounds), sdiag = diag(Sigma)
+__global__ void box_prep_kernel(int d, const double* mu, const double* lb, const double* ub,
+                                const double* Sigma, double* glo, double* ghi, double* sdiag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d) return;
+  const double l = lb[i], u = ub[i], m = mu[i];
+  glo[i] = isinf(l) ? kBigG : m - l;       // g2 = f mu + g with g = -lb  (tmg:R/tmg.R:51)
+  ghi[i] = isinf(u) ? kBigG : u - m;       //                      g = +ub
+  sdiag[i] = Sigma[(size_t)i * d + i];
+}
+
+// state[:, chain] = init[:, chain] - mu   (x_b = Ri z0 = init - mu, tmg:R/tmg.R:28)
+__global__ void box_init_state_kernel(int d, int n_chains, const double* init, int64_t init_ld,
+                                      const double* mu, double* state) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)d * n_chains) return;
+  const int i = (int)(idx % d);
+  const size_t ch = idx / d;
+  state[idx] = init[ch * (size_t)init_ld + i] - mu[i];
+}
+
+// independent audit of the emitted samples: counts entries outside [lb, ub]
+__global__ void box_violation_kernel(int d, size_t n_cols, const double* out, const double* lb,
+                                     const double* ub, unsigned long long* count) {
+  unsigned long long bad = 0;
+  const size_t total = (size_t)d * n_cols;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(idx % d);
+    const double v = out[idx];
+    if (!(v >= lb[i] && v <= ub[i])) ++bad;     // NaN counts as a violation
+  }
+  bad = (unsigned long long)warp_sum((double)bad);
+  if ((threadIdx.x & 31) == 0 && bad) atomicAdd(count, bad);
+}
+
+template <int G, int CPT, bool GSM, int MINB>
+static cudaError_t launch_box_t(const BoxParams& p, int grid, cudaStream_t st) {
+  const size_t smem = ((size_t)p.d + (GSM ? 2 * CPT * 32 * G : 0)) * sizeof(double);
+  auto kern = hmc_box_kernel<G, CPT, GSM, MINB>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  if (grid <= 0) {
+    int per_sm = 0, dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * G, smem);
+    if (e != cudaSuccess) return e;
+    grid = sms * (per_sm > 0 ? per_sm : 1);          // persistent: every resident slot, once
+  }
+  if (grid > p.n_chains) grid = p.n_chains;
+  kern<<<grid, 32 * G, smem, st>>>(p);
+  ++launch_counter();
+  return cudaGetLastError();
+}
+
+// picks (warps per chain, coordinates per thread) from d
+cudaError_t launch_hmc_box(const BoxParams& p, int grid, cudaStream_t st) {
+  const int d = p.d;
+  if (d <= 32)   return launch_box_t<1, 1, false, 16>(p, grid, st);
+  if (d <= 64)   return launch_box_t<1, 2, false, 16>(p, grid, st);
+  if (d <= 128)  return launch_box_t<1, 4, false, 16>(p, grid, st);
+  if (d <= 256)  return launch_box_t<2, 4, false, 8>(p, grid, st);
+  if (d <= 512)  return launch_box_t<4, 4, false, 4>(p, grid, st);
+  if (d <= 1024) return launch_box_t<4, 8, true, 4>(p, grid, st);
+  if (d <= 2048) return launch_box_t<8, 8, true, 2>(p, grid, st);
+  if (d <= 4096) return launch_box_t<8, 16, true, 1>(p, grid, st);
+  if (d <= 8192) return launch_box_t<16, 16, true, 1>(p, grid, st);
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_box_prep(int d, const double* mu, const double* lb, const double* ub,
+                            const double* Sigma, double* glo, double* ghi, double* sdiag,
+                            cudaStream_t st) {
+  box_prep_kernel<<<(d + 127) / 128, 128, 0, st>>>(d, mu, lb, ub, Sigma, glo, ghi, sdiag);
+  ++launch_counter();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_box_init_state(int d, int n_chains, const double* init, int64_t init_ld,
+                                  const double* mu, double* state, cudaStream_t st) {
+  const size_t total = (size_t)d * n_chains;
+  box_init_state_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d, n_chains, init, init_ld, mu, state);
+  ++launch_counter();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_box_violations(int d, size_t n_cols, const double* out, const double* lb,
+                                  const double* ub, unsigned long long* count, cudaStream_t st) {
+  box_violation_kernel<<<148 * 8, 256, 0, st>>>(d, n_cols, out, lb, ub, count);
+  ++launch_counter();
+  return cudaGetLastError();
+}
+
+}  // namespace lqg

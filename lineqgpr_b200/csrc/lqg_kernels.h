@@ -1,0 +1,122 @@
+// Internal launch interfaces between the C-ABI layer (lqg_capi.cu) and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lqg {
+
+// ---- box-form HMC (lqg_hmc_box.cu) -----------------------------------------------------
+struct BoxParams {
+  int d;
+  const double* mu;        // [d]
+  const double* lb;        // [d]
+  const double* ub;        // [d]
+  const double* U;         // d x d col-major, U U' = Sigma
+  int u_upper;
+  const double* Sigma;     // d x d col-major
+  const double* glo;       // [d] mu - lb  (kBigG when lb = -Inf)
+  const double* ghi;       // [d] ub - mu  (kBigG when ub = +Inf)
+  const double* sdiag;     // [d] Sigma_jj
+  double abs_eps;          // absolute part of the filter margin
+  double* state;           // d x n_chains, centred position x_b, in/out
+  const double* xa_pre;    // nullable: d x (n_chains * (s_end - s_begin)) pre-pass momenta
+  int n_chains;
+  int s_begin, s_end;      // transitions [s_begin, s_end) of every chain run in this launch
+  int burn_in, n_per_chain;
+  double* out;             // d x (n_chains * n_per_chain)
+  uint64_t seed;
+  int64_t chain_offset;
+  const double* injected;  // nullable [n_chains][n_injected]
+  int64_t n_injected;
+  int64_t* inj_pos;        // nullable [n_chains]
+  int max_restarts;
+  int* next_chain;         // work queue head (zeroed before launch)
+  unsigned long long* stats;  // [8]: transitions,bounces,searches,vel,chk,exact,violations,failed
+  int* chain_status;       // [n_chains]
+};
+
+cudaError_t launch_hmc_box(const BoxParams& p, int grid, cudaStream_t st);
+cudaError_t launch_box_prep(int d, const double* mu, const double* lb, const double* ub,
+                            const double* Sigma, double* glo, double* ghi, double* sdiag,
+                            cudaStream_t st);
+cudaError_t launch_box_init_state(int d, int n_chains, const double* init, int64_t init_ld,
+                                  const double* mu, double* state, cudaStream_t st);
+cudaError_t launch_box_violations(int d, size_t n_cols, const double* out, const double* lb,
+                                  const double* ub, unsigned long long* count, cudaStream_t st);
+
+// ---- canonical-frame HMC with dense constraints (lqg_hmc_canonical.cu) ------------------
+struct CanonParams {
+  int d, c;
+  const double* F;         // c x d col-major (16-byte aligned, padded to an even element count)
+  const double* g;         // [c]
+  const double* frow2;     // [c] f.f per row
+  const double* fnorm;     // [c] |f|
+  double* state;           // d x n_chains (position b in the canonical frame), in/out
+  int n_chains;
+  int s_begin, s_end, burn_in, n_per_chain;
+  double* out;             // d x (n_chains * n_per_chain)
+  uint64_t seed;
+  int64_t chain_offset;
+  const double* injected;
+  int64_t n_injected;
+  int64_t* inj_pos;
+  int max_restarts;
+  int f_in_smem;           // stage F in shared memory with one bulk (TMA) copy per CTA
+  int* next_chain;
+  unsigned long long* stats;
+  int* chain_status;
+};
+cudaError_t launch_hmc_canonical(const CanonParams& p, int grid, cudaStream_t st);
+cudaError_t launch_canon_rownorms(int d, int c, const double* F, double* frow2, double* fnorm,
+                                  cudaStream_t st);
+cudaError_t launch_canon_violations(int d, int c, size_t n_cols, const double* F, const double* g,
+                                    const double* fnorm, const double* out,
+                                    unsigned long long* count, cudaStream_t st);
+size_t canon_smem_bytes(int d, int c, int f_in_smem);
+int canon_f_fits_smem(int d, int c);
+
+// ---- momentum pre-pass + generic FP64 tensor-core GEMM (lqg_dgemm.cu) -------------------
+// B operand generated on the fly: B[k, col] = N(0,1) draw (chain = col / round_len,
+// transition = s_begin + col % round_len, restart 0, coordinate k)
+struct NormalGen {
+  uint64_t seed;
+  int64_t chain_offset;
+  int round_len;
+  int s_begin;
+};
+cudaError_t launch_dgemm(int m, int n, int k, const double* A, int64_t lda, const double* B,
+                         int64_t ldb, double* C, int64_t ldc, double* row_sum, int a_upper,
+                         cudaStream_t st);
+cudaError_t launch_fill_normals(int d, size_t n_cols, double* A, const NormalGen& g, cudaStream_t st);
+
+// ---- RSM (lqg_rsm.cu) -------------------------------------------------------------------
+struct RsmParams {
+  int d;
+  const double* map; const double* factor; const double* w; const double* lb; const double* ub;
+  uint64_t seed;
+  int64_t first_proposal;  // global index of the first proposal of this round
+  int64_t n_proposals;     // proposals in this round
+  const double* inj_z;     // nullable d x P
+  const double* inj_u;     // nullable
+  int64_t n_inj_u;
+  int64_t inbox_before;    // in-box proposals in earlier rounds (rank offset of inj_u)
+  unsigned char* flags;    // [n_proposals] bit0 = in box, bit1 = accepted
+  double* tval;            // [n_proposals] exp((map - x)' w) for in-box proposals
+};
+int rsm_blocks(int64_t n_proposals);
+// one round: evaluate, rank, accept, ordered compaction + emission
+//   block_cnt [rsm_blocks], inbox_off / acc_off [rsm_blocks + 1] scratch; counters [2]
+cudaError_t launch_rsm_round(const RsmParams& q, int* block_cnt, int64_t* inbox_off, int64_t* acc_off,
+                             int64_t slot_base, int64_t nsim, double* out,
+                             unsigned long long* counters, cudaStream_t st);
+
+// ---- bands (lqg_bands.cu) ---------------------------------------------------------------
+// ysim n_t x N col-major (ld).  scratch: N x n_t doubles (transposed copy).
+cudaError_t launch_bands(int n_t, int64_t N, const double* ysim, int64_t ld, const double* probs_host,
+                         int nprobs, double* mean, double* qtls, double* scratch,
+                         cudaStream_t st);
+
+// ---- peaks (lqg_peaks.cu) ---------------------------------------------------------------
+cudaError_t measure_fp64_peaks(double* dfma_tflops, double* dmma_tflops, cudaStream_t st);
+
+}  // namespace lqg

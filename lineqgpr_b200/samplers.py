@@ -1,0 +1,193 @@
+"""`tmvrnorm` and its samplers: the reference's operator interface for the hot path, same names,
+argument meaning and error behaviour, with the bodies replaced by calls into the C ABI
+(include/lineqgpr_b200.h).  Mirrors
+
+  tmvrnorm generic      R/lineqGPutils.R:57-58     (S3 dispatch on class(object))
+  tmvrnorm.HMC          R/lineqGPsamplers.R:99-143 (+ tmg::rtmg's R wrapper, tmg:R/tmg.R:1-108)
+  tmvrnorm.RSM          R/lineqGPsamplers.R:36-61
+  tmvrnorm.ExpT         R/lineqGPsamplers.R:179-185
+
+`object` is the R list `list(mu, [map], Sigma, lb, ub)` as a dict; its S3 class is the key
+"class" (or the `method=` argument).  The result is a d x nsim array, samples in columns.
+
+What stays on the host, exactly where the reference has it on the host: the one-off O(d^3)
+whitening algebra (solve, chol, triangular inverse).  Everything per-sample runs on the GPU.
+Extensions (all optional keys of `control`): "n.chains" (independent chains; 1 reproduces the
+reference's single serial chain), "seed", "prepass", "injected", "max.restarts",
+"chain.offset", "device" (keep results in device memory as a torch tensor).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib as L
+
+EPSILON = 1e-9       # R/lineqGPsamplers.R:127
+
+
+class TmvStats(dict):
+    """Counters of the last sampler call (bounces, restarts, timings ...)."""
+
+
+last_stats = TmvStats()
+
+
+def _as_par(object):
+    tmvPar = dict(object)
+    mu = np.asarray(tmvPar["mu"], float).ravel()
+    if "map" not in tmvPar or tmvPar["map"] is None:
+        tmvPar["map"] = mu                                             # R/lineqGPsamplers.R:39-40, :107-108
+    tmvPar["mu"] = mu
+    tmvPar["map"] = np.asarray(tmvPar["map"], float).ravel()
+    tmvPar["Sigma"] = np.asarray(tmvPar["Sigma"], float)
+    d = mu.size
+    for k in ("lb", "ub"):
+        v = np.asarray(tmvPar[k], float).ravel()
+        tmvPar[k] = np.repeat(v, d) if v.size == 1 else v
+    return tmvPar
+
+
+def whiten_box(mu, Sigma):
+    """The whitening of tmg::rtmg for tmvrnorm.HMC's call (R/lineqGPsamplers.R:139-141 ->
+    tmg:R/tmg.R:15-28): H = solve(Sigma); M = (H+H')/2; positive-definiteness check;
+    R = chol(M); Ri = solve(R).  Returns Ri (upper triangular, Ri Ri' = M^-1 ~ Sigma)."""
+    H = np.linalg.inv(Sigma)                                           # solve(Sigma)
+    M = (H + H.T) / 2                                                  # tmg:R/tmg.R:15
+    try:
+        Rl = np.linalg.cholesky(M)                                     # R = chol(M) = Rl'
+    except np.linalg.LinAlgError:
+        raise ValueError("Error: M must be positive definite.")        # tmg:R/tmg.R:17-20
+    import scipy.linalg as sla
+    Ri = sla.solve_triangular(Rl.T, np.eye(M.shape[0]), lower=False)   # Ri = solve(R)
+    return np.triu(Ri)
+
+
+def tmvrnorm_HMC(object, nsim, control=None, **kw):
+    """tmvrnorm.HMC (R/lineqGPsamplers.R:99-143) on the GPU: box-form exact HMC, lqg_hmc_box."""
+    control = dict(control or {})
+    control.setdefault("burn.in", 100)                                 # :100-101
+    tmvPar = _as_par(object)
+    mu, Sigma, lb, ub = tmvPar["mu"], tmvPar["Sigma"], tmvPar["lb"], tmvPar["ub"]
+    d = mu.size
+    control.setdefault("mvec", d)                                      # :102-103 (treated as length(mu): Q3)
+    if lb.size != d or ub.size != d:
+        raise ValueError("The bounds have to be d-dimensionals")       # R/lineqGPutils.R:355-356
+    if np.any(lb >= ub):
+        raise ValueError('The elements from "u" has to be greater than the elements from "l"')
+    init = np.minimum(np.maximum(tmvPar["map"], lb + EPSILON), ub - EPSILON)   # :133-135
+    nsim = int(nsim)
+    n_chains = int(control.get("n.chains", min(nsim, 1024)))
+    n_chains = max(1, min(n_chains, nsim))
+    n_per = -(-nsim // n_chains)
+    U = control.get("U")
+    if U is None:
+        U = whiten_box(mu, Sigma)
+    seed = control.get("seed")
+    if seed is None:
+        seed = int(np.random.randint(1, 10000000))                     # tmg:R/tmg.R:102
+    injected = control.get("injected")
+    n_inj = 0
+    if injected is not None:
+        injected = np.ascontiguousarray(injected, dtype=np.float64).reshape(n_chains, -1)
+        n_inj = injected.shape[1]
+    opts = L.make_opts(mem=L.MEM_HOST, seed=seed, n_chains=n_chains,
+                       max_restarts=int(control.get("max.restarts", 0)),
+                       chain_offset=int(control.get("chain.offset", 0)),
+                       injected=injected, n_injected=n_inj, prepass=int(control.get("prepass", -1)))
+    Uf, Sf = L.f64(U), L.f64(Sigma)
+    mu_c, lb_c, ub_c, init_c = (np.ascontiguousarray(v, dtype=np.float64) for v in (mu, lb, ub, init))
+    out = np.empty((d, n_chains * n_per), order="F")
+    stats = L.HmcStats()
+    rc = L.lib().lqg_hmc_box(d, L.ptr(mu_c), L.ptr(Uf), 1, L.ptr(Sf), L.ptr(lb_c), L.ptr(ub_c),
+                             L.ptr(init_c), 0, n_per, int(control["burn.in"]), opts, L.ptr(out), None, stats)
+    last_stats.clear(); last_stats.update(stats.asdict(), sampler="HMC", n_chains=n_chains, n_per_chain=n_per, seed=seed)
+    L.check(rc, "tmvrnorm.HMC")
+    return out[:, :nsim]                                               # :142  t(xi): d x nsim
+
+
+def mvrnorm_factor(Sigma):
+    """MASS::mvrnorm's factor eS$vectors %*% diag(sqrt(pmax(ev, 0))) (the reference recomputes
+    eigen(Sigma) at every proposal, R/lineqGPsamplers.R:50; it is hoisted here)."""
+    ev, V = np.linalg.eigh(np.asarray(Sigma, float))
+    ev, V = ev[::-1], V[:, ::-1]
+    return V * np.sqrt(np.maximum(ev, 0.0))[None, :]
+
+
+def tmvrnorm_RSM(object, nsim, control=None, **kw):
+    """tmvrnorm.RSM (R/lineqGPsamplers.R:36-61) on the GPU: batched proposals, lqg_rsm."""
+    control = dict(control or {})
+    tmvPar = _as_par(object)
+    map_, Sigma, lb, ub = tmvPar["map"], tmvPar["Sigma"], tmvPar["lb"], tmvPar["ub"]
+    d = map_.size
+    Lc = np.linalg.cholesky(Sigma)                                     # chol2inv(chol(Sigma)) :42
+    Li = np.linalg.inv(Lc)
+    w = (Li.T @ Li) @ map_                                             # :43
+    factor = control.get("factor")
+    if factor is None:
+        factor = mvrnorm_factor(Sigma)
+    seed = control.get("seed")
+    if seed is None:
+        seed = int(np.random.randint(1, 2 ** 31 - 1))
+    inj_z, inj_u = control.get("injected"), control.get("injected.u")
+    n_z = n_u = 0
+    if inj_z is not None:
+        inj_z = L.f64(np.asarray(inj_z, float).reshape(d, -1)); n_z = inj_z.shape[1]
+    if inj_u is not None:
+        inj_u = np.ascontiguousarray(inj_u, dtype=np.float64); n_u = inj_u.size
+    opts = L.make_opts(mem=L.MEM_HOST, seed=seed, injected=inj_z, n_injected=n_z, injected_u=inj_u, n_injected_u=n_u)
+    nsim = int(nsim)
+    out = np.empty((d, nsim), order="F")
+    stats = L.RsmStats()
+    ff = L.f64(factor)
+    map_c, w_c, lb_c, ub_c = (np.ascontiguousarray(v, dtype=np.float64) for v in (map_, w, lb, ub))
+    rc = L.lib().lqg_rsm(d, L.ptr(map_c), L.ptr(ff), L.ptr(w_c), L.ptr(lb_c), L.ptr(ub_c), nsim,
+                         int(control.get("max.proposals", 0)), opts, L.ptr(out), stats)
+    last_stats.clear(); last_stats.update(stats.asdict(), sampler="RSM", seed=seed)
+    L.check(rc, "tmvrnorm.RSM")
+    return out
+
+
+def tmvrnorm_ExpT(object, nsim, control=None, **kw):
+    """tmvrnorm.ExpT (R/lineqGPsamplers.R:179-185) delegates to TruncatedNormal::mvrandn, whose
+    source is not part of the reference tree (no kernel in north_star (a)-(d),
+    parity unpinned).  Not provided on the GPU path; there is deliberately no CPU stand-in."""
+    raise NotImplementedError(
+        'sampler "ExpT" (TruncatedNormal::mvrandn) has no GPU implementation in lineqgpr_b200; '
+        'set model$localParam$sampler to "HMC" or "RSM"')
+
+
+_METHODS = {"HMC": tmvrnorm_HMC, "RSM": tmvrnorm_RSM, "ExpT": tmvrnorm_ExpT}
+
+
+def tmvrnorm(object, nsim, control=None, method=None, **kw):
+    """tmvrnorm <- function(object, nsim, ...) UseMethod("tmvrnorm")   (R/lineqGPutils.R:57-58)."""
+    cls = method or object.get("class")
+    if cls not in _METHODS:
+        raise TypeError(f'no applicable method for \'tmvrnorm\' applied to an object of class "{cls}"')
+    return _METHODS[cls](object, nsim, control, **kw)
+
+
+# --------------------------------------------------------------------------- canonical-frame access
+def rtmg_canonical(n, seed, initial, F, g, n_chains=1, burn_in=0, injected=None, max_restarts=0):
+    """The reference's native contract, .Call("rtmg", n, seed, initial, numlin, F, g, 0, NULL)
+    (tmg:R/tmg.R:104), served by lqg_hmc_canonical.  Returns (d x (n_chains*n) samples in the
+    canonical frame, stats)."""
+    initial = np.asarray(initial, float)
+    d = initial.shape[0]
+    F = L.f64(np.asarray(F, float).reshape(-1, d))
+    g = np.ascontiguousarray(g, dtype=np.float64)
+    c = F.shape[0]
+    n_inj = 0
+    if injected is not None:
+        injected = np.ascontiguousarray(injected, dtype=np.float64).reshape(n_chains, -1)
+        n_inj = injected.shape[1]
+    ld = 0 if initial.ndim == 1 else d
+    init_c = np.ascontiguousarray(initial.T if initial.ndim == 2 else initial, dtype=np.float64)
+    opts = L.make_opts(mem=L.MEM_HOST, seed=seed, n_chains=n_chains, max_restarts=max_restarts,
+                       injected=injected, n_injected=n_inj)
+    out = np.empty((d, n_chains * n), order="F")
+    stats = L.HmcStats()
+    rc = L.lib().lqg_hmc_canonical(d, c, L.ptr(F), L.ptr(g), L.ptr(init_c), ld, int(n), int(burn_in),
+                                   opts, L.ptr(out), None, stats)
+    L.check(rc, "rtmg")
+    return out, stats.asdict()

@@ -1,0 +1,122 @@
+"""simulate.lineqGP / simulate.lineqAGP tails and the band summaries, with the per-sample work
+on the GPU.  Mirrors
+
+  simulate.lineqGP    R/lineqGP.R:601-643   (eta-space parameters :611-614, tmvrnorm :626,
+                                             xi.sim = qr.solve(Lambda, eta) :639, ysim :640)
+  simulate.lineqAGP   R/lineqAGP.R:520-596  (mu := eta_MAP :567 (Q4), tmvrnorm :573, qr.solve :575;
+                                             PhiAll.test %*% xiAll.sim is left to the user :509-512)
+  band summaries      R/lineqGPutils.R:422-423, :294-296
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+
+from . import _lib as L
+from . import model as M
+from .samplers import tmvrnorm, last_stats
+
+
+def dgemm(A, B, row_sum=False, want_C=True):
+    """C = A %*% B on the FP64 tensor cores (lqg_dgemm). Host arrays in, host arrays out."""
+    A = L.f64(np.atleast_2d(np.asarray(A, float))); B = L.f64(np.atleast_2d(np.asarray(B, float)))
+    m, k = A.shape
+    k2, n = B.shape
+    if k != k2:
+        raise ValueError("non-conformable arguments")
+    C = np.empty((m, n), order="F") if want_C else None
+    rs = np.zeros(m) if row_sum else None
+    ms = L.C.c_double(0.0)
+    rc = L.lib().lqg_dgemm(m, n, k, L.ptr(A), m, L.ptr(B), k, L.ptr(C), m, L.ptr(rs),
+                           L.make_opts(mem=L.MEM_HOST), L.C.byref(ms))
+    L.check(rc, "lqg_dgemm")
+    return (C, rs) if row_sum else C
+
+
+def bands(ysim, probs=(0.025, 0.975)):
+    """(ymean, qtls) = (apply(ysim,1,mean), apply(ysim,1,quantile,probs)); qtls is nprobs x n_t."""
+    ysim = L.f64(np.atleast_2d(np.asarray(ysim, float)))
+    n_t, N = ysim.shape
+    probs = np.ascontiguousarray(probs, dtype=np.float64)
+    mean = np.empty(n_t)
+    q = np.empty((probs.size, n_t), order="F")
+    ms = L.C.c_double(0.0)
+    rc = L.lib().lqg_bands(n_t, N, L.ptr(ysim), n_t, L.ptr(probs), probs.size, L.ptr(mean), L.ptr(q),
+                           L.make_opts(mem=L.MEM_HOST), L.C.byref(ms))
+    L.check(rc, "lqg_bands")
+    return mean, q
+
+
+def lambda_pinv(Lambda):
+    """The operator of qr.solve(Lambda, .) (R/lineqGP.R:639): inverse for a square Lambda, the
+    least-squares pseudo-inverse for a tall full-column-rank Lambda (Q8).  O(d m^2), once."""
+    Lambda = np.asarray(Lambda, float)
+    if Lambda.shape[0] == Lambda.shape[1]:
+        return np.linalg.inv(Lambda)
+    Q, R = np.linalg.qr(Lambda)
+    return np.linalg.solve(R, Q.T)
+
+
+def simulate_lineqGP(model, nsim=1, seed=None, xtest=None, control=None):
+    """simulate.lineqGP (R/lineqGP.R:601-643)."""
+    t0 = time.perf_counter()
+    pred = M.predict_lineqGP(model, xtest)
+    predtime = time.perf_counter() - t0
+    mdl = pred.pop("model")
+    Lam = pred["Lambda"]
+    eta_mu = Lam @ pred["mu"]                                           # :611
+    eta_map = Lam @ pred["xi.map"]                                      # :612
+    Sigma_eta = Lam @ pred["Sigma"] @ Lam.T                             # :613
+    Sigma_eta = Sigma_eta + mdl["kernParam"]["nugget"] * np.eye(Sigma_eta.shape[0])   # :614
+    ctl = dict(mdl["localParam"]["samplingParams"])                     # :617
+    ctl["mvec"] = mdl["localParam"]["mvec"]; ctl["constrType"] = mdl["constrType"]   # :618-619
+    ctl.update(control or {})
+    if seed is not None:
+        ctl.setdefault("seed", int(seed))                               # set.seed(seed) :624
+    tmvPar = {"mu": eta_mu, "map": eta_map, "Sigma": Sigma_eta, "lb": pred["lb"], "ub": pred["ub"],
+              "class": mdl["localParam"]["sampler"]}                    # :622-623
+    t0 = time.perf_counter()
+    eta = tmvrnorm(tmvPar, nsim, ctl)                                   # :626
+    simtime = time.perf_counter() - t0
+    xi_sim = dgemm(lambda_pinv(Lam), eta)                               # :639
+    ysim = dgemm(pred["Phi.test"], xi_sim)                              # :640
+    return dict(cls="lineqGP", x=mdl["x"], y=mdl["y"], xtest=xtest, **{"Phi.test": pred["Phi.test"]},
+                predtime=predtime, simtime=simtime, **{"xi.map": pred["xi.map"], "xi.sim": xi_sim},
+                ysim=ysim, eta=eta, stats=dict(last_stats))
+
+
+def simulate_lineqAGP(model, nsim=1, seed=None, xtest=None, control=None):
+    """simulate.lineqAGP (R/lineqAGP.R:520-596)."""
+    t0 = time.perf_counter()
+    pred = M.predict_lineqAGP(model, xtest)
+    predtime = time.perf_counter() - t0
+    mdl = pred.pop("model")
+    LamAll = mdl["lineqSys"]["LambdaAll"]
+    eta_map = LamAll @ pred["xiAll.map"]                                # :558
+    Sigma_eta = LamAll @ pred["SigmaAll"] @ LamAll.T                    # :559
+    Sigma_eta = Sigma_eta + mdl["nugget"] * np.eye(Sigma_eta.shape[0])  # :560
+    ctl = dict(mdl["localParam"]["samplingParams"])
+    ctl["mvec"] = mdl["localParam"]["mtotal"]; ctl["constrType"] = mdl["constrType"]   # :564-565
+    ctl.update(control or {})
+    if seed is not None:
+        ctl.setdefault("seed", int(seed))
+    tmvPar = {"mu": eta_map, "Sigma": Sigma_eta, "lb": mdl["lineqSys"]["lb"], "ub": mdl["lineqSys"]["ub"],
+              "class": mdl["localParam"]["sampler"]}                    # :567-570 (mean := MAP, Q4)
+    t0 = time.perf_counter()
+    etaAll = tmvrnorm(tmvPar, nsim, ctl)                                # :573
+    simtime = time.perf_counter() - t0
+    xiAll_sim = dgemm(lambda_pinv(LamAll), etaAll)                      # :575
+    return dict(cls="lineqAGP", x=mdl["x"], y=mdl["y"], xtest=xtest, **{"Phi.test": pred["Phi.test"]},
+                predtime=predtime, simtime=simtime, muAll=pred["muAll"],
+                **{"xiAll.map": pred["xiAll.map"], "xiAll.sim": xiAll_sim, "PhiAll.test": pred["PhiAll.test"]},
+                eta=etaAll, stats=dict(last_stats))
+
+
+def simulate(model, nsim=1, seed=None, xtest=None, control=None):
+    """S3 dispatch of stats::simulate on the model class."""
+    if model.get("cls") == "lineqGP":
+        return simulate_lineqGP(model, nsim, seed, xtest, control)
+    if model.get("cls") == "lineqAGP":
+        return simulate_lineqAGP(model, nsim, seed, xtest, control)
+    raise TypeError(f"no applicable method for 'simulate' applied to an object of class {model.get('cls')!r}")

@@ -1,0 +1,237 @@
+"""GPU parity tests of the HMC path, all through the C ABI (ctypes), against the oracle and the
+committed golden vectors (outputs of the compiled reference source).
+
+Tolerance: north_star asks for trajectories within 1e-10 relative (FP64) under injected Gaussian
+draws.  RTOL below is that bound, relative to the largest coordinate of the compared state."""
+import numpy as np
+import pytest
+from scipy import stats
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+
+SMALL = ["rd_example_2d", "dense_d10_c8", "roxygen_box_d100", "cfg1_canonical"]
+
+
+def rel_err(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_canonical_chain_matches_reference_golden(lqg, golden, name):
+    """Free-running chain, same injected draws as the compiled reference consumed."""
+    G = golden(name)
+    n = int(G["n"])
+    z, st = lqg.rtmg_canonical(n, 0, G["z0"], G["F"], G["g"], injected=G["draws"])
+    assert rel_err(z.T, G["z_ref"]) < RTOL
+    assert st["bounces"] == int(G["bounces"])
+    assert st["vel_restarts"] == int(G["vel_restarts"]) and st["chk_restarts"] == int(G["chk_restarts"])
+    assert st["violations"] == 0 and st["transitions"] == n
+
+
+@pytest.mark.parametrize("name", SMALL + ["stiff_d60_c200"])
+def test_canonical_teacher_forced_transitions(lqg, oracle, golden, name):
+    """Per-transition parity: K chains, chain k starts at the reference state k-1 and gets the
+    draws of a fresh stream; one transition each; compared with the oracle's transition."""
+    G = golden(name)
+    d = G["z0"].size
+    states = np.vstack([G["z0"][None, :], G["z_ref"][:-1]])
+    K = min(states.shape[0], 24)
+    L = 400 * d
+    rng = np.random.default_rng(17)
+    draws = rng.standard_normal((K, L))
+    want = np.zeros((K, d)); nb = 0; nr = 0
+    for k in range(K):
+        zk, info = oracle.rtmg_canonical(1, 0, states[k], G["F"], G["g"], injected=draws[k])
+        assert info["rc"] == 0
+        want[k] = zk[0]; nb += info["bounces"]; nr += info["vel_restarts"] + info["chk_restarts"]
+    z, st = lqg.rtmg_canonical(1, 0, states[:K].T, G["F"], G["g"], n_chains=K, injected=draws)
+    assert rel_err(z.T, want) < RTOL
+    assert st["bounces"] == nb and st["vel_restarts"] + st["chk_restarts"] == nr
+
+
+def test_canonical_constraints_and_layout(lqg, golden):
+    G = golden("dense_d10_c8")
+    z, st = lqg.rtmg_canonical(40, 5, G["z0"], G["F"], G["g"], n_chains=7, burn_in=3)
+    assert z.shape == (10, 7 * 40) and st["transitions"] == 7 * 43
+    assert (G["F"] @ z + G["g"][:, None]).min() >= -1e-12
+    assert st["violations"] == 0
+    # Philox streams are keyed by chain: chain 0 of a 7-chain run == a 1-chain run
+    z1, _ = lqg.rtmg_canonical(40, 5, G["z0"], G["F"], G["g"], n_chains=1, burn_in=3)
+    assert np.array_equal(z1, z[:, :40])
+
+
+def test_lqg_rtmg_entry_point_mirrors_dot_call(lqg, golden):
+    """lqg_rtmg(n, seed, initial, numlin, F, g, numquad, quads) -> n x d, row = sample."""
+    from lineqgpr_b200 import _lib as L
+    G = golden("rd_example_2d")
+    n, d = 50, 2
+    F = L.f64(G["F"]); g = np.ascontiguousarray(G["g"]); z0 = np.ascontiguousarray(G["z0"])
+    out = np.zeros((n, d), order="F")
+    rc = L.lib().lqg_rtmg(n, 123, L.ptr(z0), d, 2, L.ptr(F), L.ptr(g), 0, None, L.ptr(out))
+    assert rc == 0
+    assert (G["F"] @ out.T + G["g"][:, None]).min() >= 0
+    z, _ = lqg.rtmg_canonical(n, 123, G["z0"], G["F"], G["g"])
+    assert np.array_equal(out, z.T)
+    rc = L.lib().lqg_rtmg(n, 123, L.ptr(z0), d, 2, L.ptr(F), L.ptr(g), 1, None, L.ptr(out))
+    assert rc == 2 and "quadratic" in L.last_error()
+
+
+# ------------------------------------------------------------------------------------- box form
+def _box_problem(oracle, par):
+    H, r, init, f, g = oracle.hmc_setup(par["mu"], par["Sigma"], par["lb"], par["ub"], par.get("map"))
+    w = oracle.whiten(H, r, init, f, g)
+    return w, init
+
+
+def _box_cases():
+    from lineqgpr_b200 import workloads as W
+    rng = np.random.default_rng(3)
+    B = rng.standard_normal((12, 12)); S = B @ B.T / 12 + 0.05 * np.eye(12); mu = 0.3 * rng.standard_normal(12)
+    lb = np.where(rng.uniform(size=12) < 0.3, -np.inf, mu - rng.uniform(0.05, 1.0, 12))
+    ub = np.where(rng.uniform(size=12) < 0.3, np.inf, mu + rng.uniform(0.05, 1.0, 12))
+    yield "random_d12", dict(mu=mu, Sigma=S, lb=lb, ub=ub), 60
+    yield "cfg2", W.cfg2()[0], 80
+    yield "cfg3", W.cfg3()[0], 80
+    yield "cfg1", W.cfg1()[0], 30
+    yield "cfg4_m100", W.cfg4(m=100)[0], 12        # d = 200 stacked bounded + monotone, 2 warps/chain
+    yield "cfg5_D30", W.cfg5(D=30, knots=10, n=150, n_test=10)[0], 12   # d = 300, 4 warps/chain
+
+
+@pytest.mark.parametrize("case", list(_box_cases()), ids=lambda c: c[0])
+def test_box_chain_matches_oracle_canonical_chain(lqg, oracle, case):
+    """lqg_hmc_box (eta frame) vs the oracle's whitened chain un-whitened (tmg:R/tmg.R:106),
+    same U = Ri and same injected draws; free-running short horizon + teacher-forced steps."""
+    name, par, n = case
+    w, init = _box_problem(oracle, par)
+    d = init.size
+    seed = 77
+    z, info = oracle.rtmg_canonical(n, seed, w["initial2"], w["f2"], w["g2"])
+    x_ref = z @ w["Ri"].T + w["Mir"][None, :]
+    draws = oracle.normal_stream(seed, info["draws"])
+    ctl = {"burn.in": 0, "n.chains": 1, "U": w["Ri"], "injected": draws[None, :]}
+    x = lqg.tmvrnorm(dict(par, **{"class": "HMC"}), n, ctl)
+    st = dict(lqg.last_stats)
+    assert st["violations"] == 0
+    lbv, ubv = np.asarray(par["lb"]), np.asarray(par["ub"])
+    assert np.all(x >= lbv[:, None]) and np.all(x <= ubv[:, None])            # exact, no tolerance
+    # teacher-forced: K chains started from consecutive reference states
+    K = min(n, 16)
+    rng = np.random.default_rng(5)
+    dr = rng.standard_normal((K, 300 * d))
+    starts_z = np.vstack([w["initial2"][None, :], z[:-1]])[:K]
+    want = np.zeros((K, d))
+    for k in range(K):
+        zk, ik = oracle.rtmg_canonical(1, 0, starts_z[k], w["f2"], w["g2"], injected=dr[k])
+        want[k] = zk[0] @ w["Ri"].T + w["Mir"]
+    starts_x = starts_z @ w["Ri"].T + w["Mir"][None, :]
+    # the start must be strictly inside the box for the C ABI's feasibility check
+    starts_x = np.minimum(np.maximum(starts_x, lbv + 1e-13), ubv - 1e-13)
+    from lineqgpr_b200 import _lib as L
+    out = np.empty((d, K), order="F")
+    hs = L.HmcStats()
+    opts = L.make_opts(n_chains=K, injected=np.ascontiguousarray(dr), n_injected=dr.shape[1], prepass=0)
+    Uf, Sf = L.f64(w["Ri"]), L.f64(par["Sigma"])
+    mu_c = np.ascontiguousarray(par["mu"], dtype=np.float64)
+    lb_c = np.ascontiguousarray(lbv, dtype=np.float64); ub_c = np.ascontiguousarray(ubv, dtype=np.float64)
+    sx = np.ascontiguousarray(starts_x)
+    rc = L.lib().lqg_hmc_box(d, L.ptr(mu_c), L.ptr(Uf), 1, L.ptr(Sf), L.ptr(lb_c), L.ptr(ub_c), L.ptr(sx), d,
+                             1, 0, opts, L.ptr(out), None, hs)
+    L.check(rc, "lqg_hmc_box")
+    scale = np.abs(want).max()
+    assert np.abs(out.T - want).max() / scale < 1e-9, name         # one transition, conditioning of Ri included
+    # free-running: agree until rounding flips a discrete event; the first samples must match
+    head = max(2, min(n, 5))
+    assert np.abs(x[:, :head].T - x_ref[:head]).max() / np.abs(x_ref).max() < 1e-8, name
+
+
+def test_box_errors(lqg):
+    from lineqgpr_b200 import _lib as L
+    obj = dict(mu=np.zeros(3), Sigma=np.eye(3), lb=-np.ones(3), ub=np.ones(3), map=np.array([0.0, 5.0, 0.0]))
+    # clamp keeps the start inside: fine
+    x = lqg.tmvrnorm(obj, 10, {"burn.in": 2}, method="HMC")
+    assert x.shape == (3, 10)
+    mu = np.zeros(3); S = L.f64(np.eye(3)); lb = -np.ones(3); ub = np.ones(3); bad = np.array([0.0, 1.0, 0.0])
+    out = np.zeros((3, 4), order="F")
+    rc = L.lib().lqg_hmc_box(3, L.ptr(mu), L.ptr(S), 1, L.ptr(S), L.ptr(lb), L.ptr(ub), L.ptr(bad), 0, 4, 0,
+                             L.make_opts(), L.ptr(out), None, None)
+    assert rc == 3 and "initial point violates" in L.last_error()
+    rc = L.lib().lqg_hmc_box(3, L.ptr(mu), L.ptr(S), 1, L.ptr(S), L.ptr(ub), L.ptr(lb), L.ptr(mu), 0, 4, 0,
+                             L.make_opts(), L.ptr(out), None, None)
+    assert rc == 1
+
+
+def test_box_unconstrained_limit_is_gaussian(lqg):
+    """Anchor: bounds far away -> each transition returns mu + U a, i.i.d. N(mu, Sigma)."""
+    rng = np.random.default_rng(0)
+    B = rng.standard_normal((5, 5)); S = B @ B.T + 0.5 * np.eye(5); mu = rng.standard_normal(5)
+    obj = dict(mu=mu, Sigma=S, lb=np.full(5, -1e6), ub=np.full(5, np.inf))
+    x = lqg.tmvrnorm(obj, 20000, {"burn.in": 0, "n.chains": 64, "seed": 3}, method="HMC")
+    assert lqg.last_stats["bounces"] == 0
+    assert np.abs(x.mean(1) - mu).max() < 4 * np.sqrt(np.diag(S).max() / 20000)
+    assert np.abs(np.cov(x) - S).max() < 0.08 * np.abs(S).max()
+    for i in range(5):
+        assert stats.kstest((x[i] - mu[i]) / np.sqrt(S[i, i]), "norm").pvalue > 1e-3
+
+
+def test_box_prepass_equals_in_kernel_draws(lqg):
+    """The DMMA pre-pass and the per-chain product draw the same Philox normals."""
+    from lineqgpr_b200 import workloads as W
+    par, _ = W.cfg5(D=30, knots=10, n=150, n_test=10)          # d = 300
+    a = lqg.tmvrnorm(dict(par, **{"class": "HMC"}), 64, {"burn.in": 2, "n.chains": 32, "seed": 11, "prepass": 0})
+    sa = dict(lqg.last_stats)
+    b = lqg.tmvrnorm(dict(par, **{"class": "HMC"}), 64, {"burn.in": 2, "n.chains": 32, "seed": 11, "prepass": 1})
+    sb = dict(lqg.last_stats)
+    assert sb["prepass_ms"] > 0 and sa["prepass_ms"] == 0
+    # same draws, different summation order in U a: first emitted sample of every chain agrees tightly
+    assert np.abs(a[:, ::2] - b[:, ::2]).max() / np.abs(a).max() < 1e-7
+    assert sa["violations"] == 0 and sb["violations"] == 0
+
+
+def test_box_sharding_invariance(lqg):
+    """chain_offset: 8 chains in one call == two calls of 4 chains (what the multi-GPU launcher does)."""
+    from lineqgpr_b200 import workloads as W
+    par, _ = W.cfg3()
+    obj = dict(par, **{"class": "HMC"})
+    full = lqg.tmvrnorm(obj, 80, {"burn.in": 5, "n.chains": 8, "seed": 9})
+    lo = lqg.tmvrnorm(obj, 40, {"burn.in": 5, "n.chains": 4, "seed": 9, "chain.offset": 0})
+    hi = lqg.tmvrnorm(obj, 40, {"burn.in": 5, "n.chains": 4, "seed": 9, "chain.offset": 4})
+    assert np.array_equal(full, np.hstack([lo, hi]))
+
+
+@pytest.mark.parametrize("cfg", ["cfg1", "cfg2", "cfg3"])
+def test_box_statistical_agreement_with_oracle(lqg, oracle, cfg):
+    """L-stat: per-coordinate KS p > 0.01 and mean/variance within 3 Monte-Carlo standard errors
+    of an oracle chain (libstdc++ RNG) on the same (mu, Sigma, lb, ub)."""
+    from lineqgpr_b200 import workloads as W
+    par, _ = W.CONFIGS[cfg]()
+    n = 6000
+    xo, _ = oracle.tmvrnorm_HMC(par, n, {"burn.in": 100}, seed=4)
+    xg = lqg.tmvrnorm(dict(par, **{"class": "HMC"}), n, {"burn.in": 100, "n.chains": 60, "seed": 8})
+    assert lqg.last_stats["violations"] == 0
+    thin = 4
+    xo_t, xg_t = xo[:, ::thin], xg[:, ::thin]
+    d = xo.shape[0]
+    pvals = np.array([stats.ks_2samp(xo_t[i], xg_t[i]).pvalue for i in range(d)])
+    # d simultaneous tests at level 0.01: allow the expected handful of chance rejections
+    assert (pvals < 0.01).sum() <= max(1, int(0.05 * d)), pvals.min()
+    ne = xo_t.shape[1]
+    se_mean = np.sqrt((xo_t.var(1) + xg_t.var(1)) / ne)
+    assert (np.abs(xo_t.mean(1) - xg_t.mean(1)) > 3 * se_mean).sum() <= max(1, int(0.05 * d))
+    se_var = np.sqrt(2.0 / (ne - 1)) * np.sqrt(xo_t.var(1) ** 2 + xg_t.var(1) ** 2) * 1.5   # kurtosis slack
+    assert (np.abs(xo_t.var(1) - xg_t.var(1)) > 3 * se_var).sum() <= max(1, int(0.05 * d))
+
+
+def test_full_size_m1000_properties(lqg):
+    """BASELINE size (cfg4: d = 2000, c = 2999; cfg5: d = 1000, c = 900): size-independent
+    properties — every emitted value inside the box, counters consistent, finite output."""
+    from lineqgpr_b200 import workloads as W
+    for par, n_chains, n in ((W.cfg4()[0], 296, 592), (W.cfg5(n_test=10)[0], 296, 592)):
+        x = lqg.tmvrnorm(dict(par, **{"class": "HMC"}), n, {"burn.in": 3, "n.chains": n_chains, "seed": 1})
+        st = dict(lqg.last_stats)
+        lb, ub = np.asarray(par["lb"]), np.asarray(par["ub"])
+        assert np.isfinite(x).all()
+        assert np.all(x >= lb[:, None]) and np.all(x <= ub[:, None])
+        assert st["violations"] == 0 and st["failed_chains"] == 0
+        assert st["transitions"] == n_chains * (3 + n // n_chains)
+        assert st["hit_searches"] >= st["bounces"] + st["transitions"]

@@ -1,0 +1,112 @@
+"""GPU parity tests of RSM, the FP64 tensor-core GEMM and the band summaries (through the C ABI)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_rsm_decisions_match_oracle_golden(lqg, golden):
+    """Same injected normals and uniforms -> identical accept/reject decisions, same columns."""
+    G = golden("rsm_cfg2")
+    nsim = G["xi"].shape[1]
+    obj = dict(mu=G["map"], map=G["map"], Sigma=G["factor"] @ G["factor"].T, lb=G["lb"], ub=G["ub"])
+    x = lqg.tmvrnorm(obj, nsim, {"factor": G["factor"], "injected": G["Z"], "injected.u": G["U"]}, method="RSM")
+    st = dict(lqg.last_stats)
+    assert np.abs(x - G["xi"]).max() < 1e-12
+    assert st["accepted"] == nsim
+    assert st["proposals"] == int(G["accepted_idx"][-1]) + 1
+    assert st["in_box"] == int(G["inbox"][:st["proposals"]].sum())
+
+
+def test_rsm_fewer_samples_is_a_prefix(lqg, golden):
+    G = golden("rsm_cfg2")
+    obj = dict(mu=G["map"], map=G["map"], Sigma=G["factor"] @ G["factor"].T, lb=G["lb"], ub=G["ub"])
+    x = lqg.tmvrnorm(obj, 10, {"factor": G["factor"], "injected": G["Z"], "injected.u": G["U"]}, method="RSM")
+    assert np.abs(x - G["xi"][:, :10]).max() < 1e-12
+    assert lqg.last_stats["proposals"] == int(G["accepted_idx"][9]) + 1
+
+
+def test_rsm_exhausted_draws_is_an_error(lqg, golden):
+    from lineqgpr_b200 import _lib as L
+    G = golden("rsm_cfg2")
+    obj = dict(mu=G["map"], map=G["map"], Sigma=G["factor"] @ G["factor"].T, lb=G["lb"], ub=G["ub"])
+    with pytest.raises(L.LqgError) as e:
+        lqg.tmvrnorm(obj, 500, {"factor": G["factor"], "injected": G["Z"], "injected.u": G["U"]}, method="RSM")
+    assert e.value.status == 6
+
+
+def test_rsm_philox_statistics(lqg, oracle):
+    """Philox mode on cfg2: all samples in the box; moments agree with an oracle run."""
+    from lineqgpr_b200 import workloads as W
+    par, _ = W.cfg2(sampler="RSM")
+    n = 4000
+    x = lqg.tmvrnorm(par, n, {"seed": 5})
+    st = dict(lqg.last_stats)
+    assert x.shape == (20, n) and st["accepted"] == n and st["proposals"] > st["in_box"] >= n
+    assert np.all(x >= par["lb"][:, None]) and np.all(x <= par["ub"][:, None])
+    rng = np.random.default_rng(0)
+    P = int(st["proposals"] * 1.3)
+    xo, info = oracle.tmvrnorm_RSM(par, n, rng.standard_normal((20, P)), rng.uniform(size=P))
+    assert xo.shape[1] == n
+    se = np.sqrt((x.var(1) + xo.var(1)) / n)
+    assert (np.abs(x.mean(1) - xo.mean(1)) > 3.5 * se).sum() <= 1
+    rate_g = n / st["proposals"]; rate_o = n / info["n_proposals"]
+    assert abs(rate_g - rate_o) < 5 * np.sqrt(rate_o / info["n_proposals"]) + 0.002
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1), (7, 5, 3), (128, 64, 16), (130, 67, 19), (300, 1000, 300), (1000, 257, 1000)])
+def test_dgemm_matches_numpy(lqg, shape):
+    m, n, k = shape
+    rng = np.random.default_rng(m * 31 + n)
+    A = rng.standard_normal((m, k)); B = rng.standard_normal((k, n))
+    C, rs = lqg.dgemm(A, B, row_sum=True)
+    ref = A @ B
+    tol = 1e-13 * k * max(1.0, np.abs(A).max() * np.abs(B).max())
+    assert np.abs(C - ref).max() < tol
+    assert np.abs(rs - ref.sum(1)).max() < tol * n
+
+
+def test_simulate_tail_matches_oracle(lqg, oracle):
+    """xi.sim = qr.solve(Lambda, eta); ysim = Phi.test %*% xi.sim  (R/lineqGP.R:639-640)."""
+    from lineqgpr_b200 import workloads as W
+    from lineqgpr_b200.simulate import lambda_pinv
+    par, aux = W.cfg4(m=40)                  # tall Lambda (80 x 40): least-squares branch (Q8)
+    rng = np.random.default_rng(1)
+    eta = rng.standard_normal((80, 333))
+    xi = lqg.dgemm(lambda_pinv(aux["Lambda"]), eta)
+    ysim = lqg.dgemm(aux["Phi_test"], xi)
+    xi_o, y_o = oracle.simulate_tail(aux["Lambda"], aux["Phi_test"], eta)
+    assert np.abs(xi - xi_o).max() < 1e-10 * max(1, np.abs(xi_o).max())
+    assert np.abs(ysim - y_o).max() < 1e-10 * max(1, np.abs(y_o).max())
+
+
+def test_bands_golden_and_random(lqg, oracle, golden):
+    G = golden("bands")
+    mean, q = lqg.bands(G["y"], G["probs"])
+    assert np.allclose(mean, G["mean"], rtol=1e-14, atol=1e-15)
+    assert np.array_equal(q, G["q"])                      # order statistics are exact
+    rng = np.random.default_rng(9)
+    for (n_t, N) in [(1, 1), (3, 2), (5, 10), (33, 4097), (200, 10000)]:
+        y = rng.standard_normal((n_t, N)) * 10.0 ** rng.integers(-3, 4, size=(n_t, 1))
+        y[0, : N // 2] = y[0, 0]                           # ties
+        probs = np.array([0.0, 0.025, 0.05, 0.5, 0.95, 0.975, 1.0])
+        mean, q = lqg.bands(y, probs)
+        mo, qo = oracle.bands(y, probs)
+        assert np.allclose(mean, mo, rtol=1e-13, atol=1e-300)
+        assert np.array_equal(q, qo), (n_t, N)
+
+
+def test_simulate_end_to_end_cfg1(lqg):
+    """create -> simulate (HMC) -> bands on config 1: constraints hold for eta and for xi
+    (square Lambda), sample paths are monotone at the knots."""
+    from lineqgpr_b200 import workloads as W
+    par, aux = W.cfg1()
+    sim = lqg.simulate(aux["lineq_model"], nsim=1000, seed=1, xtest=aux["xtest"])
+    xi = sim["xi.sim"]
+    assert xi.shape == (100, 1000) and sim["ysim"].shape == (100, 1000)
+    assert np.diff(xi, axis=0).min() > -1e-9
+    assert sim["stats"]["violations"] == 0
+    mean, q = lqg.bands(sim["ysim"])
+    assert np.all(q[0] <= mean + 1e-12) and np.all(mean <= q[1] + 1e-12)
+    # posterior mean path follows the sigmoid data
+    assert abs(mean[0]) < 0.2 and abs(mean[-1] - 1.0) < 0.2

@@ -1,0 +1,120 @@
+"""CPU tests: host logic, C-ABI surface, loud failure without a GPU."""
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_header_and_library_export_the_same_symbols(lqg):
+    from lineqgpr_b200 import _lib
+    header = (ROOT / "include" / "lineqgpr_b200.h").read_text()
+    declared = set(re.findall(r"\b(lqg_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.SYMBOLS)
+    L = ctypes.CDLL(str(_lib.LIB_PATH))
+    for s in declared:
+        assert hasattr(L, s), s
+    assert b"sm_100a" in _lib.lib().lqg_version()
+
+
+def test_struct_layouts_match_header(lqg):
+    from lineqgpr_b200 import _lib
+    assert ctypes.sizeof(_lib.Opts) == 80
+    assert ctypes.sizeof(_lib.HmcStats) == 80
+    assert ctypes.sizeof(_lib.RsmStats) == 40
+
+
+def test_no_gpu_fails_loudly(lqg):
+    """No CPU fallback: without a device the product path raises, it never computes on the host."""
+    from lineqgpr_b200 import _lib
+    if _lib.lib().lqg_device_count() > 0:
+        pytest.skip("a GPU is present")
+    obj = dict(mu=np.zeros(3), Sigma=np.eye(3), lb=-np.ones(3), ub=np.ones(3))
+    with pytest.raises(_lib.LqgError) as e:
+        lqg.tmvrnorm(obj, 5, {"burn.in": 1}, method="HMC")
+    assert e.value.status == 4 and "no CPU fallback" in str(e.value)
+    with pytest.raises(_lib.LqgError):
+        lqg.tmvrnorm(obj, 5, method="RSM")
+    with pytest.raises(_lib.LqgError):
+        lqg.dgemm(np.eye(2), np.eye(2))
+
+
+def test_product_package_never_imports_the_oracle():
+    for p in (ROOT / "lineqgpr_b200").rglob("*.py"):
+        assert "oracle" not in p.read_text().lower(), p
+    for p in (ROOT / "lineqgpr_b200" / "csrc").glob("*.cu*"):
+        assert "oracle" not in p.read_text().lower(), p
+
+
+def test_tmvrnorm_dispatch_and_argument_errors(lqg):
+    obj = dict(mu=np.zeros(2), Sigma=np.eye(2), lb=np.zeros(2), ub=np.ones(2))
+    with pytest.raises(TypeError):
+        lqg.tmvrnorm(obj, 3)                                   # no class
+    with pytest.raises(NotImplementedError):
+        lqg.tmvrnorm(dict(obj, **{"class": "ExpT"}), 3)
+    bad = dict(obj, lb=np.array([0.0, 2.0]))
+    with pytest.raises(ValueError, match='has to be greater'):
+        lqg.tmvrnorm(bad, 3, method="HMC")
+    with pytest.raises(ValueError, match="d-dimensionals"):
+        lqg.tmvrnorm(dict(obj, lb=np.zeros(3)), 3, method="HMC")
+
+
+def test_hat_basis_and_systems(lqg):
+    u = np.linspace(0, 1, 5)
+    x = np.array([0.0, 0.1, 0.25, 0.99, 1.0])
+    Phi = lqg.basisCompute_lineqGP(x, u)
+    assert np.allclose(Phi.sum(1), 1.0) and np.allclose(Phi @ u, x)      # partition of unity, linear precision
+    assert (Phi > 0).sum(1).max() <= 2
+    with pytest.raises(ValueError):
+        lqg.basisCompute_lineqGP(np.array([1.2]), u)
+    s = lqg.lineqGPSys(5, "monotonicity", 0, np.inf, lineqSysType="oneside")
+    assert s["M"].shape == (4, 5) and np.allclose(s["M"] @ np.arange(5.0), 1.0)
+    s2 = lqg.lineqGPSys(5, "monotonicity", 0, np.inf, rmInf=False)
+    assert s2["A"].shape == (5, 5) and s2["l"][0] == -np.inf and np.all(s2["l"][1:] == 0)
+    s3 = lqg.lineqGPSys([3, 2], "monotonicity", 0, np.inf, d=2, rmInf=False)
+    assert s3["A"].shape == (12, 6)
+    s4 = lqg.lineqGPSys(4, "convexity", 0, np.inf, lineqSysType="oneside")
+    assert s4["M"].shape == (2, 4) and np.allclose(s4["M"] @ (np.arange(4.0) ** 2), 2.0)
+
+
+def test_config_shapes_match_survey_table(lqg):
+    from lineqgpr_b200 import workloads as W
+    expect = {"cfg1": (100, 100, 99), "cfg2": (10, 20, 13), "cfg3": (10, 10, 8)}
+    for name, (m, d, c) in expect.items():
+        par, aux = W.CONFIGS[name]()
+        assert aux["Lambda"].shape == (d, m)
+        assert par["Sigma"].shape == (d, d)
+        assert int(np.isfinite(par["lb"]).sum() + np.isfinite(par["ub"]).sum()) == c
+        init = np.minimum(np.maximum(par.get("map", par["mu"]), par["lb"] + 1e-9), par["ub"] - 1e-9)
+        assert np.all(init > par["lb"]) and np.all(init < par["ub"])
+    par, aux = W.cfg4(m=60)
+    assert aux["Lambda"].shape == (120, 60) and int(np.isfinite(par["lb"]).sum() + np.isfinite(par["ub"]).sum()) == 179
+    par, aux = W.cfg5(D=6, knots=5, n=60, n_test=50)
+    assert aux["Lambda"].shape == (30, 30) and int(np.isfinite(par["lb"]).sum()) == 24
+
+
+def test_qp_solver_kkt(lqg):
+    from lineqgpr_b200.model import solve_qp
+    rng = np.random.default_rng(0)
+    B = rng.standard_normal((15, 15)); D = B @ B.T + 0.1 * np.eye(15); dv = rng.standard_normal(15)
+    A = np.vstack([np.eye(15), -np.eye(15)]); b = np.concatenate([np.full(15, -0.1), np.full(15, -0.3)])
+    x = solve_qp(D, dv, A, b)
+    s = A @ x - b
+    assert s.min() > -1e-9
+    grad = D @ x - dv                      # = A' lam with lam >= 0 supported on the active set
+    active = s < 1e-6
+    lam, *_ = np.linalg.lstsq(A[active].T, grad, rcond=None)
+    assert np.allclose(A[active].T @ lam, grad, atol=1e-6) and lam.min() > -1e-6
+
+
+def test_lambda_pinv_is_qr_solve(lqg, oracle):
+    from lineqgpr_b200.simulate import lambda_pinv
+    rng = np.random.default_rng(4)
+    sq = lqg.lineqGPSys(6, "monotonicity", 0, np.inf, rmInf=False)["A"]
+    tall = np.vstack([np.eye(6), sq])
+    for Lam in (sq, tall):
+        eta = rng.standard_normal((Lam.shape[0], 5))
+        assert np.allclose(lambda_pinv(Lam) @ eta, oracle.qr_solve(Lam, eta), atol=1e-12)
