@@ -132,7 +132,8 @@ bands_kernel(int n_t, int64_t N, const double* __restrict__ yT, int64_t ldT, Ban
       const double h = tg.h[tid];
       double qv = xlo;
       if (h == 1.0) qv = xhi;
-      else if (h > 0.0 && h < 1.0 && xlo != xhi) qv = (1.0 - h) * xlo + h * xhi;
+      else if (h > 0.0 && h < 1.0 && xlo != xhi)   // no FMA contraction: R rounds both products
+        qv = __dadd_rn(__dmul_rn(1.0 - h, xlo), __dmul_rn(h, xhi));
       qtls[(size_t)row * (tg.n / 2) + tid] = qv;
     }
     __syncthreads();
