@@ -174,19 +174,24 @@ extern "C" int lqg_hmc_box(int32_t d, const double* mu, const double* U, int32_t
   if (o.injected && (rc = i_inj.stage(o.injected, (size_t)n_chains * o.n_injected, mem, st))) return rc;
 
   const size_t n_cols = (size_t)n_chains * n_per_chain;
-  DevBuf b_out, b_state, b_glo, b_ghi, b_sd, b_misc, b_status, b_injpos;
+  DevBuf b_out, b_state, b_glo, b_ghi, b_sd, b_misc, b_status, b_sdone, b_pos, b_rcount, b_act;
   double* d_out = out;
   if (mem == LQG_MEM_HOST) { LQG_CUDA_TRY(b_out.alloc(n_cols * d * sizeof(double))); d_out = b_out.as<double>(); }
   LQG_CUDA_TRY(b_state.alloc((size_t)d * n_chains * sizeof(double)));
   LQG_CUDA_TRY(b_glo.alloc(d * sizeof(double)));
   LQG_CUDA_TRY(b_ghi.alloc(d * sizeof(double)));
   LQG_CUDA_TRY(b_sd.alloc(d * sizeof(double)));
-  LQG_CUDA_TRY(b_misc.alloc(16 * sizeof(unsigned long long)));      // [0..7] stats, [8] queue head
+  LQG_CUDA_TRY(b_misc.alloc(16 * sizeof(unsigned long long)));      // [0..7] stats, [8] queue head, [9] n_active
   LQG_CUDA_TRY(b_status.alloc((size_t)n_chains * sizeof(int)));
-  LQG_CUDA_TRY(b_injpos.alloc((size_t)n_chains * sizeof(int64_t)));
+  LQG_CUDA_TRY(b_sdone.alloc((size_t)n_chains * sizeof(int)));
+  LQG_CUDA_TRY(b_pos.alloc((size_t)n_chains * sizeof(int64_t)));
+  LQG_CUDA_TRY(b_rcount.alloc((size_t)n_chains * sizeof(int)));
+  LQG_CUDA_TRY(b_act.alloc((size_t)2 * n_chains * sizeof(int)));
   LQG_CUDA_TRY(cudaMemsetAsync(b_misc.p, 0, b_misc.bytes, st));
   LQG_CUDA_TRY(cudaMemsetAsync(b_status.p, 0, b_status.bytes, st));
-  LQG_CUDA_TRY(cudaMemsetAsync(b_injpos.p, 0, b_injpos.bytes, st));
+  LQG_CUDA_TRY(cudaMemsetAsync(b_sdone.p, 0, b_sdone.bytes, st));
+  LQG_CUDA_TRY(cudaMemsetAsync(b_pos.p, 0, b_pos.bytes, st));
+  LQG_CUDA_TRY(cudaMemsetAsync(b_rcount.p, 0, b_rcount.bytes, st));
 
   LQG_CUDA_TRY(launch_box_prep(d, i_mu.dev, i_lb.dev, i_ub.dev, i_S.dev, b_glo.as<double>(),
                                b_ghi.as<double>(), b_sd.as<double>(), st));
@@ -206,50 +211,62 @@ extern "C" int lqg_hmc_box(int32_t d, const double* mu, const double* U, int32_t
   p.d = d; p.mu = i_mu.dev; p.lb = i_lb.dev; p.ub = i_ub.dev; p.U = i_U.dev; p.u_upper = u_upper;
   p.Sigma = i_S.dev; p.glo = b_glo.as<double>(); p.ghi = b_ghi.as<double>(); p.sdiag = b_sd.as<double>();
   p.abs_eps = kFilterRel * std::sqrt(sd_max);
-  p.state = b_state.as<double>(); p.xa_pre = nullptr; p.n_chains = n_chains;
+  p.state = b_state.as<double>(); p.n_chains = n_chains;
+  p.s_done = b_sdone.as<int>(); p.pos = b_pos.as<int64_t>(); p.rcount = b_rcount.as<int>();
   p.burn_in = burn_in; p.n_per_chain = n_per_chain; p.out = d_out; p.seed = o.seed;
   p.chain_offset = o.chain_offset; p.injected = o.injected ? i_inj.dev : nullptr;
-  p.n_injected = o.n_injected; p.inj_pos = b_injpos.as<int64_t>();
+  p.n_injected = o.n_injected;
   p.max_restarts = o.max_restarts > 0 ? o.max_restarts : 100000;
   p.stats = b_misc.as<unsigned long long>();
   p.next_chain = reinterpret_cast<int*>(b_misc.as<unsigned long long>() + 8);
+  int* d_nactive = reinterpret_cast<int*>(b_misc.as<unsigned long long>() + 9);
   p.chain_status = b_status.as<int>();
 
   const int total = burn_in + n_per_chain;
-  // ---- momentum pre-pass: X_a = U A for the first draw of every transition, as ONE GEMM ----
-  const bool use_pre = !o.injected && (o.prepass == 1 || (o.prepass == -1 && d >= 256));
+  // ---- momentum pool: X_a = U A for the next `attempts` draws of every active chain, ONE GEMM ----
+  const bool use_pool = !o.injected && (o.prepass == 1 || (o.prepass == -1 && d >= 256));
   double chain_ms = 0.0, pre_ms = 0.0;
   Timer t_chain(st), t_pre(st);
-  if (!use_pre) {
-    p.s_begin = 0; p.s_end = total;
+  if (!use_pool) {
+    p.active = nullptr; p.n_active = n_chains; p.attempts = 0x7fffffff; p.pool = nullptr;
     t_chain.start();
     LQG_CUDA_TRY(launch_hmc_box(p, 0, st));
     t_chain.stop();
     chain_ms = t_chain.ms();
   } else {
-    // rounds sized so that the momentum scratch stays below ~6 GB
-    const size_t budget = (size_t)4 << 30;   // per buffer (draws + momenta)
-    int round_len = (int)std::max<size_t>(1, std::min<size_t>(total, budget / ((size_t)d * n_chains * sizeof(double))));
-    DevBuf b_xa, b_a;
-    LQG_CUDA_TRY(b_xa.alloc((size_t)d * n_chains * round_len * sizeof(double)));
-    LQG_CUDA_TRY(b_a.alloc((size_t)d * n_chains * round_len * sizeof(double)));
-    for (int s0 = 0; s0 < total; s0 += round_len) {
-      const int s1 = std::min(total, s0 + round_len);
-      const int len = s1 - s0;
-      NormalGen gen{o.seed, o.chain_offset, len, s0};
+    // attempts per round: pool + draw buffers stay below ~2 GB each
+    const size_t budget = (size_t)2 << 30;
+    int attempts = (int)std::max<size_t>(4, std::min<size_t>(32, budget / ((size_t)d * n_chains * sizeof(double))));
+    attempts = std::min(attempts, total + 8);
+    DevBuf b_pool, b_a;
+    LQG_CUDA_TRY(b_pool.alloc((size_t)d * n_chains * attempts * sizeof(double)));
+    LQG_CUDA_TRY(b_a.alloc((size_t)d * n_chains * attempts * sizeof(double)));
+    int n_active = n_chains;
+    int* act[2] = {b_act.as<int>(), b_act.as<int>() + n_chains};
+    int cur = 0;
+    bool first = true;
+    // every round consumes `attempts` momenta per active chain, so this terminates after at most
+    // (total + restarts) / attempts rounds; max_restarts bounds the restarts of every transition
+    while (n_active > 0) {
+      NormalGen gen{o.seed, o.chain_offset, attempts, first ? nullptr : act[cur], p.pos};
       t_pre.start();
-      LQG_CUDA_TRY(launch_fill_normals(d, (size_t)n_chains * len, b_a.as<double>(), gen, st));
-      LQG_CUDA_TRY(launch_dgemm(d, n_chains * len, d, i_U.dev, d, b_a.as<double>(), d,
-                                b_xa.as<double>(), d, nullptr, u_upper, st));
+      LQG_CUDA_TRY(launch_fill_normals(d, (size_t)n_active * attempts, b_a.as<double>(), gen, st));
+      LQG_CUDA_TRY(launch_dgemm(d, n_active * attempts, d, i_U.dev, d, b_a.as<double>(), d,
+                                b_pool.as<double>(), d, nullptr, u_upper, st));
       t_pre.stop();
-      p.xa_pre = b_xa.as<double>();
-      p.s_begin = s0; p.s_end = s1;
-      LQG_CUDA_TRY(cudaMemsetAsync(p.next_chain, 0, sizeof(int), st));
+      p.active = first ? nullptr : act[cur]; p.n_active = n_active; p.attempts = attempts;
+      p.pool = b_pool.as<double>();
+      LQG_CUDA_TRY(cudaMemsetAsync(p.next_chain, 0, 2 * sizeof(unsigned long long), st));   // queue head + n_active
       t_chain.start();
       LQG_CUDA_TRY(launch_hmc_box(p, 0, st));
       t_chain.stop();
+      LQG_CUDA_TRY(launch_box_compact(n_chains, total, p.s_done, p.chain_status, act[cur ^ 1], d_nactive, st));
+      LQG_CUDA_TRY(cudaMemcpyAsync(&n_active, d_nactive, sizeof(int), cudaMemcpyDeviceToHost, st));
+      LQG_CUDA_TRY(cudaStreamSynchronize(st));
       pre_ms += t_pre.ms();
       chain_ms += t_chain.ms();
+      cur ^= 1;
+      first = false;
     }
   }
 

@@ -64,12 +64,13 @@ __host__ __device__ inline double u01(uint32_t hi, uint32_t lo) {
   return ((double)b + 0.5) * (1.0 / 9007199254740992.0);
 }
 
-// Two N(0,1) for the coordinate pair (2p, 2p+1) of momentum draw (chain, transition, restart).
-// Box-Muller in FP64.
-__device__ inline void normal_pair(uint64_t seed, uint64_t chain, uint32_t transition,
-                                   uint32_t restart, uint32_t pair, double& n0, double& n1) {
+// Two N(0,1) for the coordinate pair (2p, 2p+1) of the `draw`-th momentum of `chain`
+// (draws are consumed sequentially, d normals per (re)start, like nd(eng1) at
+// tmg:src/HmcSampler.cpp:54-55).  Box-Muller in FP64.
+__device__ inline void normal_pair(uint64_t seed, uint64_t chain, uint64_t draw, uint32_t pair,
+                                   double& n0, double& n1) {
   uint32_t r[4];
-  Philox::gen(pair, transition, restart, (uint32_t)chain,
+  Philox::gen(pair, (uint32_t)draw, (uint32_t)(draw >> 32), (uint32_t)chain,
               (uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(chain >> 32) * 0x85EBCA6Bu, r);
   double u1 = u01(r[0], r[1]), u2 = u01(r[2], r[3]);
   double rad = sqrt(-2.0 * log(u1));
@@ -106,21 +107,26 @@ static __device__ __noinline__ double hit_time_exact(double fa, double fb, doubl
 }
 
 // Conservative filter in front of hit_time_exact.  y(t) = fa sin t + fb cos t + g is the
-// constraint value along the trajectory; only hits with t <= tt can matter to sampleNext
-// (tmg:src/HmcSampler.cpp:82 breaks when tt < t), and such a hit needs a zero of y on [0,tt].
-// On an interval no longer than pi/2, y has at most one interior extremum; it is a minimum
-// iff y'(0) = fa < 0 and y'(tt) = fa cos tt - fb sin tt > 0.  Otherwise min y = min(y(0), y(tt)).
-// A constraint is skipped only when that minimum is above a margin far larger than any
+// constraint value along the trajectory; u = sqrt(fa^2 + fb^2) its amplitude.
+//  (1) tmg only considers a wall when u > |g| (tmg:src/HmcSampler.cpp:160): if u < g - margin
+//      the wall is out of reach for this whole orbit.
+//  (2) only hits with t <= tt can matter to sampleNext (:82 breaks when tt < t), and such a hit
+//      needs a zero of y on [0, tt].  On an interval no longer than pi/2, y has at most one
+//      interior extremum; it is a minimum iff y'(0) = fa < 0 and y'(tt) = fa cos tt - fb sin tt > 0
+//      (then min y = g - u, covered by (1)); otherwise min y = min(y(0), y(tt)).
+// A constraint is skipped only when those bounds clear zero by a margin far larger than any
 // rounding difference, so every constraint that can win the arg-min is still evaluated by
 // hit_time_exact and tie/threshold semantics are untouched.
-//   S = sin tt, C = cos tt; scale >= |fa|+|fb|+|g|
+//   S = sin tt, C = cos tt; margin ~ 1e-9 * scale of (fa, fb, g)
 __device__ __forceinline__ bool may_hit(double fa, double fb, double g, double S, double C,
                                         double margin) {
-  double y0 = fb + g;
-  double y1 = fma(fa, S, fma(fb, C, g));
-  double d1 = fma(fa, C, -fb * S);
-  bool interior_min = (fa < 0.0) && (d1 > 0.0);
-  return !(y0 > margin && y1 > margin) || interior_min;
+  const double gm = g - margin;
+  if (gm > 0.0 && gm * gm > fma(fa, fa, fb * fb)) return false;      // (1) u < g - margin
+  const double y0 = fb + g;
+  const double y1 = fma(fa, S, fma(fb, C, g));
+  const double d1 = fma(fa, C, -fb * S);
+  const bool interior_min = (fa < 0.0) && (d1 > 0.0);
+  return !(y0 > margin && y1 > margin) || interior_min;               // (2)
 }
 
 // (t, key) lexicographic min with t == 0 meaning "none": lowest key wins ties, which is the

@@ -132,9 +132,9 @@ dgemm_dmma_kernel(int m, int n, int k, const double* __restrict__ A, int64_t lda
   }
 }
 
-// A[kk, col] = N(0,1) draw of (chain = chain_offset + col / round_len,
-//                              transition = s_begin + col % round_len, restart 0, coordinate kk)
-// — the same Philox addressing the chain kernels use, so pre-pass and in-kernel draws agree.
+// A[kk, col] = N(0,1) draw of (chain = active[col / attempts], draw index = pos[chain] + col % attempts,
+// coordinate kk) — the same Philox addressing the chain kernels use, so pool and in-kernel
+// draws agree.
 __global__ void fill_normals_kernel(int d, size_t n_cols, double* __restrict__ A, NormalGen g) {
   const int pairs = (d + 1) / 2;
   const size_t total = (size_t)pairs * n_cols;
@@ -142,10 +142,11 @@ __global__ void fill_normals_kernel(int d, size_t n_cols, double* __restrict__ A
        idx += (size_t)gridDim.x * blockDim.x) {
     const uint32_t pr = (uint32_t)(idx % pairs);
     const size_t col = idx / pairs;
-    const uint64_t chain = (uint64_t)(g.chain_offset + (int64_t)(col / g.round_len));
-    const uint32_t s = (uint32_t)(g.s_begin + (int)(col % g.round_len));
+    const int a = (int)(col / g.attempts);
+    const int chain = g.active ? g.active[a] : a;
+    const uint64_t draw = (uint64_t)(g.pos[chain] + (int64_t)(col % g.attempts));
     double n0, n1;
-    normal_pair(g.seed, chain, s, 0u, pr, n0, n1);
+    normal_pair(g.seed, (uint64_t)(g.chain_offset + chain), draw, pr, n0, n1);
     double* dst = A + col * d + 2 * (size_t)pr;
     dst[0] = n0;
     if (2 * pr + 1 < (uint32_t)d) dst[1] = n1;

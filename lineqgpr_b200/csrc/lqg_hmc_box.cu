@@ -18,6 +18,15 @@
 // filter (may_hit) -> exact tmg formula for the survivors -> warp-shuffle arg-min ->
 // one shared-memory slot per warp -> one barrier.  CTAs are persistent and pull chains from
 // an atomic queue, so chains with very different bounce counts do not stall an SM.
+//
+// Momenta: a transition attempt (one pass of tmg's while(2) body) consumes ONE fresh momentum
+// x_a = U a and ends either in an accepted end point or in a restart; a restart keeps nothing
+// but the wall position x_b.  A chain therefore is just a sequential consumer of momenta, like
+// tmg's sequential use of nd(eng1) (tmg:src/HmcSampler.cpp:54-55).  In pool mode the momenta of
+// the next `attempts` draws of every active chain are produced up front by one FP64
+// tensor-core GEMM (lqg_dgemm.cu) and the kernel runs each chain until its pool is used up;
+// the host loops rounds until every chain has finished.  Draws are Philox-addressed by
+// (chain, draw index), so the samples do not depend on the round size or on the pool.
 #include <limits.h>
 
 #include "lqg_common.cuh"
@@ -29,25 +38,31 @@ struct RedSlot {
   double t; double xa; double xb; int key; int ok;
 };
 
+// Survivors of the filter are compacted into a per-warp queue and evaluated 32 at a time:
+// hit_time_exact (sqrt, atan2, acos) then runs once per ~32 candidates instead of once per
+// call site with one or two active lanes.
+constexpr int QCAP = 64;
+struct Cand {
+  double fa, fb, g; int key; int pad;
+};
+
 // fresh momentum x_a = U a for this chain, computed by the CTA itself (restarts, injected
 // draws, or when the GEMM pre-pass is off).  a ~ N(0, I_d) drawn like tmg:src/HmcSampler.cpp:54-55.
 template <int G, int CPT>
-__device__ __forceinline__ bool draw_momentum(const BoxParams& p, int chain, uint32_t s,
-                                              uint32_t restart, int64_t& inj_pos,
+__device__ __forceinline__ bool draw_momentum(const BoxParams& p, int chain, int64_t draw,
                                               double* a_sm, double (&xa)[CPT]) {
   constexpr int T = 32 * G;
   const int tid = threadIdx.x;
   const int d = p.d;
   if (p.injected) {
-    if (inj_pos + d > p.n_injected) return false;                 // uniform across the CTA
-    const double* src = p.injected + (size_t)chain * p.n_injected + inj_pos;
+    if ((draw + 1) * d > p.n_injected) return false;              // uniform across the CTA
+    const double* src = p.injected + (size_t)chain * p.n_injected + (size_t)draw * d;
     for (int i = tid; i < d; i += T) a_sm[i] = src[i];
-    inj_pos += d;
   } else {
     const uint64_t gchain = (uint64_t)(p.chain_offset + chain);
     for (int pr = tid; 2 * pr < d; pr += T) {
       double n0, n1;
-      normal_pair(p.seed, gchain, s, restart, (uint32_t)pr, n0, n1);
+      normal_pair(p.seed, gchain, (uint64_t)draw, (uint32_t)pr, n0, n1);
       a_sm[2 * pr] = n0;
       if (2 * pr + 1 < d) a_sm[2 * pr + 1] = n1;
     }
@@ -57,15 +72,29 @@ __device__ __forceinline__ bool draw_momentum(const BoxParams& p, int chain, uin
 #pragma unroll
   for (int k = 0; k < CPT; ++k) acc[k] = 0.0;
   const double* U = p.U;
-  // x_a[i] = sum_col U[i,col] a[col]; U column-major so a warp reads 256 contiguous bytes
-#pragma unroll 2
-  for (int col = 0; col < d; ++col) {
-    const double av = a_sm[col];
-    const double* ucol = U + (size_t)col * d;
+  // x_a[i] = sum_col U[i,col] a[col]; U column-major so a warp reads 256 contiguous bytes.
+  // Loads are unconditional (row index clamped) so that CB columns x CPT rows are in flight
+  // per thread; for an upper-triangular U the slabs k with k*T > col are all zero and are
+  // skipped with a CTA-uniform test.
+  constexpr int CB = 4;
+  int rows[CPT];
 #pragma unroll
-    for (int k = 0; k < CPT; ++k) {
-      const int i = tid + k * T;
-      if (i < d && (!p.u_upper || i <= col)) acc[k] = fma(__ldg(ucol + i), av, acc[k]);
+  for (int k = 0; k < CPT; ++k) rows[k] = min(tid + k * T, d - 1);
+  for (int col0 = 0; col0 < d; col0 += CB) {
+    double u[CB][CPT];
+#pragma unroll
+    for (int c = 0; c < CB; ++c) {
+      const int col = min(col0 + c, d - 1);
+      const double* ucol = U + (size_t)col * d;
+#pragma unroll
+      for (int k = 0; k < CPT; ++k)
+        u[c][k] = (!p.u_upper || k * T <= col0 + CB - 1) ? __ldg(ucol + rows[k]) : 0.0;
+    }
+#pragma unroll
+    for (int c = 0; c < CB; ++c) {
+      const double av = (col0 + c < d) ? a_sm[col0 + c] : 0.0;
+#pragma unroll
+      for (int k = 0; k < CPT; ++k) acc[k] = fma(u[c][k], av, acc[k]);
     }
   }
 #pragma unroll
@@ -80,6 +109,7 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
   extern __shared__ double a_sm[];                 // d doubles: staging of a fresh draw
                                                    // (+ 2d doubles of bound offsets when GSM)
   __shared__ RedSlot red[2][G];
+  __shared__ Cand queue[G][QCAP];
   __shared__ int chain_sm;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -107,12 +137,14 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
   }
   const double abs_eps = p.abs_eps;
 
+  const int total = p.burn_in + p.n_per_chain;
   for (;;) {
     if (tid == 0) chain_sm = atomicAdd(p.next_chain, 1);
     __syncthreads();
-    const int chain = chain_sm;
+    const int aidx = chain_sm;
     __syncthreads();
-    if (chain >= p.n_chains) break;
+    if (aidx >= p.n_active) break;
+    const int chain = p.active ? p.active[aidx] : aidx;
 
     double xa[CPT], xb[CPT];
 #pragma unroll
@@ -121,25 +153,27 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
       xb[k] = i < d ? p.state[(size_t)chain * d + i] : 0.0;
       xa[k] = 0.0;
     }
-    int64_t inj_pos = p.inj_pos ? p.inj_pos[chain] : 0;
+    int s = p.s_done[chain];                       // transitions completed so far
+    int64_t draw = p.pos[chain];                   // momenta consumed so far
+    int rcount = p.rcount[chain];                  // restarts inside the current transition
     int status = p.chain_status[chain];
     unsigned long long n_bounce = 0, n_search = 0, n_vel = 0, n_chk = 0, n_exact = 0, n_trans = 0;
     int parity = 0;
 
-    for (int s = p.s_begin; s < p.s_end && status == 0; ++s) {
-      uint32_t restart = 0;
-      for (;;) {                                                   // while(2), HmcSampler.cpp:51
-        if (restart == 0 && p.xa_pre != nullptr) {
-          const double* src = p.xa_pre + ((size_t)chain * (p.s_end - p.s_begin) + (s - p.s_begin)) * d;
+    for (int att = 0; att < p.attempts && s < total && status == 0; ++att) {   // while(2), HmcSampler.cpp:51
+      {
+        if (p.pool != nullptr) {
+          const double* src = p.pool + ((size_t)aidx * p.attempts + att) * d;
 #pragma unroll
           for (int k = 0; k < CPT; ++k) {
             const int i = tid + k * T;
             xa[k] = i < d ? src[i] : 0.0;
           }
-        } else if (!draw_momentum<G, CPT>(p, chain, (uint32_t)s, restart, inj_pos, a_sm, xa)) {
+        } else if (!draw_momentum<G, CPT>(p, chain, draw, a_sm, xa)) {
           status = LQG_ERR_DRAWS_EXHAUSTED;
           break;
         }
+        ++draw;
         double tt = kHalfPi;                                       // :57
         double velsign = 0.0;                                      // :53
         bool end_ok = false;
@@ -148,6 +182,34 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
           sincos(tt, &S, &C);
           // ---- hit search over this thread's coordinates (both sides) ----
           double bt = 0.0, bxa = 0.0, bxb = 0.0; int bkey = INT_MAX; bool ok = true;
+          Cand* q = queue[warp];
+          int qn = 0;                                              // warp-uniform queue length
+          const unsigned lt_mask = (1u << lane) - 1u;
+          auto flush = [&]() {
+            for (int e = lane; e < qn; e += 32) {
+              const Cand cnd = q[e];
+              const double t = hit_time_exact(cnd.fa, cnd.fb, cnd.g);
+              if (hit_better(t, cnd.key, bt, bkey)) {
+                bt = t; bkey = cnd.key;
+                const double sgn = cnd.key < d ? 1.0 : -1.0;      // stored (fa, fb) = sgn * (x_a, x_b)
+                bxa = sgn * cnd.fa; bxb = sgn * cnd.fb;
+              }
+            }
+            n_exact += (lane == 0) ? qn : 0;
+            qn = 0;
+            __syncwarp();
+          };
+          auto push = [&](bool need, double fa, double fb, double g, int key) {
+            const unsigned m = __ballot_sync(0xffffffffu, need);
+            if (m == 0u) return;
+            if (qn + __popc(m) > QCAP) flush();
+            if (need) {
+              Cand& c = q[qn + __popc(m & lt_mask)];
+              c.fa = fa; c.fb = fb; c.g = g; c.key = key;
+            }
+            qn += __popc(m);
+            __syncwarp();
+          };
 #pragma unroll
           for (int k = 0; k < CPT; ++k) {
             const int i = tid + k * T;
@@ -155,29 +217,25 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
             const double y = fma(a_, S, b_ * C);                   // position at time tt (:119)
             const double dy = fma(a_, C, -b_ * S);
             const double base = fabs(a_) + fabs(b_);
+            const double u2 = fma(a_, a_, b_ * b_);                // amplitude^2, same for both sides
             {                                                      // lower bound row: f = +e_i
               const double g = GSM ? glo_s[i] : glo_r[GSM ? 0 : k];
               const double m = fma(kFilterRel, base + fabs(g), abs_eps);
-              const double y0 = b_ + g, y1 = y + g;
+              const double y0 = b_ + g, y1 = y + g, gm = g - m;
               ok = ok && (y1 >= 0.0);
-              if (!(y0 > m && y1 > m) || (a_ < 0.0 && dy > 0.0)) {
-                const double t = hit_time_exact(a_, b_, g);
-                ++n_exact;
-                if (hit_better(t, i, bt, bkey)) { bt = t; bkey = i; bxa = a_; bxb = b_; }
-              }
+              const bool reach = !(gm > 0.0 && gm * gm > u2);      // tmg needs u > |g| (:160)
+              push(reach && (!(y0 > m && y1 > m) || (a_ < 0.0 && dy > 0.0)), a_, b_, g, i);
             }
             {                                                      // upper bound row: f = -e_i
               const double g = GSM ? ghi_s[i] : ghi_r[GSM ? 0 : k];
               const double m = fma(kFilterRel, base + fabs(g), abs_eps);
-              const double y0 = g - b_, y1 = g - y;
+              const double y0 = g - b_, y1 = g - y, gm = g - m;
               ok = ok && (y1 >= 0.0);
-              if (!(y0 > m && y1 > m) || (a_ > 0.0 && dy < 0.0)) {
-                const double t = hit_time_exact(-a_, -b_, g);
-                ++n_exact;
-                if (hit_better(t, d + i, bt, bkey)) { bt = t; bkey = d + i; bxa = a_; bxb = b_; }
-              }
+              const bool reach = !(gm > 0.0 && gm * gm > u2);
+              push(reach && (!(y0 > m && y1 > m) || (a_ > 0.0 && dy < 0.0)), -a_, -b_, g, d + i);
             }
           }
+          flush();
           // ---- arg-min: warp shuffle, then one slot per warp ----
           Hit w = warp_min_hit(Hit{bt, bkey});
           const bool wok = __all_sync(0xffffffffu, ok);
@@ -229,7 +287,7 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
         }
         if (velsign < 0.0) {                                       // :117
           ++n_vel;
-          if (++restart > (uint32_t)p.max_restarts) { status = LQG_ERR_RESTART_CAP; break; }
+          if (++rcount > p.max_restarts) status = LQG_ERR_RESTART_CAP;
           continue;
         }
         // ---- end point: reference check (:121) and exact check of the emitted value ----
@@ -246,23 +304,24 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
           }
         }
         fine = (G > 1) ? (__syncthreads_and(fine) != 0) : __all_sync(0xffffffffu, fine);
-        if (fine) {
-#pragma unroll
-          for (int k = 0; k < CPT; ++k) xb[k] = fma(xa[k], S, xb[k] * C);   // lastSample = bb (:123)
-          break;
+        if (!fine) {                                               // :130
+          ++n_chk;
+          if (++rcount > p.max_restarts) status = LQG_ERR_RESTART_CAP;
+          continue;
         }
-        ++n_chk;                                                   // :130
-        if (++restart > (uint32_t)p.max_restarts) { status = LQG_ERR_RESTART_CAP; break; }
-      }
-      if (status != 0) break;
-      ++n_trans;
-      if (s >= p.burn_in) {                                        // tmg:R/tmg.R:105 drops burn-in
-        double* dst = p.out + ((size_t)chain * p.n_per_chain + (s - p.burn_in)) * d;
 #pragma unroll
-        for (int k = 0; k < CPT; ++k) {
-          const int i = tid + k * T;
-          if (i < d) dst[i] = __ldg(p.mu + i) + xb[k];             // tmg:R/tmg.R:106
+        for (int k = 0; k < CPT; ++k) xb[k] = fma(xa[k], S, xb[k] * C);   // lastSample = bb (:123)
+        rcount = 0;
+        ++n_trans;
+        if (s >= p.burn_in) {                                      // tmg:R/tmg.R:105 drops burn-in
+          double* dst = p.out + ((size_t)chain * p.n_per_chain + (s - p.burn_in)) * d;
+#pragma unroll
+          for (int k = 0; k < CPT; ++k) {
+            const int i = tid + k * T;
+            if (i < d) dst[i] = __ldg(p.mu + i) + xb[k];           // tmg:R/tmg.R:106
+          }
         }
+        ++s;
       }
     }
 
@@ -272,10 +331,9 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
       const int i = tid + k * T;
       if (i < d) p.state[(size_t)chain * d + i] = xb[k];
     }
-    n_exact = (unsigned long long)warp_sum((double)n_exact);
     if (lane == 0) atomicAdd(p.stats + 5, n_exact);
     if (tid == 0) {
-      if (p.inj_pos) p.inj_pos[chain] = inj_pos;
+      p.s_done[chain] = s; p.pos[chain] = draw; p.rcount[chain] = rcount;
       p.chain_status[chain] = status;
       atomicAdd(p.stats + 0, n_trans);
       atomicAdd(p.stats + 1, n_bounce);
@@ -307,6 +365,14 @@ __global__ void box_init_state_kernel(int d, int n_chains, const double* init, i
   state[idx] = init[ch * (size_t)init_ld + i] - mu[i];
 }
 
+// chains that still have transitions to run (and did not fail) -> next round's work list
+__global__ void box_compact_kernel(int n_chains, int total, const int* s_done, const int* status,
+                                   int* active_out, int* n_active_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_chains) return;
+  if (s_done[c] < total && status[c] == 0) active_out[atomicAdd(n_active_out, 1)] = c;
+}
+
 // independent audit of the emitted samples: counts entries outside [lb, ub]
 __global__ void box_violation_kernel(int d, size_t n_cols, const double* out, const double* lb,
                                      const double* ub, unsigned long long* count) {
@@ -336,7 +402,8 @@ static cudaError_t launch_box_t(const BoxParams& p, int grid, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     grid = sms * (per_sm > 0 ? per_sm : 1);          // persistent: every resident slot, once
   }
-  if (grid > p.n_chains) grid = p.n_chains;
+  if (grid > p.n_active) grid = p.n_active;
+  if (grid <= 0) return cudaSuccess;
   kern<<<grid, 32 * G, smem, st>>>(p);
   ++launch_counter();
   return cudaGetLastError();
@@ -355,6 +422,13 @@ cudaError_t launch_hmc_box(const BoxParams& p, int grid, cudaStream_t st) {
   if (d <= 4096) return launch_box_t<8, 16, true, 1>(p, grid, st);
   if (d <= 8192) return launch_box_t<16, 16, true, 1>(p, grid, st);
   return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_box_compact(int n_chains, int total, const int* s_done, const int* status,
+                               int* active_out, int* n_active_out, cudaStream_t st) {
+  box_compact_kernel<<<(n_chains + 255) / 256, 256, 0, st>>>(n_chains, total, s_done, status, active_out, n_active_out);
+  ++launch_counter();
+  return cudaGetLastError();
 }
 
 cudaError_t launch_box_prep(int d, const double* mu, const double* lb, const double* ub,

@@ -133,19 +133,19 @@ __global__ void __launch_bounds__(NT) hmc_canonical_kernel(const CanonParams p) 
       for (;;) {                                                   // while(2), :51
         // ---- fresh velocity a ~ N(0, I) (:54-55) ----
         if (p.injected) {
-          if (inj_pos + d > p.n_injected) { status = LQG_ERR_DRAWS_EXHAUSTED; break; }
-          const double* src = p.injected + (size_t)chain * p.n_injected + inj_pos;
+          if ((inj_pos + 1) * d > p.n_injected) { status = LQG_ERR_DRAWS_EXHAUSTED; break; }
+          const double* src = p.injected + (size_t)chain * p.n_injected + (size_t)inj_pos * d;
           for (int j = tid; j < d; j += NT) ab[j].x = src[j];
-          inj_pos += d;
         } else {
           const uint64_t gchain = (uint64_t)(p.chain_offset + chain);
           for (int pr = tid; 2 * pr < d; pr += NT) {
             double n0, n1;
-            normal_pair(p.seed, gchain, (uint32_t)s, restart, (uint32_t)pr, n0, n1);
+            normal_pair(p.seed, gchain, (uint64_t)inj_pos, (uint32_t)pr, n0, n1);
             ab[2 * pr].x = n0;
             if (2 * pr + 1 < d) ab[2 * pr + 1].x = n1;
           }
         }
+        ++inj_pos;                                                 // the chain's draw index
         __syncthreads();
         // energy |a|^2 + |b|^2 is invariant under rotation and reflection: scale of the filter
         double e2 = 0.0;

@@ -19,16 +19,21 @@ struct BoxParams {
   const double* sdiag;     // [d] Sigma_jj
   double abs_eps;          // absolute part of the filter margin
   double* state;           // d x n_chains, centred position x_b, in/out
-  const double* xa_pre;    // nullable: d x (n_chains * (s_end - s_begin)) pre-pass momenta
   int n_chains;
-  int s_begin, s_end;      // transitions [s_begin, s_end) of every chain run in this launch
+  const int* active;       // nullable: chain ids to run in this launch (NULL = 0..n_active-1)
+  int n_active;
+  int attempts;            // momenta each active chain may consume in this launch
+  const double* pool;      // nullable: d x (n_active * attempts) pre-computed momenta U a;
+                           // column a*attempts + j is draw pos[chain(a)] + j
+  int* s_done;             // [n_chains] transitions completed
+  int64_t* pos;            // [n_chains] momenta consumed (the chain's draw index)
+  int* rcount;             // [n_chains] restarts inside the current transition
   int burn_in, n_per_chain;
   double* out;             // d x (n_chains * n_per_chain)
   uint64_t seed;
   int64_t chain_offset;
   const double* injected;  // nullable [n_chains][n_injected]
   int64_t n_injected;
-  int64_t* inj_pos;        // nullable [n_chains]
   int max_restarts;
   int* next_chain;         // work queue head (zeroed before launch)
   unsigned long long* stats;  // [8]: transitions,bounces,searches,vel,chk,exact,violations,failed
@@ -41,6 +46,8 @@ cudaError_t launch_box_prep(int d, const double* mu, const double* lb, const dou
                             cudaStream_t st);
 cudaError_t launch_box_init_state(int d, int n_chains, const double* init, int64_t init_ld,
                                   const double* mu, double* state, cudaStream_t st);
+cudaError_t launch_box_compact(int n_chains, int total, const int* s_done, const int* status,
+                               int* active_out, int* n_active_out, cudaStream_t st);
 cudaError_t launch_box_violations(int d, size_t n_cols, const double* out, const double* lb,
                                   const double* ub, unsigned long long* count, cudaStream_t st);
 
@@ -76,13 +83,14 @@ size_t canon_smem_bytes(int d, int c, int f_in_smem);
 int canon_f_fits_smem(int d, int c);
 
 // ---- momentum pre-pass + generic FP64 tensor-core GEMM (lqg_dgemm.cu) -------------------
-// B operand generated on the fly: B[k, col] = N(0,1) draw (chain = col / round_len,
-// transition = s_begin + col % round_len, restart 0, coordinate k)
+// Philox normals for the momentum pool: column a*attempts + j holds the d draws of
+// (chain = active[a] (or a), draw index = pos[chain] + j)
 struct NormalGen {
   uint64_t seed;
   int64_t chain_offset;
-  int round_len;
-  int s_begin;
+  int attempts;
+  const int* active;       // nullable
+  const int64_t* pos;      // [n_chains]
 };
 cudaError_t launch_dgemm(int m, int n, int k, const double* A, int64_t lda, const double* B,
                          int64_t ldb, double* C, int64_t ldc, double* row_sum, int a_upper,
