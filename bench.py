@@ -81,6 +81,10 @@ class ClockSampler:
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
+        self.t_lo, self.t_hi = 0.0, float("inf")
+
+    def window(self, lo, hi):
+        self.t_lo, self.t_hi = lo, hi
 
     def start(self):
         try:
@@ -92,15 +96,16 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
     def stop(self):
         if self.proc:
             self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        rows = [r for t, r in self.rows if self.t_lo <= t <= self.t_hi] or [r for _, r in self.rows]
+        sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        reasons = sorted({n for r in rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
 
@@ -213,12 +218,13 @@ def run_ours(a):
     dfma, dmma = ctypes.c_double(), ctypes.c_double()
     L.check(lib.lqg_measure_fp64_peaks(ctypes.byref(dfma), ctypes.byref(dmma), None), "peaks")
 
+    clocks = ClockSampler(local); clocks.start()        # started before warm-up: nvidia-smi start-up stays out of the timed window
     for w in range(a.warmup):
         flush_t.fill_(w)
         step_device(10 + w)
     barrier()
-    clocks = ClockSampler(local); clocks.start()
     lib.lqg_launch_count(1)
+    t_win0 = time.perf_counter()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
     stats = []
     t_wall = time.perf_counter()
@@ -253,9 +259,11 @@ def run_ours(a):
         L.check(rc, "lqg_hmc_box(host)")
         return st
 
-    step_host(7)
+    t_win1 = time.perf_counter()
+    clocks.window(t_win0, t_win1)
+    step_host(7); step_host(8)
     barrier()
-    e2e_steps = max(2, min(a.steps, 3))
+    e2e_steps = max(2, min(a.steps, 5))
     t0 = time.perf_counter()
     for s in range(e2e_steps):
         step_host(200 + s)
@@ -298,7 +306,7 @@ def run_ours(a):
                     "h2d_bytes_per_step": int((2 * d * d + 4 * d) * 8), "d2h_bytes_per_step": int(n_gpu * d * 8),
                     "steps": e2e_steps, "api": "lqg_hmc_box, LQG_MEM_HOST, pinned buffers"},
             "gpu_launches": launches, "clocks": clk, "roofline": roof, "roofline_prepass": roof_pre,
-            "setup_s": P["setup_s"], "wall_s_timed_region": t_wall,
+            "setup_s": P["setup_s"], "wall_s_timed_region": t_wall, "step_ms": [round(x, 3) for x in step_ms],
             "counters": {"transitions": tr, "bounces_per_transition": bo / tr, "hit_searches": se,
                          "restarts_per_transition": rs / tr, "exact_evals_per_search": sum(s.exact_evals for s in stats) / se,
                          "violations": sum(s.violations for s in stats) + viol_host,

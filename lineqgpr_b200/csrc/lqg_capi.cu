@@ -1,7 +1,9 @@
 // C-ABI layer of lineqgpr_b200 (see include/lineqgpr_b200.h): argument validation, staging
 // of host buffers, launch orchestration, status codes.  No compute happens on the host.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <atomic>
 #include <cmath>
@@ -31,21 +33,38 @@ static void fold_launches() {
   g_launch_tls = 0;
 }
 
-// owning device allocation
+// owning device allocation from the stream-ordered pool: after the first call the pool keeps
+// the memory (release threshold = max), so repeated calls do not pay cudaMalloc/cudaFree
+static void retain_pool_once() {
+  static bool done = false;
+  if (done) return;
+  int dev = 0;
+  cudaMemPool_t pool;
+  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    uint64_t thr = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  done = true;
+}
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
+  cudaStream_t st = nullptr;
+  static thread_local cudaStream_t cur_stream;
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
-  ~DevBuf() { if (p) cudaFree(p); }
+  ~DevBuf() { if (p) cudaFreeAsync(p, st); }
   cudaError_t alloc(size_t n) {
-    if (p) { cudaFree(p); p = nullptr; }
+    if (p) { cudaFreeAsync(p, st); p = nullptr; }
+    retain_pool_once();
     bytes = n ? n : 16;
-    return cudaMalloc(&p, bytes);
+    st = cur_stream;
+    return cudaMallocAsync(&p, bytes, st);
   }
   template <class T> T* as() { return reinterpret_cast<T*>(p); }
 };
+thread_local cudaStream_t DevBuf::cur_stream = nullptr;
 
 // A read-only input that is either already on the device or staged from the host.
 struct Input {
@@ -94,6 +113,14 @@ static void fill_stats(lqg_hmc_stats* s, const unsigned long long* h, double cha
   s->chain_ms = chain_ms; s->prepass_ms = pre_ms;
 }
 
+// LQG_TRACE=1 prints host wall-clock phase timings of the entry points to stderr
+struct Phase {
+  bool on; double t0; const char* who;
+  static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+  explicit Phase(const char* w) : on(getenv("LQG_TRACE") != nullptr), t0(now()), who(w) {}
+  void mark(const char* what) { if (on) { double t = now(); fprintf(stderr, "[lqg %s] %-18s %8.2f ms\n", who, what, t - t0); t0 = t; } }
+};
+
 struct Timer {
   cudaEvent_t a = nullptr, b = nullptr;
   cudaStream_t st;
@@ -132,6 +159,7 @@ extern "C" int lqg_hmc_box(int32_t d, const double* mu, const double* U, int32_t
                            double* state_out, lqg_hmc_stats* stats) {
   if (stats) memset(stats, 0, sizeof(*stats));
   if (!have_device()) return LQG_ERR_CUDA;
+  Phase ph("hmc_box");
   const lqg_opts o = opts_ ? *opts_ : default_opts();
   const int n_chains = o.n_chains > 0 ? o.n_chains : 1;
   if (d <= 0 || d > 8192 || !mu || !U || !Sigma || !lb || !ub || !init || !out || n_per_chain <= 0 ||
@@ -141,6 +169,7 @@ extern "C" int lqg_hmc_box(int32_t d, const double* mu, const double* U, int32_t
     return LQG_ERR_INVALID;
   }
   cudaStream_t st = (cudaStream_t)o.stream;
+  DevBuf::cur_stream = st;
   const int mem = o.mem;
   const size_t dd = (size_t)d * d;
   const size_t n_init = init_ld == 0 ? (size_t)d : (size_t)init_ld * (n_chains - 1) + d;
@@ -165,6 +194,7 @@ extern "C" int lqg_hmc_box(int32_t d, const double* mu, const double* U, int32_t
       }
     }
 
+  ph.mark("validate");
   // ---- stage inputs ----
   Input i_mu, i_U, i_S, i_lb, i_ub, i_init, i_inj;
   if ((rc = i_mu.stage(mu, d, mem, st)) || (rc = i_U.stage(U, dd, mem, st)) ||
@@ -193,6 +223,7 @@ extern "C" int lqg_hmc_box(int32_t d, const double* mu, const double* U, int32_t
   LQG_CUDA_TRY(cudaMemsetAsync(b_pos.p, 0, b_pos.bytes, st));
   LQG_CUDA_TRY(cudaMemsetAsync(b_rcount.p, 0, b_rcount.bytes, st));
 
+  ph.mark("stage+alloc");
   LQG_CUDA_TRY(launch_box_prep(d, i_mu.dev, i_lb.dev, i_ub.dev, i_S.dev, b_glo.as<double>(),
                                b_ghi.as<double>(), b_sd.as<double>(), st));
   // x_b(0) = init - mu for every chain (init_ld == 0 broadcasts one shared start)
@@ -222,6 +253,7 @@ extern "C" int lqg_hmc_box(int32_t d, const double* mu, const double* U, int32_t
   int* d_nactive = reinterpret_cast<int*>(b_misc.as<unsigned long long>() + 9);
   p.chain_status = b_status.as<int>();
 
+  ph.mark("prep");
   const int total = burn_in + n_per_chain;
   // ---- momentum pool: X_a = U A for the next `attempts` draws of every active chain, ONE GEMM ----
   const bool use_pool = !o.injected && (o.prepass == 1 || (o.prepass == -1 && d >= 256));
@@ -241,6 +273,7 @@ extern "C" int lqg_hmc_box(int32_t d, const double* mu, const double* U, int32_t
     DevBuf b_pool, b_a;
     LQG_CUDA_TRY(b_pool.alloc((size_t)d * n_chains * attempts * sizeof(double)));
     LQG_CUDA_TRY(b_a.alloc((size_t)d * n_chains * attempts * sizeof(double)));
+    ph.mark("pool alloc");
     int n_active = n_chains;
     int* act[2] = {b_act.as<int>(), b_act.as<int>() + n_chains};
     int cur = 0;
@@ -267,6 +300,7 @@ extern "C" int lqg_hmc_box(int32_t d, const double* mu, const double* U, int32_t
       chain_ms += t_chain.ms();
       cur ^= 1;
       first = false;
+      ph.mark("round");
     }
   }
 
@@ -290,6 +324,7 @@ extern "C" int lqg_hmc_box(int32_t d, const double* mu, const double* U, int32_t
     else LQG_CUDA_TRY(cudaMemcpyAsync(state_out, h_state.data(), h_state.size() * sizeof(double), cudaMemcpyHostToDevice, st));
   }
   LQG_CUDA_TRY(cudaStreamSynchronize(st));
+  ph.mark("audit+copy out");
   rc = chain_status_rc(h_status, &h_stats[7]);
   fill_stats(stats, h_stats, chain_ms, pre_ms);
   fold_launches();
@@ -314,6 +349,7 @@ extern "C" int lqg_hmc_canonical(int32_t d, int32_t c, const double* F, const do
     return LQG_ERR_INVALID;
   }
   cudaStream_t st = (cudaStream_t)o.stream;
+  DevBuf::cur_stream = st;
   const int mem = o.mem;
   const size_t n_init = initial_ld == 0 ? (size_t)d : (size_t)initial_ld * (n_chains - 1) + d;
   const size_t n_F = (size_t)c * d;
@@ -443,6 +479,7 @@ extern "C" int lqg_rsm(int32_t d, const double* map, const double* factor, const
     return LQG_ERR_INVALID;
   }
   cudaStream_t st = (cudaStream_t)o.stream;
+  DevBuf::cur_stream = st;
   const int mem = o.mem;
   int rc;
   Input i_map, i_fac, i_w, i_lb, i_ub, i_z, i_u;
@@ -537,6 +574,7 @@ extern "C" int lqg_dgemm(int32_t m, int32_t n, int32_t k, const double* A, int64
     return LQG_ERR_INVALID;
   }
   cudaStream_t st = (cudaStream_t)o.stream;
+  DevBuf::cur_stream = st;
   const int mem = o.mem;
   int rc;
   Input i_A, i_B;
@@ -577,6 +615,7 @@ extern "C" int lqg_bands(int32_t n_t, int64_t N, const double* ysim, int64_t ld,
     return LQG_ERR_INVALID;
   }
   cudaStream_t st = (cudaStream_t)o.stream;
+  DevBuf::cur_stream = st;
   const int mem = o.mem;
   int rc;
   std::vector<double> h_probs;
