@@ -28,6 +28,7 @@
 // the host loops rounds until every chain has finished.  Draws are Philox-addressed by
 // (chain, draw index), so the samples do not depend on the round size or on the pool.
 #include <limits.h>
+#include <stdlib.h>
 
 #include "lqg_common.cuh"
 #include "lqg_kernels.h"
@@ -35,7 +36,7 @@
 namespace lqg {
 
 struct RedSlot {
-  double t; double xa; double xb; int key; int ok;
+  double t; double xa; double xb; int key; int pad;
 };
 
 // Survivors of the filter are compacted into a per-warp queue and evaluated 32 at a time:
@@ -76,7 +77,7 @@ __device__ __forceinline__ bool draw_momentum(const BoxParams& p, int chain, int
   // Loads are unconditional (row index clamped) so that CB columns x CPT rows are in flight
   // per thread; for an upper-triangular U the slabs k with k*T > col are all zero and are
   // skipped with a CTA-uniform test.
-  constexpr int CB = 4;
+  constexpr int CB = (CPT >= 16) ? 2 : 4;
   int rows[CPT];
 #pragma unroll
   for (int k = 0; k < CPT; ++k) rows[k] = min(tid + k * T, d - 1);
@@ -115,27 +116,31 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int d = p.d;
 
-  // per-coordinate bound offsets: registers for small CPT, shared memory (padded to CPT*T
-  // entries, read conflict-free) when the register budget is better spent on occupancy
+  // Per-coordinate filter thresholds h = g - m, with g the bound offset (mu - lb or ub - mu) and
+  // m = 3e-9 |g| + abs_eps the safety margin (orders of magnitude above any rounding difference
+  // between this eta-frame recursion and tmg's whitened dot products).  Registers for small
+  // CPT, shared memory (padded to CPT*T entries, conflict-free) when the register budget is
+  // better spent on occupancy.
   constexpr int NG = GSM ? 1 : CPT;
-  double glo_r[NG], ghi_r[NG];
-  double* glo_s = a_sm + d;
-  double* ghi_s = glo_s + CPT * T;
+  double hlo_r[NG], hhi_r[NG];
+  double* hlo_s = a_sm + d;
+  double* hhi_s = hlo_s + CPT * T;
+  const double abs_eps = p.abs_eps;
+  auto thr = [&](double g) { return g - fma(3.0 * kFilterRel, fabs(g), abs_eps); };
   if (GSM) {
     for (int i = tid; i < CPT * T; i += T) {
-      glo_s[i] = i < d ? p.glo[i] : kBigG;
-      ghi_s[i] = i < d ? p.ghi[i] : kBigG;
+      hlo_s[i] = thr(i < d ? p.glo[i] : kBigG);
+      hhi_s[i] = thr(i < d ? p.ghi[i] : kBigG);
     }
     __syncthreads();
   } else {
 #pragma unroll
     for (int k = 0; k < NG; ++k) {
       const int i = tid + k * T;
-      glo_r[k] = i < d ? p.glo[i] : kBigG;
-      ghi_r[k] = i < d ? p.ghi[i] : kBigG;
+      hlo_r[k] = thr(i < d ? p.glo[i] : kBigG);
+      hhi_r[k] = thr(i < d ? p.ghi[i] : kBigG);
     }
   }
-  const double abs_eps = p.abs_eps;
 
   const int total = p.burn_in + p.n_per_chain;
   for (;;) {
@@ -176,12 +181,13 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
         ++draw;
         double tt = kHalfPi;                                       // :57
         double velsign = 0.0;                                      // :53
-        bool end_ok = false;
-        double S = 1.0, C = 0.0;
+        bool no_hit = false;
+        // sin/cos of the remaining time.  Inside the loop they only feed the filter, so after a
+        // bounce they are advanced by angle subtraction; the final move recomputes them exactly.
+        double S = 1.0, C = 6.123233995736766e-17;                 // sin(M_PI/2), cos(M_PI/2)
         for (;;) {                                                 // while(1), :64
-          sincos(tt, &S, &C);
           // ---- hit search over this thread's coordinates (both sides) ----
-          double bt = 0.0, bxa = 0.0, bxb = 0.0; int bkey = INT_MAX; bool ok = true;
+          double bt = 0.0, bxa = 0.0, bxb = 0.0; int bkey = INT_MAX;
           Cand* q = queue[warp];
           int qn = 0;                                              // warp-uniform queue length
           const unsigned lt_mask = (1u << lane) - 1u;
@@ -199,108 +205,109 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
             qn = 0;
             __syncwarp();
           };
-          auto push = [&](bool need, double fa, double fb, double g, int key) {
+          auto push = [&](bool need, double fa, double fb, const double* gsrc, int i, int key) {
             const unsigned m = __ballot_sync(0xffffffffu, need);
             if (m == 0u) return;
             if (qn + __popc(m) > QCAP) flush();
             if (need) {
               Cand& c = q[qn + __popc(m & lt_mask)];
-              c.fa = fa; c.fb = fb; c.g = g; c.key = key;
+              c.fa = fa; c.fb = fb; c.g = __ldg(gsrc + i); c.key = key;
             }
             qn += __popc(m);
             __syncwarp();
           };
+          // Filter (see may_hit in lqg_common.cuh).  With y = position at time tt, dy = velocity
+          // at time tt, u^2 = a^2 + b^2 and the threshold h = g - margin:
+          //   lower row (f = +e_i):  safe iff min(b, y) > -h, unless the orbit dips in between
+          //                          (a < 0 and dy > 0) AND reaches the wall (u^2 >= h^2)
+          //   upper row (f = -e_i):  mirrored.
+          // h |h| compares like h^2 for h > 0 and is negative (always reachable) for h <= 0.
 #pragma unroll
           for (int k = 0; k < CPT; ++k) {
             const int i = tid + k * T;
             const double a_ = xa[k], b_ = xb[k];
-            const double y = fma(a_, S, b_ * C);                   // position at time tt (:119)
+            const double y = fma(a_, S, b_ * C);
             const double dy = fma(a_, C, -b_ * S);
-            const double base = fabs(a_) + fabs(b_);
-            const double u2 = fma(a_, a_, b_ * b_);                // amplitude^2, same for both sides
-            {                                                      // lower bound row: f = +e_i
-              const double g = GSM ? glo_s[i] : glo_r[GSM ? 0 : k];
-              const double m = fma(kFilterRel, base + fabs(g), abs_eps);
-              const double y0 = b_ + g, y1 = y + g, gm = g - m;
-              ok = ok && (y1 >= 0.0);
-              const bool reach = !(gm > 0.0 && gm * gm > u2);      // tmg needs u > |g| (:160)
-              push(reach && (!(y0 > m && y1 > m) || (a_ < 0.0 && dy > 0.0)), a_, b_, g, i);
-            }
-            {                                                      // upper bound row: f = -e_i
-              const double g = GSM ? ghi_s[i] : ghi_r[GSM ? 0 : k];
-              const double m = fma(kFilterRel, base + fabs(g), abs_eps);
-              const double y0 = g - b_, y1 = g - y, gm = g - m;
-              ok = ok && (y1 >= 0.0);
-              const bool reach = !(gm > 0.0 && gm * gm > u2);
-              push(reach && (!(y0 > m && y1 > m) || (a_ > 0.0 && dy < 0.0)), -a_, -b_, g, d + i);
-            }
+            const double u2 = fma(a_, a_, b_ * b_);
+            const double hl = GSM ? hlo_s[i] : hlo_r[GSM ? 0 : k];
+            const double hh = GSM ? hhi_s[i] : hhi_r[GSM ? 0 : k];
+            const bool need_lo = !(fmin(b_, y) > -hl) || (a_ < 0.0 && dy > 0.0 && u2 >= hl * fabs(hl));
+            const bool need_hi = !(fmax(b_, y) < hh) || (a_ > 0.0 && dy < 0.0 && u2 >= hh * fabs(hh));
+            push(need_lo, a_, b_, p.glo, i, i);
+            push(need_hi, -a_, -b_, p.ghi, i, d + i);
           }
           flush();
           // ---- arg-min: warp shuffle, then one slot per warp ----
           Hit w = warp_min_hit(Hit{bt, bkey});
-          const bool wok = __all_sync(0xffffffffu, ok);
           const unsigned owner = __ballot_sync(0xffffffffu, bt == w.t && bkey == w.key);
           const int src = __ffs(owner) - 1;
           double wxa = __shfl_sync(0xffffffffu, bxa, src);
           double wxb = __shfl_sync(0xffffffffu, bxb, src);
-          bool all_ok = wok;
           if (G > 1) {
             if (lane == 0) {
               RedSlot& r = red[parity][warp];
-              r.t = w.t; r.key = w.key; r.xa = wxa; r.xb = wxb; r.ok = wok;
+              r.t = w.t; r.key = w.key; r.xa = wxa; r.xb = wxb;
             }
             __syncthreads();
-            w.t = 0.0; w.key = INT_MAX; all_ok = true;
+            w.t = 0.0; w.key = INT_MAX;
 #pragma unroll
             for (int g2 = 0; g2 < G; ++g2) {
               const RedSlot r = red[parity][g2];
-              all_ok = all_ok && r.ok;
               if (hit_better(r.t, r.key, w.t, w.key)) { w.t = r.t; w.key = r.key; wxa = r.xa; wxb = r.xb; }
             }
             parity ^= 1;
           }
           ++n_search;
           const double t = w.t;
-          if (t == 0.0 || tt < t) { end_ok = all_ok; break; }      // :82
+          if (t == 0.0 || tt < t) { no_hit = true; break; }        // :82
           // ---- bounce: rotate to the wall, reflect (:90-110) ----
           ++n_bounce;
           tt = tt - t;                                             // :90
-          double st, ct;
-          sincos(t, &st, &ct);
           const int j = w.key < d ? w.key : w.key - d;
           const double side = w.key < d ? 1.0 : -1.0;
-          const double sjj = __ldg(p.sdiag + j);
-          const double vj = __dsub_rn(__dmul_rn(ct, wxa), __dmul_rn(st, wxb));   // hit_vel[j]
-          const double alpha2 = 2.0 * (vj / sjj);                  // 2*alpha, alpha = f.v / f.f
           const double* scol = p.Sigma + (size_t)j * d;
+          // column j of Sigma is requested first so its L2 latency overlaps sincos(t)
+          double sc[CPT];
 #pragma unroll
           for (int k = 0; k < CPT; ++k) {
             const int i = tid + k * T;
-            const double sc = i < d ? __ldg(scol + i) : 0.0;
+            sc[k] = i < d ? __ldg(scol + i) : 0.0;
+          }
+          const double sjj = __ldg(p.sdiag + j);
+          double st, ct;
+          sincos(t, &st, &ct);
+          const double vj = __dsub_rn(__dmul_rn(ct, wxa), __dmul_rn(st, wxb));   // hit_vel[j]
+          const double alpha2 = 2.0 * (vj / sjj);                  // 2*alpha, alpha = f.v / f.f
+#pragma unroll
+          for (int k = 0; k < CPT; ++k) {
             const double a_ = xa[k], b_ = xb[k];
             xb[k] = fma(st, a_, ct * b_);                          // new_b  (:91)
             const double v = fma(ct, a_, -st * b_);                // hit_vel (:92)
-            xa[k] = fma(-alpha2, sc, v);                           // reflected velocity (:109)
+            xa[k] = fma(-alpha2, sc[k], v);                        // reflected velocity (:109)
           }
           velsign = side * __dsub_rn(vj, __dmul_rn(alpha2, sjj));  // a.f (:110)
           if (velsign < 0.0) break;                                // :112
+          const double Sn = fma(S, ct, -C * st), Cn = fma(C, ct, S * st);   // sin/cos(tt - t)
+          S = Sn; C = Cn;
         }
+        (void)no_hit;
         if (velsign < 0.0) {                                       // :117
           ++n_vel;
           if (++rcount > p.max_restarts) status = LQG_ERR_RESTART_CAP;
           continue;
         }
-        // ---- end point: reference check (:121) and exact check of the emitted value ----
-        // (S, C) are still sin/cos of the final tt: bb = sin(tt) a + cos(tt) b  (:119)
-        bool fine = end_ok;
-        if (fine) {
+        // ---- end point: bb = sin(tt) a + cos(tt) b (:119), tmg's check min(F bb + g) >= 0 (:121)
+        //      in its eta form, and the exact check of the value that would be emitted ----
+        sincos(tt, &S, &C);
+        bool fine = true;
 #pragma unroll
-          for (int k = 0; k < CPT; ++k) {
-            const int i = tid + k * T;
-            if (i < d) {
-              const double e = __ldg(p.mu + i) + fma(xa[k], S, xb[k] * C);
-              fine = fine && (e >= __ldg(p.lb + i)) && (e <= __ldg(p.ub + i));
-            }
+        for (int k = 0; k < CPT; ++k) {
+          const int i = tid + k * T;
+          if (i < d) {
+            const double bb = fma(xa[k], S, xb[k] * C);
+            const double e = __ldg(p.mu + i) + bb;
+            fine = fine && (bb + __ldg(p.glo + i) >= 0.0) && (__ldg(p.ghi + i) - bb >= 0.0) &&
+                   (e >= __ldg(p.lb + i)) && (e <= __ldg(p.ub + i));
           }
         }
         fine = (G > 1) ? (__syncthreads_and(fine) != 0) : __all_sync(0xffffffffu, fine);
@@ -418,7 +425,12 @@ cudaError_t launch_hmc_box(const BoxParams& p, int grid, cudaStream_t st) {
   if (d <= 256)  return launch_box_t<2, 4, false, 8>(p, grid, st);
   if (d <= 512)  return launch_box_t<4, 4, false, 4>(p, grid, st);
   if (d <= 1024) return launch_box_t<4, 8, true, 4>(p, grid, st);
-  if (d <= 2048) return launch_box_t<8, 8, true, 2>(p, grid, st);
+  if (d <= 2048) {
+    static const char* v = getenv("LQG_BOX_VARIANT");          // tuning aid: "4" = 4 warps x 16 coordinates, "2" = 8x8 at 2 CTAs/SM
+    if (v && v[0] == '4') return launch_box_t<4, 16, true, 4>(p, grid, st);
+    if (v && v[0] == '2') return launch_box_t<8, 8, true, 2>(p, grid, st);     // 2 CTAs/SM (128 registers)
+    return launch_box_t<8, 8, true, 3>(p, grid, st);                           // 3 CTAs/SM (80 registers): measured best
+  }
   if (d <= 4096) return launch_box_t<8, 16, true, 1>(p, grid, st);
   if (d <= 8192) return launch_box_t<16, 16, true, 1>(p, grid, st);
   return cudaErrorInvalidValue;

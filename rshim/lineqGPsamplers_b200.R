@@ -1,0 +1,53 @@
+# Patched bodies of tmvrnorm.HMC / tmvrnorm.RSM for lineqGPR (dev/lineqGPR/R/lineqGPsamplers.R).
+# SOURCE ONLY: R is not installed in the build image, so this file has not been executed here.
+# Same function names, same arguments, same d x nsim return value; only the sampling itself
+# moves to the GPU through the .Call shim rshim/lqg_rcall.c.
+#
+# dyn.load("lqg_rcall.so") once (or useDynLib in NAMESPACE).
+
+tmvrnorm.HMC <- function(object, nsim, control = list(burn.in = 1e2), ...) {
+  if (!("burn.in" %in% names(control))) control$burn.in <- 1e2
+  if (!("n.chains" %in% names(control))) control$n.chains <- min(nsim, 1024L)   # extension
+  tmvPar <- object
+  if (!("map" %in% names(tmvPar))) tmvPar$map <- tmvPar$mu
+  d <- length(tmvPar$mu)
+  # the checks of bounds2lineqSys(d, lb, ub, A = diag(d), "oneside")  (mvec := length(mu), see Q3)
+  if (!is.element(length(tmvPar$lb), c(1, d)) || !is.element(length(tmvPar$ub), c(1, d)))
+    stop('The bounds have to be d-dimensionals')
+  if (any(tmvPar$lb >= tmvPar$ub))
+    stop('The elements from "u" has to be greater than the elements from "l"')
+  lb <- rep_len(tmvPar$lb, d); ub <- rep_len(tmvPar$ub, d)
+  epsilon <- 1e-9
+  init_vec <- pmin(pmax(tmvPar$map, lb + epsilon), ub - epsilon)
+  # whitening exactly as tmg::rtmg does it on the host (tmg/R/tmg.R:15-27)
+  H <- solve(tmvPar$Sigma)
+  M <- (H + t(H)) / 2
+  if (any(eigen(M, symmetric = TRUE, only.values = TRUE)$values <= 0))
+    stop("Error: M must be positive definite.")
+  Ri <- solve(chol(M))                      # upper triangular, Ri %*% t(Ri) = Sigma
+  n.per <- ceiling(nsim / control$n.chains)
+  seed <- sample(1:10000000, 1)             # tmg/R/tmg.R:102: set.seed() still determines the run
+  xi <- .Call("lqg_hmc_box_call", as.double(tmvPar$mu), Ri, tmvPar$Sigma, as.double(lb), as.double(ub),
+              as.double(init_vec), as.integer(n.per), as.integer(control$burn.in),
+              as.integer(control$n.chains), as.integer(seed))
+  return(xi[, seq_len(nsim), drop = FALSE])
+}
+
+tmvrnorm.RSM <- function(object, nsim, control = NULL, ...) {
+  tmvPar <- object
+  if (!("map" %in% names(tmvPar))) tmvPar$map <- tmvPar$mu
+  invSigma <- chol2inv(chol(tmvPar$Sigma))
+  w <- as.vector(invSigma %*% tmvPar$map)
+  eS <- eigen(tmvPar$Sigma, symmetric = TRUE)            # MASS::mvrnorm's factor, hoisted out of the loop
+  fac <- eS$vectors %*% diag(sqrt(pmax(eS$values, 0)), length(w))
+  d <- length(w)
+  seed <- sample(1:10000000, 1)
+  .Call("lqg_rsm_call", as.double(tmvPar$map), fac, w, as.double(rep_len(tmvPar$lb, d)),
+        as.double(rep_len(tmvPar$ub, d)), as.integer(nsim), as.integer(seed))
+}
+
+# simulate.lineqGP tail (R/lineqGP.R:639-640) on the GPU:
+#   simModel$xi.sim <- .Call("lqg_dgemm_call", qr.solve(pred$Lambda, diag(nrow(pred$Lambda))), eta)
+#   simModel$ysim   <- .Call("lqg_dgemm_call", pred$Phi.test, simModel$xi.sim)
+# plot.lineqGP bands (R/lineqGPutils.R:422-423):
+#   b <- .Call("lqg_bands_call", ysim, probs); qtls <- b[[2]]; ymean <- b[[1]]

@@ -1,0 +1,101 @@
+/* .Call shim between R and liblineqgpr_b200.so — SOURCE ONLY in this repository.
+ *
+ * R (and Rinternals.h) are not installed in the build image, so this file is not compiled
+ * or executed here; it shows the reference-side binding a maintainer adds.
+ * It replaces the only FFI of the reference,
+ *     .Call("rtmg", n+burn.in, seed, initial2, numlin, f2, g2, numquad, quads, PACKAGE="tmg")
+ *                                                                       tmg:R/tmg.R:104
+ * and adds the box-form / RSM / path entry points used by the patched lineqGPsamplers.R.
+ * All matrices arrive column-major, exactly as the C ABI expects; outputs are allocated with
+ * Rf_allocMatrix and PROTECTed; status codes become R errors (tmg itself only cat()s and
+ * returns NULL, tmg:R/tmg.R:4-57).
+ *
+ * Build (where R exists):  R CMD SHLIB lqg_rcall.c -I../include -L../lineqgpr_b200 -llineqgpr_b200
+ */
+#include <R.h>
+#include <Rinternals.h>
+#include <string.h>
+
+#include "lineqgpr_b200.h"
+
+static void lqg_check(int rc, const char* where) {
+  if (rc != LQG_OK) Rf_error("%s: lineqgpr_b200 status %d: %s", where, rc, lqg_last_error());
+}
+
+/* drop-in for tmg's native entry: same argument list, same n x d (row = sample) result */
+SEXP lqg_rtmg_call(SEXP n_, SEXP seed_, SEXP initial_, SEXP numlin_, SEXP F_, SEXP g_,
+                   SEXP numquad_, SEXP quads_) {
+  const int n = Rf_asInteger(n_), seed = Rf_asInteger(seed_);
+  const int numlin = Rf_asInteger(numlin_), numquad = Rf_asInteger(numquad_);
+  const int d = Rf_length(initial_);
+  SEXP out = PROTECT(Rf_allocMatrix(REALSXP, n, d));
+  int rc = lqg_rtmg(n, seed, REAL(initial_), d, numlin, numlin > 0 ? REAL(F_) : NULL,
+                    numlin > 0 ? REAL(g_) : NULL, numquad, numquad > 0 ? REAL(quads_) : NULL,
+                    REAL(out));
+  UNPROTECT(1);
+  lqg_check(rc, "lqg_rtmg");
+  return out;
+}
+
+/* tmvrnorm.HMC body: returns the d x nsim matrix directly (R/lineqGPsamplers.R:142) */
+SEXP lqg_hmc_box_call(SEXP mu_, SEXP U_, SEXP Sigma_, SEXP lb_, SEXP ub_, SEXP init_,
+                      SEXP n_per_chain_, SEXP burn_in_, SEXP n_chains_, SEXP seed_) {
+  const int d = Rf_length(mu_);
+  const int n_per = Rf_asInteger(n_per_chain_), burn = Rf_asInteger(burn_in_);
+  lqg_opts o;
+  memset(&o, 0, sizeof(o));
+  o.mem = LQG_MEM_HOST;
+  o.n_chains = Rf_asInteger(n_chains_);
+  o.seed = (uint64_t)Rf_asInteger(seed_);
+  o.prepass = -1;
+  lqg_hmc_stats st;
+  SEXP out = PROTECT(Rf_allocMatrix(REALSXP, d, o.n_chains * n_per));
+  int rc = lqg_hmc_box(d, REAL(mu_), REAL(U_), 1, REAL(Sigma_), REAL(lb_), REAL(ub_), REAL(init_), 0,
+                       n_per, burn, &o, REAL(out), NULL, &st);
+  UNPROTECT(1);
+  lqg_check(rc, "lqg_hmc_box");
+  if (st.violations != 0) Rf_error("lqg_hmc_box: %lld emitted values outside the bounds", (long long)st.violations);
+  return out;
+}
+
+/* tmvrnorm.RSM body */
+SEXP lqg_rsm_call(SEXP map_, SEXP factor_, SEXP w_, SEXP lb_, SEXP ub_, SEXP nsim_, SEXP seed_) {
+  const int d = Rf_length(map_);
+  const int nsim = Rf_asInteger(nsim_);
+  lqg_opts o;
+  memset(&o, 0, sizeof(o));
+  o.mem = LQG_MEM_HOST;
+  o.seed = (uint64_t)Rf_asInteger(seed_);
+  lqg_rsm_stats st;
+  SEXP out = PROTECT(Rf_allocMatrix(REALSXP, d, nsim));
+  int rc = lqg_rsm(d, REAL(map_), REAL(factor_), REAL(w_), REAL(lb_), REAL(ub_), nsim, 0, &o, REAL(out), &st);
+  UNPROTECT(1);
+  lqg_check(rc, "lqg_rsm");
+  return out;
+}
+
+/* A %*% B on the FP64 tensor cores: xi.sim = Lambda^+ eta, ysim = Phi.test %*% xi.sim */
+SEXP lqg_dgemm_call(SEXP A_, SEXP B_) {
+  const int m = Rf_nrows(A_), k = Rf_ncols(A_), n = Rf_ncols(B_);
+  if (Rf_nrows(B_) != k) Rf_error("non-conformable arguments");
+  SEXP out = PROTECT(Rf_allocMatrix(REALSXP, m, n));
+  int rc = lqg_dgemm(m, n, k, REAL(A_), m, REAL(B_), k, REAL(out), m, NULL, NULL, NULL);
+  UNPROTECT(1);
+  lqg_check(rc, "lqg_dgemm");
+  return out;
+}
+
+/* list(mean = apply(ysim,1,mean), qtls = apply(ysim,1,quantile,probs)) */
+SEXP lqg_bands_call(SEXP ysim_, SEXP probs_) {
+  const int n_t = Rf_nrows(ysim_), np = Rf_length(probs_);
+  const long long N = Rf_ncols(ysim_);
+  SEXP mean = PROTECT(Rf_allocVector(REALSXP, n_t));
+  SEXP q = PROTECT(Rf_allocMatrix(REALSXP, np, n_t));
+  int rc = lqg_bands(n_t, N, REAL(ysim_), n_t, REAL(probs_), np, REAL(mean), REAL(q), NULL, NULL);
+  SEXP res = PROTECT(Rf_allocVector(VECSXP, 2));
+  SET_VECTOR_ELT(res, 0, mean);
+  SET_VECTOR_ELT(res, 1, q);
+  UNPROTECT(3);
+  lqg_check(rc, "lqg_bands");
+  return res;
+}
