@@ -7,8 +7,8 @@
 Workload (config.workload): BASELINE.json configs[3] — 1-D bounded + monotone lineqGP, m = 1000 hat
 knots (d = 2000 eta coordinates, 2999 finite bound rows), HMC, 10^6 samples sharded over 8 GPUs,
 i.e. 125 000 samples per GPU (weak scaling: per-GPU work fixed).  tmvrnorm.HMC defaults:
-burn.in = 100 per chain; 1000 chains per GPU x 125 samples.  One "step" = one full pass: every
-chain's burn-in + its samples.  Synthetic data, seeded (lineqgpr_b200.workloads.cfg4).
+burn.in = 100 per chain; one chain per resident CTA slot of the device (444 on a B200 at d = 2000)
+x 282 samples.  One "step" = one full pass: every chain's burn-in + its samples.  Synthetic data, seeded (lineqgpr_b200.workloads.cfg4).
 
 value   = samples/s with all inputs resident in HBM (lqg_hmc_box, LQG_MEM_DEVICE), CUDA events.
 e2e     = samples/s through the C ABI with pinned HOST buffers (H2D of mu,U,Sigma,lb,ub,init and
@@ -38,7 +38,7 @@ sys.path.insert(0, str(ROOT))
 METRIC = "constrained TMVN samples/sec (HMC, m=1000 knots)"
 UNIT = "samples/s"
 WORKLOAD = ("cfg4: 1-D bounded+monotone lineqGP, m=1000 knots (d=2000, 2999 bound rows), HMC T=pi/2, "
-            "125000 samples per GPU (10^6 over 8), burn.in=100, 1000 chains/GPU x 125 samples")
+            "125000 samples per GPU (10^6 over 8), burn.in=100 per chain, one chain per resident CTA slot")
 
 
 def parse():
@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg4", choices=["cfg4", "cfg5"])
     ap.add_argument("--nsim-per-gpu", type=int, default=125000)
-    ap.add_argument("--chains-per-gpu", type=int, default=1000)
+    ap.add_argument("--chains-per-gpu", type=int, default=0, help="0 = lqg_hmc_box_slots(d)")
     ap.add_argument("--burn-in", type=int, default=100)
     ap.add_argument("--prepass", type=int, default=-1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -122,18 +122,27 @@ def cpu_reference_sample(P, n_tr, cores, seed0=100):
     w = O.whiten(H, r, init, f, g)
     use_ref = O.ref_lib() is not None
     results = [None] * cores
+    burn = 3                                   # untimed: leave the cold clamped-MAP start
+
+    def run(n, seed, z0):
+        if use_ref:
+            return O.ref_rtmg_canonical(n, seed, z0, w["f2"], w["g2"])
+        return O.rtmg_canonical(n, seed, z0, w["f2"], w["g2"], faithful_copy=True)[0]
+
+    starts = [None] * cores
+
+    def warm(i):
+        starts[i] = run(burn, seed0 + i, w["initial2"])[-1].copy()
 
     def work(i):
         t = time.perf_counter()
-        if use_ref:
-            z = O.ref_rtmg_canonical(n_tr, seed0 + i, w["initial2"], w["f2"], w["g2"])
-            info = {}
-        else:
-            z, info = O.rtmg_canonical(n_tr, seed0 + i, w["initial2"], w["f2"], w["g2"], faithful_copy=True)
-        results[i] = (time.perf_counter() - t, z.shape[0], info)
+        z = run(n_tr, 7919 + seed0 + i, starts[i])
+        results[i] = (time.perf_counter() - t, z.shape[0], {})
 
+    th = [threading.Thread(target=warm, args=(i,)) for i in range(cores)]      # ctypes drops the GIL
+    [t.start() for t in th]; [t.join() for t in th]
     t0 = time.perf_counter()
-    th = [threading.Thread(target=work, args=(i,)) for i in range(cores)]      # ctypes drops the GIL
+    th = [threading.Thread(target=work, args=(i,)) for i in range(cores)]
     [t.start() for t in th]; [t.join() for t in th]
     wall = time.perf_counter() - t0
     n = sum(r[1] for r in results)
@@ -146,7 +155,7 @@ def run_reference_arm(a):
         return
     P = build_problem(a.workload)
     cores = os.cpu_count() or 1
-    n_tr = a.cpu_transitions or 4
+    n_tr = a.cpu_transitions or 8
     times = []
     for s in range(a.warmup + a.steps):
         v, kind, wall, _ = cpu_reference_sample(P, n_tr, cores, seed0=1000 * s)
@@ -159,8 +168,8 @@ def run_reference_arm(a):
             "warmup": a.warmup, "ms_per_step": 1e3 * tot_wall / max(1, len(times)), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD if a.workload == "cfg4" else a.workload,
-                       "note": "CPU arm: one serial tmg chain per host core from the clamped MAP start; each step is a bounded "
-                               f"sample of {n_tr} transitions per core"},
+                       "note": "CPU arm: one serial tmg chain per host core (3 untimed burn-in transitions from the clamped MAP, "
+                               f"then a timed bounded sample of {n_tr} transitions per core per step); no burn-in is charged to the CPU"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
                              "sample": f"{len(times)} steps x {cores} chains x {n_tr} transitions (d={P['d']}, c={P['c']})"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -187,7 +196,7 @@ def run_ours(a):
 
     P = build_problem(a.workload)
     d = P["d"]
-    n_chains = a.chains_per_gpu
+    n_chains = a.chains_per_gpu or lib.lqg_hmc_box_slots(d)
     n_per = -(-a.nsim_per_gpu // n_chains)
     n_gpu = n_chains * n_per
     burn = a.burn_in
@@ -320,8 +329,8 @@ def run_ours(a):
         n_tr = a.cpu_transitions or 40
         v, kind, wall, res = cpu_reference_sample(P, n_tr, cores)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
-                                "sample": f"{cores} serial chains x {n_tr} transitions from the clamped MAP start, "
-                                          f"same canonical inputs (d={d}, c={c}), wall {wall:.1f} s"}
+                                "sample": f"{cores} serial chains x {n_tr} timed transitions after 3 untimed burn-in transitions, "
+                                          f"same canonical inputs (d={d}, c={c}), wall {wall:.1f} s; burn-in not charged"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -135,6 +135,11 @@ int lqg_hmc_box(int32_t d, const double* mu, const double* U, int32_t u_upper,
                 int32_t n_per_chain, int32_t burn_in, const lqg_opts* opts,
                 double* out, double* state_out, lqg_hmc_stats* stats);
 
+/* Number of chains lqg_hmc_box keeps resident at once for dimension d on the current device
+ * (SMs x CTAs per SM of the kernel variant it would launch).  n_chains equal to a multiple of
+ * this fills every wave; the host wrappers use it as the default chain count.  <= 0 on error. */
+int lqg_hmc_box_slots(int32_t d);
+
 /* ---- RSM ---------------------------------------------------------------------------- */
 
 /* Rejection sampling from the mode, R/lineqGPsamplers.R:36-61.

@@ -18,7 +18,7 @@ STATUS = {0: "LQG_OK", 1: "LQG_ERR_INVALID", 2: "LQG_ERR_UNSUPPORTED", 3: "LQG_E
 MEM_HOST, MEM_DEVICE = 0, 1
 
 # every symbol include/lineqgpr_b200.h declares
-SYMBOLS = ["lqg_rtmg", "lqg_hmc_canonical", "lqg_hmc_box", "lqg_rsm", "lqg_dgemm", "lqg_bands",
+SYMBOLS = ["lqg_rtmg", "lqg_hmc_canonical", "lqg_hmc_box", "lqg_hmc_box_slots", "lqg_rsm", "lqg_dgemm", "lqg_bands",
            "lqg_version", "lqg_last_error", "lqg_device_count", "lqg_measure_fp64_peaks",
            "lqg_launch_count"]
 
@@ -79,6 +79,8 @@ def lib():
     L.lqg_hmc_box.restype = C.c_int
     L.lqg_hmc_box.argtypes = [i32, vp, vp, i32, vp, vp, vp, vp, i64, i32, i32, C.POINTER(Opts), vp, vp,
                               C.POINTER(HmcStats)]
+    L.lqg_hmc_box_slots.restype = C.c_int
+    L.lqg_hmc_box_slots.argtypes = [i32]
     L.lqg_rsm.restype = C.c_int
     L.lqg_rsm.argtypes = [i32, vp, vp, vp, vp, vp, i64, i64, C.POINTER(Opts), vp, C.POINTER(RsmStats)]
     L.lqg_dgemm.restype = C.c_int

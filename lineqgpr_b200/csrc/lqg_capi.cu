@@ -258,6 +258,7 @@ extern "C" int lqg_hmc_box(int32_t d, const double* mu, const double* U, int32_t
   // ---- momentum pool: X_a = U A for the next `attempts` draws of every active chain, ONE GEMM ----
   const bool use_pool = !o.injected && (o.prepass == 1 || (o.prepass == -1 && d >= 256));
   double chain_ms = 0.0, pre_ms = 0.0;
+  bool out_copied = false;
   Timer t_chain(st), t_pre(st);
   if (!use_pool) {
     p.active = nullptr; p.n_active = n_chains; p.attempts = 0x7fffffff; p.pool = nullptr;
@@ -278,6 +279,25 @@ extern "C" int lqg_hmc_box(int32_t d, const double* mu, const double* U, int32_t
     int* act[2] = {b_act.as<int>(), b_act.as<int>() + n_chains};
     int cur = 0;
     bool first = true;
+    const int max_attempts = attempts;
+    // round counters come back through mapped pinned memory (allocated once per thread)
+    static thread_local volatile int* h_flags = nullptr;
+    static thread_local int* d_flags = nullptr;
+    if (!h_flags) {
+      void* hp = nullptr;
+      LQG_CUDA_TRY(cudaHostAlloc(&hp, 64, cudaHostAllocMapped));
+      LQG_CUDA_TRY(cudaHostGetDevicePointer((void**)&d_flags, hp, 0));
+      h_flags = (volatile int*)hp;
+    }
+    // HOST mode: samples every chain has already emitted are copied out while later rounds run
+    // (one strided 2-D copy per round: chain-major columns, pitch = n_per_chain * d doubles)
+    cudaStream_t copy_st = nullptr;
+    cudaEvent_t ev_round = nullptr;
+    int copied = 0;                      // samples per chain already on their way to the host
+    if (mem == LQG_MEM_HOST) {
+      LQG_CUDA_TRY(cudaStreamCreateWithFlags(&copy_st, cudaStreamNonBlocking));
+      LQG_CUDA_TRY(cudaEventCreateWithFlags(&ev_round, cudaEventDisableTiming));
+    }
     // every round consumes `attempts` momenta per active chain, so this terminates after at most
     // (total + restarts) / attempts rounds; max_restarts bounds the restarts of every transition
     while (n_active > 0) {
@@ -289,18 +309,46 @@ extern "C" int lqg_hmc_box(int32_t d, const double* mu, const double* U, int32_t
       t_pre.stop();
       p.active = first ? nullptr : act[cur]; p.n_active = n_active; p.attempts = attempts;
       p.pool = b_pool.as<double>();
-      LQG_CUDA_TRY(cudaMemsetAsync(p.next_chain, 0, 2 * sizeof(unsigned long long), st));   // queue head + n_active
+      // queue head = 0, n_active = 0, min s_done = 0x7f7f7f7f  (memsets: no copy-engine traffic)
+      LQG_CUDA_TRY(cudaMemsetAsync(p.next_chain, 0, 3 * sizeof(int), st));
+      LQG_CUDA_TRY(cudaMemsetAsync(d_nactive + 1, 0x7f, sizeof(int), st));
       t_chain.start();
       LQG_CUDA_TRY(launch_hmc_box(p, 0, st));
       t_chain.stop();
-      LQG_CUDA_TRY(launch_box_compact(n_chains, total, p.s_done, p.chain_status, act[cur ^ 1], d_nactive, st));
-      LQG_CUDA_TRY(cudaMemcpyAsync(&n_active, d_nactive, sizeof(int), cudaMemcpyDeviceToHost, st));
+      LQG_CUDA_TRY(launch_box_compact(n_chains, total, p.s_done, p.chain_status, act[cur ^ 1], d_nactive, d_flags, st));
+      if (ev_round) LQG_CUDA_TRY(cudaEventRecord(ev_round, st));
       LQG_CUDA_TRY(cudaStreamSynchronize(st));
+      n_active = h_flags[0];
+      const int s_min = std::min((int)h_flags[1], total);
+      if (copy_st && s_min - burn_in > copied) {
+        const int upto = s_min - burn_in;
+        LQG_CUDA_TRY(cudaStreamWaitEvent(copy_st, ev_round, 0));
+        const size_t pitch = (size_t)n_per_chain * d * sizeof(double);
+        LQG_CUDA_TRY(cudaMemcpy2DAsync(out + (size_t)copied * d, pitch, d_out + (size_t)copied * d, pitch,
+                                       (size_t)(upto - copied) * d * sizeof(double), n_chains,
+                                       cudaMemcpyDeviceToHost, copy_st));
+        copied = upto;
+      }
+      // shrink the last rounds' pool to what the slowest chain can still need
+      attempts = std::max(4, std::min(max_attempts, (int)((total - s_min) * 1.25) + 4));
       pre_ms += t_pre.ms();
       chain_ms += t_chain.ms();
       cur ^= 1;
       first = false;
       ph.mark("round");
+    }
+    if (copy_st) {
+      // chains that failed never advance s_min: whatever is left is copied by the common tail below
+      if (copied < n_per_chain) {
+        const size_t pitch = (size_t)n_per_chain * d * sizeof(double);
+        LQG_CUDA_TRY(cudaMemcpy2DAsync(out + (size_t)copied * d, pitch, d_out + (size_t)copied * d, pitch,
+                                       (size_t)(n_per_chain - copied) * d * sizeof(double), n_chains,
+                                       cudaMemcpyDeviceToHost, st));
+      }
+      LQG_CUDA_TRY(cudaStreamSynchronize(copy_st));
+      cudaStreamDestroy(copy_st);
+      cudaEventDestroy(ev_round);
+      out_copied = true;
     }
   }
 
@@ -310,7 +358,7 @@ extern "C" int lqg_hmc_box(int32_t d, const double* mu, const double* U, int32_t
   std::vector<int> h_status(n_chains);
   LQG_CUDA_TRY(cudaMemcpyAsync(h_stats, p.stats, sizeof(h_stats), cudaMemcpyDeviceToHost, st));
   LQG_CUDA_TRY(cudaMemcpyAsync(h_status.data(), b_status.p, n_chains * sizeof(int), cudaMemcpyDeviceToHost, st));
-  if (mem == LQG_MEM_HOST)
+  if (mem == LQG_MEM_HOST && !out_copied)
     LQG_CUDA_TRY(cudaMemcpyAsync(out, d_out, n_cols * d * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (state_out) {
     // state_out holds positions in the ORIGINAL frame: mu + x_b, chain by chain
@@ -448,6 +496,10 @@ extern "C" int lqg_rtmg(int32_t n, int32_t seed, const double* initial, int32_t 
 // ===========================================================================================
 extern "C" const char* lqg_version(void) { return "lineqgpr_b200 0.1.0 (sm_100a)"; }
 extern "C" const char* lqg_last_error(void) { return g_err; }
+extern "C" int lqg_hmc_box_slots(int32_t d) {
+  if (!have_device() || d <= 0 || d > 8192) return 0;
+  return hmc_box_slots(d);
+}
 extern "C" int lqg_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }

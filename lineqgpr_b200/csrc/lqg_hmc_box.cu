@@ -29,6 +29,7 @@
 // (chain, draw index), so the samples do not depend on the round size or on the pool.
 #include <limits.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "lqg_common.cuh"
 #include "lqg_kernels.h"
@@ -378,6 +379,16 @@ __global__ void box_compact_kernel(int n_chains, int total, const int* s_done, c
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n_chains) return;
   if (s_done[c] < total && status[c] == 0) active_out[atomicAdd(n_active_out, 1)] = c;
+  if (status[c] == 0) atomicMin(n_active_out + 1, s_done[c]);
+}
+
+// publishes the two round counters into mapped pinned host memory with plain stores, so the
+// host can read them after a stream sync without a D2H copy (which would queue behind the bulk
+// sample copies on the copy engine)
+__global__ void box_publish_kernel(const int* src, volatile int* host_mapped) {
+  host_mapped[0] = src[0];
+  host_mapped[1] = src[1];
+  __threadfence_system();
 }
 
 // independent audit of the emitted samples: counts entries outside [lb, ub]
@@ -395,12 +406,21 @@ __global__ void box_violation_kernel(int d, size_t n_cols, const double* out, co
   if ((threadIdx.x & 31) == 0 && bad) atomicAdd(count, bad);
 }
 
+// grid == -1: query only, *slots_out = resident CTAs on the device
 template <int G, int CPT, bool GSM, int MINB>
-static cudaError_t launch_box_t(const BoxParams& p, int grid, cudaStream_t st) {
+static cudaError_t launch_box_t(const BoxParams& p, int grid, cudaStream_t st, int* slots_out = nullptr) {
   const size_t smem = ((size_t)p.d + (GSM ? 2 * CPT * 32 * G : 0)) * sizeof(double);
   auto kern = hmc_box_kernel<G, CPT, GSM, MINB>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
+  if (slots_out) {
+    int per_sm = 0, dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * G, smem);
+    *slots_out = sms * (per_sm > 0 ? per_sm : 1);
+    return e;
+  }
   if (grid <= 0) {
     int per_sm = 0, dev = 0, sms = 0;
     cudaGetDevice(&dev);
@@ -417,29 +437,39 @@ static cudaError_t launch_box_t(const BoxParams& p, int grid, cudaStream_t st) {
 }
 
 // picks (warps per chain, coordinates per thread) from d
-cudaError_t launch_hmc_box(const BoxParams& p, int grid, cudaStream_t st) {
+static cudaError_t dispatch_box(const BoxParams& p, int grid, cudaStream_t st, int* slots) {
   const int d = p.d;
-  if (d <= 32)   return launch_box_t<1, 1, false, 16>(p, grid, st);
-  if (d <= 64)   return launch_box_t<1, 2, false, 16>(p, grid, st);
-  if (d <= 128)  return launch_box_t<1, 4, false, 16>(p, grid, st);
-  if (d <= 256)  return launch_box_t<2, 4, false, 8>(p, grid, st);
-  if (d <= 512)  return launch_box_t<4, 4, false, 4>(p, grid, st);
-  if (d <= 1024) return launch_box_t<4, 8, true, 4>(p, grid, st);
+  if (d <= 32)   return launch_box_t<1, 1, false, 16>(p, grid, st, slots);
+  if (d <= 64)   return launch_box_t<1, 2, false, 16>(p, grid, st, slots);
+  if (d <= 128)  return launch_box_t<1, 4, false, 16>(p, grid, st, slots);
+  if (d <= 256)  return launch_box_t<2, 4, false, 8>(p, grid, st, slots);
+  if (d <= 512)  return launch_box_t<4, 4, false, 4>(p, grid, st, slots);
+  if (d <= 1024) return launch_box_t<4, 8, true, 4>(p, grid, st, slots);
   if (d <= 2048) {
     static const char* v = getenv("LQG_BOX_VARIANT");          // tuning aid: "4" = 4 warps x 16 coordinates, "2" = 8x8 at 2 CTAs/SM
-    if (v && v[0] == '4') return launch_box_t<4, 16, true, 4>(p, grid, st);
-    if (v && v[0] == '2') return launch_box_t<8, 8, true, 2>(p, grid, st);     // 2 CTAs/SM (128 registers)
-    return launch_box_t<8, 8, true, 3>(p, grid, st);                           // 3 CTAs/SM (80 registers): measured best
+    if (v && v[0] == '4') return launch_box_t<4, 16, true, 4>(p, grid, st, slots);
+    if (v && v[0] == '2') return launch_box_t<8, 8, true, 2>(p, grid, st, slots);     // 2 CTAs/SM (128 registers)
+    return launch_box_t<8, 8, true, 3>(p, grid, st, slots);                           // 3 CTAs/SM (80 registers): measured best
   }
-  if (d <= 4096) return launch_box_t<8, 16, true, 1>(p, grid, st);
-  if (d <= 8192) return launch_box_t<16, 16, true, 1>(p, grid, st);
+  if (d <= 4096) return launch_box_t<8, 16, true, 1>(p, grid, st, slots);
+  if (d <= 8192) return launch_box_t<16, 16, true, 1>(p, grid, st, slots);
   return cudaErrorInvalidValue;
+}
+cudaError_t launch_hmc_box(const BoxParams& p, int grid, cudaStream_t st) { return dispatch_box(p, grid, st, nullptr); }
+int hmc_box_slots(int d) {
+  BoxParams p;
+  memset(&p, 0, sizeof(p));
+  p.d = d;
+  int slots = 0;
+  if (dispatch_box(p, -1, nullptr, &slots) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return slots;
 }
 
 cudaError_t launch_box_compact(int n_chains, int total, const int* s_done, const int* status,
-                               int* active_out, int* n_active_out, cudaStream_t st) {
+                               int* active_out, int* n_active_out, int* host_mapped, cudaStream_t st) {
   box_compact_kernel<<<(n_chains + 255) / 256, 256, 0, st>>>(n_chains, total, s_done, status, active_out, n_active_out);
-  ++launch_counter();
+  box_publish_kernel<<<1, 1, 0, st>>>(n_active_out, host_mapped);
+  launch_counter() += 2;
   return cudaGetLastError();
 }
 

@@ -41,13 +41,16 @@ struct BoxParams {
 };
 
 cudaError_t launch_hmc_box(const BoxParams& p, int grid, cudaStream_t st);
+int hmc_box_slots(int d);        // resident CTAs (= chains in flight) for dimension d, current device
 cudaError_t launch_box_prep(int d, const double* mu, const double* lb, const double* ub,
                             const double* Sigma, double* glo, double* ghi, double* sdiag,
                             cudaStream_t st);
 cudaError_t launch_box_init_state(int d, int n_chains, const double* init, int64_t init_ld,
                                   const double* mu, double* state, cudaStream_t st);
+// n_active_out[0] = number of unfinished chains, n_active_out[1] = min over healthy chains of s_done
+// host_mapped: device alias of 2 ints of mapped pinned host memory that receive n_active_out[0..1]
 cudaError_t launch_box_compact(int n_chains, int total, const int* s_done, const int* status,
-                               int* active_out, int* n_active_out, cudaStream_t st);
+                               int* active_out, int* n_active_out, int* host_mapped, cudaStream_t st);
 cudaError_t launch_box_violations(int d, size_t n_cols, const double* out, const double* lb,
                                   const double* ub, unsigned long long* count, cudaStream_t st);
 

@@ -76,7 +76,9 @@ def tmvrnorm_HMC(object, nsim, control=None, **kw):
         raise ValueError('The elements from "u" has to be greater than the elements from "l"')
     init = np.minimum(np.maximum(tmvPar["map"], lb + EPSILON), ub - EPSILON)   # :133-135
     nsim = int(nsim)
-    n_chains = int(control.get("n.chains", min(nsim, 1024)))
+    # default: one chain per resident CTA slot of the device (every wave full, least burn-in work)
+    slots = L.lib().lqg_hmc_box_slots(d) or 1024
+    n_chains = int(control.get("n.chains", min(nsim, slots)))
     n_chains = max(1, min(n_chains, nsim))
     n_per = -(-nsim // n_chains)
     U = control.get("U")
