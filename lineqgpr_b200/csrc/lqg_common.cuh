@@ -87,11 +87,28 @@ __device__ inline void normal_pair(uint64_t seed, uint64_t chain, uint64_t draw,
 // Deliberately NOT inlined: it runs for the few survivors of the filter only, and keeping its
 // atan2/acos/sqrt temporaries out of the callers' register budget buys occupancy.
 static __device__ __noinline__ double hit_time_exact(double fa, double fb, double g) {
-  double u = sqrt(__dadd_rn(__dmul_rn(fa, fa), __dmul_rn(fb, fb)));     // :159
+  const double u2 = __dadd_rn(__dmul_rn(fa, fa), __dmul_rn(fb, fb));
+  double u = sqrt(u2);                                                  // :159
   if (!(u > g && u > -g)) return 0.0;                                   // :160
-  double phi = atan2(-fa, fb);                                          // :161
-  double t1 = acos(-g / u) - phi;                                       // :162
-  if (t1 < 0) t1 += kTwoPi;                                             // :165
+  double phi, t1;
+  const double w2 = fma(-g, g, u2);                                     // u^2 - g^2 = (u sin theta0)^2
+  if (w2 > 1e-4 * u2) {
+    // Well-conditioned wall (not grazing): t1 = acos(-g/u) - atan2(-fa, fb) is the angle of
+    // (-g + i w)(fb + i fa), w = sqrt(u^2 - g^2): one atan2 instead of atan2 + acos + a division,
+    // equal to tmg's value to a few ulp.  t2 (below) needs phi only as -t1 - 2 phi; with
+    // theta0 = t1 + phi it is written t2 = t1 - 2 theta0' where theta0' is recovered from the
+    // same complex form, so phi is computed lazily only if the dead zones require t2.
+    const double w = sqrt(w2);
+    t1 = atan2(fma(w, fb, -g * fa), fma(-g, fb, -w * fa));
+    if (t1 < 0) t1 += kTwoPi;
+    if (fb + g > 1e-9 * (fabs(fb) + fabs(g)) && t1 > 2.0 * kMinT && t1 < kTwoPi - 2.0 * kMinT)
+      return t1;           // strictly feasible start: t1 < t2 always, no dead zone
+    phi = atan2(-fa, fb);
+  } else {
+    phi = atan2(-fa, fb);                                               // :161
+    t1 = acos(-g / u) - phi;                                            // :162
+    if (t1 < 0) t1 += kTwoPi;                                           // :165
+  }
   if (fabs(t1) < kMinT) t1 = 0;                                         // :166
   else if (fabs(t1 - kTwoPi) < kMinT) t1 = 0;                           // :167
   double t2 = __dsub_rn(-t1, __dmul_rn(2.0, phi));                      // :170
@@ -146,6 +163,30 @@ __device__ __forceinline__ Hit warp_min_hit(Hit h) {
   }
   return h;
 }
+// Arg-min of (t, key) over a warp with the hardware warp-reduce (REDUX): a positive double
+// orders like its bit pattern, "no hit" is +inf, ties on t go to the lowest key (tmg's strict <
+// at tmg:src/HmcSampler.cpp:183).  tb = time bits (kNoHitBits when none).
+// Returns the winning lane (every lane gets the same tb_min / key_min).
+constexpr unsigned long long kNoHitBits = 0x7ff0000000000000ull;      // bits of +inf
+__device__ __forceinline__ unsigned long long hit_bits(double t) {
+  return t > 0.0 ? (unsigned long long)__double_as_longlong(t) : kNoHitBits;
+}
+__device__ __forceinline__ double hit_from_bits(unsigned long long tb) {
+  return tb == kNoHitBits ? 0.0 : __longlong_as_double((long long)tb);
+}
+__device__ __forceinline__ int warp_argmin_hit(unsigned long long tb, int key,
+                                               unsigned long long& tb_min, int& key_min) {
+  const unsigned hi = (unsigned)(tb >> 32), lo = (unsigned)tb;
+  const unsigned hi_min = __reduce_min_sync(0xffffffffu, hi);
+  const unsigned lo_min = __reduce_min_sync(0xffffffffu, hi == hi_min ? lo : 0xffffffffu);
+  const bool is_min = (hi == hi_min) && (lo == lo_min);
+  const unsigned k_min = __reduce_min_sync(0xffffffffu, is_min ? (unsigned)key : 0x7fffffffu);
+  tb_min = ((unsigned long long)hi_min << 32) | lo_min;
+  key_min = (int)k_min;
+  const unsigned owner = __ballot_sync(0xffffffffu, is_min && (unsigned)key == k_min);
+  return __ffs(owner) - 1;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);

@@ -37,7 +37,7 @@
 namespace lqg {
 
 struct RedSlot {
-  double t; double xa; double xb; int key; int pad;
+  unsigned long long tb; double xa; double xb; int key; int pad;
 };
 
 // Survivors of the filter are compacted into a per-warp queue and evaluated 32 at a time:
@@ -188,16 +188,17 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
         double S = 1.0, C = 6.123233995736766e-17;                 // sin(M_PI/2), cos(M_PI/2)
         for (;;) {                                                 // while(1), :64
           // ---- hit search over this thread's coordinates (both sides) ----
-          double bt = 0.0, bxa = 0.0, bxb = 0.0; int bkey = INT_MAX;
+          unsigned long long btb = kNoHitBits;                     // best hit time of this lane, as bits
+          double bxa = 0.0, bxb = 0.0; int bkey = INT_MAX;
           Cand* q = queue[warp];
           int qn = 0;                                              // warp-uniform queue length
           const unsigned lt_mask = (1u << lane) - 1u;
           auto flush = [&]() {
             for (int e = lane; e < qn; e += 32) {
               const Cand cnd = q[e];
-              const double t = hit_time_exact(cnd.fa, cnd.fb, cnd.g);
-              if (hit_better(t, cnd.key, bt, bkey)) {
-                bt = t; bkey = cnd.key;
+              const unsigned long long tb = hit_bits(hit_time_exact(cnd.fa, cnd.fb, cnd.g));
+              if (tb < btb || (tb == btb && cnd.key < bkey)) {
+                btb = tb; bkey = cnd.key;
                 const double sgn = cnd.key < d ? 1.0 : -1.0;      // stored (fa, fb) = sgn * (x_a, x_b)
                 bxa = sgn * cnd.fa; bxb = sgn * cnd.fb;
               }
@@ -238,26 +239,28 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
             push(need_hi, -a_, -b_, p.ghi, i, d + i);
           }
           flush();
-          // ---- arg-min: warp shuffle, then one slot per warp ----
-          Hit w = warp_min_hit(Hit{bt, bkey});
-          const unsigned owner = __ballot_sync(0xffffffffu, bt == w.t && bkey == w.key);
-          const int src = __ffs(owner) - 1;
+          // ---- arg-min: hardware warp-reduce, one slot per warp, warp-reduce over the slots ----
+          unsigned long long wtb; int wkey;
+          int src = warp_argmin_hit(btb, bkey, wtb, wkey);
           double wxa = __shfl_sync(0xffffffffu, bxa, src);
           double wxb = __shfl_sync(0xffffffffu, bxb, src);
           if (G > 1) {
             if (lane == 0) {
               RedSlot& r = red[parity][warp];
-              r.t = w.t; r.key = w.key; r.xa = wxa; r.xb = wxb;
+              r.tb = wtb; r.key = wkey; r.xa = wxa; r.xb = wxb;
             }
             __syncthreads();
-            w.t = 0.0; w.key = INT_MAX;
-#pragma unroll
-            for (int g2 = 0; g2 < G; ++g2) {
-              const RedSlot r = red[parity][g2];
-              if (hit_better(r.t, r.key, w.t, w.key)) { w.t = r.t; w.key = r.key; wxa = r.xa; wxb = r.xb; }
-            }
+            // lane l < G holds warp l's candidate; every warp reduces the G slots redundantly
+            RedSlot r;
+            r.tb = kNoHitBits; r.key = INT_MAX; r.xa = 0.0; r.xb = 0.0;
+            if (lane < G) r = red[parity][lane];
+            src = warp_argmin_hit(r.tb, r.key, wtb, wkey);
+            wxa = __shfl_sync(0xffffffffu, r.xa, src);
+            wxb = __shfl_sync(0xffffffffu, r.xb, src);
             parity ^= 1;
           }
+          Hit w;
+          w.t = hit_from_bits(wtb); w.key = wkey;
           ++n_search;
           const double t = w.t;
           if (t == 0.0 || tt < t) { no_hit = true; break; }        // :82
