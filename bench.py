@@ -67,7 +67,7 @@ def build_problem(name):
     map_ = np.asarray(par.get("map", mu), float)
     init = np.minimum(np.maximum(map_, lb + EPSILON), ub - EPSILON)          # R/lineqGPsamplers.R:133-135
     t0 = time.perf_counter()
-    U = whiten_box(mu, Sigma)                                                # tmg:R/tmg.R:15-27
+    U = whiten_box(mu, Sigma)                                                # one Cholesky (UL factor = tmg's Ri)
     setup_s = time.perf_counter() - t0
     return dict(mu=mu, Sigma=Sigma, lb=lb, ub=ub, init=init, U=U, setup_s=setup_s, d=mu.size,
                 c=int(np.isfinite(lb).sum() + np.isfinite(ub).sum()))

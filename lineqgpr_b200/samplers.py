@@ -14,7 +14,7 @@ What stays on the host, exactly where the reference has it on the host: the one-
 whitening algebra (solve, chol, triangular inverse).  Everything per-sample runs on the GPU.
 Extensions (all optional keys of `control`): "n.chains" (independent chains; 1 reproduces the
 reference's single serial chain), "seed", "prepass", "injected", "max.restarts",
-"chain.offset", "device" (keep results in device memory as a torch tensor).
+"chain.offset", "U" (a precomputed factor), "whiten" ("ul" | "tmg", see whiten_box).
 """
 from __future__ import annotations
 
@@ -47,10 +47,27 @@ def _as_par(object):
     return tmvPar
 
 
-def whiten_box(mu, Sigma):
-    """The whitening of tmg::rtmg for tmvrnorm.HMC's call (R/lineqGPsamplers.R:139-141 ->
+def whiten_box(mu, Sigma, method="ul"):
+    """The factor tmg::rtmg whitens with for tmvrnorm.HMC's call (R/lineqGPsamplers.R:139-141 ->
     tmg:R/tmg.R:15-28): H = solve(Sigma); M = (H+H')/2; positive-definiteness check;
-    R = chol(M); Ri = solve(R).  Returns Ri (upper triangular, Ri Ri' = M^-1 ~ Sigma)."""
+    R = chol(M); Ri = solve(R) — an upper-triangular Ri with Ri Ri' = M^-1 = Sigma.
+
+    method="tmg": that literal sequence (inverse, Cholesky, triangular inverse; ~8/3 d^3 flop and
+                  one inversion of an ill-conditioned Sigma) — used by the parity tests.
+    method="ul" : the same matrix obtained directly: the upper-triangular factor with positive
+                  diagonal and U U' = Sigma is unique, and equals J chol(J Sigma J) J with J the
+                  exchange matrix (a "reverse Cholesky"): one Cholesky, d^3/3 flop, no inversion.
+    Both raise tmg's error when Sigma (equivalently M) is not positive definite."""
+    Sigma = np.asarray(Sigma, float)
+    if method == "ul":
+        S = (Sigma + Sigma.T) / 2
+        try:
+            Lf = np.linalg.cholesky(S[::-1, ::-1])
+        except np.linalg.LinAlgError:
+            raise ValueError("Error: M must be positive definite.")    # tmg:R/tmg.R:17-20
+        return np.ascontiguousarray(Lf[::-1, ::-1])
+    if method != "tmg":
+        raise ValueError(f"unknown whitening method {method!r}")
     H = np.linalg.inv(Sigma)                                           # solve(Sigma)
     M = (H + H.T) / 2                                                  # tmg:R/tmg.R:15
     try:
@@ -83,7 +100,7 @@ def tmvrnorm_HMC(object, nsim, control=None, **kw):
     n_per = -(-nsim // n_chains)
     U = control.get("U")
     if U is None:
-        U = whiten_box(mu, Sigma)
+        U = whiten_box(mu, Sigma, control.get("whiten", "ul"))
     seed = control.get("seed")
     if seed is None:
         seed = int(np.random.randint(1, 10000000))                     # tmg:R/tmg.R:102

@@ -48,6 +48,52 @@ def bands(ysim, probs=(0.025, 0.975)):
     return mean, q
 
 
+def paths_bands(Phi_test, xi_sim, probs=(0.025, 0.975), slab_rows=None, return_ysim=False):
+    """Band summaries of ysim = Phi.test %*% xi.sim without materialising ysim (config 5:
+    10^5 x 10^6 doubles = 800 GB).  Phi.test (n_t x m) is processed in row slabs: each slab's
+    sample paths are produced by the FP64 tensor-core GEMM into device memory, summarised by
+    lqg_bands (exact type-7 quantiles + mean) and dropped.  xi.sim is uploaded once.
+    Device buffers are torch tensors (plumbing); all compute goes through the C ABI.
+    Returns (ymean[n_t], qtls[nprobs, n_t]) and timing info."""
+    import torch
+    Phi = np.asarray(Phi_test, float)
+    xi = np.asarray(xi_sim, float)
+    n_t, m = Phi.shape
+    m2, N = xi.shape
+    if m != m2:
+        raise ValueError("non-conformable arguments")
+    probs = np.ascontiguousarray(probs, dtype=np.float64)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    st = torch.cuda.current_stream().cuda_stream
+    if slab_rows is None:                                   # ysim slab + its transposed copy <= ~8 GB
+        slab_rows = int(max(1, min(n_t, (4 << 30) // (8 * N))))
+    xi_d = torch.from_numpy(np.asfortranarray(xi).T.copy()).to(dev)               # column-major m x N
+    y_d = torch.empty((N, slab_rows), dtype=torch.float64, device=dev)            # column-major slab x N
+    mean_d = torch.empty(slab_rows, dtype=torch.float64, device=dev)
+    q_d = torch.empty((slab_rows, probs.size), dtype=torch.float64, device=dev)   # column-major nprobs x slab
+    probs_d = torch.from_numpy(probs).to(dev)
+    mean = np.empty(n_t); q = np.empty((probs.size, n_t), order="F")
+    o = L.make_opts(mem=L.MEM_DEVICE, stream=st)
+    gemm_ms = bands_ms = 0.0
+    ms = L.C.c_double(0.0)
+    lib = L.lib()
+    for r0 in range(0, n_t, slab_rows):
+        r1 = min(n_t, r0 + slab_rows)
+        nr = r1 - r0
+        Phi_d = torch.from_numpy(np.asfortranarray(Phi[r0:r1]).T.copy()).to(dev)  # column-major nr x m
+        L.check(lib.lqg_dgemm(nr, N, m, Phi_d.data_ptr(), nr, xi_d.data_ptr(), m, y_d.data_ptr(), nr, None, o, L.C.byref(ms)),
+                "lqg_dgemm")
+        gemm_ms += ms.value
+        L.check(lib.lqg_bands(nr, N, y_d.data_ptr(), nr, probs_d.data_ptr(), probs.size, mean_d.data_ptr(), q_d.data_ptr(), o,
+                              L.C.byref(ms)), "lqg_bands")
+        bands_ms += ms.value
+        mean[r0:r1] = mean_d[:nr].cpu().numpy()
+        q[:, r0:r1] = q_d.reshape(-1)[: nr * probs.size].cpu().numpy().reshape(nr, probs.size).T
+    info = dict(gemm_ms=gemm_ms, bands_ms=bands_ms, slab_rows=slab_rows,
+                gemm_tflops=2.0 * n_t * m * N / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None)
+    return mean, q, info
+
+
 def lambda_pinv(Lambda):
     """The operator of qr.solve(Lambda, .) (R/lineqGP.R:639): inverse for a square Lambda, the
     least-squares pseudo-inverse for a tall full-column-rank Lambda (Q8).  O(d m^2), once."""

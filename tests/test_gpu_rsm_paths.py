@@ -110,3 +110,19 @@ def test_simulate_end_to_end_cfg1(lqg):
     assert np.all(q[0] <= mean + 1e-12) and np.all(mean <= q[1] + 1e-12)
     # posterior mean path follows the sigmoid data
     assert abs(mean[0]) < 0.2 and abs(mean[-1] - 1.0) < 0.2
+
+
+def test_paths_bands_slabs_match_materialised(lqg, oracle):
+    """Slab-wise Phi xi -> bands on device memory == bands of the materialised ysim (cfg5-like, small)."""
+    from lineqgpr_b200 import workloads as W
+    par, aux = W.cfg5(D=8, knots=10, n=80, n_test=333)
+    rng = np.random.default_rng(2)
+    xi = rng.standard_normal((80, 2501))
+    Phi = aux["Phi_test"]
+    probs = (0.025, 0.5, 0.975)
+    mean, q, info = lqg.paths_bands(Phi, xi, probs, slab_rows=100)
+    y = Phi @ xi
+    mo, qo = oracle.bands(y, probs)
+    assert np.allclose(mean, mo, rtol=1e-11, atol=1e-13)
+    assert np.allclose(q, qo, rtol=1e-11, atol=1e-13)       # GEMM rounding differs from numpy's, selection is exact
+    assert info["gemm_ms"] > 0 and info["bands_ms"] > 0

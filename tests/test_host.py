@@ -118,3 +118,22 @@ def test_lambda_pinv_is_qr_solve(lqg, oracle):
     for Lam in (sq, tall):
         eta = rng.standard_normal((Lam.shape[0], 5))
         assert np.allclose(lambda_pinv(Lam) @ eta, oracle.qr_solve(Lam, eta), atol=1e-12)
+
+
+def test_whitening_factor_ul_equals_tmg_sequence(lqg):
+    """The one-Cholesky 'ul' factor is the matrix tmg's inverse/chol/inverse sequence produces."""
+    from lineqgpr_b200.samplers import whiten_box
+    from lineqgpr_b200 import workloads as W
+    rng = np.random.default_rng(6)
+    B = rng.standard_normal((30, 30)); S = B @ B.T + 0.5 * np.eye(30)
+    for Sigma in (S, W.cfg1()[0]["Sigma"]):
+        Uu = whiten_box(None, Sigma, "ul"); Ut = whiten_box(None, Sigma, "tmg")
+        assert np.allclose(np.tril(Uu, -1), 0) and np.all(np.diag(Uu) > 0)
+        assert np.allclose(Uu @ Uu.T, Sigma, rtol=1e-10, atol=1e-12 * np.abs(Sigma).max())
+        # tmg's sequence inverts Sigma twice: agreement is limited by cond(Sigma) * eps
+        scale = np.abs(Uu).max()
+        assert np.abs(Uu - Ut).max() / scale < 1e-16 * np.linalg.cond(Sigma) * 100
+    with pytest.raises(ValueError, match="positive definite"):
+        whiten_box(None, np.array([[1.0, 2.0], [2.0, 1.0]]), "ul")
+    with pytest.raises(ValueError, match="positive definite"):
+        whiten_box(None, np.array([[1.0, 2.0], [2.0, 1.0]]), "tmg")
