@@ -294,9 +294,17 @@ def run_ours(a):
     # is the pre-pass GEMM (d^2 each, triangular U halves the executed work)
     w_chain = 40.0 * c * se + 8.0 * d * bo + 3.0 * d * tr + float(d) * d * rs
     w_pre = float(d) * d * tr
+    traffic = None
+    try:      # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+        tj = json.load(open(ROOT / "profiles" / "r01_traffic.json"))["hmc_box_kernel"]
+        traffic = {"dram_bytes_per_launch": tj["dram_bytes_read"] + tj["dram_bytes_write"],
+                   "algorithmic_bytes_per_launch": tj["algorithmic_bytes"], "launch": tj["launch"],
+                   "note": "HBM is not the bound of this kernel (DRAM throughput ~1.5% of peak); traffic ~ algorithmic: no re-reads"}
+    except Exception:
+        pass
     roof = {"bound": "fp64", "kernel": "hmc_box_kernel", "achieved": w_chain / (chain_ms * 1e-3) / 1e12,
             "peak": dfma.value, "peak_source": "lqg_measure_fp64_peaks DFMA micro-benchmark, this run",
-            "unit": "TFLOP/s", "frac": w_chain / (chain_ms * 1e-3) / 1e12 / dfma.value, "traffic": None,
+            "unit": "TFLOP/s", "frac": w_chain / (chain_ms * 1e-3) / 1e12 / dfma.value, "traffic": traffic,
             "launch_ms": chain_ms / len(stats), "share_of_step": chain_ms / sum(step_ms)}
     roof_pre = {"bound": "tensor", "kernel": "dgemm_dmma_kernel (momentum pre-pass)",
                 "achieved": w_pre / (pre_ms * 1e-3) / 1e12 if pre_ms > 0 else None, "peak": dmma.value,
