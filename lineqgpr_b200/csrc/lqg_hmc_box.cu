@@ -47,6 +47,22 @@ constexpr int QCAP = 64;
 struct Cand {
   double fa, fb, g; int key; int pad;
 };
+struct LaneBest {                    // best candidate seen by this lane
+  unsigned long long tb; double xa, xb; int key;
+};
+// evaluates queue entries [0, qn) with tmg's exact formula, 32 at a time (one per lane)
+static __device__ __noinline__ void flush_queue(const Cand* q, int qn, int lane, int d, LaneBest& b) {
+  for (int e = lane; e < qn; e += 32) {
+    const Cand cnd = q[e];
+    const unsigned long long tb = hit_bits(hit_time_exact(cnd.fa, cnd.fb, cnd.g));
+    if (tb < b.tb || (tb == b.tb && cnd.key < b.key)) {
+      b.tb = tb; b.key = cnd.key;
+      const double sgn = cnd.key < d ? 1.0 : -1.0;               // stored (fa, fb) = sgn * (x_a, x_b)
+      b.xa = sgn * cnd.fa; b.xb = sgn * cnd.fb;
+    }
+  }
+  __syncwarp();
+}
 
 // fresh momentum x_a = U a for this chain, computed by the CTA itself (restarts, injected
 // draws, or when the GEMM pre-pass is off).  a ~ N(0, I_d) drawn like tmg:src/HmcSampler.cpp:54-55.
@@ -188,24 +204,15 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
         double S = 1.0, C = 6.123233995736766e-17;                 // sin(M_PI/2), cos(M_PI/2)
         for (;;) {                                                 // while(1), :64
           // ---- hit search over this thread's coordinates (both sides) ----
-          unsigned long long btb = kNoHitBits;                     // best hit time of this lane, as bits
-          double bxa = 0.0, bxb = 0.0; int bkey = INT_MAX;
+          LaneBest best;
+          best.tb = kNoHitBits; best.xa = 0.0; best.xb = 0.0; best.key = INT_MAX;
           Cand* q = queue[warp];
           int qn = 0;                                              // warp-uniform queue length
           const unsigned lt_mask = (1u << lane) - 1u;
           auto flush = [&]() {
-            for (int e = lane; e < qn; e += 32) {
-              const Cand cnd = q[e];
-              const unsigned long long tb = hit_bits(hit_time_exact(cnd.fa, cnd.fb, cnd.g));
-              if (tb < btb || (tb == btb && cnd.key < bkey)) {
-                btb = tb; bkey = cnd.key;
-                const double sgn = cnd.key < d ? 1.0 : -1.0;      // stored (fa, fb) = sgn * (x_a, x_b)
-                bxa = sgn * cnd.fa; bxb = sgn * cnd.fb;
-              }
-            }
+            flush_queue(q, qn, lane, d, best);
             n_exact += (lane == 0) ? qn : 0;
             qn = 0;
-            __syncwarp();
           };
           auto push = [&](bool need, double fa, double fb, const double* gsrc, int i, int key) {
             const unsigned m = __ballot_sync(0xffffffffu, need);
@@ -233,17 +240,23 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
             const double u2 = fma(a_, a_, b_ * b_);
             const double hl = GSM ? hlo_s[i] : hlo_r[GSM ? 0 : k];
             const double hh = GSM ? hhi_s[i] : hhi_r[GSM ? 0 : k];
-            const bool need_lo = !(fmin(b_, y) > -hl) || (a_ < 0.0 && dy > 0.0 && u2 >= hl * fabs(hl));
-            const bool need_hi = !(fmax(b_, y) < hh) || (a_ > 0.0 && dy < 0.0 && u2 >= hh * fabs(hh));
+            // straight-line predicates (bitwise & |: no short-circuit branches, no fmin/fmax NaN fix-ups)
+            const double nhl = -hl;
+            const bool safe_lo = (b_ > nhl) & (y > nhl);
+            const bool safe_hi = (b_ < hh) & (y < hh);
+            const bool dip_lo = (a_ < 0.0) & (dy > 0.0) & (u2 >= hl * fabs(hl));
+            const bool dip_hi = (a_ > 0.0) & (dy < 0.0) & (u2 >= hh * fabs(hh));
+            const bool need_lo = !safe_lo | dip_lo;
+            const bool need_hi = !safe_hi | dip_hi;
             push(need_lo, a_, b_, p.glo, i, i);
             push(need_hi, -a_, -b_, p.ghi, i, d + i);
           }
           flush();
           // ---- arg-min: hardware warp-reduce, one slot per warp, warp-reduce over the slots ----
           unsigned long long wtb; int wkey;
-          int src = warp_argmin_hit(btb, bkey, wtb, wkey);
-          double wxa = __shfl_sync(0xffffffffu, bxa, src);
-          double wxb = __shfl_sync(0xffffffffu, bxb, src);
+          int src = warp_argmin_hit(best.tb, best.key, wtb, wkey);
+          double wxa = __shfl_sync(0xffffffffu, best.xa, src);
+          double wxb = __shfl_sync(0xffffffffu, best.xb, src);
           if (G > 1) {
             if (lane == 0) {
               RedSlot& r = red[parity][warp];
@@ -452,6 +465,7 @@ static cudaError_t dispatch_box(const BoxParams& p, int grid, cudaStream_t st, i
     static const char* v = getenv("LQG_BOX_VARIANT");          // tuning aid: "4" = 4 warps x 16 coordinates, "2" = 8x8 at 2 CTAs/SM
     if (v && v[0] == '4') return launch_box_t<4, 16, true, 4>(p, grid, st, slots);
     if (v && v[0] == '2') return launch_box_t<8, 8, true, 2>(p, grid, st, slots);     // 2 CTAs/SM (128 registers)
+    if (v && v[0] == '5') return launch_box_t<8, 8, true, 4>(p, grid, st, slots);     // 4 CTAs/SM (64 registers)
     return launch_box_t<8, 8, true, 3>(p, grid, st, slots);                           // 3 CTAs/SM (80 registers): measured best
   }
   if (d <= 4096) return launch_box_t<8, 16, true, 1>(p, grid, st, slots);
