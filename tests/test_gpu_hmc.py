@@ -245,3 +245,48 @@ def test_full_size_m1000_properties(lqg):
         assert st["violations"] == 0 and st["failed_chains"] == 0
         assert st["transitions"] == n_chains * (3 + n // n_chains)
         assert st["hit_searches"] >= st["bounces"] + st["transitions"]
+
+
+# ------------------------------------------------------------------------------------- edge cases
+def test_edge_cases_shapes_and_bounds(lqg):
+    """d = 1, one-sided and unbounded coordinates, more chains than samples, a single long chain."""
+    # d = 1 box: exact truncated normal support, KS against scipy
+    obj = dict(mu=[0.3], Sigma=[[1.7 ** 2]], lb=[-0.5], ub=[1.0])
+    x = lqg.tmvrnorm(obj, 4000, {"burn.in": 20, "n.chains": 50, "seed": 2}, method="HMC").ravel()
+    assert x.min() >= -0.5 and x.max() <= 1.0
+    cdf = stats.truncnorm((-0.5 - 0.3) / 1.7, (1.0 - 0.3) / 1.7, loc=0.3, scale=1.7).cdf
+    assert stats.kstest(x[::2], cdf).pvalue > 0.01
+    # mixed: coordinate 0 unbounded, 1 lower only, 2 upper only
+    rng = np.random.default_rng(1)
+    B = rng.standard_normal((3, 3)); S = B @ B.T + 0.3 * np.eye(3)
+    obj = dict(mu=np.zeros(3), Sigma=S, lb=np.array([-np.inf, 0.1, -np.inf]), ub=np.array([np.inf, np.inf, -0.2]),
+               map=np.array([0.0, 0.5, -0.5]))
+    x = lqg.tmvrnorm(obj, 2000, {"burn.in": 10, "seed": 3}, method="HMC")
+    assert x.shape == (3, 2000) and x[1].min() >= 0.1 and x[2].max() <= -0.2
+    assert lqg.last_stats["violations"] == 0
+    # nsim smaller than the default chain count; nsim not divisible by n.chains
+    assert lqg.tmvrnorm(obj, 7, {"burn.in": 2, "seed": 4}, method="HMC").shape == (3, 7)
+    assert lqg.tmvrnorm(obj, 10, {"burn.in": 2, "n.chains": 3, "seed": 4}, method="HMC").shape == (3, 10)
+    # the reference's layout: ONE serial chain (n.chains = 1), burn.in = 0
+    x1 = lqg.tmvrnorm(obj, 300, {"burn.in": 0, "n.chains": 1, "seed": 5}, method="HMC")
+    assert lqg.last_stats["transitions"] == 300 and x1[1].min() >= 0.1
+
+
+def test_canonical_without_constraints_and_restart_cap(lqg):
+    """numlin = 0: every transition returns the drawn momentum (T = pi/2).  An impossible
+    geometry trips max_restarts and is reported as a status code instead of tmg's endless loop."""
+    from lineqgpr_b200 import _lib as L
+    d = 5
+    draws = np.random.default_rng(0).standard_normal(4 * d)
+    z, st = lqg.rtmg_canonical(4, 0, np.zeros(d), np.zeros((0, d)), np.zeros(0), injected=draws)
+    assert st["bounces"] == 0
+    assert np.allclose(z.T, draws.reshape(4, d), rtol=0, atol=1e-15)
+    # infeasible start whose orbit (amplitude ~40) never reaches the region z_0 >= 50: every end
+    # point fails _verifyConstraints, tmg would loop forever (tmg:src/HmcSampler.cpp:51,130)
+    F = np.array([[1.0, 0.0]]); g = np.array([-50.0])
+    with pytest.raises(L.LqgError) as e:
+        lqg.rtmg_canonical(2, 1, np.array([40.0, 0.0]), F, g, max_restarts=20)
+    assert e.value.status == 5
+    # the far tail itself (start inside z_0 >= 50) is sampled fine
+    z, st = lqg.rtmg_canonical(50, 1, np.array([50.5, 0.0]), F, g)
+    assert z[0].min() >= 50.0 and st["bounces"] > 0
