@@ -34,6 +34,19 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not needs_build():
         return LIB
+    import fcntl
+    lock = open(PKG / ".build.lock", "w")
+    fcntl.flock(lock, fcntl.LOCK_EX)          # several ranks may get here at once: one compiles
+    try:
+        if not force and not needs_build():
+            return LIB
+        return _build_locked(verbose)
+    finally:
+        fcntl.flock(lock, fcntl.LOCK_UN)
+        lock.close()
+
+
+def _build_locked(verbose: bool) -> Path:
     nvcc = _nvcc()
     objdir = PKG.parent / "build"
     objdir.mkdir(exist_ok=True)
@@ -50,10 +63,12 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
         if verbose and out.strip():
             print(out)
-    cmd = [nvcc, "-shared", "-o", str(LIB), *objs, "-lcudart"]
+    tmp = LIB.with_suffix(".so.tmp")
+    cmd = [nvcc, "-shared", "-o", str(tmp), *objs, "-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, LIB)                      # atomic: a concurrent loader never sees a partial file
     return LIB
 
 

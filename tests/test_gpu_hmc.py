@@ -232,6 +232,25 @@ def test_box_statistical_agreement_with_oracle(lqg, oracle, cfg):
     assert (np.abs(xo_t.var(1) - xg_t.var(1)) > 3 * se_var).sum() <= max(1, int(0.05 * d))
 
 
+def test_stacked_constraints_statistics_m150(lqg, oracle):
+    """Bounded + monotone stacked system (the cfg4 structure, Lambda = [I; D], rank-deficient
+    Sigma_eta + nugget) at m = 150 (d = 300, 4 warps per chain): moments vs an oracle chain."""
+    from lineqgpr_b200 import workloads as W
+    par, _ = W.cfg4(m=150)
+    n = 3000
+    xo, _ = oracle.tmvrnorm_HMC(par, n, {"burn.in": 200}, seed=12)
+    xg = lqg.tmvrnorm(dict(par, **{"class": "HMC"}), n, {"burn.in": 200, "n.chains": 30, "seed": 21})
+    assert lqg.last_stats["violations"] == 0
+    thin = 5
+    xo_t, xg_t = xo[:, ::thin], xg[:, ::thin]
+    d = xo.shape[0]
+    pvals = np.array([stats.ks_2samp(xo_t[i], xg_t[i]).pvalue for i in range(d)])
+    assert (pvals < 0.01).sum() <= int(0.05 * d), ((pvals < 0.01).sum(), pvals.min())
+    ne = xo_t.shape[1]
+    se = np.sqrt((xo_t.var(1) + xg_t.var(1)) / ne)
+    assert (np.abs(xo_t.mean(1) - xg_t.mean(1)) > 3 * se).sum() <= int(0.05 * d)
+
+
 def test_full_size_m1000_properties(lqg):
     """BASELINE size (cfg4: d = 2000, c = 2999; cfg5: d = 1000, c = 900): size-independent
     properties — every emitted value inside the box, counters consistent, finite output."""
