@@ -152,6 +152,27 @@ int lqg_rsm(int32_t d, const double* map, const double* factor, const double* w,
             const double* lb, const double* ub, int64_t nsim, int64_t max_proposals,
             const lqg_opts* opts, double* out, lqg_rsm_stats* stats);
 
+/* ---- ExpT --------------------------------------------------------------------------- */
+
+typedef struct lqg_expt_stats {
+  int64_t proposals;       /* tilted proposals consumed up to the nsim-th accept                */
+  int64_t accepted;
+  int64_t rounds;
+  double  kernel_ms;
+} lqg_expt_stats;
+
+/* The accept-reject loop of TruncatedNormal::mvrandn(l, u, Sig, n), i.e. the per-sample part of
+ * tmvrnorm.ExpT (R/lineqGPsamplers.R:179-185); TruncatedNormal is not vendored in the reference,
+ * this follows Botev (2017), JRSS-B 79(1):125-148.  The host computes (as the R package does)
+ * the permuted Cholesky factor, its scaling and the tilt:
+ *   L0    d x d column-major: row-scaled factor with ZERO diagonal
+ *   l, u  scaled and permuted bounds; mu tilt parameters with mu[d-1] = 0; psistar = psi(x*, mu*)
+ * Z_out (d x nsim): the first nsim ACCEPTED proposals Z in proposal order; the caller finishes
+ * with  x = Lfull[order,] %*% Z  (lqg_dgemm).  max_proposals: budget (0 -> 2^40). */
+int lqg_expt(int32_t d, const double* L0, const double* l, const double* u, const double* mu,
+             double psistar, int64_t nsim, int64_t max_proposals, const lqg_opts* opts,
+             double* Z_out, lqg_expt_stats* stats);
+
 /* ---- sample paths and bands --------------------------------------------------------- */
 
 /* C (m x n) = A (m x k) * B (k x n), all column-major FP64, on the FP64 tensor cores.

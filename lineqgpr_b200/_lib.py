@@ -18,7 +18,7 @@ STATUS = {0: "LQG_OK", 1: "LQG_ERR_INVALID", 2: "LQG_ERR_UNSUPPORTED", 3: "LQG_E
 MEM_HOST, MEM_DEVICE = 0, 1
 
 # every symbol include/lineqgpr_b200.h declares
-SYMBOLS = ["lqg_rtmg", "lqg_hmc_canonical", "lqg_hmc_box", "lqg_hmc_box_slots", "lqg_rsm", "lqg_dgemm", "lqg_bands",
+SYMBOLS = ["lqg_rtmg", "lqg_hmc_canonical", "lqg_hmc_box", "lqg_hmc_box_slots", "lqg_rsm", "lqg_expt", "lqg_dgemm", "lqg_bands",
            "lqg_version", "lqg_last_error", "lqg_device_count", "lqg_measure_fp64_peaks",
            "lqg_launch_count"]
 
@@ -44,6 +44,13 @@ class HmcStats(C.Structure):
                 ("vel_restarts", C.c_int64), ("chk_restarts", C.c_int64), ("exact_evals", C.c_int64),
                 ("violations", C.c_int64), ("failed_chains", C.c_int64), ("chain_ms", C.c_double),
                 ("prepass_ms", C.c_double)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class ExptStats(C.Structure):
+    _fields_ = [("proposals", C.c_int64), ("accepted", C.c_int64), ("rounds", C.c_int64), ("kernel_ms", C.c_double)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -83,6 +90,8 @@ def lib():
     L.lqg_hmc_box_slots.argtypes = [i32]
     L.lqg_rsm.restype = C.c_int
     L.lqg_rsm.argtypes = [i32, vp, vp, vp, vp, vp, i64, i64, C.POINTER(Opts), vp, C.POINTER(RsmStats)]
+    L.lqg_expt.restype = C.c_int
+    L.lqg_expt.argtypes = [i32, vp, vp, vp, vp, C.c_double, i64, i64, C.POINTER(Opts), vp, C.POINTER(ExptStats)]
     L.lqg_dgemm.restype = C.c_int
     L.lqg_dgemm.argtypes = [i32, i32, i32, vp, i64, vp, i64, vp, i64, vp, C.POINTER(Opts), _dp]
     L.lqg_bands.restype = C.c_int

@@ -615,6 +615,81 @@ extern "C" int lqg_rsm(int32_t d, const double* map, const double* factor, const
 }
 
 // ===========================================================================================
+extern "C" int lqg_expt(int32_t d, const double* L0, const double* l, const double* u, const double* mu,
+                        double psistar, int64_t nsim, int64_t max_proposals, const lqg_opts* opts_,
+                        double* Z_out, lqg_expt_stats* stats) {
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (!have_device()) return LQG_ERR_CUDA;
+  const lqg_opts o = opts_ ? *opts_ : default_opts();
+  if (d <= 0 || d > 8192 || !L0 || !l || !u || !mu || !Z_out || nsim <= 0) {
+    set_error("lqg_expt: invalid argument (d=%d, nsim=%lld)", d, (long long)nsim);
+    return LQG_ERR_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)o.stream;
+  DevBuf::cur_stream = st;
+  const int mem = o.mem;
+  int rc;
+  Input i_L, i_l, i_u, i_mu;
+  if ((rc = i_L.stage(L0, (size_t)d * d, mem, st)) || (rc = i_l.stage(l, d, mem, st)) ||
+      (rc = i_u.stage(u, d, mem, st)) || (rc = i_mu.stage(mu, d, mem, st)))
+    return rc;
+  const int64_t budget = max_proposals > 0 ? max_proposals : ((int64_t)1 << 40);
+  // round size: Z scratch (d doubles per proposal) stays below ~1 GB
+  const int64_t kMaxRound = std::max<int64_t>(4096, std::min<int64_t>((int64_t)1 << 20, ((int64_t)1 << 30) / ((int64_t)d * 8)));
+  int64_t round = std::min<int64_t>(kMaxRound, std::max<int64_t>(4096, 2 * nsim));
+  round = std::min(round, budget);
+  DevBuf b_Lt, b_out, b_Z, b_flags, b_cnt, b_off, b_ctr;
+  double* d_out = Z_out;
+  if (mem == LQG_MEM_HOST) { LQG_CUDA_TRY(b_out.alloc((size_t)nsim * d * sizeof(double))); d_out = b_out.as<double>(); }
+  const int nb_max = expt_blocks(kMaxRound);
+  LQG_CUDA_TRY(b_Lt.alloc((size_t)d * d * sizeof(double)));
+  LQG_CUDA_TRY(b_Z.alloc((size_t)kMaxRound * d * sizeof(double)));
+  LQG_CUDA_TRY(b_flags.alloc((size_t)kMaxRound));
+  LQG_CUDA_TRY(b_cnt.alloc((size_t)nb_max * sizeof(int)));
+  LQG_CUDA_TRY(b_off.alloc((size_t)(nb_max + 1) * sizeof(int64_t)));
+  LQG_CUDA_TRY(b_ctr.alloc(2 * sizeof(unsigned long long)));
+  LQG_CUDA_TRY(cudaMemsetAsync(b_ctr.p, 0, 2 * sizeof(unsigned long long), st));
+  LQG_CUDA_TRY(launch_expt_transpose(d, i_L.dev, b_Lt.as<double>(), st));
+  ExptParams q;
+  memset(&q, 0, sizeof(q));
+  q.d = d; q.Lt = b_Lt.as<double>(); q.l = i_l.dev; q.u = i_u.dev; q.mu = i_mu.dev; q.psistar = psistar;
+  q.seed = o.seed; q.Z = b_Z.as<double>(); q.flags = b_flags.as<unsigned char>();
+  int64_t got = 0, first = 0, rounds = 0;
+  Timer tm(st);
+  tm.start();
+  while (got < nsim && first < budget) {
+    const int64_t P = std::min(round, budget - first);
+    q.first_proposal = first; q.n_proposals = P;
+    LQG_CUDA_TRY(launch_expt_round(q, b_cnt.as<int>(), b_off.as<int64_t>(), got, nsim, d_out, b_ctr.as<unsigned long long>(), st));
+    int64_t tot = 0;
+    LQG_CUDA_TRY(cudaMemcpyAsync(&tot, b_off.as<int64_t>() + expt_blocks(P), sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    LQG_CUDA_TRY(cudaStreamSynchronize(st));
+    got += tot; first += P; ++rounds;
+    const double rate = (double)std::max<int64_t>(got, 1) / (double)first;
+    round = (int64_t)std::min<double>((double)kMaxRound, std::max<double>(4096.0, (double)(nsim - got) / rate * 1.3 + 1024.0));
+  }
+  tm.stop();
+  const double ms = tm.ms();
+  unsigned long long ctr[2] = {0, 0};
+  LQG_CUDA_TRY(cudaMemcpyAsync(ctr, b_ctr.p, sizeof(ctr), cudaMemcpyDeviceToHost, st));
+  const int64_t n_emit = std::min(got, nsim);
+  if (mem == LQG_MEM_HOST && n_emit > 0)
+    LQG_CUDA_TRY(cudaMemcpyAsync(Z_out, d_out, (size_t)n_emit * d * sizeof(double), cudaMemcpyDeviceToHost, st));
+  LQG_CUDA_TRY(cudaStreamSynchronize(st));
+  if (stats) {
+    stats->proposals = got >= nsim ? (int64_t)ctr[0] : first;
+    stats->accepted = n_emit; stats->rounds = rounds; stats->kernel_ms = ms;
+  }
+  fold_launches();
+  if (got < nsim) {
+    set_error("lqg_expt: proposal budget %lld exhausted (%lld of %lld accepted)", (long long)budget,
+              (long long)got, (long long)nsim);
+    return LQG_ERR_BUDGET;
+  }
+  return LQG_OK;
+}
+
+// ===========================================================================================
 extern "C" int lqg_dgemm(int32_t m, int32_t n, int32_t k, const double* A, int64_t lda,
                          const double* B, int64_t ldb, double* C, int64_t ldc, double* row_sum,
                          const lqg_opts* opts_, double* kernel_ms) {

@@ -121,6 +121,23 @@ cudaError_t launch_rsm_round(const RsmParams& q, int* block_cnt, int64_t* inbox_
                              int64_t slot_base, int64_t nsim, double* out,
                              unsigned long long* counters, cudaStream_t st);
 
+// ---- ExpT (lqg_expt.cu) ------------------------------------------------------------------
+struct ExptParams {
+  int d;
+  const double* Lt;        // d x d, row k of the scaled zero-diagonal factor contiguous: Lt[j + k*d] = L0[k,j]
+  const double* l; const double* u; const double* mu;   // scaled/permuted bounds, tilt (mu[d-1] = 0)
+  double psistar;
+  uint64_t seed;
+  int64_t first_proposal, n_proposals;
+  double* Z;               // coordinate-major proposals: Z[k*n_proposals + p]
+  unsigned char* flags;    // [n_proposals] accepted
+};
+int expt_blocks(int64_t n);
+cudaError_t launch_expt_transpose(int d, const double* L0, double* Lt, cudaStream_t st);
+cudaError_t launch_expt_round(const ExptParams& q, int* block_cnt, int64_t* acc_off, int64_t slot_base,
+                              int64_t nsim, double* out, unsigned long long* counters, cudaStream_t st);
+cudaError_t launch_add_colvec(int m, size_t n, double* out, int64_t ld, const double* v, cudaStream_t st);
+
 // ---- bands (lqg_bands.cu) ---------------------------------------------------------------
 // ysim n_t x N col-major (ld).  scratch: N x n_t doubles (transposed copy).
 cudaError_t launch_bands(int n_t, int64_t N, const double* ysim, int64_t ld, const double* probs_host,

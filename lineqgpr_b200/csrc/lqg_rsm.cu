@@ -19,12 +19,13 @@
 //                their output column.
 #include "lqg_common.cuh"
 #include "lqg_kernels.h"
+#include "lqg_scan.cuh"
 
 namespace lqg {
 
 namespace {
 
-constexpr int PPB = 256;      // proposals per block (= threads per block in accept/emit)
+constexpr int PPB = kScanBlock;   // proposals per block (= threads per block in accept/emit)
 constexpr int WPB = 8;        // warps per block in eval/emit
 constexpr uint32_t TAG_Z = 0x52534D31u, TAG_U = 0x52534D32u;
 
@@ -70,25 +71,6 @@ __device__ __forceinline__ double proposal_coord(const RsmParams& q, const doubl
   return __ldg(q.map + i) + acc;
 }
 
-__device__ __forceinline__ int block_excl_scan(int v, int* warp_tot, int* total) {
-  // exclusive scan over the 256 threads of a block
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int inc = v;
-#pragma unroll
-  for (int off = 1; off < 32; off <<= 1) {
-    int o = __shfl_up_sync(0xffffffffu, inc, off);
-    if (lane >= off) inc += o;
-  }
-  if (lane == 31) warp_tot[warp] = inc;
-  __syncthreads();
-  int base = 0, tot = 0;
-#pragma unroll
-  for (int w = 0; w < PPB / 32; ++w) { const int t = warp_tot[w]; if (w < warp) base += t; tot += t; }
-  __syncthreads();
-  *total = tot;
-  return base + inc - v;
-}
-
 }  // namespace
 
 __global__ void __launch_bounds__(WPB * 32)
@@ -124,34 +106,6 @@ rsm_eval_kernel(const RsmParams q, int* block_inbox) {
   if (lane == 0 && my_inbox) atomicAdd(&cnt, my_inbox);
   __syncthreads();
   if (threadIdx.x == 0) block_inbox[blockIdx.x] = cnt;
-}
-
-// exclusive scan of n ints by one CTA of 1024 threads; off[n] = total
-__global__ void __launch_bounds__(1024) rsm_scan_kernel(const int* in, int64_t* off, int n) {
-  __shared__ int64_t wt[32];
-  __shared__ int64_t carry;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  for (int base = 0; base < n; base += 1024) {
-    const int i = base + threadIdx.x;
-    int64_t v = i < n ? in[i] : 0, inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int64_t t = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += t;
-    }
-    if (lane == 31) wt[warp] = inc;
-    __syncthreads();
-    int64_t wb = 0, tot = 0;
-    for (int w = 0; w < 32; ++w) { if (w < warp) wb += wt[w]; tot += wt[w]; }
-    const int64_t c = carry;
-    if (i < n) off[i] = c + wb + inc - v;
-    __syncthreads();
-    if (threadIdx.x == 0) carry = c + tot;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) off[n] = carry;
 }
 
 __global__ void __launch_bounds__(PPB)
@@ -234,9 +188,9 @@ cudaError_t launch_rsm_round(const RsmParams& q, int* block_cnt, int64_t* inbox_
   if ((e = cudaFuncSetAttribute(rsm_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(rsm_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
   rsm_eval_kernel<<<nb, WPB * 32, smem, st>>>(q, block_cnt);
-  rsm_scan_kernel<<<1, 1024, 0, st>>>(block_cnt, inbox_off, nb);
+  scan_counts_kernel<<<1, 1024, 0, st>>>(block_cnt, inbox_off, nb);
   rsm_accept_kernel<<<nb, PPB, 0, st>>>(q, inbox_off, block_cnt);
-  rsm_scan_kernel<<<1, 1024, 0, st>>>(block_cnt, acc_off, nb);
+  scan_counts_kernel<<<1, 1024, 0, st>>>(block_cnt, acc_off, nb);
   rsm_emit_kernel<<<nb, PPB, smem, st>>>(q, acc_off, inbox_off, slot_base, nsim, out, counters);
   launch_counter() += 5;
   return cudaGetLastError();

@@ -167,12 +167,39 @@ def tmvrnorm_RSM(object, nsim, control=None, **kw):
 
 
 def tmvrnorm_ExpT(object, nsim, control=None, **kw):
-    """tmvrnorm.ExpT (R/lineqGPsamplers.R:179-185) delegates to TruncatedNormal::mvrandn, whose
-    source is not part of the reference tree (no kernel in north_star (a)-(d),
-    parity unpinned).  Not provided on the GPU path; there is deliberately no CPU stand-in."""
-    raise NotImplementedError(
-        'sampler "ExpT" (TruncatedNormal::mvrandn) has no GPU implementation in lineqgpr_b200; '
-        'set model$localParam$sampler to "HMC" or "RSM"')
+    """tmvrnorm.ExpT (R/lineqGPsamplers.R:179-185):
+        xi <- mu + TruncatedNormal::mvrandn(lb - mu, ub - mu, Sigma, nsim)
+    Set-up on the host as in the R package (lineqgpr_b200/expt.py: permuted Cholesky, minimax tilt),
+    proposals / accept / compaction on the GPU (lqg_expt), back-transformation Lfull[order,] Z on
+    the FP64 tensor cores (lqg_dgemm).  Samples are i.i.d. and exact; TruncatedNormal's source is
+    not in the reference tree, so parity with R is unpinned (Botev 2017 restated)."""
+    from . import expt
+    control = dict(control or {})
+    tmvPar = _as_par(object)
+    mu, Sigma, lb, ub = tmvPar["mu"], tmvPar["Sigma"], tmvPar["lb"], tmvPar["ub"]
+    d = mu.size
+    nsim = int(nsim)
+    su = control.get("setup") or expt.setup(lb - mu, ub - mu, Sigma)
+    seed = control.get("seed")
+    if seed is None:
+        seed = int(np.random.randint(1, 2 ** 31 - 1))
+    opts = L.make_opts(mem=L.MEM_HOST, seed=seed)
+    L0 = L.f64(su["L0"])
+    l_c, u_c, m_c = (np.ascontiguousarray(v, dtype=np.float64) for v in (su["l"], su["u"], su["mu"]))
+    Z = np.empty((d, nsim), order="F")
+    stats = L.ExptStats()
+    rc = L.lib().lqg_expt(d, L.ptr(L0), L.ptr(l_c), L.ptr(u_c), L.ptr(m_c), float(su["psistar"]), nsim,
+                          int(control.get("max.proposals", 0)), opts, L.ptr(Z), stats)
+    last_stats.clear(); last_stats.update(stats.asdict(), sampler="ExpT", seed=seed, psistar=float(su["psistar"]))
+    L.check(rc, "tmvrnorm.ExpT")
+    if control.get("return.Z"):
+        return Z
+    A = L.f64(su["Lfull"][su["order"], :])                              # rv[order, ] = (Lfull %*% Z)[order, ]
+    C_ = np.empty((d, nsim), order="F")
+    ms = L.C.c_double(0.0)
+    rc = L.lib().lqg_dgemm(d, nsim, d, L.ptr(A), d, L.ptr(Z), d, L.ptr(C_), d, None, L.make_opts(mem=L.MEM_HOST), L.C.byref(ms))
+    L.check(rc, "tmvrnorm.ExpT (L Z)")
+    return C_ + mu[:, None]
 
 
 _METHODS = {"HMC": tmvrnorm_HMC, "RSM": tmvrnorm_RSM, "ExpT": tmvrnorm_ExpT}

@@ -46,6 +46,24 @@ tmvrnorm.RSM <- function(object, nsim, control = NULL, ...) {
         as.double(rep_len(tmvPar$ub, d)), as.integer(nsim), as.integer(seed))
 }
 
+tmvrnorm.ExpT <- function(object, nsim, control = NULL, ...) {
+  tmvPar <- object
+  d <- length(tmvPar$mu)
+  l <- tmvPar$lb - tmvPar$mu; u <- tmvPar$ub - tmvPar$mu
+  # set-up exactly as TruncatedNormal::mvrandn does it (its internal helpers)
+  out <- TruncatedNormal:::cholperm(tmvPar$Sigma, l, u)
+  Lfull <- out$L; D <- diag(Lfull); perm <- out$perm
+  L0 <- Lfull / D - diag(d); l <- out$l / D; u <- out$u / D
+  xmu <- TruncatedNormal:::nleq(l, u, L0)
+  x <- xmu[1:(d - 1)]; mu <- c(xmu[d:(2 * d - 2)], 0)
+  psistar <- TruncatedNormal:::psy(x, L0, l, u, mu)
+  seed <- sample(1:10000000, 1)
+  Z <- .Call("lqg_expt_call", L0, as.double(l), as.double(u), as.double(mu), as.double(psistar),
+             as.integer(nsim), as.integer(seed))
+  xi <- .Call("lqg_dgemm_call", Lfull[order(perm), , drop = FALSE], Z)
+  matrix(tmvPar$mu, nrow = d, ncol = nsim) + xi
+}
+
 # simulate.lineqGP tail (R/lineqGP.R:639-640) on the GPU:
 #   simModel$xi.sim <- .Call("lqg_dgemm_call", qr.solve(pred$Lambda, diag(nrow(pred$Lambda))), eta)
 #   simModel$ysim   <- .Call("lqg_dgemm_call", pred$Phi.test, simModel$xi.sim)

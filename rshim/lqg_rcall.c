@@ -74,6 +74,22 @@ SEXP lqg_rsm_call(SEXP map_, SEXP factor_, SEXP w_, SEXP lb_, SEXP ub_, SEXP nsi
   return out;
 }
 
+/* accept-reject loop of TruncatedNormal::mvrandn: returns the d x nsim accepted proposals Z */
+SEXP lqg_expt_call(SEXP L0_, SEXP l_, SEXP u_, SEXP mu_, SEXP psistar_, SEXP nsim_, SEXP seed_) {
+  const int d = Rf_length(l_);
+  const int nsim = Rf_asInteger(nsim_);
+  lqg_opts o;
+  memset(&o, 0, sizeof(o));
+  o.mem = LQG_MEM_HOST;
+  o.seed = (uint64_t)Rf_asInteger(seed_);
+  lqg_expt_stats st;
+  SEXP out = PROTECT(Rf_allocMatrix(REALSXP, d, nsim));
+  int rc = lqg_expt(d, REAL(L0_), REAL(l_), REAL(u_), REAL(mu_), Rf_asReal(psistar_), nsim, 0, &o, REAL(out), &st);
+  UNPROTECT(1);
+  lqg_check(rc, "lqg_expt");
+  return out;
+}
+
 /* A %*% B on the FP64 tensor cores: xi.sim = Lambda^+ eta, ysim = Phi.test %*% xi.sim */
 SEXP lqg_dgemm_call(SEXP A_, SEXP B_) {
   const int m = Rf_nrows(A_), k = Rf_ncols(A_), n = Rf_ncols(B_);

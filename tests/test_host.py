@@ -25,6 +25,7 @@ def test_struct_layouts_match_header(lqg):
     assert ctypes.sizeof(_lib.Opts) == 80
     assert ctypes.sizeof(_lib.HmcStats) == 80
     assert ctypes.sizeof(_lib.RsmStats) == 40
+    assert ctypes.sizeof(_lib.ExptStats) == 32
 
 
 def test_no_gpu_fails_loudly(lqg):
@@ -53,8 +54,8 @@ def test_tmvrnorm_dispatch_and_argument_errors(lqg):
     obj = dict(mu=np.zeros(2), Sigma=np.eye(2), lb=np.zeros(2), ub=np.ones(2))
     with pytest.raises(TypeError):
         lqg.tmvrnorm(obj, 3)                                   # no class
-    with pytest.raises(NotImplementedError):
-        lqg.tmvrnorm(dict(obj, **{"class": "ExpT"}), 3)
+    with pytest.raises(TypeError):
+        lqg.tmvrnorm(dict(obj, **{"class": "Gibbs"}), 3)          # removed after lineqGPR 0.0.3
     bad = dict(obj, lb=np.array([0.0, 2.0]))
     with pytest.raises(ValueError, match='has to be greater'):
         lqg.tmvrnorm(bad, 3, method="HMC")
@@ -137,3 +138,23 @@ def test_whitening_factor_ul_equals_tmg_sequence(lqg):
         whiten_box(None, np.array([[1.0, 2.0], [2.0, 1.0]]), "ul")
     with pytest.raises(ValueError, match="positive definite"):
         whiten_box(None, np.array([[1.0, 2.0], [2.0, 1.0]]), "tmg")
+
+
+def test_expt_setup_anchors(lqg):
+    """Independent case: minimax tilting is exact, psi* = log P(l < X < u); the two independently
+    written set-ups (product / oracle) agree."""
+    from scipy.stats import norm
+    from lineqgpr_b200 import expt
+    from oracle import expt_oracle as EO
+    l = np.array([0.5, -1.0, -np.inf]); u = np.array([2.0, 0.3, 1.0])
+    su = expt.setup(l, u, np.eye(3))
+    exact = np.log((norm.cdf(2) - norm.cdf(.5)) * (norm.cdf(.3) - norm.cdf(-1)) * norm.cdf(1.0))
+    assert abs(su["psistar"] - exact) < 1e-12
+    rng = np.random.default_rng(0)
+    B = rng.standard_normal((5, 5)); S = B @ B.T + 0.3 * np.eye(5)
+    l = -rng.uniform(0.1, 1, 5); u = rng.uniform(0.1, 2, 5)
+    a, b = expt.setup(l, u, S), EO.setup(l, u, S)
+    assert np.array_equal(a["perm"], b["perm"]) and abs(a["psistar"] - b["psistar"]) < 1e-9
+    assert np.abs(a["L0"] - b["L0"]).max() < 1e-12 and np.abs(a["mu"] - b["mu"]).max() < 1e-7
+    with pytest.raises(ValueError):
+        expt.setup(np.array([1.0]), np.array([0.0]), np.eye(1))
