@@ -251,6 +251,47 @@ def test_stacked_constraints_statistics_m150(lqg, oracle):
     assert (np.abs(xo_t.mean(1) - xg_t.mean(1)) > 3 * se).sum() <= int(0.05 * d)
 
 
+@pytest.mark.parametrize("cfg", ["cfg4", "cfg5"])
+def test_full_size_teacher_forced_parity(lqg, oracle, cfg):
+    """Trajectory parity AT the BASELINE shapes (cfg4: d = 2000, c = 2999, the 8-warp kernel
+    variant; cfg5: d = 1000, c = 900, the 4-warp variant): K chains started at states of an oracle
+    chain, one transition each with injected draws, compared with the oracle's transition."""
+    from lineqgpr_b200 import workloads as W
+    from lineqgpr_b200 import _lib as L
+    par = W.cfg4()[0] if cfg == "cfg4" else W.cfg5(n_test=10)[0]
+    H, r, init, f, g = oracle.hmc_setup(par["mu"], par["Sigma"], par["lb"], par["ub"], par.get("map"))
+    w = oracle.whiten(H, r, init, f, g)
+    d = init.size
+    K = 6
+    z, info = oracle.rtmg_canonical(K - 1, 3, w["initial2"], w["f2"], w["g2"])      # a short oracle chain for the starts
+    starts_z = np.vstack([w["initial2"][None, :], z])
+    rng = np.random.default_rng(9)
+    dr = rng.standard_normal((K, 40 * d))
+    want = np.zeros((K, d)); nb = np.zeros(K, int)
+    for k in range(K):
+        zk, ik = oracle.rtmg_canonical(1, 0, starts_z[k], w["f2"], w["g2"], injected=dr[k])
+        assert ik["rc"] == 0
+        want[k] = zk[0] @ w["Ri"].T + w["Mir"]; nb[k] = ik["bounces"]
+    lbv, ubv = np.asarray(par["lb"], float), np.asarray(par["ub"], float)
+    starts_x = starts_z @ w["Ri"].T + w["Mir"][None, :]
+    starts_x = np.ascontiguousarray(np.minimum(np.maximum(starts_x, lbv + 1e-13), ubv - 1e-13))
+    out = np.empty((d, K), order="F")
+    hs = L.HmcStats()
+    opts = L.make_opts(n_chains=K, injected=np.ascontiguousarray(dr), n_injected=dr.shape[1], prepass=0)
+    Uf, Sf = L.f64(w["Ri"]), L.f64(par["Sigma"])
+    mu_c = np.ascontiguousarray(par["mu"], dtype=np.float64)
+    rc = L.lib().lqg_hmc_box(d, L.ptr(mu_c), L.ptr(Uf), 1, L.ptr(Sf), L.ptr(lbv), L.ptr(ubv), L.ptr(starts_x), d,
+                             1, 0, opts, L.ptr(out), None, hs)
+    L.check(rc, "lqg_hmc_box")
+    assert hs.violations == 0
+    assert np.all(out >= lbv[:, None]) and np.all(out <= ubv[:, None])
+    # eta-frame recursion vs whitened recursion: agreement is limited by cond(Ri) * eps per bounce
+    # (Sigma_eta has condition ~1e7 at cfg4); chains whose discrete events match must agree tightly
+    err = np.abs(out.T - want).max(axis=1) / np.abs(want).max()
+    assert hs.bounces == nb.sum(), (hs.bounces, nb.sum())
+    assert err.max() < 1e-7, err
+
+
 def test_full_size_m1000_properties(lqg):
     """BASELINE size (cfg4: d = 2000, c = 2999; cfg5: d = 1000, c = 900): size-independent
     properties — every emitted value inside the box, counters consistent, finite output."""
