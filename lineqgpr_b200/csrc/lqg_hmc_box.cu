@@ -460,13 +460,22 @@ static cudaError_t dispatch_box(const BoxParams& p, int grid, cudaStream_t st, i
   if (d <= 128)  return launch_box_t<1, 4, false, 16>(p, grid, st, slots);
   if (d <= 256)  return launch_box_t<2, 4, false, 8>(p, grid, st, slots);
   if (d <= 512)  return launch_box_t<4, 4, false, 4>(p, grid, st, slots);
-  if (d <= 1024) return launch_box_t<4, 8, true, 4>(p, grid, st, slots);
+  static const char* v = getenv("LQG_BOX_VARIANT");            // tuning aid, see below
+  if (d <= 1024) {
+    if (v && v[0] == 'a') return launch_box_t<4, 8, true, 4>(p, grid, st, slots);     // 4 warps x 8, 4 CTAs/SM
+    if (v && v[0] == 'b') return launch_box_t<4, 8, true, 2>(p, grid, st, slots);     // 4 warps x 8, 2 CTAs/SM
+    if (v && v[0] == 'c') return launch_box_t<8, 4, true, 2>(p, grid, st, slots);     // 8 warps x 4, 2 CTAs/SM
+    if (v && v[0] == 'd') return launch_box_t<8, 4, true, 3>(p, grid, st, slots);     // 8 warps x 4, 3 CTAs/SM
+    return launch_box_t<4, 8, true, 4>(p, grid, st, slots);
+  }
   if (d <= 2048) {
-    static const char* v = getenv("LQG_BOX_VARIANT");          // tuning aid: "4" = 4 warps x 16 coordinates, "2" = 8x8 at 2 CTAs/SM
+    // Fewer, longer chains do less burn-in work for the same number of samples, and the measured
+    // per-transition throughput of 2 and 3 resident CTAs per SM is the same: 2 CTAs/SM
+    // (128 registers, no spills) is the default.  "3" = 3 CTAs/SM (80 registers), "4" = 4 warps x 16.
     if (v && v[0] == '4') return launch_box_t<4, 16, true, 4>(p, grid, st, slots);
-    if (v && v[0] == '2') return launch_box_t<8, 8, true, 2>(p, grid, st, slots);     // 2 CTAs/SM (128 registers)
-    if (v && v[0] == '5') return launch_box_t<8, 8, true, 4>(p, grid, st, slots);     // 4 CTAs/SM (64 registers)
-    return launch_box_t<8, 8, true, 3>(p, grid, st, slots);                           // 3 CTAs/SM (80 registers): measured best
+    if (v && v[0] == '3') return launch_box_t<8, 8, true, 3>(p, grid, st, slots);
+    if (v && v[0] == '5') return launch_box_t<8, 8, true, 4>(p, grid, st, slots);
+    return launch_box_t<8, 8, true, 2>(p, grid, st, slots);
   }
   if (d <= 4096) return launch_box_t<8, 16, true, 1>(p, grid, st, slots);
   if (d <= 8192) return launch_box_t<16, 16, true, 1>(p, grid, st, slots);
