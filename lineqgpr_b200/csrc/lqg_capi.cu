@@ -269,7 +269,9 @@ extern "C" int lqg_hmc_box(int32_t d, const double* mu, const double* U, int32_t
   } else {
     // attempts per round: pool + draw buffers stay below ~2 GB each
     const size_t budget = (size_t)2 << 30;
-    int attempts = (int)std::max<size_t>(4, std::min<size_t>(32, budget / ((size_t)d * n_chains * sizeof(double))));
+    static const char* env_att = getenv("LQG_POOL_ATTEMPTS");          // tuning aid
+    const size_t att_cap = env_att ? (size_t)std::max(4, atoi(env_att)) : 64;
+    int attempts = (int)std::max<size_t>(4, std::min<size_t>(att_cap, budget / ((size_t)d * n_chains * sizeof(double))));
     attempts = std::min(attempts, total + 8);
     DevBuf b_pool, b_a;
     LQG_CUDA_TRY(b_pool.alloc((size_t)d * n_chains * attempts * sizeof(double)));
