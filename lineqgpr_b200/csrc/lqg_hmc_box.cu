@@ -61,7 +61,6 @@ static __device__ __noinline__ void flush_queue(const Cand* q, int qn, int lane,
       b.xa = sgn * cnd.fa; b.xb = sgn * cnd.fb;
     }
   }
-  __syncwarp();
 }
 
 // fresh momentum x_a = U a for this chain, computed by the CTA itself (restarts, injected
@@ -210,7 +209,9 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
           int qn = 0;                                              // warp-uniform queue length
           const unsigned lt_mask = (1u << lane) - 1u;
           auto flush = [&]() {
+            __syncwarp();                                          // queue writes visible to every lane
             flush_queue(q, qn, lane, d, best);
+            __syncwarp();                                          // entries consumed before they are overwritten
             n_exact += (lane == 0) ? qn : 0;
             qn = 0;
           };
@@ -223,7 +224,6 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
               c.fa = fa; c.fb = fb; c.g = __ldg(gsrc + i); c.key = key;
             }
             qn += __popc(m);
-            __syncwarp();
           };
           // Filter (see may_hit in lqg_common.cuh).  With y = position at time tt, dy = velocity
           // at time tt, u^2 = a^2 + b^2 and the threshold h = g - margin:
