@@ -115,6 +115,16 @@ int lqg_hmc_canonical(int32_t d, int32_t c, const double* F, const double* g,
                       int32_t n_per_chain, int32_t burn_in, const lqg_opts* opts,
                       double* out, double* state_out, lqg_hmc_stats* stats);
 
+/* Parity tooling: lqg_hmc_canonical for n_per_chain transitions (burn_in = 0) that also records,
+ * for every chain, the first trace_cap wall hits as (hit time t, constraint row cn) — the pair
+ * _getNextLinearHitTime returns (tmg:src/HmcSampler.cpp:152-189) — in trace_t / trace_cn
+ * [n_chains x trace_cap, chain-major]; trace_n[n_chains] = number of hits seen.  Host pointers
+ * only.  Used to teacher-force single hit searches against the CPU oracle's trace. */
+int lqg_hmc_canonical_trace(int32_t d, int32_t c, const double* F, const double* g,
+                            const double* initial, int64_t initial_ld, int32_t n_per_chain,
+                            const lqg_opts* opts, double* out, int32_t trace_cap,
+                            double* trace_t, int32_t* trace_cn, int32_t* trace_n);
+
 /* Box-constrained form: what tmvrnorm.HMC always builds (R/lineqGPsamplers.R:128-141:
  * f = [I; -I] rows with finite bounds, g = c(-lb, ub)), sampled directly in the eta frame.
  * With U = Ri of tmg:R/tmg.R:27 (so U U' = Sigma) the chain is algebraically the reference's

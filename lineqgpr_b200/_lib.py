@@ -18,7 +18,7 @@ STATUS = {0: "LQG_OK", 1: "LQG_ERR_INVALID", 2: "LQG_ERR_UNSUPPORTED", 3: "LQG_E
 MEM_HOST, MEM_DEVICE = 0, 1
 
 # every symbol include/lineqgpr_b200.h declares
-SYMBOLS = ["lqg_rtmg", "lqg_hmc_canonical", "lqg_hmc_box", "lqg_hmc_box_slots", "lqg_rsm", "lqg_expt", "lqg_dgemm", "lqg_bands",
+SYMBOLS = ["lqg_rtmg", "lqg_hmc_canonical", "lqg_hmc_canonical_trace", "lqg_hmc_box", "lqg_hmc_box_slots", "lqg_rsm", "lqg_expt", "lqg_dgemm", "lqg_bands",
            "lqg_version", "lqg_last_error", "lqg_device_count", "lqg_measure_fp64_peaks",
            "lqg_launch_count"]
 
@@ -83,6 +83,8 @@ def lib():
     L.lqg_hmc_canonical.restype = C.c_int
     L.lqg_hmc_canonical.argtypes = [i32, i32, vp, vp, vp, i64, i32, i32, C.POINTER(Opts), vp, vp,
                                     C.POINTER(HmcStats)]
+    L.lqg_hmc_canonical_trace.restype = C.c_int
+    L.lqg_hmc_canonical_trace.argtypes = [i32, i32, vp, vp, vp, i64, i32, C.POINTER(Opts), vp, i32, vp, vp, vp]
     L.lqg_hmc_box.restype = C.c_int
     L.lqg_hmc_box.argtypes = [i32, vp, vp, i32, vp, vp, vp, vp, i64, i32, i32, C.POINTER(Opts), vp, vp,
                               C.POINTER(HmcStats)]

@@ -385,10 +385,11 @@ extern "C" int lqg_hmc_box(int32_t d, const double* mu, const double* U, int32_t
 }
 
 // ===========================================================================================
-extern "C" int lqg_hmc_canonical(int32_t d, int32_t c, const double* F, const double* g,
-                                 const double* initial, int64_t initial_ld, int32_t n_per_chain,
-                                 int32_t burn_in, const lqg_opts* opts_, double* out,
-                                 double* state_out, lqg_hmc_stats* stats) {
+static int hmc_canonical_impl(int32_t d, int32_t c, const double* F, const double* g,
+                              const double* initial, int64_t initial_ld, int32_t n_per_chain,
+                              int32_t burn_in, const lqg_opts* opts_, double* out,
+                              double* state_out, lqg_hmc_stats* stats, int32_t trace_cap,
+                              double* trace_t, int32_t* trace_cn, int32_t* trace_n) {
   if (stats) memset(stats, 0, sizeof(*stats));
   if (!have_device()) return LQG_ERR_CUDA;
   const lqg_opts o = opts_ ? *opts_ : default_opts();
@@ -448,11 +449,26 @@ extern "C" int lqg_hmc_canonical(int32_t d, int32_t c, const double* F, const do
   p.next_chain = reinterpret_cast<int*>(b_misc.as<unsigned long long>() + 8);
   p.chain_status = b_status.as<int>();
 
+  DevBuf b_tt, b_tc, b_tn;
+  if (trace_cap > 0 && trace_t && trace_cn && trace_n) {
+    LQG_CUDA_TRY(b_tt.alloc((size_t)n_chains * trace_cap * sizeof(double)));
+    LQG_CUDA_TRY(b_tc.alloc((size_t)n_chains * trace_cap * sizeof(int)));
+    LQG_CUDA_TRY(b_tn.alloc((size_t)n_chains * sizeof(int)));
+    LQG_CUDA_TRY(cudaMemsetAsync(b_tt.p, 0, b_tt.bytes, st));
+    LQG_CUDA_TRY(cudaMemsetAsync(b_tc.p, 0xff, b_tc.bytes, st));
+    LQG_CUDA_TRY(cudaMemsetAsync(b_tn.p, 0, b_tn.bytes, st));
+    p.trace_t = b_tt.as<double>(); p.trace_cn = b_tc.as<int>(); p.trace_cap = trace_cap; p.trace_n = b_tn.as<int>();
+  }
   Timer t_chain(st);
   t_chain.start();
   LQG_CUDA_TRY(launch_hmc_canonical(p, 0, st));
   t_chain.stop();
   const double chain_ms = t_chain.ms();
+  if (p.trace_t) {
+    LQG_CUDA_TRY(cudaMemcpyAsync(trace_t, b_tt.p, (size_t)n_chains * trace_cap * sizeof(double), cudaMemcpyDeviceToHost, st));
+    LQG_CUDA_TRY(cudaMemcpyAsync(trace_cn, b_tc.p, (size_t)n_chains * trace_cap * sizeof(int), cudaMemcpyDeviceToHost, st));
+    LQG_CUDA_TRY(cudaMemcpyAsync(trace_n, b_tn.p, (size_t)n_chains * sizeof(int), cudaMemcpyDeviceToHost, st));
+  }
 
   if (c > 0)
     LQG_CUDA_TRY(launch_canon_violations(d, c, n_cols, i_F.dev, i_g.dev, b_fn.as<double>(), d_out, p.stats + 6, st));
@@ -472,6 +488,24 @@ extern "C" int lqg_hmc_canonical(int32_t d, int32_t c, const double* F, const do
   if (rc == LQG_ERR_RESTART_CAP) set_error("lqg_hmc_canonical: %llu chain(s) exceeded max_restarts=%d", h_stats[7], p.max_restarts);
   if (rc == LQG_ERR_DRAWS_EXHAUSTED) set_error("lqg_hmc_canonical: injected Gaussian stream too short for %llu chain(s)", h_stats[7]);
   return rc;
+}
+
+extern "C" int lqg_hmc_canonical(int32_t d, int32_t c, const double* F, const double* g,
+                                 const double* initial, int64_t initial_ld, int32_t n_per_chain,
+                                 int32_t burn_in, const lqg_opts* opts_, double* out,
+                                 double* state_out, lqg_hmc_stats* stats) {
+  return hmc_canonical_impl(d, c, F, g, initial, initial_ld, n_per_chain, burn_in, opts_, out, state_out, stats,
+                            0, nullptr, nullptr, nullptr);
+}
+
+extern "C" int lqg_hmc_canonical_trace(int32_t d, int32_t c, const double* F, const double* g,
+                                       const double* initial, int64_t initial_ld, int32_t n_per_chain,
+                                       const lqg_opts* opts_, double* out, int32_t trace_cap,
+                                       double* trace_t, int32_t* trace_cn, int32_t* trace_n) {
+  if (opts_ && opts_->mem != LQG_MEM_HOST) { set_error("lqg_hmc_canonical_trace: host pointers only"); return LQG_ERR_INVALID; }
+  if (trace_cap <= 0 || !trace_t || !trace_cn || !trace_n) { set_error("lqg_hmc_canonical_trace: invalid trace buffers"); return LQG_ERR_INVALID; }
+  return hmc_canonical_impl(d, c, F, g, initial, initial_ld, n_per_chain, 0, opts_, out, nullptr, nullptr,
+                            trace_cap, trace_t, trace_cn, trace_n);
 }
 
 // ===========================================================================================

@@ -191,6 +191,11 @@ __global__ void __launch_bounds__(NT) hmc_canonical_kernel(const CanonParams p) 
           const double t = w.t;
           if (t == 0.0 || tt < t) break;                           // :82
           // ---- bounce (:90-110) ----
+          if (p.trace_t != nullptr && tid == 0) {
+            const int e = p.trace_n[chain];
+            if (e < p.trace_cap) { p.trace_t[(size_t)chain * p.trace_cap + e] = t; p.trace_cn[(size_t)chain * p.trace_cap + e] = w.key; }
+            p.trace_n[chain] = e + 1;
+          }
           ++n_bounce;
           tt = tt - t;                                             // :90
           double st, ct;

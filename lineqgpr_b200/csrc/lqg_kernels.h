@@ -72,6 +72,8 @@ struct CanonParams {
   int64_t* inj_pos;
   int max_restarts;
   int f_in_smem;           // stage F in shared memory with one bulk (TMA) copy per CTA
+  // optional per-bounce trace (parity tooling): event e of chain ch -> trace_t/cn[ch*trace_cap + e]
+  double* trace_t; int* trace_cn; int trace_cap; int* trace_n;   // trace_n[ch] = events seen
   int* next_chain;
   unsigned long long* stats;
   int* chain_status;

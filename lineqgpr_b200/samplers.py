@@ -237,3 +237,23 @@ def rtmg_canonical(n, seed, initial, F, g, n_chains=1, burn_in=0, injected=None,
                                    opts, L.ptr(out), None, stats)
     L.check(rc, "rtmg")
     return out, stats.asdict()
+
+
+def rtmg_canonical_trace(n, initial, F, g, injected, n_chains=1, trace_cap=256):
+    """Parity tooling: lqg_hmc_canonical_trace.  Returns (samples d x (n_chains*n), trace_t, trace_cn,
+    trace_n) with the per-chain sequence of wall hits (t, cn) of tmg's _getNextLinearHitTime."""
+    initial = np.asarray(initial, float)
+    d = initial.shape[0]
+    F = L.f64(np.asarray(F, float).reshape(-1, d))
+    g = np.ascontiguousarray(g, dtype=np.float64)
+    injected = np.ascontiguousarray(injected, dtype=np.float64).reshape(n_chains, -1)
+    ld = 0 if initial.ndim == 1 else d
+    init_c = np.ascontiguousarray(initial.T if initial.ndim == 2 else initial, dtype=np.float64)
+    opts = L.make_opts(mem=L.MEM_HOST, n_chains=n_chains, injected=injected, n_injected=injected.shape[1])
+    out = np.empty((d, n_chains * n), order="F")
+    tt = np.zeros((n_chains, trace_cap)); tc = np.zeros((n_chains, trace_cap), dtype=np.int32)
+    tn = np.zeros(n_chains, dtype=np.int32)
+    rc = L.lib().lqg_hmc_canonical_trace(d, F.shape[0], L.ptr(F), L.ptr(g), L.ptr(init_c), ld, int(n), opts, L.ptr(out),
+                                         int(trace_cap), L.ptr(tt), L.ptr(tc), L.ptr(tn))
+    L.check(rc, "rtmg (trace)")
+    return out, tt, tc, tn
