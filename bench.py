@@ -73,6 +73,26 @@ def build_problem(name):
                 c=int(np.isfinite(lb).sum() + np.isfinite(ub).sum()))
 
 
+def bind_to_gpu_numa(index):
+    """Restrict this rank to the CPUs NVML reports as local to its GPU, so that first-touch places
+    the pinned host buffers of the e2e leg on that NUMA node.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (max(n_cpu, 64) + 63) // 64 + 8)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if use and use != allowed:
+            os.sched_setaffinity(0, use)
+            return len(use)
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -193,6 +213,7 @@ def run_ours(a):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; lineqgpr_b200 has no CPU fallback")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa(local) if world > 1 else None       # pinned buffers land next to the GPU's PCIe root
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
@@ -326,7 +347,7 @@ def run_ours(a):
                     "h2d_bytes_per_step": int((2 * d * d + 4 * d) * 8), "d2h_bytes_per_step": int(n_gpu * d * 8),
                     "steps": e2e_steps, "api": "lqg_hmc_box, LQG_MEM_HOST, pinned buffers"},
             "gpu_launches": launches, "clocks": clk, "roofline": roof, "roofline_prepass": roof_pre,
-            "setup_s": P["setup_s"], "wall_s_timed_region": t_wall, "step_ms": [round(x, 3) for x in step_ms],
+            "setup_s": P["setup_s"], "numa_bound_cpus": numa, "wall_s_timed_region": t_wall, "step_ms": [round(x, 3) for x in step_ms],
             "counters": {"transitions": tr, "bounces_per_transition": bo / tr, "hit_searches": se,
                          "restarts_per_transition": rs / tr, "exact_evals_per_search": sum(s.exact_evals for s in stats) / se,
                          "violations": sum(s.violations for s in stats) + viol_host,
