@@ -12,12 +12,13 @@
 //   emitted sample = mu + x_b  (no un-whitening GEMM, tmg:R/tmg.R:106)
 // so the hit search is O(c) and the reflection O(d) instead of O(c d).
 //
-// Mapping: one chain per CTA of G warps; every thread keeps CPT coordinates of (x_a, x_b)
-// and their two bound offsets in REGISTERS (coordinate i = tid + k*32G, so the Sigma column
-// and the output are read/written coalesced).  The bounce-time search is: register-only
-// filter (may_hit) -> exact tmg formula for the survivors -> warp-shuffle arg-min ->
-// one shared-memory slot per warp -> one barrier.  CTAs are persistent and pull chains from
-// an atomic queue, so chains with very different bounce counts do not stall an SM.
+// Mapping: one chain per CTA of G warps; every thread keeps CPT coordinates of (x_a, x_b) in
+// REGISTERS (coordinate i = tid + k*32G, so the Sigma column and the output are read/written
+// coalesced); the per-coordinate filter thresholds sit in registers (small d) or shared memory.
+// The bounce-time search is: branch-free register filter -> survivors compacted (ballot/popc)
+// into a per-warp shared-memory queue -> tmg's exact formula 32 candidates at a time ->
+// integer arg-min with the hardware warp-reduce (REDUX) -> one slot per warp -> one barrier ->
+// REDUX over the slots.  CTAs are persistent and pull chains from an atomic queue.
 //
 // Momenta: a transition attempt (one pass of tmg's while(2) body) consumes ONE fresh momentum
 // x_a = U a and ends either in an accepted end point or in a restart; a restart keeps nothing
@@ -197,7 +198,6 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
         ++draw;
         double tt = kHalfPi;                                       // :57
         double velsign = 0.0;                                      // :53
-        bool no_hit = false;
         // sin/cos of the remaining time.  Inside the loop they only feed the filter, so after a
         // bounce they are advanced by angle subtraction; the final move recomputes them exactly.
         double S = 1.0, C = 6.123233995736766e-17;                 // sin(M_PI/2), cos(M_PI/2)
@@ -272,16 +272,14 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
             wxb = __shfl_sync(0xffffffffu, r.xb, src);
             parity ^= 1;
           }
-          Hit w;
-          w.t = hit_from_bits(wtb); w.key = wkey;
           ++n_search;
-          const double t = w.t;
-          if (t == 0.0 || tt < t) { no_hit = true; break; }        // :82
+          const double t = hit_from_bits(wtb);
+          if (t == 0.0 || tt < t) break;                           // :82
           // ---- bounce: rotate to the wall, reflect (:90-110) ----
           ++n_bounce;
           tt = tt - t;                                             // :90
-          const int j = w.key < d ? w.key : w.key - d;
-          const double side = w.key < d ? 1.0 : -1.0;
+          const int j = wkey < d ? wkey : wkey - d;
+          const double side = wkey < d ? 1.0 : -1.0;
           const double* scol = p.Sigma + (size_t)j * d;
           // column j of Sigma is requested first so its L2 latency overlaps sincos(t)
           double sc[CPT];
@@ -307,7 +305,6 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
           const double Sn = fma(S, ct, -C * st), Cn = fma(C, ct, S * st);   // sin/cos(tt - t)
           S = Sn; C = Cn;
         }
-        (void)no_hit;
         if (velsign < 0.0) {                                       // :117
           ++n_vel;
           if (++rcount > p.max_restarts) status = LQG_ERR_RESTART_CAP;

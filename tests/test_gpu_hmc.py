@@ -187,6 +187,38 @@ def test_box_chain_matches_oracle_canonical_chain(lqg, oracle, case):
     assert np.abs(x[:, :head].T - x_ref[:head]).max() / np.abs(x_ref).max() < 1e-8, name
 
 
+def test_box_queue_overflow_is_bitwise_neutral(lqg):
+    """A tight box (+-0.3 sd, d = 128) gives ~85 surviving walls per search in ONE warp: the
+    64-entry candidate queue overflows and is flushed mid-search all the time.  Padding the same
+    problem with unconstrained, independent coordinates (d = 300) maps it to the 4-warp kernel
+    variant, where no warp overflows, without changing a single operation on the constrained
+    block — so the two runs must agree BIT FOR BIT (chaos-proof, unlike an oracle comparison:
+    one transition here is ~1900 bounces)."""
+    d, pad = 128, 172
+    rng = np.random.default_rng(d)
+    B = rng.standard_normal((d, d)); S = B @ B.T / d + 0.5 * np.eye(d)
+    mu = 0.1 * rng.standard_normal(d); sd = np.sqrt(np.diag(S))
+    lb, ub = mu - 0.3 * sd, mu + 0.3 * sd
+    from lineqgpr_b200.samplers import whiten_box
+    U = whiten_box(mu, S)
+    n, chains = 2, 3
+    draws = rng.standard_normal((chains, 400, d))                        # 400 momenta per chain (restarts are frequent here)
+    ctl = {"burn.in": 0, "n.chains": chains, "max.restarts": 1000}
+    x1 = lqg.tmvrnorm(dict(mu=mu, Sigma=S, lb=lb, ub=ub), n * chains, dict(ctl, U=U, injected=draws.reshape(chains, -1)), method="HMC")
+    s1 = dict(lqg.last_stats)
+    S2 = np.eye(d + pad); S2[:d, :d] = S
+    U2 = np.eye(d + pad); U2[:d, :d] = U
+    mu2 = np.concatenate([mu, np.zeros(pad)])
+    lb2 = np.concatenate([lb, np.full(pad, -np.inf)]); ub2 = np.concatenate([ub, np.full(pad, np.inf)])
+    draws2 = np.concatenate([draws, rng.standard_normal((chains, 400, pad))], axis=2)
+    x2 = lqg.tmvrnorm(dict(mu=mu2, Sigma=S2, lb=lb2, ub=ub2), n * chains, dict(ctl, U=U2, injected=draws2.reshape(chains, -1)), method="HMC")
+    s2 = dict(lqg.last_stats)
+    assert s1["exact_evals"] / s1["hit_searches"] > 70                   # single warp: more than one queue-full
+    assert s1["bounces"] == s2["bounces"] and s1["vel_restarts"] == s2["vel_restarts"] and s1["chk_restarts"] == s2["chk_restarts"]
+    assert np.array_equal(x1, x2[:d])
+    assert s1["violations"] == 0 and np.all(x1 >= lb[:, None]) and np.all(x1 <= ub[:, None])
+
+
 def test_box_errors(lqg):
     from lineqgpr_b200 import _lib as L
     obj = dict(mu=np.zeros(3), Sigma=np.eye(3), lb=-np.ones(3), ub=np.ones(3), map=np.array([0.0, 5.0, 0.0]))
