@@ -318,18 +318,33 @@ def run_ours(a):
     # is the pre-pass GEMM (d^2 each, triangular U halves the executed work)
     w_chain = 40.0 * c * se + 8.0 * d * bo + 3.0 * d * tr + float(d) * d * rs
     w_pre = float(d) * d * tr
-    traffic = None
+    traffic = traffic_detail = None
     try:      # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
         tj = json.load(open(ROOT / "profiles" / "r01_traffic.json"))["hmc_box_kernel"]
-        traffic = {"dram_bytes_per_launch": tj["dram_bytes_read"] + tj["dram_bytes_write"],
-                   "algorithmic_bytes_per_launch": tj["algorithmic_bytes"], "launch": tj["launch"],
-                   "note": "HBM is not the bound of this kernel (DRAM throughput ~1.5% of peak); traffic ~ algorithmic: no re-reads"}
+        traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+        traffic_detail = {"algorithmic_bytes_per_launch": tj["algorithmic_bytes"], "launch": tj["launch"],
+                          "source": "profiles/r01_hmc_box_dgemm_ncu_full.txt",
+                          "note": "traffic ~ algorithmic bytes (pool columns in, samples out): no re-reads; HBM is not the bound"}
     except Exception:
         pass
     roof = {"bound": "fp64", "kernel": "hmc_box_kernel", "achieved": w_chain / (chain_ms * 1e-3) / 1e12,
             "peak": dfma.value, "peak_source": "lqg_measure_fp64_peaks DFMA micro-benchmark, this run",
             "unit": "TFLOP/s", "frac": w_chain / (chain_ms * 1e-3) / 1e12 / dfma.value, "traffic": traffic,
-            "launch_ms": chain_ms / len(stats), "share_of_step": chain_ms / sum(step_ms)}
+            "launch_ms": chain_ms / len(stats), "share_of_step": chain_ms / sum(step_ms),
+            "traffic_detail": traffic_detail,
+            "note": "bound = FP64 CUDA-core pipe (SURVEY.md par.8d): state in registers, Sigma/U L2-resident; see roofline_hbm for the HBM view"}
+    # the same kernel against the HBM roofline: algorithmic bytes = momentum columns read + samples written
+    hbm_peak = None
+    try:
+        hbm_peak = json.load(open(ROOT / "MEASURED_PEAKS.json"))["hbm_gbs"]
+    except Exception:
+        hbm_peak = 6650.0                                  # fallback of B200_PROFILING.md
+    att = tr + rs
+    bytes_chain = 8.0 * d * (att + sum(s.transitions for s in stats) * (n_per / (n_per + burn)))
+    roof_hbm = {"bound": "hbm", "kernel": "hmc_box_kernel", "achieved": bytes_chain / (chain_ms * 1e-3) / 1e9,
+                "peak": hbm_peak, "unit": "GB/s", "frac": bytes_chain / (chain_ms * 1e-3) / 1e9 / hbm_peak,
+                "traffic": traffic,
+                "note": "algorithmic bytes per step = 8 d (momenta consumed + samples emitted); a small fraction of the HBM peak: not HBM-bound"}
     roof_pre = {"bound": "tensor", "kernel": "dgemm_dmma_kernel (momentum pre-pass)",
                 "achieved": w_pre / (pre_ms * 1e-3) / 1e12 if pre_ms > 0 else None, "peak": dmma.value,
                 "unit": "TFLOP/s", "frac": (w_pre / (pre_ms * 1e-3) / 1e12 / dmma.value) if pre_ms > 0 else None,
@@ -346,7 +361,7 @@ def run_ours(a):
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": int((2 * d * d + 4 * d) * 8), "d2h_bytes_per_step": int(n_gpu * d * 8),
                     "steps": e2e_steps, "api": "lqg_hmc_box, LQG_MEM_HOST, pinned buffers"},
-            "gpu_launches": launches, "clocks": clk, "roofline": roof, "roofline_prepass": roof_pre,
+            "gpu_launches": launches, "clocks": clk, "roofline": roof, "roofline_hbm": roof_hbm, "roofline_prepass": roof_pre,
             "setup_s": P["setup_s"], "numa_bound_cpus": numa, "wall_s_timed_region": t_wall, "step_ms": [round(x, 3) for x in step_ms],
             "counters": {"transitions": tr, "bounces_per_transition": bo / tr, "hit_searches": se,
                          "restarts_per_transition": rs / tr, "exact_evals_per_search": sum(s.exact_evals for s in stats) / se,
