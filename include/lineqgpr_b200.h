@@ -201,6 +201,12 @@ int lqg_bands(int32_t n_t, int64_t N, const double* ysim, int64_t ld,
               const double* probs, int32_t nprobs, double* mean, double* qtls,
               const lqg_opts* opts, double* kernel_ms);
 
+/* Page-locked host memory for large result matrices: with it the LQG_MEM_HOST entry points copy
+ * samples out at full PCIe speed and concurrently with the sampling rounds; with ordinary
+ * (pageable) memory — e.g. an R matrix — the copies are staged and serialised by the driver. */
+void* lqg_alloc_host(uint64_t bytes);     /* NULL on failure (see lqg_last_error) */
+void  lqg_free_host(void* p);
+
 /* ---- misc --------------------------------------------------------------------------- */
 const char* lqg_version(void);
 const char* lqg_last_error(void);        /* thread-local text of the last non-OK status       */

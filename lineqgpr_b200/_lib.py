@@ -19,7 +19,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 
 # every symbol include/lineqgpr_b200.h declares
 SYMBOLS = ["lqg_rtmg", "lqg_hmc_canonical", "lqg_hmc_canonical_trace", "lqg_hmc_box", "lqg_hmc_box_slots", "lqg_rsm", "lqg_expt", "lqg_dgemm", "lqg_bands",
-           "lqg_version", "lqg_last_error", "lqg_device_count", "lqg_measure_fp64_peaks",
+           "lqg_alloc_host", "lqg_free_host", "lqg_version", "lqg_last_error", "lqg_device_count", "lqg_measure_fp64_peaks",
            "lqg_launch_count"]
 
 _dp = C.POINTER(C.c_double)
@@ -98,6 +98,10 @@ def lib():
     L.lqg_dgemm.argtypes = [i32, i32, i32, vp, i64, vp, i64, vp, i64, vp, C.POINTER(Opts), _dp]
     L.lqg_bands.restype = C.c_int
     L.lqg_bands.argtypes = [i32, i64, vp, i64, vp, i32, vp, vp, C.POINTER(Opts), _dp]
+    L.lqg_alloc_host.restype = C.c_void_p
+    L.lqg_alloc_host.argtypes = [C.c_uint64]
+    L.lqg_free_host.restype = None
+    L.lqg_free_host.argtypes = [C.c_void_p]
     L.lqg_version.restype = C.c_char_p
     L.lqg_last_error.restype = C.c_char_p
     L.lqg_device_count.restype = C.c_int
@@ -147,3 +151,20 @@ def make_opts(mem=MEM_HOST, stream=None, seed=0, n_chains=1, max_restarts=0, cha
     o.n_injected_u = int(n_injected_u)
     o.prepass = int(prepass)
     return o
+
+
+def empty_result(rows: int, cols: int) -> np.ndarray:
+    """Column-major FP64 result matrix.  Large results are backed by page-locked memory
+    (lqg_alloc_host) so that the library's D2H copies overlap the sampling and run at PCIe speed;
+    the memory is released when the array is garbage collected."""
+    import weakref
+    nbytes = rows * cols * 8
+    if nbytes < (8 << 20):
+        return np.empty((rows, cols), order="F")
+    p = lib().lqg_alloc_host(nbytes)
+    if not p:
+        return np.empty((rows, cols), order="F")
+    buf = (C.c_double * (rows * cols)).from_address(p)
+    arr = np.frombuffer(buf, dtype=np.float64).reshape((rows, cols), order="F")
+    weakref.finalize(buf, lib().lqg_free_host, p)
+    return arr

@@ -530,6 +530,15 @@ extern "C" int lqg_rtmg(int32_t n, int32_t seed, const double* initial, int32_t 
 }
 
 // ===========================================================================================
+extern "C" void* lqg_alloc_host(uint64_t bytes) {
+  if (!have_device()) return nullptr;
+  void* p = nullptr;
+  cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocDefault);
+  if (e != cudaSuccess) { cudaGetLastError(); set_error("lqg_alloc_host(%llu): %s", (unsigned long long)bytes, cudaGetErrorString(e)); return nullptr; }
+  return p;
+}
+extern "C" void lqg_free_host(void* p) { if (p) cudaFreeHost(p); }
+
 extern "C" const char* lqg_version(void) { return "lineqgpr_b200 0.1.0 (sm_100a)"; }
 extern "C" const char* lqg_last_error(void) { return g_err; }
 extern "C" int lqg_hmc_box_slots(int32_t d) {

@@ -115,7 +115,9 @@ def tmvrnorm_HMC(object, nsim, control=None, **kw):
                        injected=injected, n_injected=n_inj, prepass=int(control.get("prepass", -1)))
     Uf, Sf = L.f64(U), L.f64(Sigma)
     mu_c, lb_c, ub_c, init_c = (np.ascontiguousarray(v, dtype=np.float64) for v in (mu, lb, ub, init))
-    out = np.empty((d, n_chains * n_per), order="F")
+    out = control.get("out")                                            # optional caller-owned d x (n_chains*n_per) F-array
+    if out is None:                                                    # (e.g. _lib.empty_result(): page-locked, reusable)
+        out = np.empty((d, n_chains * n_per), order="F")
     stats = L.HmcStats()
     rc = L.lib().lqg_hmc_box(d, L.ptr(mu_c), L.ptr(Uf), 1, L.ptr(Sf), L.ptr(lb_c), L.ptr(ub_c),
                              L.ptr(init_c), 0, n_per, int(control["burn.in"]), opts, L.ptr(out), None, stats)
