@@ -7,6 +7,7 @@
 
 #include <atomic>
 #include <cmath>
+#include <mutex>
 #include <vector>
 
 #include "lqg_common.cuh"
@@ -36,16 +37,25 @@ static void fold_launches() {
 // owning device allocation from the stream-ordered pool: after the first call the pool keeps
 // the memory (release threshold = max), so repeated calls do not pay cudaMalloc/cudaFree
 static void retain_pool_once() {
-  static bool done = false;
-  if (done) return;
-  int dev = 0;
-  cudaMemPool_t pool;
-  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-    uint64_t thr = UINT64_MAX;
-    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-  }
-  done = true;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t thr = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+  });
 }
+// owning stream / event handles: released on every return path
+struct StreamGuard {
+  cudaStream_t s = nullptr;
+  ~StreamGuard() { if (s) cudaStreamDestroy(s); }
+};
+struct EventGuard {
+  cudaEvent_t e = nullptr;
+  ~EventGuard() { if (e) cudaEventDestroy(e); }
+};
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
@@ -293,13 +303,15 @@ extern "C" int lqg_hmc_box(int32_t d, const double* mu, const double* U, int32_t
     }
     // HOST mode: samples every chain has already emitted are copied out while later rounds run
     // (one strided 2-D copy per round: chain-major columns, pitch = n_per_chain * d doubles)
-    cudaStream_t copy_st = nullptr;
-    cudaEvent_t ev_round = nullptr;
+    StreamGuard copy_guard;
+    EventGuard round_guard;
     int copied = 0;                      // samples per chain already on their way to the host
     if (mem == LQG_MEM_HOST) {
-      LQG_CUDA_TRY(cudaStreamCreateWithFlags(&copy_st, cudaStreamNonBlocking));
-      LQG_CUDA_TRY(cudaEventCreateWithFlags(&ev_round, cudaEventDisableTiming));
+      LQG_CUDA_TRY(cudaStreamCreateWithFlags(&copy_guard.s, cudaStreamNonBlocking));
+      LQG_CUDA_TRY(cudaEventCreateWithFlags(&round_guard.e, cudaEventDisableTiming));
     }
+    cudaStream_t copy_st = copy_guard.s;
+    cudaEvent_t ev_round = round_guard.e;
     // every round consumes `attempts` momenta per active chain, so this terminates after at most
     // (total + restarts) / attempts rounds; max_restarts bounds the restarts of every transition
     while (n_active > 0) {
@@ -348,8 +360,6 @@ extern "C" int lqg_hmc_box(int32_t d, const double* mu, const double* U, int32_t
                                        cudaMemcpyDeviceToHost, st));
       }
       LQG_CUDA_TRY(cudaStreamSynchronize(copy_st));
-      cudaStreamDestroy(copy_st);
-      cudaEventDestroy(ev_round);
       out_copied = true;
     }
   }
