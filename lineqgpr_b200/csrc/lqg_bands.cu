@@ -17,6 +17,7 @@ namespace {
 
 constexpr int MAXT = 16;            // order statistics per row (2 per probability)
 constexpr int BT = 256;
+constexpr int UNR = 8;               // loads in flight per thread while streaming a row
 
 __device__ __forceinline__ uint64_t ordered_key(double x) {
   uint64_t b = (uint64_t)__double_as_longlong(x);
@@ -68,7 +69,21 @@ bands_kernel(int n_t, int64_t N, const double* __restrict__ yT, int64_t ldT, Ban
     const double* y = yT + (size_t)row * ldT;
     // ---- mean: per-thread strided partial sums, then a fixed-order tree (deterministic) ----
     double s = 0.0;
-    for (int64_t j = tid; j < N; j += BT) s += y[j];
+    {
+      // 8 independent loads per thread in flight (the row is streamed from HBM/L2: latency bound otherwise)
+      double part[UNR];
+#pragma unroll
+      for (int q = 0; q < UNR; ++q) part[q] = 0.0;
+      for (int64_t j0 = 0; j0 < N; j0 += (int64_t)BT * UNR) {
+#pragma unroll
+        for (int q = 0; q < UNR; ++q) {
+          const int64_t j = j0 + (int64_t)q * BT + tid;
+          part[q] += j < N ? y[j] : 0.0;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < UNR; ++q) s += part[q];
+    }
     s = warp_sum(s);
     if (lane == 0) red[warp] = s;
     __syncthreads();
@@ -96,19 +111,31 @@ bands_kernel(int n_t, int64_t N, const double* __restrict__ yT, int64_t ldT, Ban
       for (int i = tid; i < MAXT * 256; i += BT) (&hist[0][0])[i] = 0u;
       __syncthreads();
       const int ng = n_groups;
-      for (int64_t j0 = 0; j0 < N; j0 += BT) {
-        const int64_t j = j0 + tid;
-        int g = -1; unsigned digit = 0;
-        if (j < N) {
-          const uint64_t key = ordered_key(y[j]);
-          const uint64_t hi = pass == 0 ? 0ull : (key >> (shift + 8));
-          digit = (unsigned)((key >> shift) & 0xffu);
-          for (int q = 0; q < ng; ++q) if (group_prefix[q] == hi) { g = q; break; }
+      for (int64_t j0 = 0; j0 < N; j0 += (int64_t)BT * UNR) {
+        double v[UNR];
+#pragma unroll
+        for (int q = 0; q < UNR; ++q) {                     // UNR independent loads in flight per thread
+          const int64_t j = j0 + (int64_t)q * BT + tid;
+          v[q] = j < N ? y[j] : 0.0;
         }
-        // warp-aggregated shared atomics: lanes with the same (group, digit) add once
-        const unsigned code = g < 0 ? 0xffffffffu : (unsigned)(g * 256 + (int)digit);
-        const unsigned peers = __match_any_sync(0xffffffffu, code);
-        if (g >= 0 && (__ffs(peers) - 1) == lane) atomicAdd(&hist[g][digit], (unsigned)__popc(peers));
+#pragma unroll
+        for (int q = 0; q < UNR; ++q) {
+          const int64_t j = j0 + (int64_t)q * BT + tid;
+          int g = -1; unsigned digit = 0;
+          if (j < N) {
+            const uint64_t key = ordered_key(v[q]);
+            const uint64_t hi = pass == 0 ? 0ull : (key >> (shift + 8));
+            digit = (unsigned)((key >> shift) & 0xffu);
+            for (int c = 0; c < ng; ++c) if (group_prefix[c] == hi) { g = c; break; }
+          }
+          // warp-aggregated shared atomics: lanes with the same (group, digit) add once.  A warp in
+          // which no lane matched any target prefix (the common case after the first passes) skips.
+          if (__any_sync(0xffffffffu, g >= 0)) {
+            const unsigned code = g < 0 ? 0xffffffffu : (unsigned)(g * 256 + (int)digit);
+            const unsigned peers = __match_any_sync(0xffffffffu, code);
+            if (g >= 0 && (__ffs(peers) - 1) == lane) atomicAdd(&hist[g][digit], (unsigned)__popc(peers));
+          }
+        }
       }
       __syncthreads();
       if (tid < tg.n) {
