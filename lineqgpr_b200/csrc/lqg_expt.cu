@@ -97,6 +97,7 @@ expt_propose_kernel(const ExptParams q, int* block_acc) {
     for (int k = 0; k < d; ++k) {
       const double* lrow = q.Lt + (size_t)k * d;           // row k of L0 (zero diagonal), contiguous
       double col = 0.0;
+#pragma unroll 4
       for (int j = 0; j < k; ++j) col = fma(__ldg(lrow + j), q.Z[(size_t)j * P + p], col);
       const double mk = __ldg(q.mu + k);
       const double tl = __ldg(q.l + k) - mk - col, tu = __ldg(q.u + k) - mk - col;
