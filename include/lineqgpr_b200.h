@@ -215,6 +215,9 @@ int lqg_device_count(void);              /* number of CUDA devices, 0 when none 
 int lqg_measure_fp64_peaks(double* dfma_tflops, double* dmma_tflops, const lqg_opts* opts);
 /* counts kernel launches made by this library since the last reset (bench gpu_launches) */
 int64_t lqg_launch_count(int32_t reset);
+/* debugging aid: with LQG_GUARD=1 in the environment every internal device buffer carries a
+ * canary band on either side, checked when it is released; returns how many were overwritten */
+int lqg_guard_violations(void);
 
 #ifdef __cplusplus
 }

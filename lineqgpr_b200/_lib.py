@@ -20,7 +20,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 # every symbol include/lineqgpr_b200.h declares
 SYMBOLS = ["lqg_rtmg", "lqg_hmc_canonical", "lqg_hmc_canonical_trace", "lqg_hmc_box", "lqg_hmc_box_slots", "lqg_rsm", "lqg_expt", "lqg_dgemm", "lqg_bands",
            "lqg_alloc_host", "lqg_free_host", "lqg_version", "lqg_last_error", "lqg_device_count", "lqg_measure_fp64_peaks",
-           "lqg_launch_count"]
+           "lqg_launch_count", "lqg_guard_violations"]
 
 _dp = C.POINTER(C.c_double)
 
@@ -109,6 +109,8 @@ def lib():
     L.lqg_measure_fp64_peaks.argtypes = [_dp, _dp, C.POINTER(Opts)]
     L.lqg_launch_count.restype = i64
     L.lqg_launch_count.argtypes = [i32]
+    L.lqg_guard_violations.restype = C.c_int
+    L.lqg_guard_violations.argtypes = []
     _lib = L
     return L
 

@@ -56,7 +56,17 @@ struct EventGuard {
   cudaEvent_t e = nullptr;
   ~EventGuard() { if (e) cudaEventDestroy(e); }
 };
+// LQG_GUARD=1 (debugging aid): every device buffer gets a 256-byte canary band on either side,
+// checked when the buffer is released; lqg_guard_violations() reports how many were overwritten.
+// This is the library's own out-of-bounds-write detector for small cases.
+static std::atomic<int> g_guard_violations{0};
+static bool guard_mode() {
+  static const bool on = [] { const char* e = getenv("LQG_GUARD"); return e && *e && *e != '0'; }();
+  return on;
+}
 struct DevBuf {
+  static constexpr size_t kGuard = 256;
+  static constexpr int kPattern = 0xA5;
   void* p = nullptr;
   size_t bytes = 0;
   cudaStream_t st = nullptr;
@@ -64,13 +74,44 @@ struct DevBuf {
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
-  ~DevBuf() { if (p) cudaFreeAsync(p, st); }
+  ~DevBuf() { release(); }
+  void release() {
+    if (!p) return;
+    if (!guard_mode()) { cudaFreeAsync(p, st); p = nullptr; return; }
+    unsigned char* base = static_cast<unsigned char*>(p) - kGuard;
+    unsigned char h[2 * kGuard];
+    bool ok = cudaStreamSynchronize(st) == cudaSuccess &&
+              cudaMemcpy(h, base, kGuard, cudaMemcpyDeviceToHost) == cudaSuccess &&
+              cudaMemcpy(h + kGuard, base + kGuard + bytes, kGuard, cudaMemcpyDeviceToHost) == cudaSuccess;
+    if (ok) {
+      for (size_t i = 0; i < 2 * kGuard; ++i)
+        if (h[i] != kPattern) {
+          ++g_guard_violations;
+          fprintf(stderr, "[lqg guard] %s band of a %zu-byte buffer overwritten at offset %zu\n",
+                  i < kGuard ? "leading" : "trailing", bytes, i < kGuard ? i : i - kGuard);
+          break;
+        }
+    } else {
+      cudaGetLastError();
+    }
+    cudaFreeAsync(base, st);
+    p = nullptr;
+  }
   cudaError_t alloc(size_t n) {
-    if (p) { cudaFreeAsync(p, st); p = nullptr; }
+    release();
     retain_pool_once();
     bytes = n ? n : 16;
     st = cur_stream;
-    return cudaMallocAsync(&p, bytes, st);
+    if (!guard_mode()) return cudaMallocAsync(&p, bytes, st);
+    bytes = (bytes + 15) & ~size_t(15);
+    void* base = nullptr;
+    cudaError_t e = cudaMallocAsync(&base, bytes + 2 * kGuard, st);
+    if (e != cudaSuccess) return e;
+    unsigned char* b = static_cast<unsigned char*>(base);
+    if ((e = cudaMemsetAsync(b, kPattern, kGuard, st)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(b + kGuard + bytes, kPattern, kGuard, st)) != cudaSuccess) return e;
+    p = b + kGuard;
+    return cudaSuccess;
   }
   template <class T> T* as() { return reinterpret_cast<T*>(p); }
 };
@@ -560,6 +601,7 @@ extern "C" int lqg_device_count(void) {
   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
   return n;
 }
+extern "C" int lqg_guard_violations(void) { return g_guard_violations.load(); }
 extern "C" int64_t lqg_launch_count(int32_t reset) {
   fold_launches();
   int64_t v = g_launches.load();

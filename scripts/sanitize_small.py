@@ -1,0 +1,33 @@
+"""Tiny end-to-end pass over every kernel family, for compute-sanitizer (memcheck / racecheck)."""
+import sys
+import numpy as np
+sys.path.insert(0, ".")
+import lineqgpr_b200 as lqg
+from lineqgpr_b200 import workloads as W
+
+rng = np.random.default_rng(0)
+# box kernel variants: d = 10 (1 warp), 100 (1 warp x 4), 200 (2 warps), 300 (4 warps), 1100 (8 warps, smem thresholds)
+for name, par, n, ch in (("cfg3", W.cfg3()[0], 12, 4), ("cfg1", W.cfg1()[0], 8, 4), ("cfg4_m100", W.cfg4(m=100)[0], 6, 3),
+                         ("cfg5_D30", W.cfg5(D=30, knots=10, n=150, n_test=10)[0], 6, 3), ("cfg4_m550", W.cfg4(m=550)[0], 4, 2)):
+    for prepass in (0, 1):
+        x = lqg.tmvrnorm(dict(par, **{"class": "HMC"}), n, {"burn.in": 1, "n.chains": ch, "seed": 1, "prepass": prepass})
+        assert lqg.last_stats["violations"] == 0, name
+    print("box", name, x.shape, flush=True)
+# canonical kernel: F in shared memory (TMA bulk copy) and streamed
+F = rng.standard_normal((8, 10)); z0 = 0.1 * rng.standard_normal(10); g = 0.5 + np.maximum(0, -(F @ z0))
+z, st = lqg.rtmg_canonical(5, 3, z0, F, g, n_chains=3, burn_in=1); print("canonical small", z.shape, st["bounces"], flush=True)
+F = rng.standard_normal((300, 120)); z0 = np.zeros(120); g = np.full(300, 6.0)
+z, st = lqg.rtmg_canonical(2, 3, z0, F, g, n_chains=2, max_restarts=20000); print("canonical streamed", z.shape, st["bounces"], flush=True)
+# RSM, ExpT
+par, _ = W.cfg2(sampler="RSM")
+x = lqg.tmvrnorm(par, 50, {"seed": 2}); print("rsm", x.shape, flush=True)
+x = lqg.tmvrnorm(dict(W.cfg3()[0], **{"class": "ExpT"}), 300, {"seed": 2}); print("expt", x.shape, flush=True)
+# GEMM with ragged sizes + row sums, bands with ties
+A = rng.standard_normal((130, 19)); B = rng.standard_normal((19, 67))
+C, rs = lqg.dgemm(A, B, row_sum=True); assert np.allclose(C, A @ B)
+y = rng.standard_normal((5, 300)); y[0, :100] = y[0, 0]
+m, q = lqg.bands(y, (0.025, 0.5, 0.975)); print("gemm/bands ok", flush=True)
+from lineqgpr_b200 import _lib
+import os
+print("guard mode", os.environ.get("LQG_GUARD", "0"), "violations", _lib.lib().lqg_guard_violations(), flush=True)
+assert _lib.lib().lqg_guard_violations() == 0

@@ -54,3 +54,14 @@ def lqg():
     from lineqgpr_b200 import build
     build.build()
     return lineqgpr_b200
+
+
+@pytest.fixture(autouse=True)
+def _guard_bands_intact(request):
+    """Under LQG_GUARD=1 (canary bands around every internal device buffer) each GPU test also
+    asserts that none of the bands was overwritten while it ran."""
+    yield
+    import os
+    if "gpu" in request.keywords and os.environ.get("LQG_GUARD", "0") not in ("", "0"):
+        from lineqgpr_b200 import _lib
+        assert _lib.lib().lqg_guard_violations() == 0

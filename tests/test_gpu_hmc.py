@@ -414,3 +414,19 @@ def test_canonical_without_constraints_and_restart_cap(lqg):
     # the far tail itself (start inside z_0 >= 50) is sampled fine
     z, st = lqg.rtmg_canonical(50, 1, np.array([50.5, 0.0]), F, g)
     assert z[0].min() >= 50.0 and st["bounces"] > 0
+
+
+@pytest.mark.gpu
+def test_guard_band_mode_finds_no_out_of_bounds_writes():
+    """LQG_GUARD=1 puts canary bands around every internal device buffer; a pass over every kernel
+    family at ragged small sizes must leave all of them intact (the library's own bounds check)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, LQG_GUARD="1")
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "sanitize_small.py")], cwd=root, env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "guard mode 1 violations 0" in r.stdout
+    assert "[lqg guard]" not in r.stderr
