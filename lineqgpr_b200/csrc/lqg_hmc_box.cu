@@ -44,22 +44,28 @@ struct RedSlot {
 // Survivors of the filter are compacted into a per-warp queue and evaluated 32 at a time:
 // hit_time_exact (sqrt, atan2, acos) then runs once per ~32 candidates instead of once per
 // call site with one or two active lanes.
+// The queue is a structure of arrays (8-byte lanes -> conflict-free stores) and holds only what
+// the filter already has in registers; the bound offset g is fetched once per candidate at
+// evaluation time, 32 lanes in parallel, instead of inside the (divergent) push.
 constexpr int QCAP = 64;
 struct Cand {
-  double fa, fb, g; int key; int pad;
+  double fa[QCAP]; double fb[QCAP]; int key[QCAP];
 };
 struct LaneBest {                    // best candidate seen by this lane
   unsigned long long tb; double xa, xb; int key;
 };
 // evaluates queue entries [0, qn) with tmg's exact formula, 32 at a time (one per lane)
-static __device__ __noinline__ void flush_queue(const Cand* q, int qn, int lane, int d, LaneBest& b) {
+static __device__ __noinline__ void flush_queue(const Cand* q, int qn, int lane, int d,
+                                                const double* glo, const double* ghi, LaneBest& b) {
   for (int e = lane; e < qn; e += 32) {
-    const Cand cnd = q[e];
-    const unsigned long long tb = hit_bits(hit_time_exact(cnd.fa, cnd.fb, cnd.g));
-    if (tb < b.tb || (tb == b.tb && cnd.key < b.key)) {
-      b.tb = tb; b.key = cnd.key;
-      const double sgn = cnd.key < d ? 1.0 : -1.0;               // stored (fa, fb) = sgn * (x_a, x_b)
-      b.xa = sgn * cnd.fa; b.xb = sgn * cnd.fb;
+    const int key = q->key[e];
+    const double fa = q->fa[e], fb = q->fb[e];
+    const double g = __ldg(key < d ? glo + key : ghi + (key - d));
+    const unsigned long long tb = hit_bits(hit_time_exact(fa, fb, g));
+    if (tb < b.tb || (tb == b.tb && key < b.key)) {
+      b.tb = tb; b.key = key;
+      const double sgn = key < d ? 1.0 : -1.0;                   // stored (fa, fb) = sgn * (x_a, x_b)
+      b.xa = sgn * fa; b.xb = sgn * fb;
     }
   }
 }
@@ -127,7 +133,7 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
   extern __shared__ double a_sm[];                 // d doubles: staging of a fresh draw
                                                    // (+ 2d doubles of bound offsets when GSM)
   __shared__ RedSlot red[2][G];
-  __shared__ Cand queue[G][QCAP];
+  __shared__ Cand queue[G];
   __shared__ int chain_sm;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -205,23 +211,23 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
           // ---- hit search over this thread's coordinates (both sides) ----
           LaneBest best;
           best.tb = kNoHitBits; best.xa = 0.0; best.xb = 0.0; best.key = INT_MAX;
-          Cand* q = queue[warp];
+          Cand* q = &queue[warp];
           int qn = 0;                                              // warp-uniform queue length
           const unsigned lt_mask = (1u << lane) - 1u;
           auto flush = [&]() {
             __syncwarp();                                          // queue writes visible to every lane
-            flush_queue(q, qn, lane, d, best);
+            flush_queue(q, qn, lane, d, p.glo, p.ghi, best);
             __syncwarp();                                          // entries consumed before they are overwritten
             n_exact += (lane == 0) ? qn : 0;
             qn = 0;
           };
-          auto push = [&](bool need, double fa, double fb, const double* gsrc, int i, int key) {
+          auto push = [&](bool need, double fa, double fb, int key) {
             const unsigned m = __ballot_sync(0xffffffffu, need);
             if (m == 0u) return;
             if (qn + __popc(m) > QCAP) flush();
             if (need) {
-              Cand& c = q[qn + __popc(m & lt_mask)];
-              c.fa = fa; c.fb = fb; c.g = __ldg(gsrc + i); c.key = key;
+              const int e = qn + __popc(m & lt_mask);
+              q->fa[e] = fa; q->fb[e] = fb; q->key[e] = key;
             }
             qn += __popc(m);
           };
@@ -248,8 +254,8 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
             const bool dip_hi = (a_ > 0.0) & (dy < 0.0) & (u2 >= hh * fabs(hh));
             const bool need_lo = !safe_lo | dip_lo;
             const bool need_hi = !safe_hi | dip_hi;
-            push(need_lo, a_, b_, p.glo, i, i);
-            push(need_hi, -a_, -b_, p.ghi, i, d + i);
+            push(need_lo, a_, b_, i);
+            push(need_hi, -a_, -b_, d + i);
           }
           flush();
           // ---- arg-min: hardware warp-reduce, one slot per warp, warp-reduce over the slots ----
