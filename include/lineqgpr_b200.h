@@ -29,6 +29,7 @@ extern "C" {
 #define LQG_ERR_CUDA             4   /* no device / CUDA runtime error (see lqg_last_error)   */
 #define LQG_ERR_RESTART_CAP      5   /* a chain exceeded max_restarts in one transition        */
 #define LQG_ERR_DRAWS_EXHAUSTED  6   /* injected Gaussian stream too short                     */
+#define LQG_ERR_NOT_PD           8   /* tmg:R/tmg.R:17-20 "M must be positive definite"        */
 #define LQG_ERR_BUDGET           7   /* RSM: proposal budget exhausted before nsim accepts     */
 
 /* where the caller's pointers live */
@@ -200,6 +201,45 @@ int lqg_dgemm(int32_t m, int32_t n, int32_t k, const double* A, int64_t lda,
 int lqg_bands(int32_t n_t, int64_t N, const double* ysim, int64_t ld,
               const double* probs, int32_t nprobs, double* mean, double* qtls,
               const lqg_opts* opts, double* kernel_ms);
+
+/* ---- set-up stage on the device --------------------------- */
+/* All matrices column-major FP64; pointers host or device according to opts->mem; every
+ * product runs on the FP64 tensor cores (blocked algorithms, lqg_linalg.cu).                 */
+
+/* U (d x d, upper triangular, positive diagonal) with U U' = (Sigma + Sigma')/2: the matrix
+ * tmg::rtmg whitens with when tmvrnorm.HMC calls it with M = solve(Sigma)
+ * (R/lineqGPsamplers.R:139-141; tmg:R/tmg.R:15 symmetrise, :17-20 PD test, :21 R = chol(M),
+ * :27 Ri = solve(R)): Ri is upper triangular with Ri Ri' = M^-1 = Sigma, and that factor is
+ * unique, so it is computed directly as a reversed Cholesky factorisation — no inverse of the
+ * ill-conditioned Sigma.  LQG_ERR_NOT_PD (tmg's "M must be positive definite") otherwise.
+ * lqg_hmc_box calls this internally when its U argument is NULL.                              */
+int lqg_whiten_box(int32_t d, const double* Sigma, const lqg_opts* opts, double* U_out, double* kernel_ms);
+
+/* chol(): lower factor L with L L' = (A + A')/2.  L_out nullable (test only).  *bad_pivot
+ * (nullable) = 0 when A is positive definite, else the 1-based index of the first non-positive
+ * pivot and the call returns LQG_ERR_NOT_PD.  Replaces the eigen()-based tests of
+ * tmg:R/tmg.R:17 and R/lineqGP.R:527-528 (min eigenvalue <= 0  <=>  the factorisation fails). */
+int lqg_chol(int32_t d, const double* A, const lqg_opts* opts, double* L_out, int32_t* bad_pivot);
+
+/* X = solve(A, B) for a symmetric positive definite A (d x d) and B (d x nrhs): the
+ * chol2inv/solve products of the posterior algebra (R/lineqGP.R:514-523).                     */
+int lqg_solve_spd(int32_t d, int32_t nrhs, const double* A, const double* B, const lqg_opts* opts,
+                  double* X_out);
+
+/* eta-space parameters of simulate.lineqGP (R/lineqGP.R:611-614; R/lineqAGP.R:558-566):
+ *   eta_mu = Lambda mu, eta_map = Lambda xi_map, Sigma_eta = Lambda Sigma Lambda' + nugget I
+ * Lambda d x m, mu[m], xi_map[m], Sigma m x m; outputs eta_mu[d], eta_map[d], Sigma_eta d x d
+ * (mu / xi_map / eta_mu / eta_map nullable).                                                  */
+int lqg_eta_params(int32_t d, int32_t m, const double* Lambda, const double* mu, const double* xi_map,
+                   const double* Sigma, double nugget, const lqg_opts* opts,
+                   double* eta_mu, double* eta_map, double* Sigma_eta);
+
+/* Lambda^+ (m x d) with Lambda^+ eta = qr.solve(Lambda, eta) (R/lineqGP.R:639,
+ * R/lineqAGP.R:575) for a full-column-rank Lambda (d x m, d >= m): normal equations
+ * (Lambda'Lambda) X = Lambda' by blocked Cholesky, followed by one step of iterative refinement
+ * X += G^-1 Lambda' (I - Lambda X), which restores QR-level accuracy for the constraint
+ * matrices lineqGPR builds (cond(Lambda) <~ 1e4).  LQG_ERR_NOT_PD if Lambda is rank deficient.  */
+int lqg_lambda_pinv(int32_t d, int32_t m, const double* Lambda, const lqg_opts* opts, double* Lp_out);
 
 /* Page-locked host memory for large result matrices: with it the LQG_MEM_HOST entry points copy
  * samples out at full PCIe speed and concurrently with the sampling rounds; with ordinary

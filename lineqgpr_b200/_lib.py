@@ -14,13 +14,15 @@ LIB_PATH = PKG / "liblineqgpr_b200.so"
 
 LQG_OK = 0
 STATUS = {0: "LQG_OK", 1: "LQG_ERR_INVALID", 2: "LQG_ERR_UNSUPPORTED", 3: "LQG_ERR_INIT_INFEASIBLE",
-          4: "LQG_ERR_CUDA", 5: "LQG_ERR_RESTART_CAP", 6: "LQG_ERR_DRAWS_EXHAUSTED", 7: "LQG_ERR_BUDGET"}
+          4: "LQG_ERR_CUDA", 5: "LQG_ERR_RESTART_CAP", 6: "LQG_ERR_DRAWS_EXHAUSTED", 7: "LQG_ERR_BUDGET",
+          8: "LQG_ERR_NOT_PD"}
 MEM_HOST, MEM_DEVICE = 0, 1
 
 # every symbol include/lineqgpr_b200.h declares
 SYMBOLS = ["lqg_rtmg", "lqg_hmc_canonical", "lqg_hmc_canonical_trace", "lqg_hmc_box", "lqg_hmc_box_slots", "lqg_rsm", "lqg_expt", "lqg_dgemm", "lqg_bands",
            "lqg_alloc_host", "lqg_free_host", "lqg_version", "lqg_last_error", "lqg_device_count", "lqg_measure_fp64_peaks",
-           "lqg_launch_count", "lqg_guard_violations"]
+           "lqg_launch_count", "lqg_guard_violations",
+           "lqg_whiten_box", "lqg_chol", "lqg_solve_spd", "lqg_eta_params", "lqg_lambda_pinv"]
 
 _dp = C.POINTER(C.c_double)
 
@@ -111,6 +113,16 @@ def lib():
     L.lqg_launch_count.argtypes = [i32]
     L.lqg_guard_violations.restype = C.c_int
     L.lqg_guard_violations.argtypes = []
+    L.lqg_whiten_box.restype = C.c_int
+    L.lqg_whiten_box.argtypes = [i32, vp, C.POINTER(Opts), vp, _dp]
+    L.lqg_chol.restype = C.c_int
+    L.lqg_chol.argtypes = [i32, vp, C.POINTER(Opts), vp, C.POINTER(i32)]
+    L.lqg_solve_spd.restype = C.c_int
+    L.lqg_solve_spd.argtypes = [i32, i32, vp, vp, C.POINTER(Opts), vp]
+    L.lqg_eta_params.restype = C.c_int
+    L.lqg_eta_params.argtypes = [i32, i32, vp, vp, vp, vp, C.c_double, C.POINTER(Opts), vp, vp, vp]
+    L.lqg_lambda_pinv.restype = C.c_int
+    L.lqg_lambda_pinv.argtypes = [i32, i32, vp, C.POINTER(Opts), vp]
     _lib = L
     return L
 

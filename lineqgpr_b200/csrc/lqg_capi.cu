@@ -202,6 +202,8 @@ static int chain_status_rc(const std::vector<int>& st, unsigned long long* faile
 
 using namespace lqg;
 
+static int ul_factor_device(int d, const double* S_dev, double* U_dev, cudaStream_t st);
+
 // ===========================================================================================
 extern "C" int lqg_hmc_box(int32_t d, const double* mu, const double* U, int32_t u_upper,
                            const double* Sigma, const double* lb, const double* ub,
@@ -213,7 +215,7 @@ extern "C" int lqg_hmc_box(int32_t d, const double* mu, const double* U, int32_t
   Phase ph("hmc_box");
   const lqg_opts o = opts_ ? *opts_ : default_opts();
   const int n_chains = o.n_chains > 0 ? o.n_chains : 1;
-  if (d <= 0 || d > 8192 || !mu || !U || !Sigma || !lb || !ub || !init || !out || n_per_chain <= 0 ||
+  if (d <= 0 || d > 8192 || !mu || !Sigma || !lb || !ub || !init || !out || n_per_chain <= 0 ||
       burn_in < 0 || (init_ld != 0 && init_ld < d)) {
     set_error("lqg_hmc_box: invalid argument (d=%d, n_per_chain=%d, burn_in=%d, init_ld=%lld)", d,
               n_per_chain, burn_in, (long long)init_ld);
@@ -248,11 +250,19 @@ extern "C" int lqg_hmc_box(int32_t d, const double* mu, const double* U, int32_t
   ph.mark("validate");
   // ---- stage inputs ----
   Input i_mu, i_U, i_S, i_lb, i_ub, i_init, i_inj;
-  if ((rc = i_mu.stage(mu, d, mem, st)) || (rc = i_U.stage(U, dd, mem, st)) ||
+  if ((rc = i_mu.stage(mu, d, mem, st)) || (U && (rc = i_U.stage(U, dd, mem, st))) ||
       (rc = i_S.stage(Sigma, dd, mem, st)) || (rc = i_lb.stage(lb, d, mem, st)) ||
       (rc = i_ub.stage(ub, d, mem, st)) || (rc = i_init.stage(init, n_init, mem, st)))
     return rc;
   if (o.injected && (rc = i_inj.stage(o.injected, (size_t)n_chains * o.n_injected, mem, st))) return rc;
+
+  if (!U) {                                  // whiten on the device: U U' = Sigma (see lqg_whiten_box)
+    LQG_CUDA_TRY(i_U.buf.alloc(dd * sizeof(double)));
+    if ((rc = ul_factor_device(d, i_S.dev, i_U.buf.as<double>(), st))) return rc;
+    i_U.dev = i_U.buf.as<double>();
+    u_upper = 1;
+    ph.mark("whiten");
+  }
 
   const size_t n_cols = (size_t)n_chains * n_per_chain;
   DevBuf b_out, b_state, b_glo, b_ghi, b_sd, b_misc, b_status, b_sdone, b_pos, b_rcount, b_act;
@@ -823,6 +833,219 @@ extern "C" int lqg_dgemm(int32_t m, int32_t n, int32_t k, const double* A, int64
     }
     if (row_sum) LQG_CUDA_TRY(cudaMemcpyAsync(row_sum, d_rs, m * sizeof(double), cudaMemcpyDeviceToHost, st));
   }
+  LQG_CUDA_TRY(cudaStreamSynchronize(st));
+  fold_launches();
+  return LQG_OK;
+}
+
+// ===========================================================================================
+// Set-up stage on the device (lqg_linalg.cu)
+constexpr int kInfoClean = 0x7f7f7f7f;
+
+// copies a result back to the caller (host) or leaves it where it was computed (device)
+static int deliver(double* dst, const double* src_dev, size_t n, int mem, cudaStream_t st) {
+  if (!dst || dst == src_dev) return LQG_OK;
+  LQG_CUDA_TRY(cudaMemcpyAsync(dst, src_dev, n * sizeof(double),
+                               mem == LQG_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+  return LQG_OK;
+}
+
+// L (device, d x d) <- lower Cholesky factor of sym(A) (reversed index order when rev); Winv
+// receives the inverted diagonal blocks.  Synchronises the stream.  *bad = 0 or first bad pivot.
+static int chol_device(int d, const double* A_dev, int rev, double* L_dev, double* Winv_dev, int* bad,
+                       cudaStream_t st) {
+  DevBuf b_w, b_info;
+  LQG_CUDA_TRY(b_w.alloc((size_t)d * d * sizeof(double)));
+  LQG_CUDA_TRY(b_info.alloc(sizeof(int)));
+  LQG_CUDA_TRY(cudaMemsetAsync(b_info.p, 0x7f, sizeof(int), st));
+  LQG_CUDA_TRY(launch_sym_reverse(d, A_dev, d, b_w.as<double>(), d, rev, st));
+  LQG_CUDA_TRY(launch_chol(d, b_w.as<double>(), d, L_dev, d, Winv_dev, b_info.as<int>(), st));
+  int info = 0;
+  LQG_CUDA_TRY(cudaMemcpyAsync(&info, b_info.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  LQG_CUDA_TRY(cudaStreamSynchronize(st));
+  *bad = info == kInfoClean ? 0 : info;
+  return LQG_OK;
+}
+
+// U_dev (d x d) <- the upper factor with U U' = sym(Sigma):  U = J chol(J Sigma J) J
+static int ul_factor_device(int d, const double* S_dev, double* U_dev, cudaStream_t st) {
+  DevBuf b_l, b_winv;
+  LQG_CUDA_TRY(b_l.alloc((size_t)d * d * sizeof(double)));
+  LQG_CUDA_TRY(b_winv.alloc(chol_winv_elems(d) * sizeof(double)));
+  int bad = 0, rc;
+  if ((rc = chol_device(d, S_dev, 1, b_l.as<double>(), b_winv.as<double>(), &bad, st))) return rc;
+  if (bad) {
+    set_error("Error: M must be positive definite. (pivot %d of the reversed factorisation of Sigma is not positive)", bad);
+    return LQG_ERR_NOT_PD;                                          // tmg:R/tmg.R:17-20
+  }
+  LQG_CUDA_TRY(launch_reverse(d, b_l.as<double>(), U_dev, st));
+  return LQG_OK;
+}
+
+extern "C" int lqg_whiten_box(int32_t d, const double* Sigma, const lqg_opts* opts_, double* U_out,
+                              double* kernel_ms) {
+  if (!have_device()) return LQG_ERR_CUDA;
+  const lqg_opts o = opts_ ? *opts_ : default_opts();
+  if (d <= 0 || d > 32768 || !Sigma || !U_out) { set_error("lqg_whiten_box: invalid argument (d=%d)", d); return LQG_ERR_INVALID; }
+  cudaStream_t st = (cudaStream_t)o.stream;
+  DevBuf::cur_stream = st;
+  const size_t dd = (size_t)d * d;
+  int rc;
+  Input i_S;
+  if ((rc = i_S.stage(Sigma, dd, o.mem, st))) return rc;
+  DevBuf b_U;
+  double* d_U = U_out;
+  if (o.mem == LQG_MEM_HOST) { LQG_CUDA_TRY(b_U.alloc(dd * sizeof(double))); d_U = b_U.as<double>(); }
+  Timer tm(st);
+  tm.start();
+  if ((rc = ul_factor_device(d, i_S.dev, d_U, st))) return rc;
+  tm.stop();
+  if (kernel_ms) *kernel_ms = tm.ms();
+  if ((rc = deliver(U_out, d_U, dd, o.mem, st))) return rc;
+  LQG_CUDA_TRY(cudaStreamSynchronize(st));
+  fold_launches();
+  return LQG_OK;
+}
+
+extern "C" int lqg_chol(int32_t d, const double* A, const lqg_opts* opts_, double* L_out, int32_t* bad_pivot) {
+  if (!have_device()) return LQG_ERR_CUDA;
+  const lqg_opts o = opts_ ? *opts_ : default_opts();
+  if (d <= 0 || d > 32768 || !A) { set_error("lqg_chol: invalid argument (d=%d)", d); return LQG_ERR_INVALID; }
+  cudaStream_t st = (cudaStream_t)o.stream;
+  DevBuf::cur_stream = st;
+  const size_t dd = (size_t)d * d;
+  int rc;
+  Input i_A;
+  if ((rc = i_A.stage(A, dd, o.mem, st))) return rc;
+  DevBuf b_l, b_winv;
+  LQG_CUDA_TRY(b_l.alloc(dd * sizeof(double)));
+  LQG_CUDA_TRY(b_winv.alloc(chol_winv_elems(d) * sizeof(double)));
+  int bad = 0;
+  if ((rc = chol_device(d, i_A.dev, 0, b_l.as<double>(), b_winv.as<double>(), &bad, st))) return rc;
+  if (bad_pivot) *bad_pivot = bad;
+  fold_launches();
+  if (bad) { set_error("lqg_chol: the matrix is not positive definite (pivot %d)", bad); return LQG_ERR_NOT_PD; }
+  if ((rc = deliver(L_out, b_l.as<double>(), dd, o.mem, st))) return rc;
+  LQG_CUDA_TRY(cudaStreamSynchronize(st));
+  return LQG_OK;
+}
+
+extern "C" int lqg_solve_spd(int32_t d, int32_t nrhs, const double* A, const double* B, const lqg_opts* opts_,
+                             double* X_out) {
+  if (!have_device()) return LQG_ERR_CUDA;
+  const lqg_opts o = opts_ ? *opts_ : default_opts();
+  if (d <= 0 || d > 32768 || nrhs <= 0 || !A || !B || !X_out) {
+    set_error("lqg_solve_spd: invalid argument (d=%d nrhs=%d)", d, nrhs);
+    return LQG_ERR_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)o.stream;
+  DevBuf::cur_stream = st;
+  const size_t dd = (size_t)d * d, dn = (size_t)d * nrhs;
+  int rc;
+  Input i_A, i_B;
+  if ((rc = i_A.stage(A, dd, o.mem, st)) || (rc = i_B.stage(B, dn, o.mem, st))) return rc;
+  DevBuf b_l, b_winv, b_x, b_t;
+  LQG_CUDA_TRY(b_l.alloc(dd * sizeof(double)));
+  LQG_CUDA_TRY(b_winv.alloc(chol_winv_elems(d) * sizeof(double)));
+  LQG_CUDA_TRY(b_x.alloc(dn * sizeof(double)));
+  LQG_CUDA_TRY(b_t.alloc(dn * sizeof(double)));
+  int bad = 0;
+  if ((rc = chol_device(d, i_A.dev, 0, b_l.as<double>(), b_winv.as<double>(), &bad, st))) return rc;
+  if (bad) { set_error("lqg_solve_spd: the matrix is not positive definite (pivot %d)", bad); fold_launches(); return LQG_ERR_NOT_PD; }
+  LQG_CUDA_TRY(cudaMemcpyAsync(b_x.p, i_B.dev, dn * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  LQG_CUDA_TRY(launch_chol_solve(d, b_l.as<double>(), d, b_winv.as<double>(), b_x.as<double>(), d,
+                                 b_t.as<double>(), d, nrhs, st));
+  if ((rc = deliver(X_out, b_x.as<double>(), dn, o.mem, st))) return rc;
+  LQG_CUDA_TRY(cudaStreamSynchronize(st));
+  fold_launches();
+  return LQG_OK;
+}
+
+extern "C" int lqg_eta_params(int32_t d, int32_t m, const double* Lambda, const double* mu, const double* xi_map,
+                              const double* Sigma, double nugget, const lqg_opts* opts_,
+                              double* eta_mu, double* eta_map, double* Sigma_eta) {
+  if (!have_device()) return LQG_ERR_CUDA;
+  const lqg_opts o = opts_ ? *opts_ : default_opts();
+  if (d <= 0 || m <= 0 || d > 32768 || m > 32768 || !Lambda || !Sigma || !Sigma_eta || (eta_mu && !mu) || (eta_map && !xi_map)) {
+    set_error("lqg_eta_params: invalid argument (d=%d m=%d)", d, m);
+    return LQG_ERR_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)o.stream;
+  DevBuf::cur_stream = st;
+  const int mem = o.mem;
+  const size_t dd = (size_t)d * d, dm = (size_t)d * m, mm = (size_t)m * m;
+  int rc;
+  Input i_L, i_S, i_mu, i_map;
+  if ((rc = i_L.stage(Lambda, dm, mem, st)) || (rc = i_S.stage(Sigma, mm, mem, st))) return rc;
+  if (eta_mu && (rc = i_mu.stage(mu, m, mem, st))) return rc;
+  if (eta_map && (rc = i_map.stage(xi_map, m, mem, st))) return rc;
+  DevBuf b_t, b_se, b_v;
+  LQG_CUDA_TRY(b_t.alloc(dm * sizeof(double)));
+  LQG_CUDA_TRY(b_v.alloc(2 * (size_t)d * sizeof(double)));
+  double* d_se = Sigma_eta;
+  if (mem == LQG_MEM_HOST) { LQG_CUDA_TRY(b_se.alloc(dd * sizeof(double))); d_se = b_se.as<double>(); }
+  // T = Sigma Lambda' (m x d);  Sigma_eta = Lambda T + nugget I      R/lineqGP.R:613-614
+  LQG_CUDA_TRY(launch_gemm(false, true, m, d, m, 1.0, i_S.dev, m, i_L.dev, d, 0.0, b_t.as<double>(), m, 0, st));
+  LQG_CUDA_TRY(launch_gemm(false, false, d, d, m, 1.0, i_L.dev, d, b_t.as<double>(), m, 0.0, d_se, d, 0, st));
+  if (nugget != 0.0) LQG_CUDA_TRY(launch_add_diag(d, d_se, d, nugget, st));
+  double* v = b_v.as<double>();
+  if (eta_mu) {                                                      // :611
+    LQG_CUDA_TRY(launch_gemm(false, false, d, 1, m, 1.0, i_L.dev, d, i_mu.dev, m, 0.0, v, d, 0, st));
+    if ((rc = deliver(eta_mu, v, d, mem, st))) return rc;
+  }
+  if (eta_map) {                                                     // :612
+    LQG_CUDA_TRY(launch_gemm(false, false, d, 1, m, 1.0, i_L.dev, d, i_map.dev, m, 0.0, v + d, d, 0, st));
+    if ((rc = deliver(eta_map, v + d, d, mem, st))) return rc;
+  }
+  if ((rc = deliver(Sigma_eta, d_se, dd, mem, st))) return rc;
+  LQG_CUDA_TRY(cudaStreamSynchronize(st));
+  fold_launches();
+  return LQG_OK;
+}
+
+extern "C" int lqg_lambda_pinv(int32_t d, int32_t m, const double* Lambda, const lqg_opts* opts_, double* Lp_out) {
+  if (!have_device()) return LQG_ERR_CUDA;
+  const lqg_opts o = opts_ ? *opts_ : default_opts();
+  if (d <= 0 || m <= 0 || d < m || d > 32768 || !Lambda || !Lp_out) {
+    set_error("lqg_lambda_pinv: invalid argument (d=%d m=%d; needs d >= m)", d, m);
+    return LQG_ERR_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)o.stream;
+  DevBuf::cur_stream = st;
+  const int mem = o.mem;
+  const size_t dd = (size_t)d * d, dm = (size_t)d * m, mm = (size_t)m * m;
+  int rc;
+  Input i_L;
+  if ((rc = i_L.stage(Lambda, dm, mem, st))) return rc;
+  DevBuf b_g, b_l, b_winv, b_x, b_t, b_r, b_y;
+  LQG_CUDA_TRY(b_g.alloc(mm * sizeof(double)));
+  LQG_CUDA_TRY(b_l.alloc(mm * sizeof(double)));
+  LQG_CUDA_TRY(b_winv.alloc(chol_winv_elems(m) * sizeof(double)));
+  LQG_CUDA_TRY(b_x.alloc(dm * sizeof(double)));
+  LQG_CUDA_TRY(b_t.alloc(dm * sizeof(double)));
+  LQG_CUDA_TRY(b_r.alloc(dd * sizeof(double)));
+  LQG_CUDA_TRY(b_y.alloc(dm * sizeof(double)));
+  double *G = b_g.as<double>(), *Lc = b_l.as<double>(), *X = b_x.as<double>(), *T = b_t.as<double>(),
+         *R = b_r.as<double>(), *Y = b_y.as<double>();
+  // G = Lambda' Lambda;  G = Lc Lc'
+  LQG_CUDA_TRY(launch_gemm(true, false, m, m, d, 1.0, i_L.dev, d, i_L.dev, d, 0.0, G, m, 0, st));
+  int bad = 0;
+  if ((rc = chol_device(m, G, 0, Lc, b_winv.as<double>(), &bad, st))) return rc;
+  if (bad) {
+    set_error("lqg_lambda_pinv: Lambda is rank deficient (pivot %d of Lambda'Lambda is not positive)", bad);
+    fold_launches();
+    return LQG_ERR_NOT_PD;
+  }
+  // X0 = G^-1 Lambda'
+  LQG_CUDA_TRY(launch_transpose(d, m, i_L.dev, d, X, m, st));
+  LQG_CUDA_TRY(launch_chol_solve(m, Lc, m, b_winv.as<double>(), X, m, T, m, d, st));
+  // one refinement step: X += G^-1 Lambda' (I - Lambda X0)
+  LQG_CUDA_TRY(launch_gemm(false, false, d, d, m, -1.0, i_L.dev, d, X, m, 0.0, R, d, 0, st));
+  LQG_CUDA_TRY(launch_add_diag(d, R, d, 1.0, st));
+  LQG_CUDA_TRY(launch_gemm(true, false, m, d, d, 1.0, i_L.dev, d, R, d, 0.0, Y, m, 0, st));
+  LQG_CUDA_TRY(launch_chol_solve(m, Lc, m, b_winv.as<double>(), Y, m, T, m, d, st));
+  LQG_CUDA_TRY(launch_axpy(dm, 1.0, Y, X, st));
+  if ((rc = deliver(Lp_out, X, dm, mem, st))) return rc;
   LQG_CUDA_TRY(cudaStreamSynchronize(st));
   fold_launches();
   return LQG_OK;

@@ -54,11 +54,16 @@ def whiten_box(mu, Sigma, method="ul"):
 
     method="tmg": that literal sequence (inverse, Cholesky, triangular inverse; ~8/3 d^3 flop and
                   one inversion of an ill-conditioned Sigma) — used by the parity tests.
+    method="device": method "ul" computed on the GPU (lqg_whiten_box, blocked factorisation on
+                  the FP64 tensor cores).
     method="ul" : the same matrix obtained directly: the upper-triangular factor with positive
                   diagonal and U U' = Sigma is unique, and equals J chol(J Sigma J) J with J the
                   exchange matrix (a "reverse Cholesky"): one Cholesky, d^3/3 flop, no inversion.
     Both raise tmg's error when Sigma (equivalently M) is not positive definite."""
     Sigma = np.asarray(Sigma, float)
+    if method == "device":
+        from .setup_stage import whiten_box_device
+        return whiten_box_device(Sigma)
     if method == "ul":
         S = (Sigma + Sigma.T) / 2
         try:
@@ -99,8 +104,8 @@ def tmvrnorm_HMC(object, nsim, control=None, **kw):
     n_chains = max(1, min(n_chains, nsim))
     n_per = -(-nsim // n_chains)
     U = control.get("U")
-    if U is None:
-        U = whiten_box(mu, Sigma, control.get("whiten", "ul"))
+    if U is None and control.get("whiten", "ul") != "device":
+        U = whiten_box(mu, Sigma, control.get("whiten", "ul"))     # "device": lqg_hmc_box factors Sigma itself
     seed = control.get("seed")
     if seed is None:
         seed = int(np.random.randint(1, 10000000))                     # tmg:R/tmg.R:102
@@ -113,7 +118,7 @@ def tmvrnorm_HMC(object, nsim, control=None, **kw):
                        max_restarts=int(control.get("max.restarts", 0)),
                        chain_offset=int(control.get("chain.offset", 0)),
                        injected=injected, n_injected=n_inj, prepass=int(control.get("prepass", -1)))
-    Uf, Sf = L.f64(U), L.f64(Sigma)
+    Uf, Sf = (L.f64(U) if U is not None else None), L.f64(Sigma)
     mu_c, lb_c, ub_c, init_c = (np.ascontiguousarray(v, dtype=np.float64) for v in (mu, lb, ub, init))
     out = control.get("out")                                            # optional caller-owned d x (n_chains*n_per) F-array
     if out is None:                                                    # (e.g. _lib.empty_result(): page-locked, reusable)

@@ -1,0 +1,137 @@
+"""Set-up stage on the device against numpy/LAPACK on the same inputs.
+
+Tolerances (FP64, stated per test): a Cholesky factor is backward stable, so the checked
+quantity is the reconstruction ||F F' - A|| / ||A|| <= 50 d eps; factors of well-conditioned
+matrices are also compared entry-wise with LAPACK's at 1e-11 relative."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+EPS = np.finfo(float).eps
+
+
+def _spd(rng, d, cond=1e3):
+    Q, _ = np.linalg.qr(rng.standard_normal((d, d)))
+    ev = np.logspace(0, -np.log10(cond), d)
+    return (Q * ev) @ Q.T
+
+
+@pytest.mark.parametrize("d", [1, 2, 63, 64, 65, 130, 500])
+def test_chol_matches_lapack(lqg, d):
+    from lineqgpr_b200 import setup_stage as S
+    A = _spd(np.random.default_rng(d), d)
+    Lf = S.chol(A)
+    ref = np.linalg.cholesky((A + A.T) / 2)
+    assert np.array_equal(np.triu(Lf, 1), np.zeros((d, d)))
+    assert np.linalg.norm(Lf @ Lf.T - A) <= 50 * d * EPS * np.linalg.norm(A)
+    assert np.max(np.abs(Lf - ref)) <= 1e-11 * np.max(np.abs(ref))
+
+
+@pytest.mark.parametrize("d", [5, 64, 200, 333])
+def test_whiten_box_device_is_tmgs_Ri(lqg, oracle, d):
+    """U upper triangular, positive diagonal, U U' = Sigma; equals the oracle's literal tmg sequence
+    (solve, chol, solve: tmg:R/tmg.R:15-28) to rounding on a well-conditioned Sigma."""
+    from lineqgpr_b200 import setup_stage as S, samplers
+    Sigma = _spd(np.random.default_rng(100 + d), d, cond=50.0)
+    U = S.whiten_box_device(Sigma)
+    assert np.array_equal(np.tril(U, -1), np.zeros((d, d)))
+    assert np.all(np.diag(U) > 0)
+    assert np.linalg.norm(U @ U.T - Sigma) <= 50 * d * EPS * np.linalg.norm(Sigma)
+    assert np.max(np.abs(U - samplers.whiten_box(None, Sigma, "ul"))) <= 1e-12 * np.max(np.abs(U))
+    Ri = oracle.whiten(np.linalg.inv(Sigma), np.zeros(d), np.zeros(d), np.zeros((0, d)), np.zeros(0))["Ri"] \
+        if hasattr(oracle, "whiten") else samplers.whiten_box(None, Sigma, "tmg")
+    assert np.max(np.abs(U - np.triu(Ri))) <= 1e-9 * np.max(np.abs(U))
+
+
+def test_not_positive_definite_is_reported(lqg):
+    from lineqgpr_b200 import setup_stage as S
+    rng = np.random.default_rng(3)
+    B = rng.standard_normal((150, 40))
+    A = B @ B.T                                     # rank 40 < 150
+    A[np.diag_indices(150)] -= 1e-3                 # indefinite
+    assert not S.is_positive_definite(A)
+    with pytest.raises(ValueError, match="positive definite"):
+        S.whiten_box_device(A)
+    with pytest.raises(ValueError):
+        S.chol(A)
+    assert S.is_positive_definite(A + 1.0 * np.eye(150))
+    nanm = np.eye(70); nanm[69, 69] = np.nan
+    assert not S.is_positive_definite(nanm)
+
+
+@pytest.mark.parametrize("d,nrhs", [(3, 1), (64, 7), (129, 1), (300, 65)])
+def test_solve_spd(lqg, d, nrhs):
+    from lineqgpr_b200 import setup_stage as S
+    rng = np.random.default_rng(d + nrhs)
+    A = _spd(rng, d, cond=1e4)
+    B = rng.standard_normal((d, nrhs))
+    X = S.solve_spd(A, B)
+    ref = np.linalg.solve(A, B)
+    assert np.max(np.abs(X - ref)) <= 1e-10 * np.max(np.abs(ref))          # cond 1e4 x a few hundred eps
+
+
+def test_eta_params_and_lambda_pinv_cfg1_cfg3(lqg):
+    import importlib
+    from lineqgpr_b200 import setup_stage as S
+    sim_mod = importlib.import_module("lineqgpr_b200.simulate")   # (the package also exports a function of that name)
+    rng = np.random.default_rng(5)
+    for d, m in ((100, 100), (200, 100), (37, 20)):
+        if d == m:
+            Lam = np.tril(np.ones((m, m)))                                   # monotone-type square Lambda
+        else:
+            Lam = np.vstack([np.eye(m), np.diff(np.eye(m), axis=0), rng.standard_normal((d - 2 * m + 1, m))]) \
+                if d >= 2 * m - 1 else rng.standard_normal((d, m))
+        Sig = _spd(rng, m, 1e6)
+        mu, xm = rng.standard_normal(m), rng.standard_normal(m)
+        e_mu, e_map, Se = S.eta_params(Lam, mu, xm, Sig, 1e-5)
+        assert np.allclose(e_mu, Lam @ mu, rtol=1e-13, atol=1e-13)
+        assert np.allclose(e_map, Lam @ xm, rtol=1e-13, atol=1e-13)
+        ref = Lam @ Sig @ Lam.T + 1e-5 * np.eye(d)
+        assert np.max(np.abs(Se - ref)) <= 1e-13 * np.max(np.abs(ref)) * m
+        Lp = S.lambda_pinv_device(Lam)
+        ref = sim_mod.lambda_pinv(Lam)
+        assert np.max(np.abs(Lp - ref)) <= 1e-11 * np.max(np.abs(ref)), (d, m)
+        eta = Lam @ rng.standard_normal((m, 4))
+        assert np.allclose(Lp @ eta, np.linalg.lstsq(Lam, eta, rcond=None)[0], rtol=1e-10, atol=1e-11)
+
+
+def test_lambda_pinv_rank_deficient(lqg):
+    from lineqgpr_b200 import setup_stage as S
+    Lam = np.ones((10, 3))
+    with pytest.raises(ValueError, match="rank"):
+        S.lambda_pinv_device(Lam)
+
+
+def test_hmc_box_whitens_on_device_when_U_is_null(lqg):
+    """lqg_hmc_box(U = NULL) factors Sigma itself: same chains as with the host factor up to the
+    rounding difference between the two factorizations (short run, well-conditioned Sigma)."""
+    from lineqgpr_b200 import workloads as W
+    par, _ = W.cfg3()
+    par = dict(par, **{"class": "HMC"})
+    ctl = {"burn.in": 2, "n.chains": 8, "seed": 11}
+    a = lqg.tmvrnorm(par, 64, dict(ctl))
+    b = lqg.tmvrnorm(par, 64, dict(ctl, whiten="device"))
+    assert lqg.last_stats["violations"] == 0
+    assert np.all(b >= par["lb"][:, None]) and np.all(b <= par["ub"][:, None])
+    # first emitted sample of every chain agrees closely (a handful of bounces after 3 transitions)
+    first = np.arange(8) * 8
+    assert np.max(np.abs(a[:, first] - b[:, first])) <= 1e-8
+
+
+def test_cfg4_scale_setup(lqg):
+    """d = 2000 (cfg4): the jittered, numerically near-singular Sigma_eta of the headline workload."""
+    import time
+    from lineqgpr_b200 import setup_stage as S, workloads as W, samplers
+    par, aux = W.cfg4()
+    Sigma = par["Sigma"]
+    d = Sigma.shape[0]
+    S.whiten_box_device(Sigma[:64, :64] + np.eye(64))          # warm-up (module load, pool)
+    t0 = time.perf_counter(); U = S.whiten_box_device(Sigma); t_dev = time.perf_counter() - t0
+    t0 = time.perf_counter(); Uh = samplers.whiten_box(None, Sigma, "ul"); t_host = time.perf_counter() - t0
+    print(f"whiten d={d}: device {t_dev*1e3:.1f} ms (incl. 64 MB of PCIe copies), host LAPACK {t_host*1e3:.1f} ms")
+    nS = np.linalg.norm(Sigma)
+    assert np.linalg.norm(U @ U.T - Sigma) <= 50 * d * EPS * nS
+    assert np.linalg.norm(U @ U.T - Sigma) <= 4 * max(np.linalg.norm(Uh @ Uh.T - Sigma), d * EPS * nS)
+    Lam = aux["Lambda"]
+    Lp = S.lambda_pinv_device(Lam)
+    assert np.max(np.abs(Lp @ Lam - np.eye(Lam.shape[1]))) <= 1e-11
