@@ -234,6 +234,18 @@ int lqg_eta_params(int32_t d, int32_t m, const double* Lambda, const double* mu,
                    const double* Sigma, double nugget, const lqg_opts* opts,
                    double* eta_mu, double* eta_map, double* Sigma_eta);
 
+/* Constrained MAP: min 1/2 x'Dx - dvec'x  s.t.  A x >= b, i.e. quadprog::solve.QP(Dmat, dvec,
+ * t(A), b)$solution as called at R/lineqGP.R:530 and R/lineqAGP.R:431 (quadprog itself is not
+ * vendored in the reference: a Mehrotra predictor-corrector interior-point method replaces its
+ * active-set iteration; both return the unique minimiser).  D n x n symmetric positive definite,
+ * dvec[n], A mc x n column-major, b[mc] finite; mc = 0 returns solve(D, dvec).
+ * tol <= 0 -> 1e-10 (relative KKT residuals), max_iter <= 0 -> 200; *iters nullable.
+ * LQG_ERR_NOT_PD when D is not positive definite, LQG_ERR_BUDGET when max_iter is exhausted
+ * (x_out then holds the last iterate).                                                        */
+int lqg_solve_qp(int32_t n, int32_t mc, const double* D, const double* dvec, const double* A,
+                 const double* b, double tol, int32_t max_iter, const lqg_opts* opts,
+                 double* x_out, int32_t* iters);
+
 /* Lambda^+ (m x d) with Lambda^+ eta = qr.solve(Lambda, eta) (R/lineqGP.R:639,
  * R/lineqAGP.R:575) for a full-column-rank Lambda (d x m, d >= m): normal equations
  * (Lambda'Lambda) X = Lambda' by blocked Cholesky, followed by one step of iterative refinement

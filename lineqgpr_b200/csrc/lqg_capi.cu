@@ -1051,6 +1051,129 @@ extern "C" int lqg_lambda_pinv(int32_t d, int32_t m, const double* Lambda, const
   return LQG_OK;
 }
 
+extern "C" int lqg_solve_qp(int32_t n, int32_t mc, const double* D, const double* dvec, const double* A,
+                            const double* b, double tol, int32_t max_iter, const lqg_opts* opts_,
+                            double* x_out, int32_t* iters) {
+  if (!have_device()) return LQG_ERR_CUDA;
+  const lqg_opts o = opts_ ? *opts_ : default_opts();
+  if (n <= 0 || n > 32768 || mc < 0 || !D || !dvec || !x_out || (mc > 0 && (!A || !b))) {
+    set_error("lqg_solve_qp: invalid argument (n=%d mc=%d)", n, mc);
+    return LQG_ERR_INVALID;
+  }
+  if (tol <= 0.0) tol = 1e-10;
+  if (max_iter <= 0) max_iter = 200;
+  cudaStream_t st = (cudaStream_t)o.stream;
+  DevBuf::cur_stream = st;
+  const int mem = o.mem;
+  const size_t nn = (size_t)n * n, cn = (size_t)mc * n;
+  int rc;
+  std::vector<double> h_dvec, h_b;
+  if ((rc = fetch_host(h_dvec, dvec, n, mem, st))) return rc;
+  if (mc > 0 && (rc = fetch_host(h_b, b, mc, mem, st))) return rc;
+  double scale_d = 1.0, scale_p = 1.0;
+  for (double v : h_dvec) scale_d = std::max(scale_d, std::fabs(v));
+  for (double v : h_b) {
+    if (!std::isfinite(v)) { set_error("lqg_solve_qp: b must be finite (drop rows with infinite bounds)"); return LQG_ERR_INVALID; }
+    scale_p = std::max(scale_p, std::fabs(v));
+  }
+  Input i_D, i_dv, i_A, i_b;
+  if ((rc = i_D.stage(D, nn, mem, st)) || (rc = i_dv.stage(dvec, n, mem, st))) return rc;
+  if (mc > 0 && ((rc = i_A.stage(A, cn, mem, st)) || (rc = i_b.stage(b, mc, mem, st)))) return rc;
+
+  DevBuf b_L, b_winv, b_H, b_AW, b_vn, b_vc, b_scal;
+  LQG_CUDA_TRY(b_L.alloc(nn * sizeof(double)));
+  LQG_CUDA_TRY(b_winv.alloc(chol_winv_elems(n) * sizeof(double)));
+  LQG_CUDA_TRY(b_vn.alloc((size_t)4 * n * sizeof(double)));
+  double* x = b_vn.as<double>(); double* rd = x + n; double* rhs = rd + n; double* tn = rhs + n;
+  double* Lc = b_L.as<double>(); double* Winv = b_winv.as<double>();
+  int bad = 0;
+  // x = solve(D, dvec)
+  if ((rc = chol_device(n, i_D.dev, 0, Lc, Winv, &bad, st))) return rc;
+  if (bad) { set_error("lqg_solve_qp: Dmat is not positive definite (pivot %d)", bad); fold_launches(); return LQG_ERR_NOT_PD; }
+  LQG_CUDA_TRY(cudaMemcpyAsync(x, i_dv.dev, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  LQG_CUDA_TRY(launch_chol_solve(n, Lc, n, Winv, x, n, tn, n, 1, st));
+  int it = 0;
+  bool converged = mc == 0;
+  if (mc > 0) {
+    LQG_CUDA_TRY(b_H.alloc(nn * sizeof(double)));
+    LQG_CUDA_TRY(b_AW.alloc(cn * sizeof(double)));
+    LQG_CUDA_TRY(b_vc.alloc((size_t)8 * mc * sizeof(double)));
+    LQG_CUDA_TRY(b_scal.alloc(8 * sizeof(double)));
+    double* H = b_H.as<double>(); double* AW = b_AW.as<double>(); double* scal = b_scal.as<double>();
+    double* s = b_vc.as<double>(); double* lam = s + mc; double* ds = lam + mc; double* dl = ds + mc;
+    double* rp = dl + mc; double* t = rp + mc; double* rcv = t + mc; double* Ax = rcv + mc;
+    const double* Ad = i_A.dev; const double* bd = i_b.dev;
+    double h[8];
+    auto read_scal = [&]() -> int {
+      LQG_CUDA_TRY(cudaMemcpyAsync(h, scal, 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
+      LQG_CUDA_TRY(cudaStreamSynchronize(st));
+      return LQG_OK;
+    };
+    // one Newton step of the reduced KKT system for the complementarity target chosen by `corrector`
+    auto newton = [&](int corrector, double sigma_mu) -> int {
+      LQG_CUDA_TRY(launch_qp_prepare(n, mc, corrector, sigma_mu, s, lam, rp, rd, ds, dl, rcv, t, rhs, st));
+      LQG_CUDA_TRY(launch_gemm(true, false, n, 1, mc, 1.0, Ad, mc, t, mc, 1.0, rhs, n, 0, st));    // rhs += A' t
+      LQG_CUDA_TRY(launch_chol_solve(n, Lc, n, Winv, rhs, n, tn, n, 1, st));                        // dx
+      LQG_CUDA_TRY(launch_gemm(false, false, mc, 1, n, 1.0, Ad, mc, rhs, n, 1.0, ds, mc, 0, st));   // ds = A dx + rp
+      LQG_CUDA_TRY(launch_qp_step(mc, s, lam, ds, rcv, dl, scal, st));
+      return read_scal();
+    };
+    LQG_CUDA_TRY(launch_gemm(false, false, mc, 1, n, 1.0, Ad, mc, x, n, 0.0, Ax, mc, 0, st));
+    LQG_CUDA_TRY(launch_qp_init(mc, Ax, bd, s, lam, st));
+    for (; it < max_iter; ++it) {
+      // rd = D x - dvec - A' lam;  rp = A x - s - b;  mu = s.lam / mc
+      LQG_CUDA_TRY(launch_qp_neg_copy(n, i_dv.dev, rd, st));
+      LQG_CUDA_TRY(launch_gemm(false, false, n, 1, n, 1.0, i_D.dev, n, x, n, 1.0, rd, n, 0, st));
+      LQG_CUDA_TRY(launch_gemm(true, false, n, 1, mc, -1.0, Ad, mc, lam, mc, 1.0, rd, n, 0, st));
+      LQG_CUDA_TRY(launch_gemm(false, false, mc, 1, n, 1.0, Ad, mc, x, n, 0.0, Ax, mc, 0, st));
+      LQG_CUDA_TRY(launch_qp_resid(n, mc, rd, Ax, s, bd, lam, rp, scal, st));
+      if ((rc = read_scal())) return rc;
+      const double mu = h[2] / mc;
+      if (!(std::isfinite(h[0]) && std::isfinite(h[1]) && std::isfinite(mu))) {
+        set_error("lqg_solve_qp: the iteration diverged (non-finite residuals at iteration %d)", it);
+        fold_launches();
+        return LQG_ERR_INVALID;
+      }
+      if (h[0] < tol * scale_d * 1e3 && h[1] < tol * scale_p && mu < tol * scale_p) { converged = true; break; }
+      // H = D + A' diag(lam/s) A = Lc Lc'
+      LQG_CUDA_TRY(launch_qp_scale_rows(mc, n, Ad, lam, s, AW, st));
+      LQG_CUDA_TRY(cudaMemcpyAsync(H, i_D.dev, nn * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      LQG_CUDA_TRY(launch_gemm(true, false, n, n, mc, 1.0, Ad, mc, AW, mc, 1.0, H, n, 0, st));
+      if ((rc = chol_device(n, H, 0, Lc, Winv, &bad, st))) return rc;
+      if (bad) {                                                     // same rescue as the host restatement
+        std::vector<double> diag(n);
+        LQG_CUDA_TRY(cudaMemcpy2DAsync(diag.data(), sizeof(double), H, (size_t)(n + 1) * sizeof(double), sizeof(double), n,
+                                       cudaMemcpyDeviceToHost, st));
+        LQG_CUDA_TRY(cudaStreamSynchronize(st));
+        double tr = 0.0;
+        for (double v : diag) tr += v;
+        LQG_CUDA_TRY(launch_add_diag(n, H, n, 1e-12 * tr / n, st));
+        if ((rc = chol_device(n, H, 0, Lc, Winv, &bad, st))) return rc;
+        if (bad) { set_error("lqg_solve_qp: the KKT matrix is not positive definite at iteration %d", it); fold_launches(); return LQG_ERR_NOT_PD; }
+      }
+      auto amax = [&]() { return std::min(1.0, std::min(h[3], h[4])); };
+      if ((rc = newton(0, 0.0))) return rc;                          // predictor (affine scaling)
+      const double a_aff = amax();
+      LQG_CUDA_TRY(launch_qp_muaff(mc, a_aff, s, lam, ds, dl, scal, st));
+      if ((rc = read_scal())) return rc;
+      const double mu_aff = h[5] / mc;
+      const double sigma = (mu_aff / mu) * (mu_aff / mu) * (mu_aff / mu);
+      if ((rc = newton(1, sigma * mu))) return rc;                   // corrector
+      const double a = 0.995 * amax();
+      LQG_CUDA_TRY(launch_qp_update(n, mc, a, x, rhs, s, ds, lam, dl, st));
+    }
+  }
+  if (iters) *iters = it;
+  if ((rc = deliver(x_out, x, n, mem, st))) return rc;
+  LQG_CUDA_TRY(cudaStreamSynchronize(st));
+  fold_launches();
+  if (!converged) {
+    set_error("lqg_solve_qp: no convergence in %d iterations", max_iter);
+    return LQG_ERR_BUDGET;
+  }
+  return LQG_OK;
+}
+
 // ===========================================================================================
 extern "C" int lqg_bands(int32_t n_t, int64_t N, const double* ysim, int64_t ld, const double* probs,
                          int32_t nprobs, double* mean, double* qtls, const lqg_opts* opts_,

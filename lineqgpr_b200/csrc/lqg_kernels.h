@@ -122,6 +122,23 @@ cudaError_t launch_transpose(int rows, int cols, const double* in, int64_t ldi, 
                              cudaStream_t st);
 cudaError_t launch_axpy(size_t n, double alpha, const double* x, double* y, cudaStream_t st);
 
+// ---- interior-point QP vector kernels (lqg_qp.cu); scal = 6 doubles -------------------------
+cudaError_t launch_qp_init(int mc, const double* Ax, const double* b, double* s, double* lam, cudaStream_t st);
+cudaError_t launch_qp_neg_copy(int n, const double* src, double* dst, cudaStream_t st);
+cudaError_t launch_qp_resid(int n, int mc, const double* rd, const double* Ax, const double* s, const double* b,
+                            const double* lam, double* rp, double* scal, cudaStream_t st);
+cudaError_t launch_qp_scale_rows(int mc, int n, const double* A, const double* lam, const double* s, double* AW,
+                                 cudaStream_t st);
+cudaError_t launch_qp_prepare(int n, int mc, int corrector, double sigma_mu, const double* s, const double* lam,
+                              const double* rp, const double* rd, double* ds, const double* dl, double* rc,
+                              double* t, double* rhs, cudaStream_t st);
+cudaError_t launch_qp_step(int mc, const double* s, const double* lam, const double* ds, const double* rc,
+                           double* dl, double* scal, cudaStream_t st);
+cudaError_t launch_qp_muaff(int mc, double a, const double* s, const double* lam, const double* ds,
+                            const double* dl, double* scal, cudaStream_t st);
+cudaError_t launch_qp_update(int n, int mc, double a, double* x, const double* dx, double* s, const double* ds,
+                             double* lam, const double* dl, cudaStream_t st);
+
 // ---- RSM (lqg_rsm.cu) -------------------------------------------------------------------
 struct RsmParams {
   int d;

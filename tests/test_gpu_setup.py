@@ -135,3 +135,70 @@ def test_cfg4_scale_setup(lqg):
     Lam = aux["Lambda"]
     Lp = S.lambda_pinv_device(Lam)
     assert np.max(np.abs(Lp @ Lam - np.eye(Lam.shape[1]))) <= 1e-11
+
+
+def _kkt_ok(D, dvec, A, b, x, tol):
+    """x minimises 1/2 x'Dx - dvec'x s.t. Ax >= b iff the gradient D x - dvec is a non-negative
+    combination of the active rows; checked by a non-negative least-squares fit on those rows."""
+    import scipy.optimize as so
+    r = A @ x - b
+    assert r.min() >= -tol
+    g = D @ x - dvec
+    act = r <= 1e-6 * max(1.0, np.abs(b).max())
+    if not act.any():
+        return np.abs(g).max() <= 1e-6 * max(1.0, np.abs(dvec).max())
+    lam, res = so.nnls(A[act].T, g)
+    return res <= 1e-6 * max(1.0, np.linalg.norm(g))
+
+
+@pytest.mark.parametrize("n,mc,seed", [(5, 8, 0), (40, 100, 1), (130, 70, 2), (64, 1, 3)])
+def test_solve_qp_matches_host_ipm_and_kkt(lqg, n, mc, seed):
+    from lineqgpr_b200 import setup_stage as S, model as M
+    rng = np.random.default_rng(seed)
+    D = _spd(rng, n, 1e3) * 10
+    dvec = rng.standard_normal(n)
+    A = rng.standard_normal((mc, n))
+    b = A @ rng.standard_normal(n) - np.abs(rng.standard_normal(mc))      # strictly feasible point exists
+    x, it = S.solve_qp_device(D, dvec, A, b, return_iters=True)
+    ref = M.solve_qp(D, dvec, A, b)
+    assert 0 < it < 60
+    assert np.max(np.abs(x - ref)) <= 1e-7 * max(1.0, np.abs(ref).max())
+    assert _kkt_ok(D, dvec, A, b, x, 1e-8)
+
+
+def test_solve_qp_unconstrained_and_errors(lqg):
+    from lineqgpr_b200 import setup_stage as S, _lib
+    rng = np.random.default_rng(9)
+    D = _spd(rng, 30, 100.0)
+    dvec = rng.standard_normal(30)
+    x = S.solve_qp_device(D, dvec, np.zeros((0, 30)), np.zeros(0))
+    assert np.allclose(x, np.linalg.solve(D, dvec), rtol=1e-10, atol=1e-12)
+    with pytest.raises(_lib.LqgError, match="NOT_PD"):
+        S.solve_qp_device(-D, dvec, np.zeros((0, 30)), np.zeros(0))
+    with pytest.raises(_lib.LqgError, match="finite"):
+        S.solve_qp_device(D, dvec, np.eye(30)[:2], np.array([0.0, -np.inf]))
+    with pytest.raises(_lib.LqgError, match="BUDGET"):
+        S.solve_qp_device(D, dvec, np.eye(30), np.full(30, 5.0), max_iter=2)
+
+
+def test_map_qp_of_cfg1_and_cfg4(lqg):
+    """The xi.map programme the reference solves in predict.lineqGP (R/lineqGP.R:524-531) at the
+    cfg1 (m = 100, 99 rows) and cfg4 (m = 1000, 2999 rows) sizes, against the host IPM."""
+    import time
+    from lineqgpr_b200 import setup_stage as S, model as M, workloads as W
+    for name, build in (("cfg1", W.cfg1), ("cfg4", W.cfg4)):
+        par, aux = build()
+        mdl = aux["model"] if "model" in aux else aux["lineq_model"]
+        pred = M.predict_lineqGP(mdl, aux["xtest"], solve_map=False)
+        Sigma = pred["Sigma"]
+        inv = np.linalg.inv(Sigma); inv = (inv + inv.T) / 2
+        dvec = pred["mu"] @ inv
+        A, b = pred["model"]["lineqSys"]["M"], pred["model"]["lineqSys"]["g"]
+        S.solve_qp_device(np.eye(4), np.ones(4), np.eye(4), np.zeros(4))            # warm-up
+        t0 = time.perf_counter(); x, it = S.solve_qp_device(inv, dvec, A, b, return_iters=True); t_dev = time.perf_counter() - t0
+        t0 = time.perf_counter(); ref = M.solve_qp(inv, dvec, A, b); t_host = time.perf_counter() - t0
+        print(f"{name}: QP n={inv.shape[0]} rows={A.shape[0]}: device {t_dev*1e3:.0f} ms ({it} iterations), host IPM {t_host*1e3:.0f} ms")
+        assert (A @ x - b).min() >= -1e-8
+        f = lambda v: 0.5 * v @ inv @ v - dvec @ v
+        assert f(x) <= f(ref) + 1e-6 * max(1.0, abs(f(ref)))
+        assert np.max(np.abs(A @ (x - ref))) <= 1e-5 * max(1.0, np.abs(A @ ref).max())
