@@ -239,6 +239,46 @@ def _chol2inv(S):
     return Li.T @ Li
 
 
+class _HostAlgebra:
+    """The dense set-up algebra of predict.* as R runs it (LAPACK on the host)."""
+    chol2inv = staticmethod(_chol2inv)
+    solve_qp = staticmethod(solve_qp)
+
+    @staticmethod
+    def min_eig_nonpositive(S):
+        return np.linalg.eigvalsh((S + S.T) / 2).min() <= 0
+
+
+class _DeviceAlgebra:
+    """The same three operations through the C-ABI set-up stage (csrc/lqg_linalg.cu, lqg_qp.cu);
+    raises when the CUDA library or a device is missing (no fallback)."""
+
+    @staticmethod
+    def chol2inv(S):
+        from . import setup_stage as st
+        S = np.asarray(S, float)
+        inv = st.solve_spd(S, np.eye(S.shape[0]))
+        return (inv + inv.T) / 2
+
+    @staticmethod
+    def min_eig_nonpositive(S):
+        from . import setup_stage as st
+        return not st.is_positive_definite(S)
+
+    @staticmethod
+    def solve_qp(D, dvec, A, b):
+        from . import setup_stage as st
+        return st.solve_qp_device(D, dvec, A, b)
+
+
+def _algebra(setup):
+    if setup == "host":
+        return _HostAlgebra
+    if setup == "device":
+        return _DeviceAlgebra
+    raise ValueError(f"unknown setup {setup!r} (host | device)")
+
+
 # --------------------------------------------------------------------------- lineqGP
 
 
@@ -324,8 +364,10 @@ def augment_lineqGP(model):
     return model
 
 
-def predict_lineqGP(model, xtest, solve_map=True):
-    """predict.lineqGP, R/lineqGP.R:493-535.  solve_map=False skips the QP (xi.map = None)."""
+def predict_lineqGP(model, xtest, solve_map=True, setup="host"):
+    """predict.lineqGP, R/lineqGP.R:493-535.  solve_map=False skips the QP (xi.map = None).
+    setup="device" runs chol2inv, the positive-definiteness test and the QP on the GPU."""
+    la = _algebra(setup)
     model = augment_lineqGP(model)
     xtest = np.asarray(xtest, float)
     pred = dict(Lambda=model["Lambda"], lb=model["lb"], ub=model["ub"])
@@ -335,15 +377,15 @@ def predict_lineqGP(model, xtest, solve_map=True):
     PhiGammaPhit = Phi @ GammaPhit
     if model["varnoise"] != 0:
         PhiGammaPhit = PhiGammaPhit + model["varnoise"] * np.eye(Phi.shape[0])
-    inv = _chol2inv(PhiGammaPhit)                                            # :518
+    inv = la.chol2inv(PhiGammaPhit)                                          # :518
     pred["mu"] = (GammaPhit @ inv @ y).ravel()
     Sigma = Gamma - GammaPhit @ inv @ GammaPhit.T                            # :520
-    if np.linalg.eigvalsh((Sigma + Sigma.T) / 2).min() <= 0:                 # :527-528
+    if la.min_eig_nonpositive(Sigma):                                        # :527-528
         Sigma = Sigma + model["kernParam"]["nugget"] * np.eye(Sigma.shape[0])
     pred["Sigma"] = Sigma
     if solve_map:
-        invSigma = _chol2inv(Sigma)
-        pred["xi.map"] = solve_qp(invSigma, pred["mu"] @ invSigma, model["lineqSys"]["M"], model["lineqSys"]["g"])
+        invSigma = la.chol2inv(Sigma)
+        pred["xi.map"] = la.solve_qp(invSigma, pred["mu"] @ invSigma, model["lineqSys"]["M"], model["lineqSys"]["g"])
     else:
         pred["xi.map"] = None
     pred["model"] = model
@@ -420,8 +462,10 @@ def augment_lineqAGP(model):
     return model
 
 
-def predict_lineqAGP(model, xtest, solve_map=True):
-    """predict.lineqAGP, R/lineqAGP.R:329-443 (the mt >= nt branch and the mt < nt Woodbury branch)."""
+def predict_lineqAGP(model, xtest, solve_map=True, setup="host"):
+    """predict.lineqAGP, R/lineqAGP.R:329-443 (the mt >= nt branch and the mt < nt Woodbury branch).
+    setup="device": chol2inv and the QP on the GPU."""
+    la = _algebra(setup)
     model = augment_lineqAGP(model)
     xtest = np.asarray(xtest, float).reshape(-1, model["d"])
     D = model["localParam"]["ngroups"]
@@ -441,15 +485,15 @@ def predict_lineqAGP(model, xtest, solve_map=True):
         inv = (np.eye(nt) - Ls.T @ Ls) / model["varnoise"]
     else:                                                                    # :377-381
         PGP = bigPhi @ bigGamma @ bigPhi.T + model["nugget"] * np.eye(nt)
-        inv = _chol2inv(PGP + model["varnoise"] * np.eye(nt))
+        inv = la.chol2inv(PGP + model["varnoise"] * np.eye(nt))
     temp = bigGamma @ bigPhi.T @ inv                                         # :403
     pred["muAll"] = (temp @ y).ravel()
     C = temp @ bigPhi @ bigGamma
     C = (C + C.T) / 2
     pred["SigmaAll"] = bigGamma - C                                          # :407
     if solve_map:
-        invS = _chol2inv(pred["SigmaAll"] + model["nugget"] * np.eye(mt))    # :429
-        pred["xiAll.map"] = solve_qp(invS, pred["muAll"] @ invS, model["lineqSys"]["MAll"], model["lineqSys"]["gAll"])
+        invS = la.chol2inv(pred["SigmaAll"] + model["nugget"] * np.eye(mt))  # :429
+        pred["xiAll.map"] = la.solve_qp(invS, pred["muAll"] @ invS, model["lineqSys"]["MAll"], model["lineqSys"]["gAll"])
     else:
         pred["xiAll.map"] = None
     pred["model"] = model

@@ -14,7 +14,7 @@ What stays on the host, exactly where the reference has it on the host: the one-
 whitening algebra (solve, chol, triangular inverse).  Everything per-sample runs on the GPU.
 Extensions (all optional keys of `control`): "n.chains" (independent chains; 1 reproduces the
 reference's single serial chain), "seed", "prepass", "injected", "max.restarts",
-"chain.offset", "U" (a precomputed factor), "whiten" ("ul" | "tmg", see whiten_box).
+"chain.offset", "U" (a precomputed factor), "whiten" ("ul" | "tmg" | "device", see whiten_box).
 """
 from __future__ import annotations
 

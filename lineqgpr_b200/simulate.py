@@ -104,20 +104,44 @@ def lambda_pinv(Lambda):
     return np.linalg.solve(R, Q.T)
 
 
+def _setup_mode(control):
+    """control["setup"]: "host" (numpy/LAPACK, as R does it) or "device" (the C-ABI set-up stage:
+    QP, factorizations, eta-space parameters and Lambda^+ on the GPU)."""
+    mode = (control or {}).get("setup", "host")
+    if mode not in ("host", "device"):
+        raise ValueError(f"unknown setup {mode!r} (host | device)")
+    return mode
+
+
+def _pinv(Lambda, setup):
+    if setup == "device":
+        from .setup_stage import lambda_pinv_device
+        return lambda_pinv_device(Lambda)
+    return lambda_pinv(Lambda)
+
+
 def simulate_lineqGP(model, nsim=1, seed=None, xtest=None, control=None):
     """simulate.lineqGP (R/lineqGP.R:601-643)."""
+    setup = _setup_mode(control)
     t0 = time.perf_counter()
-    pred = M.predict_lineqGP(model, xtest)
+    pred = M.predict_lineqGP(model, xtest, setup=setup)
     predtime = time.perf_counter() - t0
     mdl = pred.pop("model")
     Lam = pred["Lambda"]
-    eta_mu = Lam @ pred["mu"]                                           # :611
-    eta_map = Lam @ pred["xi.map"]                                      # :612
-    Sigma_eta = Lam @ pred["Sigma"] @ Lam.T                             # :613
-    Sigma_eta = Sigma_eta + mdl["kernParam"]["nugget"] * np.eye(Sigma_eta.shape[0])   # :614
+    if setup == "device":
+        from . import setup_stage as st
+        eta_mu, eta_map, Sigma_eta = st.eta_params(Lam, pred["mu"], pred["xi.map"], pred["Sigma"],
+                                                   mdl["kernParam"]["nugget"])          # :611-614
+    else:
+        eta_mu = Lam @ pred["mu"]                                           # :611
+        eta_map = Lam @ pred["xi.map"]                                      # :612
+        Sigma_eta = Lam @ pred["Sigma"] @ Lam.T                             # :613
+        Sigma_eta = Sigma_eta + mdl["kernParam"]["nugget"] * np.eye(Sigma_eta.shape[0])   # :614
     ctl = dict(mdl["localParam"]["samplingParams"])                     # :617
     ctl["mvec"] = mdl["localParam"]["mvec"]; ctl["constrType"] = mdl["constrType"]   # :618-619
     ctl.update(control or {})
+    if setup == "device":
+        ctl.setdefault("whiten", "device")
     if seed is not None:
         ctl.setdefault("seed", int(seed))                               # set.seed(seed) :624
     tmvPar = {"mu": eta_mu, "map": eta_map, "Sigma": Sigma_eta, "lb": pred["lb"], "ub": pred["ub"],
@@ -125,7 +149,7 @@ def simulate_lineqGP(model, nsim=1, seed=None, xtest=None, control=None):
     t0 = time.perf_counter()
     eta = tmvrnorm(tmvPar, nsim, ctl)                                   # :626
     simtime = time.perf_counter() - t0
-    xi_sim = dgemm(lambda_pinv(Lam), eta)                               # :639
+    xi_sim = dgemm(_pinv(Lam, setup), eta)                              # :639
     ysim = dgemm(pred["Phi.test"], xi_sim)                              # :640
     return dict(cls="lineqGP", x=mdl["x"], y=mdl["y"], xtest=xtest, **{"Phi.test": pred["Phi.test"]},
                 predtime=predtime, simtime=simtime, **{"xi.map": pred["xi.map"], "xi.sim": xi_sim},
@@ -134,17 +158,25 @@ def simulate_lineqGP(model, nsim=1, seed=None, xtest=None, control=None):
 
 def simulate_lineqAGP(model, nsim=1, seed=None, xtest=None, control=None):
     """simulate.lineqAGP (R/lineqAGP.R:520-596)."""
+    setup = _setup_mode(control)
     t0 = time.perf_counter()
-    pred = M.predict_lineqAGP(model, xtest)
+    pred = M.predict_lineqAGP(model, xtest, setup=setup)
     predtime = time.perf_counter() - t0
     mdl = pred.pop("model")
     LamAll = mdl["lineqSys"]["LambdaAll"]
-    eta_map = LamAll @ pred["xiAll.map"]                                # :558
-    Sigma_eta = LamAll @ pred["SigmaAll"] @ LamAll.T                    # :559
-    Sigma_eta = Sigma_eta + mdl["nugget"] * np.eye(Sigma_eta.shape[0])  # :560
+    if setup == "device":
+        from . import setup_stage as st
+        _, eta_map, Sigma_eta = st.eta_params(LamAll, pred["xiAll.map"], pred["xiAll.map"], pred["SigmaAll"],
+                                              mdl["nugget"])            # :558-560
+    else:
+        eta_map = LamAll @ pred["xiAll.map"]                                # :558
+        Sigma_eta = LamAll @ pred["SigmaAll"] @ LamAll.T                    # :559
+        Sigma_eta = Sigma_eta + mdl["nugget"] * np.eye(Sigma_eta.shape[0])  # :560
     ctl = dict(mdl["localParam"]["samplingParams"])
     ctl["mvec"] = mdl["localParam"]["mtotal"]; ctl["constrType"] = mdl["constrType"]   # :564-565
     ctl.update(control or {})
+    if setup == "device":
+        ctl.setdefault("whiten", "device")
     if seed is not None:
         ctl.setdefault("seed", int(seed))
     tmvPar = {"mu": eta_map, "Sigma": Sigma_eta, "lb": mdl["lineqSys"]["lb"], "ub": mdl["lineqSys"]["ub"],
@@ -152,7 +184,7 @@ def simulate_lineqAGP(model, nsim=1, seed=None, xtest=None, control=None):
     t0 = time.perf_counter()
     etaAll = tmvrnorm(tmvPar, nsim, ctl)                                # :573
     simtime = time.perf_counter() - t0
-    xiAll_sim = dgemm(lambda_pinv(LamAll), etaAll)                      # :575
+    xiAll_sim = dgemm(_pinv(LamAll, setup), etaAll)                     # :575
     return dict(cls="lineqAGP", x=mdl["x"], y=mdl["y"], xtest=xtest, **{"Phi.test": pred["Phi.test"]},
                 predtime=predtime, simtime=simtime, muAll=pred["muAll"],
                 **{"xiAll.map": pred["xiAll.map"], "xiAll.sim": xiAll_sim, "PhiAll.test": pred["PhiAll.test"]},

@@ -19,12 +19,19 @@ tmvrnorm.HMC <- function(object, nsim, control = list(burn.in = 1e2), ...) {
   lb <- rep_len(tmvPar$lb, d); ub <- rep_len(tmvPar$ub, d)
   epsilon <- 1e-9
   init_vec <- pmin(pmax(tmvPar$map, lb + epsilon), ub - epsilon)
-  # whitening exactly as tmg::rtmg does it on the host (tmg/R/tmg.R:15-27)
-  H <- solve(tmvPar$Sigma)
-  M <- (H + t(H)) / 2
-  if (any(eigen(M, symmetric = TRUE, only.values = TRUE)$values <= 0))
-    stop("Error: M must be positive definite.")
-  Ri <- solve(chol(M))                      # upper triangular, Ri %*% t(Ri) = Sigma
+  # whitening: the Ri of tmg::rtmg (tmg/R/tmg.R:15-27: H <- solve(Sigma); M <- (H+t(H))/2; eigen test;
+  # Ri <- solve(chol(M))) is the unique upper-triangular factor with Ri %*% t(Ri) = Sigma; the device
+  # computes it directly (reversed blocked Cholesky) and stops with tmg's message when M is not
+  # positive definite.  control$whiten = "host" keeps the literal R sequence.
+  if (identical(control$whiten, "host")) {
+    H <- solve(tmvPar$Sigma)
+    M <- (H + t(H)) / 2
+    if (any(eigen(M, symmetric = TRUE, only.values = TRUE)$values <= 0))
+      stop("Error: M must be positive definite.")
+    Ri <- solve(chol(M))
+  } else {
+    Ri <- .Call("lqg_whiten_box_call", tmvPar$Sigma)
+  }
   n.per <- ceiling(nsim / control$n.chains)
   seed <- sample(1:10000000, 1)             # tmg/R/tmg.R:102: set.seed() still determines the run
   xi <- .Call("lqg_hmc_box_call", as.double(tmvPar$mu), Ri, tmvPar$Sigma, as.double(lb), as.double(ub),
@@ -67,5 +74,13 @@ tmvrnorm.ExpT <- function(object, nsim, control = NULL, ...) {
 # simulate.lineqGP tail (R/lineqGP.R:639-640) on the GPU:
 #   simModel$xi.sim <- .Call("lqg_dgemm_call", qr.solve(pred$Lambda, diag(nrow(pred$Lambda))), eta)
 #   simModel$ysim   <- .Call("lqg_dgemm_call", pred$Phi.test, simModel$xi.sim)
+# set-up stage of predict.lineqGP / simulate.lineqGP on the GPU (rshim/lqg_rcall.c, second half):
+#   R/lineqGP.R:518   invPhiGammaPhit <- chol2inv(chol(PhiGammaPhit))     -> .Call("lqg_solve_spd_call", PhiGammaPhit, diag(n))
+#   R/lineqGP.R:527   if (min(eigen(pred$Sigma)$values) <= 0)             -> if (!.Call("lqg_is_pd_call", pred$Sigma))
+#   R/lineqGP.R:529   invSigma <- chol2inv(chol(pred$Sigma))              -> .Call("lqg_solve_spd_call", pred$Sigma, diag(m))
+#   R/lineqGP.R:530   solve.QP(invSigma, t(mu) %*% invSigma, t(M), g)$solution
+#                                                                         -> .Call("lqg_solve_qp_call", invSigma, mu %*% invSigma, M, g)
+#   R/lineqGP.R:611-614  eta.mu / eta.map / Sigma.eta                     -> .Call("lqg_eta_params_call", Lambda, mu, xi.map, Sigma, nugget)
+#   R/lineqGP.R:639   qr.solve(pred$Lambda, eta)                          -> .Call("lqg_dgemm_call", .Call("lqg_lambda_pinv_call", pred$Lambda), eta)
 # plot.lineqGP bands (R/lineqGPutils.R:422-423):
 #   b <- .Call("lqg_bands_call", ysim, probs); qtls <- b[[2]]; ymean <- b[[1]]

@@ -115,3 +115,71 @@ SEXP lqg_bands_call(SEXP ysim_, SEXP probs_) {
   lqg_check(rc, "lqg_bands");
   return res;
 }
+
+/* ---- set-up stage ------------------------------------- */
+
+/* Ri of tmg:R/tmg.R:27 for M = solve(Sigma): upper U with U %*% t(U) == Sigma */
+SEXP lqg_whiten_box_call(SEXP Sigma_) {
+  const int d = Rf_nrows(Sigma_);
+  SEXP out = PROTECT(Rf_allocMatrix(REALSXP, d, d));
+  int rc = lqg_whiten_box(d, REAL(Sigma_), NULL, REAL(out), NULL);
+  UNPROTECT(1);
+  lqg_check(rc, "lqg_whiten_box");                  /* LQG_ERR_NOT_PD: "Error: M must be positive definite." */
+  return out;
+}
+
+/* min(eigen(S)$values) > 0   (tmg:R/tmg.R:17, R/lineqGP.R:527) */
+SEXP lqg_is_pd_call(SEXP S_) {
+  int bad = 0;
+  int rc = lqg_chol(Rf_nrows(S_), REAL(S_), NULL, NULL, &bad);
+  if (rc != LQG_OK && rc != LQG_ERR_NOT_PD) lqg_check(rc, "lqg_chol");
+  return Rf_ScalarLogical(rc == LQG_OK);
+}
+
+/* solve(A, B), A symmetric positive definite  (chol2inv(chol(A)) %*% B) */
+SEXP lqg_solve_spd_call(SEXP A_, SEXP B_) {
+  const int d = Rf_nrows(A_), nrhs = Rf_isMatrix(B_) ? Rf_ncols(B_) : 1;
+  SEXP out = PROTECT(Rf_isMatrix(B_) ? Rf_allocMatrix(REALSXP, d, nrhs) : Rf_allocVector(REALSXP, d));
+  int rc = lqg_solve_spd(d, nrhs, REAL(A_), REAL(B_), NULL, REAL(out));
+  UNPROTECT(1);
+  lqg_check(rc, "lqg_solve_spd");
+  return out;
+}
+
+/* list(eta.mu, eta.map, Sigma.eta) of R/lineqGP.R:611-614 */
+SEXP lqg_eta_params_call(SEXP Lambda_, SEXP mu_, SEXP map_, SEXP Sigma_, SEXP nugget_) {
+  const int d = Rf_nrows(Lambda_), m = Rf_ncols(Lambda_);
+  SEXP emu = PROTECT(Rf_allocVector(REALSXP, d));
+  SEXP emap = PROTECT(Rf_allocVector(REALSXP, d));
+  SEXP Se = PROTECT(Rf_allocMatrix(REALSXP, d, d));
+  int rc = lqg_eta_params(d, m, REAL(Lambda_), REAL(mu_), REAL(map_), REAL(Sigma_), Rf_asReal(nugget_), NULL,
+                          REAL(emu), REAL(emap), REAL(Se));
+  SEXP res = PROTECT(Rf_allocVector(VECSXP, 3));
+  SET_VECTOR_ELT(res, 0, emu);
+  SET_VECTOR_ELT(res, 1, emap);
+  SET_VECTOR_ELT(res, 2, Se);
+  UNPROTECT(4);
+  lqg_check(rc, "lqg_eta_params");
+  return res;
+}
+
+/* the m x d operator of qr.solve(Lambda, .)  (R/lineqGP.R:639) */
+SEXP lqg_lambda_pinv_call(SEXP Lambda_) {
+  const int d = Rf_nrows(Lambda_), m = Rf_ncols(Lambda_);
+  SEXP out = PROTECT(Rf_allocMatrix(REALSXP, m, d));
+  int rc = lqg_lambda_pinv(d, m, REAL(Lambda_), NULL, REAL(out));
+  UNPROTECT(1);
+  lqg_check(rc, "lqg_lambda_pinv");
+  return out;
+}
+
+/* solve.QP(Dmat, dvec, Amat = t(A), bvec)$solution with A passed untransposed (rows = constraints) */
+SEXP lqg_solve_qp_call(SEXP D_, SEXP dvec_, SEXP A_, SEXP b_) {
+  const int n = Rf_nrows(D_), mc = Rf_length(b_);
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, n));
+  int rc = lqg_solve_qp(n, mc, REAL(D_), REAL(dvec_), mc ? REAL(A_) : NULL, mc ? REAL(b_) : NULL, 0.0, 0, NULL,
+                        REAL(out), NULL);
+  UNPROTECT(1);
+  lqg_check(rc, "lqg_solve_qp");
+  return out;
+}

@@ -27,6 +27,19 @@ A = rng.standard_normal((130, 19)); B = rng.standard_normal((19, 67))
 C, rs = lqg.dgemm(A, B, row_sum=True); assert np.allclose(C, A @ B)
 y = rng.standard_normal((5, 300)); y[0, :100] = y[0, 0]
 m, q = lqg.bands(y, (0.025, 0.5, 0.975)); print("gemm/bands ok", flush=True)
+# set-up stage: blocked Cholesky / solves / QP at ragged sizes (1, 64 +- 1, several blocks)
+from lineqgpr_b200 import setup_stage as S
+for n in (1, 63, 65, 130):
+    Q = rng.standard_normal((n, n)); A = Q @ Q.T + n * np.eye(n)
+    Lf = S.chol(A); assert np.allclose(Lf @ Lf.T, A)
+    Uf = S.whiten_box_device(A); assert np.allclose(Uf @ Uf.T, A)
+    X = S.solve_spd(A, rng.standard_normal((n, 3)))
+    Lam = rng.standard_normal((n + 7, n)); Lp = S.lambda_pinv_device(Lam); assert np.allclose(Lp @ Lam, np.eye(n), atol=1e-8)
+    S.eta_params(Lam, np.ones(n), np.ones(n), A, 1e-6)
+    Aq = rng.standard_normal((2 * n + 1, n)); bq = Aq @ rng.standard_normal(n) - 1.0
+    S.solve_qp_device(A, rng.standard_normal(n), Aq, bq)
+x = lqg.tmvrnorm(dict(W.cfg3()[0], **{"class": "HMC"}), 16, {"burn.in": 1, "n.chains": 4, "seed": 1, "whiten": "device"})
+print("setup stage ok", flush=True)
 from lineqgpr_b200 import _lib
 import os
 print("guard mode", os.environ.get("LQG_GUARD", "0"), "violations", _lib.lib().lqg_guard_violations(), flush=True)

@@ -202,3 +202,28 @@ def test_map_qp_of_cfg1_and_cfg4(lqg):
         f = lambda v: 0.5 * v @ inv @ v - dvec @ v
         assert f(x) <= f(ref) + 1e-6 * max(1.0, abs(f(ref)))
         assert np.max(np.abs(A @ (x - ref))) <= 1e-5 * max(1.0, np.abs(A @ ref).max())
+
+
+def test_simulate_with_device_setup_matches_host_setup(lqg):
+    """simulate.lineqGP / simulate.lineqAGP with control$setup = "device": the QP, the
+    factorizations, eta-space parameters and Lambda^+ computed on the GPU give the same MAP and
+    the same sample paths (to the accuracy two different factorizations allow) as the host set-up."""
+    from lineqgpr_b200 import workloads as W
+    for build in (W.cfg1, W.cfg3):
+        par, aux = build()
+        model = aux["model"]
+        model = dict(model); model["localParam"] = dict(model["localParam"], sampler="HMC")
+        ctl = {"n.chains": 16, "burn.in": 20}
+        a = lqg.simulate(model, nsim=2000, seed=3, xtest=aux["xtest"], control=dict(ctl, setup="host"))
+        b = lqg.simulate(model, nsim=2000, seed=3, xtest=aux["xtest"], control=dict(ctl, setup="device"))
+        assert b["stats"]["violations"] == 0
+        kmap = "xi.map" if "xi.map" in a else "xiAll.map"
+        ksim = "xi.sim" if "xi.sim" in a else "xiAll.sim"
+        assert np.max(np.abs(a[kmap] - b[kmap])) <= 1e-6 * max(1.0, np.abs(a[kmap]).max())
+        sa, sb = a[ksim], b[ksim]
+        assert sa.shape == sb.shape
+        sd = sa.std(axis=1) + 1e-12
+        # same seed, same Philox draws: the two runs follow each other until rounding differences in
+        # the factor change a bounce decision; the path ensembles must agree well within MC error
+        assert np.max(np.abs(sa.mean(axis=1) - sb.mean(axis=1)) / sd) <= 0.25
+        assert np.max(np.abs(np.log(sb.std(axis=1) / sd))) <= 0.25
