@@ -234,6 +234,16 @@ int lqg_eta_params(int32_t d, int32_t m, const double* Lambda, const double* mu,
                    const double* Sigma, double nugget, const lqg_opts* opts,
                    double* eta_mu, double* eta_map, double* Sigma_eta);
 
+/* Hat-basis matrix of an additive model: PhiAll.test = [Phi_1 | ... | Phi_D] with
+ * Phi_k = basisCompute.lineqGP(x[, k], u_k)  (R/lineqGP.R:29-60; R/lineqAGP.R:341-348); D = 1 is
+ * the 1-D lineqGP basis.  x n_t x D column-major (ldx >= n_t), m_k[D] knots per block (always a
+ * HOST array), u the
+ * concatenated increasing knot vectors (sum m_k entries); Phi n_t x sum(m_k) column-major
+ * (ld >= n_t).  Bit-identical to the R expression.  LQG_ERR_INVALID when a point lies outside
+ * its knot range (R fails there on an NA index).                                              */
+int lqg_basis(int32_t n_t, int32_t D, const int32_t* m_k, const double* x, int64_t ldx, const double* u,
+              const lqg_opts* opts, double* Phi, int64_t ld);
+
 /* Constrained MAP: min 1/2 x'Dx - dvec'x  s.t.  A x >= b, i.e. quadprog::solve.QP(Dmat, dvec,
  * t(A), b)$solution as called at R/lineqGP.R:530 and R/lineqAGP.R:431 (quadprog itself is not
  * vendored in the reference: a Mehrotra predictor-corrector interior-point method replaces its

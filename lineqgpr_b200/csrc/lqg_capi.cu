@@ -1051,6 +1051,52 @@ extern "C" int lqg_lambda_pinv(int32_t d, int32_t m, const double* Lambda, const
   return LQG_OK;
 }
 
+extern "C" int lqg_basis(int32_t n_t, int32_t D, const int32_t* m_k, const double* x, int64_t ldx, const double* u,
+                         const lqg_opts* opts_, double* Phi, int64_t ld) {
+  if (!have_device()) return LQG_ERR_CUDA;
+  const lqg_opts o = opts_ ? *opts_ : default_opts();
+  if (n_t <= 0 || D <= 0 || !m_k || !x || !u || !Phi || ldx < n_t || ld < n_t) {
+    set_error("lqg_basis: invalid argument (n_t=%d D=%d ldx=%lld ld=%lld)", n_t, D, (long long)ldx, (long long)ld);
+    return LQG_ERR_INVALID;
+  }
+  size_t mt = 0;
+  for (int k = 0; k < D; ++k) {
+    if (m_k[k] < 2) { set_error("lqg_basis: block %d has %d knots (needs >= 2)", k, m_k[k]); return LQG_ERR_INVALID; }
+    mt += (size_t)m_k[k];
+  }
+  cudaStream_t st = (cudaStream_t)o.stream;
+  DevBuf::cur_stream = st;
+  const int mem = o.mem;
+  int rc;
+  Input i_x, i_u;
+  if ((rc = i_x.stage(x, (size_t)ldx * (D - 1) + n_t, mem, st)) || (rc = i_u.stage(u, mt, mem, st))) return rc;
+  DevBuf b_phi, b_flag;
+  double* d_phi = Phi;
+  const size_t n_phi = (size_t)ld * (mt - 1) + n_t;
+  if (mem == LQG_MEM_HOST) { LQG_CUDA_TRY(b_phi.alloc(n_phi * sizeof(double))); d_phi = b_phi.as<double>(); }
+  LQG_CUDA_TRY(b_flag.alloc(sizeof(int)));
+  LQG_CUDA_TRY(cudaMemsetAsync(b_flag.p, 0, sizeof(int), st));
+  size_t off = 0;
+  for (int k = 0; k < D; ++k) {
+    LQG_CUDA_TRY(launch_basis_hat(n_t, m_k[k], i_x.dev + (size_t)k * ldx, i_u.dev + off, d_phi + off * ld, ld,
+                                  b_flag.as<int>(), st));
+    off += (size_t)m_k[k];
+  }
+  int flag = 0;
+  LQG_CUDA_TRY(cudaMemcpyAsync(&flag, b_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (mem == LQG_MEM_HOST) {
+    if (ld == n_t) LQG_CUDA_TRY(cudaMemcpyAsync(Phi, d_phi, n_phi * sizeof(double), cudaMemcpyDeviceToHost, st));
+    else LQG_CUDA_TRY(cudaMemcpy2DAsync(Phi, ld * sizeof(double), d_phi, ld * sizeof(double), n_t * sizeof(double), mt, cudaMemcpyDeviceToHost, st));
+  }
+  LQG_CUDA_TRY(cudaStreamSynchronize(st));
+  fold_launches();
+  if (flag) {
+    set_error("basisCompute.lineqGP: x outside the knot range [u_1, u_m]");
+    return LQG_ERR_INVALID;
+  }
+  return LQG_OK;
+}
+
 extern "C" int lqg_solve_qp(int32_t n, int32_t mc, const double* D, const double* dvec, const double* A,
                             const double* b, double tol, int32_t max_iter, const lqg_opts* opts_,
                             double* x_out, int32_t* iters) {

@@ -139,6 +139,10 @@ cudaError_t launch_qp_muaff(int mc, double a, const double* s, const double* lam
 cudaError_t launch_qp_update(int n, int mc, double a, double* x, const double* dx, double* s, const double* ds,
                              double* lam, const double* dl, cudaStream_t st);
 
+// ---- hat basis (lqg_basis.cu) ------------------------------------------------------------------
+cudaError_t launch_basis_hat(int n_t, int m, const double* x, const double* u, double* Phi, int64_t ld, int* flag,
+                             cudaStream_t st);
+
 // ---- RSM (lqg_rsm.cu) -------------------------------------------------------------------
 struct RsmParams {
   int d;

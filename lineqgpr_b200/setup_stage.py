@@ -105,3 +105,21 @@ def solve_qp_device(D, dvec, A, b, tol=1e-10, max_iter=200, return_iters=False):
                               L.ptr(x), C.byref(it))
     L.check(rc, "solve_qp")
     return (x, it.value) if return_iters else x
+
+
+def basis_device(x, ulist):
+    """[Phi_1 | ... | Phi_D], Phi_k = basisCompute.lineqGP(x[, k], u_k) (R/lineqGP.R:29-60,
+    R/lineqAGP.R:341-348) computed on the GPU; ulist = one knot vector (1-D) or a list of D."""
+    if not isinstance(ulist, (list, tuple)):
+        ulist = [ulist]
+    D = len(ulist)
+    x = L.f64(np.asarray(x, float).reshape(-1, D))
+    n_t = x.shape[0]
+    m_k = np.ascontiguousarray([np.size(u) for u in ulist], dtype=np.int32)
+    u = np.ascontiguousarray(np.concatenate([np.ravel(u) for u in ulist]), dtype=np.float64)
+    Phi = np.empty((n_t, int(m_k.sum())), order="F")
+    rc = L.lib().lqg_basis(n_t, D, L.ptr(m_k), L.ptr(x), n_t, L.ptr(u), L.make_opts(), L.ptr(Phi), n_t)
+    if rc == 1 and "knot range" in L.last_error():
+        raise ValueError(L.last_error())
+    L.check(rc, "basis")
+    return Phi

@@ -48,17 +48,31 @@ def bands(ysim, probs=(0.025, 0.975)):
     return mean, q
 
 
-def paths_bands(Phi_test, xi_sim, probs=(0.025, 0.975), slab_rows=None, return_ysim=False):
+def paths_bands(Phi_test, xi_sim, probs=(0.025, 0.975), slab_rows=None, return_ysim=False, xtest=None, ulist=None):
     """Band summaries of ysim = Phi.test %*% xi.sim without materialising ysim (config 5:
     10^5 x 10^6 doubles = 800 GB).  Phi.test (n_t x m) is processed in row slabs: each slab's
     sample paths are produced by the FP64 tensor-core GEMM into device memory, summarised by
     lqg_bands (exact type-7 quantiles + mean) and dropped.  xi.sim is uploaded once.
+    With Phi_test = None and (xtest, ulist) given, each slab of the hat-basis matrix is built on
+    the device from the test points (lqg_basis) instead of being computed on the host and
+    uploaded (config 5: 800 MB).
     Device buffers are torch tensors (plumbing); all compute goes through the C ABI.
     Returns (ymean[n_t], qtls[nprobs, n_t]) and timing info."""
     import torch
-    Phi = np.asarray(Phi_test, float)
     xi = np.asarray(xi_sim, float)
-    n_t, m = Phi.shape
+    if Phi_test is None:
+        if xtest is None or ulist is None:
+            raise ValueError("paths_bands needs Phi_test or (xtest, ulist)")
+        if not isinstance(ulist, (list, tuple)):
+            ulist = [ulist]
+        D = len(ulist)
+        xt = np.asarray(xtest, float).reshape(-1, D)
+        m_k = np.ascontiguousarray([np.size(u) for u in ulist], dtype=np.int32)
+        n_t, m = xt.shape[0], int(m_k.sum())
+        Phi = None
+    else:
+        Phi = np.asarray(Phi_test, float)
+        n_t, m = Phi.shape
     m2, N = xi.shape
     if m != m2:
         raise ValueError("non-conformable arguments")
@@ -72,6 +86,10 @@ def paths_bands(Phi_test, xi_sim, probs=(0.025, 0.975), slab_rows=None, return_y
     mean_d = torch.empty(slab_rows, dtype=torch.float64, device=dev)
     q_d = torch.empty((slab_rows, probs.size), dtype=torch.float64, device=dev)   # column-major nprobs x slab
     probs_d = torch.from_numpy(probs).to(dev)
+    if Phi is None:
+        x_d = torch.from_numpy(np.asfortranarray(xt).T.copy()).to(dev)                # column-major n_t x D
+        u_d = torch.from_numpy(np.concatenate([np.ravel(u) for u in ulist]).astype(np.float64)).to(dev)
+        Phi_buf = torch.empty((m, slab_rows), dtype=torch.float64, device=dev)        # column-major slab x m
     mean = np.empty(n_t); q = np.empty((probs.size, n_t), order="F")
     o = L.make_opts(mem=L.MEM_DEVICE, stream=st)
     gemm_ms = bands_ms = 0.0
@@ -80,7 +98,12 @@ def paths_bands(Phi_test, xi_sim, probs=(0.025, 0.975), slab_rows=None, return_y
     for r0 in range(0, n_t, slab_rows):
         r1 = min(n_t, r0 + slab_rows)
         nr = r1 - r0
-        Phi_d = torch.from_numpy(np.asfortranarray(Phi[r0:r1]).T.copy()).to(dev)  # column-major nr x m
+        if Phi is None:
+            L.check(lib.lqg_basis(nr, D, L.ptr(m_k), x_d.data_ptr() + 8 * r0, n_t, u_d.data_ptr(), o,
+                                  Phi_buf.data_ptr(), nr), "lqg_basis")
+            Phi_d = Phi_buf
+        else:
+            Phi_d = torch.from_numpy(np.asfortranarray(Phi[r0:r1]).T.copy()).to(dev)  # column-major nr x m
         L.check(lib.lqg_dgemm(nr, N, m, Phi_d.data_ptr(), nr, xi_d.data_ptr(), m, y_d.data_ptr(), nr, None, o, L.C.byref(ms)),
                 "lqg_dgemm")
         gemm_ms += ms.value

@@ -183,3 +183,14 @@ SEXP lqg_solve_qp_call(SEXP D_, SEXP dvec_, SEXP A_, SEXP b_) {
   lqg_check(rc, "lqg_solve_qp");
   return out;
 }
+
+/* basisCompute.lineqGP(x, u) for a 1-D knot vector u (R/lineqGP.R:29-60) */
+SEXP lqg_basis_call(SEXP x_, SEXP u_) {
+  const int n_t = Rf_length(x_);
+  const int32_t m = Rf_length(u_);
+  SEXP out = PROTECT(Rf_allocMatrix(REALSXP, n_t, m));
+  int rc = lqg_basis(n_t, 1, &m, REAL(x_), n_t, REAL(u_), NULL, REAL(out), n_t);
+  UNPROTECT(1);
+  lqg_check(rc, "lqg_basis");
+  return out;
+}

@@ -227,3 +227,38 @@ def test_simulate_with_device_setup_matches_host_setup(lqg):
         # the factor change a bounce decision; the path ensembles must agree well within MC error
         assert np.max(np.abs(sa.mean(axis=1) - sb.mean(axis=1)) / sd) <= 0.25
         assert np.max(np.abs(np.log(sb.std(axis=1) / sd))) <= 0.25
+
+
+def test_basis_is_bit_identical_to_host_restatement(lqg):
+    """lqg_basis vs basisCompute_lineqGP (R/lineqGP.R:29-60): equispaced and MaxMod-style irregular
+    knots, points on knots, at both ends, ragged sizes; additive (block) form; out-of-range error."""
+    from lineqgpr_b200 import setup_stage as S, model as M
+    rng = np.random.default_rng(0)
+    for m, n_t in ((2, 1), (10, 37), (100, 1000), (1000, 513)):
+        u = np.linspace(0.0, 1.0, m)
+        x = np.concatenate([rng.uniform(0, 1, n_t), u[: min(m, 5)], [0.0, 1.0]])
+        assert np.array_equal(S.basis_device(x, u), M.basisCompute_lineqGP(x, u))
+    u = np.array([0.0, 0.2047, 0.4020, 0.6275, 1.0])                      # cfg2's MaxMod knots
+    x = rng.uniform(0, 1, 200)
+    assert np.array_equal(S.basis_device(x, u), M.basisCompute_lineqGP(x, u))
+    ulist = [np.linspace(0, 1, k) for k in (6, 4, 9)]
+    X = rng.uniform(0, 1, (50, 3))
+    ref = np.hstack([M.basisCompute_lineqGP(X[:, k], ulist[k]) for k in range(3)])   # R/lineqAGP.R:341-348
+    assert np.array_equal(S.basis_device(X, ulist), ref)
+    with pytest.raises(ValueError, match="knot range"):
+        S.basis_device(np.array([0.5, 1.5]), np.linspace(0, 1, 5))
+
+
+def test_paths_bands_with_device_basis(lqg):
+    """paths_bands building each Phi slab on the device equals the run with a host-built Phi."""
+    import importlib
+    from lineqgpr_b200 import model as M
+    sim_mod = importlib.import_module("lineqgpr_b200.simulate")
+    rng = np.random.default_rng(1)
+    ulist = [np.linspace(0, 1, 10) for _ in range(4)]
+    X = rng.uniform(0, 1, (300, 4))
+    xi = rng.standard_normal((40, 5000))
+    Phi = np.hstack([M.basisCompute_lineqGP(X[:, k], ulist[k]) for k in range(4)])
+    m0, q0, _ = sim_mod.paths_bands(Phi, xi, slab_rows=128)
+    m1, q1, _ = sim_mod.paths_bands(None, xi, slab_rows=128, xtest=X, ulist=ulist)
+    assert np.array_equal(m0, m1) and np.array_equal(q0, q1)
