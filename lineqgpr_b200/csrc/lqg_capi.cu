@@ -1140,7 +1140,12 @@ extern "C" int lqg_solve_qp(int32_t n, int32_t mc, const double* D, const double
   LQG_CUDA_TRY(launch_chol_solve(n, Lc, n, Winv, x, n, tn, n, 1, st));
   int it = 0;
   bool converged = mc == 0;
+  const double* x_result = x;
+  DevBuf b_best;
   if (mc > 0) {
+    LQG_CUDA_TRY(b_best.alloc(n * sizeof(double)));
+    double best_phi = INFINITY;
+    int stall = 0;
     LQG_CUDA_TRY(b_H.alloc(nn * sizeof(double)));
     LQG_CUDA_TRY(b_AW.alloc(cn * sizeof(double)));
     LQG_CUDA_TRY(b_vc.alloc((size_t)8 * mc * sizeof(double)));
@@ -1180,7 +1185,16 @@ extern "C" int lqg_solve_qp(int32_t n, int32_t mc, const double* D, const double
         fold_launches();
         return LQG_ERR_INVALID;
       }
-      if (h[0] < tol * scale_d * 1e3 && h[1] < tol * scale_p && mu < tol * scale_p) { converged = true; break; }
+      // merit phi: converged below tol; the best iterate is kept because close to the solution the
+      // attainable dual residual grows like eps |A|^2 lam^2 / mu and phi can bottom out just above tol
+      const double phi = std::max(std::max(h[0] / (1e3 * scale_d), h[1] / scale_p), mu / scale_p);
+      if (phi < tol) { converged = true; break; }
+      if (phi < best_phi) {
+        best_phi = phi; stall = 0;
+        LQG_CUDA_TRY(cudaMemcpyAsync(b_best.p, x, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      } else if (++stall >= 5) {
+        break;
+      }
       // H = D + A' diag(lam/s) A = Lc Lc'
       LQG_CUDA_TRY(launch_qp_scale_rows(mc, n, Ad, lam, s, AW, st));
       LQG_CUDA_TRY(cudaMemcpyAsync(H, i_D.dev, nn * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -1208,13 +1222,17 @@ extern "C" int lqg_solve_qp(int32_t n, int32_t mc, const double* D, const double
       const double a = 0.995 * amax();
       LQG_CUDA_TRY(launch_qp_update(n, mc, a, x, rhs, s, ds, lam, dl, st));
     }
+    if (!converged && best_phi < 1e3 * tol) {                        // rounding floor reached: best iterate
+      converged = true;
+      x_result = b_best.as<double>();
+    }
   }
   if (iters) *iters = it;
-  if ((rc = deliver(x_out, x, n, mem, st))) return rc;
+  if ((rc = deliver(x_out, x_result, n, mem, st))) return rc;
   LQG_CUDA_TRY(cudaStreamSynchronize(st));
   fold_launches();
   if (!converged) {
-    set_error("lqg_solve_qp: no convergence in %d iterations", max_iter);
+    set_error("lqg_solve_qp: no convergence after %d iterations", it);
     return LQG_ERR_BUDGET;
   }
   return LQG_OK;

@@ -187,7 +187,12 @@ def lineqGPSys(m, constrType="boundedness", l=-np.inf, u=np.inf, A=None, d=None,
 def solve_qp(D, dvec, A, b, tol=1e-10, max_iter=200):
     """min 1/2 x'Dx - dvec'x  s.t.  A x >= b   (quadprog::solve.QP(Dmat, dvec, t(A), b) as used at
     R/lineqGP.R:530, R/lineqAGP.R:431).  quadprog is not available here; this is a Mehrotra
-    predictor-corrector interior-point method (dense, O(m^3) per iteration)."""
+    predictor-corrector interior-point method (dense, O(m^3) per iteration).
+    Merit phi = max(|rd|/(1e3 scale_d), |rp|/scale_p, mu/scale_p); converged when phi < tol.
+    With the normal-equations form the attainable dual residual grows like eps |A|^2 lam^2 / mu,
+    so close to the solution phi can bottom out just above tol and then rise again: the best
+    iterate is kept, and when phi has not improved for 5 iterations it is returned provided
+    phi_best < 1e3 tol (the rounding floor of this problem was reached)."""
     D = np.asarray(D, float); dvec = np.asarray(dvec, float).ravel()
     A = np.asarray(A, float); b = np.asarray(b, float).ravel()
     n, mc = D.shape[0], A.shape[0]
@@ -199,12 +204,20 @@ def solve_qp(D, dvec, A, b, tol=1e-10, max_iter=200):
     scale_d = max(1.0, np.abs(dvec).max())
     fin = np.isfinite(b)
     scale_p = max(1.0, np.abs(b[fin]).max() if fin.any() else 1.0)
+    best_phi, best_x, stall = np.inf, x, 0
     for _ in range(max_iter):
         rd = D @ x - dvec - A.T @ lam
         rp = A @ x - s - b
         mu = s @ lam / mc
-        if np.abs(rd).max() < tol * scale_d * 1e3 and np.abs(rp).max() < tol * scale_p and mu < tol * scale_p:
-            break
+        phi = max(np.abs(rd).max() / (1e3 * scale_d), np.abs(rp).max() / scale_p, mu / scale_p)
+        if phi < tol:
+            return x
+        if phi < best_phi:
+            best_phi, best_x, stall = phi, x.copy(), 0
+        else:
+            stall += 1
+            if stall >= 5:
+                break
         W = lam / s
         H = D + (A.T * W) @ A
         try:
@@ -230,7 +243,7 @@ def solve_qp(D, dvec, A, b, tol=1e-10, max_iter=200):
         dx, ds, dl = step(s * lam + ds * dl - sigma * mu)
         a = 0.995 * min(amax(s, ds), amax(lam, dl))
         x = x + a * dx; s = s + a * ds; lam = lam + a * dl
-    return x
+    return best_x if best_phi < 1e3 * tol else x
 
 
 def _chol2inv(S):
