@@ -850,16 +850,15 @@ static int deliver(double* dst, const double* src_dev, size_t n, int mem, cudaSt
   return LQG_OK;
 }
 
-// L (device, d x d) <- lower Cholesky factor of sym(A) (reversed index order when rev); Winv
-// receives the inverted diagonal blocks.  Synchronises the stream.  *bad = 0 or first bad pivot.
-static int chol_device(int d, const double* A_dev, int rev, double* L_dev, double* Winv_dev, int* bad,
-                       cudaStream_t st) {
+// L (device, d x d) <- lower Cholesky factor of sym(A) (reversed index order when rev).
+// Synchronises the stream.  *bad = 0 or first bad pivot.
+static int chol_device(int d, const double* A_dev, int rev, double* L_dev, int* bad, cudaStream_t st) {
   DevBuf b_w, b_info;
   LQG_CUDA_TRY(b_w.alloc((size_t)d * d * sizeof(double)));
   LQG_CUDA_TRY(b_info.alloc(sizeof(int)));
   LQG_CUDA_TRY(cudaMemsetAsync(b_info.p, 0x7f, sizeof(int), st));
   LQG_CUDA_TRY(launch_sym_reverse(d, A_dev, d, b_w.as<double>(), d, rev, st));
-  LQG_CUDA_TRY(launch_chol(d, b_w.as<double>(), d, L_dev, d, Winv_dev, b_info.as<int>(), st));
+  LQG_CUDA_TRY(launch_chol(d, b_w.as<double>(), d, L_dev, d, b_info.as<int>(), st));
   int info = 0;
   LQG_CUDA_TRY(cudaMemcpyAsync(&info, b_info.p, sizeof(int), cudaMemcpyDeviceToHost, st));
   LQG_CUDA_TRY(cudaStreamSynchronize(st));
@@ -869,11 +868,10 @@ static int chol_device(int d, const double* A_dev, int rev, double* L_dev, doubl
 
 // U_dev (d x d) <- the upper factor with U U' = sym(Sigma):  U = J chol(J Sigma J) J
 static int ul_factor_device(int d, const double* S_dev, double* U_dev, cudaStream_t st) {
-  DevBuf b_l, b_winv;
+  DevBuf b_l;
   LQG_CUDA_TRY(b_l.alloc((size_t)d * d * sizeof(double)));
-  LQG_CUDA_TRY(b_winv.alloc(chol_winv_elems(d) * sizeof(double)));
   int bad = 0, rc;
-  if ((rc = chol_device(d, S_dev, 1, b_l.as<double>(), b_winv.as<double>(), &bad, st))) return rc;
+  if ((rc = chol_device(d, S_dev, 1, b_l.as<double>(), &bad, st))) return rc;
   if (bad) {
     set_error("Error: M must be positive definite. (pivot %d of the reversed factorisation of Sigma is not positive)", bad);
     return LQG_ERR_NOT_PD;                                          // tmg:R/tmg.R:17-20
@@ -917,11 +915,10 @@ extern "C" int lqg_chol(int32_t d, const double* A, const lqg_opts* opts_, doubl
   int rc;
   Input i_A;
   if ((rc = i_A.stage(A, dd, o.mem, st))) return rc;
-  DevBuf b_l, b_winv;
+  DevBuf b_l;
   LQG_CUDA_TRY(b_l.alloc(dd * sizeof(double)));
-  LQG_CUDA_TRY(b_winv.alloc(chol_winv_elems(d) * sizeof(double)));
   int bad = 0;
-  if ((rc = chol_device(d, i_A.dev, 0, b_l.as<double>(), b_winv.as<double>(), &bad, st))) return rc;
+  if ((rc = chol_device(d, i_A.dev, 0, b_l.as<double>(), &bad, st))) return rc;
   if (bad_pivot) *bad_pivot = bad;
   fold_launches();
   if (bad) { set_error("lqg_chol: the matrix is not positive definite (pivot %d)", bad); return LQG_ERR_NOT_PD; }
@@ -944,17 +941,14 @@ extern "C" int lqg_solve_spd(int32_t d, int32_t nrhs, const double* A, const dou
   int rc;
   Input i_A, i_B;
   if ((rc = i_A.stage(A, dd, o.mem, st)) || (rc = i_B.stage(B, dn, o.mem, st))) return rc;
-  DevBuf b_l, b_winv, b_x, b_t;
+  DevBuf b_l, b_x;
   LQG_CUDA_TRY(b_l.alloc(dd * sizeof(double)));
-  LQG_CUDA_TRY(b_winv.alloc(chol_winv_elems(d) * sizeof(double)));
   LQG_CUDA_TRY(b_x.alloc(dn * sizeof(double)));
-  LQG_CUDA_TRY(b_t.alloc(dn * sizeof(double)));
   int bad = 0;
-  if ((rc = chol_device(d, i_A.dev, 0, b_l.as<double>(), b_winv.as<double>(), &bad, st))) return rc;
+  if ((rc = chol_device(d, i_A.dev, 0, b_l.as<double>(), &bad, st))) return rc;
   if (bad) { set_error("lqg_solve_spd: the matrix is not positive definite (pivot %d)", bad); fold_launches(); return LQG_ERR_NOT_PD; }
   LQG_CUDA_TRY(cudaMemcpyAsync(b_x.p, i_B.dev, dn * sizeof(double), cudaMemcpyDeviceToDevice, st));
-  LQG_CUDA_TRY(launch_chol_solve(d, b_l.as<double>(), d, b_winv.as<double>(), b_x.as<double>(), d,
-                                 b_t.as<double>(), d, nrhs, st));
+  LQG_CUDA_TRY(launch_chol_solve(d, b_l.as<double>(), d, b_x.as<double>(), d, nrhs, st));
   if ((rc = deliver(X_out, b_x.as<double>(), dn, o.mem, st))) return rc;
   LQG_CUDA_TRY(cudaStreamSynchronize(st));
   fold_launches();
@@ -1017,20 +1011,18 @@ extern "C" int lqg_lambda_pinv(int32_t d, int32_t m, const double* Lambda, const
   int rc;
   Input i_L;
   if ((rc = i_L.stage(Lambda, dm, mem, st))) return rc;
-  DevBuf b_g, b_l, b_winv, b_x, b_t, b_r, b_y;
+  DevBuf b_g, b_l, b_x, b_r, b_y;
   LQG_CUDA_TRY(b_g.alloc(mm * sizeof(double)));
   LQG_CUDA_TRY(b_l.alloc(mm * sizeof(double)));
-  LQG_CUDA_TRY(b_winv.alloc(chol_winv_elems(m) * sizeof(double)));
   LQG_CUDA_TRY(b_x.alloc(dm * sizeof(double)));
-  LQG_CUDA_TRY(b_t.alloc(dm * sizeof(double)));
   LQG_CUDA_TRY(b_r.alloc(dd * sizeof(double)));
   LQG_CUDA_TRY(b_y.alloc(dm * sizeof(double)));
-  double *G = b_g.as<double>(), *Lc = b_l.as<double>(), *X = b_x.as<double>(), *T = b_t.as<double>(),
-         *R = b_r.as<double>(), *Y = b_y.as<double>();
+  double *G = b_g.as<double>(), *Lc = b_l.as<double>(), *X = b_x.as<double>(), *R = b_r.as<double>(),
+         *Y = b_y.as<double>();
   // G = Lambda' Lambda;  G = Lc Lc'
   LQG_CUDA_TRY(launch_gemm(true, false, m, m, d, 1.0, i_L.dev, d, i_L.dev, d, 0.0, G, m, 0, st));
   int bad = 0;
-  if ((rc = chol_device(m, G, 0, Lc, b_winv.as<double>(), &bad, st))) return rc;
+  if ((rc = chol_device(m, G, 0, Lc, &bad, st))) return rc;
   if (bad) {
     set_error("lqg_lambda_pinv: Lambda is rank deficient (pivot %d of Lambda'Lambda is not positive)", bad);
     fold_launches();
@@ -1038,12 +1030,12 @@ extern "C" int lqg_lambda_pinv(int32_t d, int32_t m, const double* Lambda, const
   }
   // X0 = G^-1 Lambda'
   LQG_CUDA_TRY(launch_transpose(d, m, i_L.dev, d, X, m, st));
-  LQG_CUDA_TRY(launch_chol_solve(m, Lc, m, b_winv.as<double>(), X, m, T, m, d, st));
+  LQG_CUDA_TRY(launch_chol_solve(m, Lc, m, X, m, d, st));
   // one refinement step: X += G^-1 Lambda' (I - Lambda X0)
   LQG_CUDA_TRY(launch_gemm(false, false, d, d, m, -1.0, i_L.dev, d, X, m, 0.0, R, d, 0, st));
   LQG_CUDA_TRY(launch_add_diag(d, R, d, 1.0, st));
   LQG_CUDA_TRY(launch_gemm(true, false, m, d, d, 1.0, i_L.dev, d, R, d, 0.0, Y, m, 0, st));
-  LQG_CUDA_TRY(launch_chol_solve(m, Lc, m, b_winv.as<double>(), Y, m, T, m, d, st));
+  LQG_CUDA_TRY(launch_chol_solve(m, Lc, m, Y, m, d, st));
   LQG_CUDA_TRY(launch_axpy(dm, 1.0, Y, X, st));
   if ((rc = deliver(Lp_out, X, dm, mem, st))) return rc;
   LQG_CUDA_TRY(cudaStreamSynchronize(st));
@@ -1126,18 +1118,17 @@ extern "C" int lqg_solve_qp(int32_t n, int32_t mc, const double* D, const double
   if ((rc = i_D.stage(D, nn, mem, st)) || (rc = i_dv.stage(dvec, n, mem, st))) return rc;
   if (mc > 0 && ((rc = i_A.stage(A, cn, mem, st)) || (rc = i_b.stage(b, mc, mem, st)))) return rc;
 
-  DevBuf b_L, b_winv, b_H, b_AW, b_vn, b_vc, b_scal;
+  DevBuf b_L, b_H, b_AW, b_vn, b_vc, b_scal;
   LQG_CUDA_TRY(b_L.alloc(nn * sizeof(double)));
-  LQG_CUDA_TRY(b_winv.alloc(chol_winv_elems(n) * sizeof(double)));
-  LQG_CUDA_TRY(b_vn.alloc((size_t)4 * n * sizeof(double)));
-  double* x = b_vn.as<double>(); double* rd = x + n; double* rhs = rd + n; double* tn = rhs + n;
-  double* Lc = b_L.as<double>(); double* Winv = b_winv.as<double>();
+  LQG_CUDA_TRY(b_vn.alloc((size_t)3 * n * sizeof(double)));
+  double* x = b_vn.as<double>(); double* rd = x + n; double* rhs = rd + n;
+  double* Lc = b_L.as<double>();
   int bad = 0;
   // x = solve(D, dvec)
-  if ((rc = chol_device(n, i_D.dev, 0, Lc, Winv, &bad, st))) return rc;
+  if ((rc = chol_device(n, i_D.dev, 0, Lc, &bad, st))) return rc;
   if (bad) { set_error("lqg_solve_qp: Dmat is not positive definite (pivot %d)", bad); fold_launches(); return LQG_ERR_NOT_PD; }
   LQG_CUDA_TRY(cudaMemcpyAsync(x, i_dv.dev, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
-  LQG_CUDA_TRY(launch_chol_solve(n, Lc, n, Winv, x, n, tn, n, 1, st));
+  LQG_CUDA_TRY(launch_chol_solve(n, Lc, n, x, n, 1, st));
   int it = 0;
   bool converged = mc == 0;
   const double* x_result = x;
@@ -1164,7 +1155,7 @@ extern "C" int lqg_solve_qp(int32_t n, int32_t mc, const double* D, const double
     auto newton = [&](int corrector, double sigma_mu) -> int {
       LQG_CUDA_TRY(launch_qp_prepare(n, mc, corrector, sigma_mu, s, lam, rp, rd, ds, dl, rcv, t, rhs, st));
       LQG_CUDA_TRY(launch_gemm(true, false, n, 1, mc, 1.0, Ad, mc, t, mc, 1.0, rhs, n, 0, st));    // rhs += A' t
-      LQG_CUDA_TRY(launch_chol_solve(n, Lc, n, Winv, rhs, n, tn, n, 1, st));                        // dx
+      LQG_CUDA_TRY(launch_chol_solve(n, Lc, n, rhs, n, 1, st));                        // dx
       LQG_CUDA_TRY(launch_gemm(false, false, mc, 1, n, 1.0, Ad, mc, rhs, n, 1.0, ds, mc, 0, st));   // ds = A dx + rp
       LQG_CUDA_TRY(launch_qp_step(mc, s, lam, ds, rcv, dl, scal, st));
       return read_scal();
@@ -1199,7 +1190,7 @@ extern "C" int lqg_solve_qp(int32_t n, int32_t mc, const double* D, const double
       LQG_CUDA_TRY(launch_qp_scale_rows(mc, n, Ad, lam, s, AW, st));
       LQG_CUDA_TRY(cudaMemcpyAsync(H, i_D.dev, nn * sizeof(double), cudaMemcpyDeviceToDevice, st));
       LQG_CUDA_TRY(launch_gemm(true, false, n, n, mc, 1.0, Ad, mc, AW, mc, 1.0, H, n, 0, st));
-      if ((rc = chol_device(n, H, 0, Lc, Winv, &bad, st))) return rc;
+      if ((rc = chol_device(n, H, 0, Lc, &bad, st))) return rc;
       if (bad) {                                                     // same rescue as the host restatement
         std::vector<double> diag(n);
         LQG_CUDA_TRY(cudaMemcpy2DAsync(diag.data(), sizeof(double), H, (size_t)(n + 1) * sizeof(double), sizeof(double), n,
@@ -1208,7 +1199,7 @@ extern "C" int lqg_solve_qp(int32_t n, int32_t mc, const double* D, const double
         double tr = 0.0;
         for (double v : diag) tr += v;
         LQG_CUDA_TRY(launch_add_diag(n, H, n, 1e-12 * tr / n, st));
-        if ((rc = chol_device(n, H, 0, Lc, Winv, &bad, st))) return rc;
+        if ((rc = chol_device(n, H, 0, Lc, &bad, st))) return rc;
         if (bad) { set_error("lqg_solve_qp: the KKT matrix is not positive definite at iteration %d", it); fold_launches(); return LQG_ERR_NOT_PD; }
       }
       auto amax = [&]() { return std::min(1.0, std::min(h[3], h[4])); };

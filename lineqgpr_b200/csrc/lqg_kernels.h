@@ -107,13 +107,11 @@ cudaError_t launch_fill_normals(int d, size_t n_cols, double* A, const NormalGen
 cudaError_t launch_gemm(bool ta, bool tb, int m, int n, int k, double alpha, const double* A, int64_t lda,
                         const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int tri,
                         cudaStream_t st);
-size_t chol_winv_elems(int d);   // doubles needed for the inverted diagonal blocks
-// blocked Cholesky S = L L' (S: lower part read, destroyed); *info preset to INT_MAX
-cudaError_t launch_chol(int d, double* S, int64_t lds, double* L, int64_t ldl, double* Winv, int* info,
-                        cudaStream_t st);
-// (L L') X = B; B overwritten with X, T scratch of the same shape
-cudaError_t launch_chol_solve(int d, const double* L, int64_t ldl, const double* Winv, double* B, int64_t ldb,
-                              double* T, int64_t ldt, int nrhs, cudaStream_t st);
+// blocked Cholesky S = L L' (S: lower part read, destroyed); *info preset to a large value
+cudaError_t launch_chol(int d, double* S, int64_t lds, double* L, int64_t ldl, int* info, cudaStream_t st);
+// (L L') X = B in place (B d x nrhs overwritten with X)
+cudaError_t launch_chol_solve(int d, const double* L, int64_t ldl, double* B, int64_t ldb, int nrhs,
+                              cudaStream_t st);
 cudaError_t launch_sym_reverse(int d, const double* in, int64_t ldi, double* out, int64_t ldo, int rev,
                                cudaStream_t st);
 cudaError_t launch_reverse(int d, const double* in, double* out, cudaStream_t st);

@@ -8,11 +8,15 @@
 //   solve(A, B) for symmetric positive definite A          R/lineqGP.R:514-523 (posterior algebra)
 //
 // Blocked right-looking Cholesky, block size 64:
-//   diagonal block   one CTA factors S_kk = L_kk L_kk' in shared memory and also forms
-//                    W_k = L_kk^-1, so that every triangular solve below becomes a GEMM
-//   panel            L_ik = S_ik W_k'                       (GEMM, op(B) = transpose)
+//   diagonal block   one CTA factors S_kk = L_kk L_kk' in shared memory
+//   panel            L_ik L_kk' = S_ik by forward substitution, one warp per panel row
 //   trailing update  S_ij -= L_ik L_jk'  (lower tiles only) (GEMM, alpha = -1, beta = 1)
-// The SPD solve A X = B is two blocked substitutions with the same W_k blocks.
+// The SPD solve A X = B is two blocked substitutions: a warp-per-column triangular solve with
+// the 64 x 64 diagonal block, then a GEMM update of the remaining rows.  The triangular solves
+// are real substitutions, not products with an inverted diagonal block: the matrices of this
+// path (Sigma_eta with a 1e-7 nugget, the interior-point KKT matrix near convergence) have
+// condition numbers of 1e10 and more, where an explicit block inverse costs the digits that
+// decide whether the factorisation goes through.
 #include "lqg_common.cuh"
 #include "lqg_kernels.h"
 
@@ -135,14 +139,12 @@ gemm_general_kernel(int m, int n, int k, double alpha, const double* __restrict_
   }
 }
 
-// One CTA: S_kk (nbk x nbk, lower part read) = L L'; writes L into Lout (lower part) and
-// W = L^-1 (lower, 64 x 64 column-major, identity-padded) into Wout.  A non-positive or NaN
-// pivot records its 1-based global index in *info (smallest wins) and is replaced by 1.
+// One CTA: S_kk (nbk x nbk, lower part read) = L L'; writes L into Lout (lower part, zeros above).
+// A non-positive or NaN pivot records its 1-based global index in *info (smallest wins) and is
+// replaced by 1.
 __global__ void __launch_bounds__(256) chol_diag_kernel(int nbk, int k0, const double* S, int64_t lds,
-                                                        double* Lout, int64_t ldl, double* Wout, int* info) {
-  extern __shared__ double cd_sm[];
-  double* s = cd_sm;                 // s[i * 65 + l]
-  double* w = cd_sm + NB * 65;       // w[l * 64 + c] = W[l, c]
+                                                        double* Lout, int64_t ldl, int* info) {
+  __shared__ double s[NB * 65];      // s[i * 65 + l]
   const int tid = threadIdx.x;
   for (int e = tid; e < NB * NB; e += 256) {
     const int i = e % NB, l = e / NB;
@@ -173,19 +175,44 @@ __global__ void __launch_bounds__(256) chol_diag_kernel(int nbk, int k0, const d
     const int i = e % nbk, l = e / nbk;
     Lout[(size_t)l * ldl + i] = (l <= i) ? s[i * 65 + l] : 0.0;
   }
-  // W = L^-1 by forward substitution, one column per thread (uniform loops: broadcast reads of L)
-  if (tid < NB) {
-    const int c = tid;
-    for (int i = 0; i < NB; ++i) {
-      double acc = (i == c) ? 1.0 : 0.0;
-      for (int l = 0; l < i; ++l) acc = fma(-s[i * 65 + l], w[l * NB + c], acc);
-      w[i * NB + c] = acc / s[i * 65 + i];
-    }
+}
+
+// Triangular solves with one 64 x 64 diagonal block, one warp per right-hand side:
+//   trans = 0:  L x = b   (forward substitution)      trans = 1:  L' x = b   (backward)
+// Right-hand side r has its element j at B[j * sj + r * sr]; the solution is written to
+// X[j * xj + r * xr] (may alias B).  Lane l owns elements l and l + 32; the pivot element is
+// divided by the diagonal in its owner lane and broadcast.
+__global__ void __launch_bounds__(256) tri_solve_kernel(int nbk, const double* __restrict__ Lkk, int64_t ldl, int trans,
+                                                        int nrhs, const double* B, int64_t sj, int64_t sr,
+                                                        double* X, int64_t xj, int64_t xr) {
+  __shared__ double s[NB * 65];      // s[i * 65 + l] = L[i, l]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int e = tid; e < NB * NB; e += 256) {
+    const int i = e % NB, l = e / NB;
+    s[i * 65 + l] = (i < nbk && l <= i) ? Lkk[(size_t)l * ldl + i] : (i == l ? 1.0 : 0.0);
   }
   __syncthreads();
-  for (int e = tid; e < NB * NB; e += 256) {
-    const int i = e % NB, c = e / NB;
-    Wout[(size_t)c * NB + i] = (c <= i) ? w[i * NB + c] : 0.0;
+  for (int r = blockIdx.x * 8 + warp; r < nrhs; r += gridDim.x * 8) {
+    double b0 = lane < nbk ? B[(size_t)lane * sj + (size_t)r * sr] : 0.0;
+    double b1 = lane + 32 < nbk ? B[(size_t)(lane + 32) * sj + (size_t)r * sr] : 0.0;
+    const int i0 = lane, i1 = lane + 32;
+    if (!trans) {
+      for (int j = 0; j < nbk; ++j) {
+        const double mine = (j < 32 ? b0 : b1) / s[j * 65 + j];
+        const double xv = __shfl_sync(0xffffffffu, mine, j & 31);
+        if (i0 == j) b0 = xv; else if (i0 > j) b0 = fma(-s[i0 * 65 + j], xv, b0);
+        if (i1 == j) b1 = xv; else if (i1 > j) b1 = fma(-s[i1 * 65 + j], xv, b1);
+      }
+    } else {
+      for (int j = nbk - 1; j >= 0; --j) {                    // L'[i, j] = L[j, i]
+        const double mine = (j < 32 ? b0 : b1) / s[j * 65 + j];
+        const double xv = __shfl_sync(0xffffffffu, mine, j & 31);
+        if (i0 == j) b0 = xv; else if (i0 < j) b0 = fma(-s[j * 65 + i0], xv, b0);
+        if (i1 == j) b1 = xv; else if (i1 < j) b1 = fma(-s[j * 65 + i1], xv, b1);
+      }
+    }
+    if (lane < nbk) X[(size_t)lane * xj + (size_t)r * xr] = b0;
+    if (lane + 32 < nbk) X[(size_t)(lane + 32) * xj + (size_t)r * xr] = b1;
   }
 }
 
@@ -251,30 +278,32 @@ cudaError_t launch_gemm(bool ta, bool tb, int m, int n, int k, double alpha, con
   return cudaGetLastError();
 }
 
-size_t chol_winv_elems(int d) { return (size_t)((d + NB - 1) / NB) * NB * NB; }
+static cudaError_t launch_tri_solve(int nbk, const double* Lkk, int64_t ldl, int trans, int nrhs, const double* B,
+                                    int64_t sj, int64_t sr, double* X, int64_t xj, int64_t xr, cudaStream_t st) {
+  if (nrhs <= 0) return cudaSuccess;
+  const int grid = (nrhs + 7) / 8 < 148 * 4 ? (nrhs + 7) / 8 : 148 * 4;
+  tri_solve_kernel<<<grid, 256, 0, st>>>(nbk, Lkk, ldl, trans, nrhs, B, sj, sr, X, xj, xr);
+  ++launch_counter();
+  return cudaGetLastError();
+}
 
-// S (d x d, lower part, destroyed) -> L (d x d, lower, strict upper part zeroed), Winv blocks.
-// *info (device int, preset to INT_MAX) receives the first non-positive pivot (1-based) if any.
-cudaError_t launch_chol(int d, double* S, int64_t lds, double* L, int64_t ldl, double* Winv, int* info,
-                        cudaStream_t st) {
-  static const cudaError_t attr = cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                       (int)((NB * 65 + NB * NB) * sizeof(double)));
-  if (attr != cudaSuccess) return attr;
+// S (d x d, lower part, destroyed) -> L (d x d, lower, strict upper part zeroed).
+// *info (device int, preset to a large value) receives the first non-positive pivot (1-based) if any.
+cudaError_t launch_chol(int d, double* S, int64_t lds, double* L, int64_t ldl, int* info, cudaStream_t st) {
   cudaError_t e = cudaMemset2DAsync(L, ldl * sizeof(double), 0, (size_t)d * sizeof(double), d, st);
   if (e != cudaSuccess) return e;
   for (int k0 = 0; k0 < d; k0 += NB) {
     const int nbk = d - k0 < NB ? d - k0 : NB;
     const int k1 = k0 + nbk;
-    double* W = Winv + (size_t)(k0 / NB) * NB * NB;
-    chol_diag_kernel<<<1, 256, (NB * 65 + NB * NB) * sizeof(double), st>>>(
-        nbk, k0, S + (size_t)k0 * lds + k0, lds, L + (size_t)k0 * ldl + k0, ldl, W, info);
+    double* Lkk = L + (size_t)k0 * ldl + k0;
+    chol_diag_kernel<<<1, 256, 0, st>>>(nbk, k0, S + (size_t)k0 * lds + k0, lds, Lkk, ldl, info);
     ++launch_counter();
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     const int below = d - k1;
     if (below > 0) {
-      // panel: L[k1:, k0:k1] = S[k1:, k0:k1] W'
-      e = launch_gemm(false, true, below, nbk, nbk, 1.0, S + (size_t)k0 * lds + k1, lds, W, NB, 0.0,
-                      L + (size_t)k0 * ldl + k1, ldl, 0, st);
+      // panel: L[k1:, k0:k1] L_kk' = S[k1:, k0:k1]; row r of the panel is right-hand side r
+      e = launch_tri_solve(nbk, Lkk, ldl, 0, below, S + (size_t)k0 * lds + k1, lds, 1,
+                           L + (size_t)k0 * ldl + k1, ldl, 1, st);
       if (e != cudaSuccess) return e;
       // trailing: S[k1:, k1:] -= P P'   (lower tiles)
       const double* P = L + (size_t)k0 * ldl + k1;
@@ -286,31 +315,27 @@ cudaError_t launch_chol(int d, double* S, int64_t lds, double* L, int64_t ldl, d
   return cudaSuccess;
 }
 
-// Solves (L L') X = B for nrhs right-hand sides.  B (d x nrhs) is overwritten with X; T is a
-// d x nrhs scratch.  Forward: T_k = W_k B_k, B_{k+1:} -= L_{k+1:,k} T_k.  Backward:
-// B_k = W_k' T_k, T_{:k} -= L_{k,:k}' B_k.
-cudaError_t launch_chol_solve(int d, const double* L, int64_t ldl, const double* Winv, double* B, int64_t ldb,
-                              double* T, int64_t ldt, int nrhs, cudaStream_t st) {
+// Solves (L L') X = B in place for nrhs right-hand sides (B d x nrhs, overwritten with X).
+cudaError_t launch_chol_solve(int d, const double* L, int64_t ldl, double* B, int64_t ldb, int nrhs,
+                              cudaStream_t st) {
   cudaError_t e;
-  for (int k0 = 0; k0 < d; k0 += NB) {
+  for (int k0 = 0; k0 < d; k0 += NB) {                       // L Y = B
     const int nbk = d - k0 < NB ? d - k0 : NB, k1 = k0 + nbk;
-    const double* W = Winv + (size_t)(k0 / NB) * NB * NB;
-    e = launch_gemm(false, false, nbk, nrhs, nbk, 1.0, W, NB, B + k0, ldb, 0.0, T + k0, ldt, 0, st);
+    e = launch_tri_solve(nbk, L + (size_t)k0 * ldl + k0, ldl, 0, nrhs, B + k0, 1, ldb, B + k0, 1, ldb, st);
     if (e != cudaSuccess) return e;
     if (d - k1 > 0) {
-      e = launch_gemm(false, false, d - k1, nrhs, nbk, -1.0, L + (size_t)k0 * ldl + k1, ldl, T + k0, ldt, 1.0,
+      e = launch_gemm(false, false, d - k1, nrhs, nbk, -1.0, L + (size_t)k0 * ldl + k1, ldl, B + k0, ldb, 1.0,
                       B + k1, ldb, 0, st);
       if (e != cudaSuccess) return e;
     }
   }
   const int last = ((d - 1) / NB) * NB;
-  for (int k0 = last; k0 >= 0; k0 -= NB) {
+  for (int k0 = last; k0 >= 0; k0 -= NB) {                   // L' X = Y
     const int nbk = d - k0 < NB ? d - k0 : NB;
-    const double* W = Winv + (size_t)(k0 / NB) * NB * NB;
-    e = launch_gemm(true, false, nbk, nrhs, nbk, 1.0, W, NB, T + k0, ldt, 0.0, B + k0, ldb, 0, st);
+    e = launch_tri_solve(nbk, L + (size_t)k0 * ldl + k0, ldl, 1, nrhs, B + k0, 1, ldb, B + k0, 1, ldb, st);
     if (e != cudaSuccess) return e;
     if (k0 > 0) {
-      e = launch_gemm(true, false, k0, nrhs, nbk, -1.0, L + k0, ldl, B + k0, ldb, 1.0, T, ldt, 0, st);
+      e = launch_gemm(true, false, k0, nrhs, nbk, -1.0, L + k0, ldl, B + k0, ldb, 1.0, B, ldb, 0, st);
       if (e != cudaSuccess) return e;
     }
   }

@@ -262,3 +262,25 @@ def test_paths_bands_with_device_basis(lqg):
     m0, q0, _ = sim_mod.paths_bands(Phi, xi, slab_rows=128)
     m1, q1, _ = sim_mod.paths_bands(None, xi, slab_rows=128, xtest=X, ulist=ulist)
     assert np.array_equal(m0, m1) and np.array_equal(q0, q1)
+
+
+@pytest.mark.parametrize("d", [300, 1000])
+def test_factorization_is_as_robust_as_lapack_on_nearly_singular_input(lqg, d):
+    """Sigma_eta of this path is a rank-deficient product plus a tiny nugget (cfg4: cond ~ 1e10).
+    The blocked factorisation must go through wherever LAPACK's does (shift >= 1e-11 ||S||) with
+    the same backward error, and must refuse a matrix with a clearly negative direction."""
+    from lineqgpr_b200 import setup_stage as S
+    rng = np.random.default_rng(d)
+    B = rng.standard_normal((d, d // 2))
+    S0 = B @ B.T                                              # rank d/2
+    nrm = np.linalg.norm(S0, 2)
+    for shift in (1e-6, 1e-8, 1e-10, 1e-11):
+        A = S0 + shift * nrm * np.eye(d)
+        np.linalg.cholesky(A)                                 # LAPACK goes through
+        U = S.whiten_box_device(A)
+        Lf = S.chol(A)
+        for F in (U, Lf):
+            assert np.linalg.norm(F @ F.T - A) <= 50 * d * EPS * np.linalg.norm(A), shift
+        X = S.solve_spd(A, A @ np.ones((d, 2)))
+        assert np.linalg.norm(A @ X - A @ np.ones((d, 2))) <= 1e-9 * np.linalg.norm(A @ np.ones((d, 2))), shift
+    assert not S.is_positive_definite(S0 - 1e-8 * nrm * np.eye(d))
