@@ -15,8 +15,8 @@
 // the 64 x 64 diagonal block, then a GEMM update of the remaining rows.  The triangular solves
 // are real substitutions, not products with an inverted diagonal block: the matrices of this
 // path (Sigma_eta with a 1e-7 nugget, the interior-point KKT matrix near convergence) have
-// condition numbers of 1e10 and more, where an explicit block inverse costs the digits that
-// decide whether the factorisation goes through.
+// condition numbers of 1e10 and more, which leaves two or three digits of margin on the pivots;
+// an explicit block inverse is not backward stable there.
 #include "lqg_common.cuh"
 #include "lqg_kernels.h"
 
