@@ -394,8 +394,12 @@ extern "C" int lqg_hmc_box(int32_t d, const double* mu, const double* U, int32_t
                                        cudaMemcpyDeviceToHost, copy_st));
         copied = upto;
       }
-      // shrink the last rounds' pool to what the slowest chain can still need
-      attempts = std::max(4, std::min(max_attempts, (int)((total - s_min) * 1.25) + 4));
+      // shrink the last rounds' pool to what the slowest chain can still need; when the samples
+      // go to the host, the last stretch is additionally cut into halving rounds so that the copy
+      // that cannot overlap any compute (the final round's samples) is a few columns per chain
+      const int rem = total - s_min;
+      attempts = std::max(4, std::min(max_attempts, (int)(rem * 1.25) + 4));
+      if (copy_st && rem <= 2 * max_attempts) attempts = std::max(6, std::min(attempts, (int)(rem * 0.55) + 2));
       pre_ms += t_pre.ms();
       chain_ms += t_chain.ms();
       cur ^= 1;
