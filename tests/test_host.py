@@ -41,6 +41,30 @@ def test_no_gpu_fails_loudly(lqg):
         lqg.tmvrnorm(obj, 5, method="RSM")
     with pytest.raises(_lib.LqgError):
         lqg.dgemm(np.eye(2), np.eye(2))
+    # the set-up stage has no host fallback either: "device" means device
+    from lineqgpr_b200 import setup_stage as S
+    for call in (lambda: S.whiten_box_device(np.eye(3)), lambda: S.chol(np.eye(3)),
+                 lambda: S.is_positive_definite(np.eye(3)), lambda: S.solve_spd(np.eye(3), np.ones(3)),
+                 lambda: S.eta_params(np.eye(3), np.ones(3), np.ones(3), np.eye(3)),
+                 lambda: S.lambda_pinv_device(np.eye(3)), lambda: S.basis_device(np.array([0.5]), np.linspace(0, 1, 3)),
+                 lambda: S.solve_qp_device(np.eye(3), np.ones(3), np.eye(3), np.zeros(3))):
+        with pytest.raises(_lib.LqgError) as e:
+            call()
+        assert e.value.status == 4
+    with pytest.raises(_lib.LqgError):
+        lqg.tmvrnorm(obj, 5, {"burn.in": 1, "whiten": "device"}, method="HMC")
+
+
+def test_setup_mode_is_explicit(lqg):
+    """predict/simulate take setup = "host" | "device"; anything else is an error, and the host
+    algebra provider is plain numpy (usable without a GPU)."""
+    from lineqgpr_b200 import model as M
+    with pytest.raises(ValueError, match="host \\| device"):
+        M._algebra("auto")
+    S = np.array([[2.0, 0.5], [0.5, 1.0]])
+    assert np.allclose(M._algebra("host").chol2inv(S) @ S, np.eye(2))
+    assert not M._algebra("host").min_eig_nonpositive(S)
+    assert M._algebra("host").min_eig_nonpositive(S - 3 * np.eye(2))
 
 
 def test_product_package_never_imports_the_oracle():
@@ -158,3 +182,24 @@ def test_expt_setup_anchors(lqg):
     assert np.abs(a["L0"] - b["L0"]).max() < 1e-12 and np.abs(a["mu"] - b["mu"]).max() < 1e-7
     with pytest.raises(ValueError):
         expt.setup(np.array([1.0]), np.array([0.0]), np.eye(1))
+
+
+def test_solve_qp_stops_at_the_rounding_floor(lqg):
+    """A problem where the merit bottoms out just above tol (the dual residual floor grows like
+    1/mu in the normal-equations form): the best iterate is returned instead of iterating to
+    max_iter while the residual drifts."""
+    from lineqgpr_b200 import model as M
+    rng = np.random.default_rng(1)
+    for n in (1, 63, 65, 130):                              # the n = 130 draw of this stream used to stall
+        Q = rng.standard_normal((n, n)); D = Q @ Q.T + n * np.eye(n)
+        A = rng.standard_normal((2 * n + 1, n)); b = A @ rng.standard_normal(n) - 1.0
+        dvec = rng.standard_normal(n)
+        x = M.solve_qp(D, dvec, A, b)
+        x_ref = M.solve_qp(D, dvec, A, b, tol=1e-9)
+        assert (A @ x - b).min() >= -1e-9
+        assert np.max(np.abs(x - x_ref)) <= 1e-7 * max(1.0, np.abs(x_ref).max())
+        g = D @ x - dvec                                     # stationarity on the active set
+        act = (A @ x - b) < 1e-7
+        lam = np.linalg.lstsq(A[act].T, g, rcond=None)[0] if act.any() else np.zeros(0)
+        assert np.linalg.norm(A[act].T @ lam - g) <= 1e-6 * max(1.0, np.linalg.norm(g))
+        assert lam.min(initial=0.0) >= -1e-6
