@@ -249,9 +249,12 @@ int lqg_basis(int32_t n_t, int32_t D, const int32_t* m_k, const double* x, int64
  * vendored in the reference: a Mehrotra predictor-corrector interior-point method replaces its
  * active-set iteration; both return the unique minimiser).  D n x n symmetric positive definite,
  * dvec[n], A mc x n column-major, b[mc] finite; mc = 0 returns solve(D, dvec).
- * tol <= 0 -> 1e-10 on the merit max(|rd|/(1e3 scale_d), |rp|/scale_p, mu/scale_p); when the
+ * tol == 0 -> 1e-10 on the merit max(|rd|/(1e3 scale_d), |rp|/scale_p, mu/scale_p); when the
  * merit stalls at the rounding floor for 5 iterations the best iterate is returned if its merit
- * is below 1e3 tol.  max_iter <= 0 -> 200; *iters nullable.
+ * is below 1e3 tol.  The result is then polished by an active-set solve (guess lam_i > s_i,
+ * Schur-complement solve, KKT check, a few adjustments) so that, like quadprog, the exact
+ * minimiser is returned; tol < 0 means tolerance |tol| without the polish.
+ * max_iter <= 0 -> 200; *iters nullable.
  * LQG_ERR_NOT_PD when D is not positive definite, LQG_ERR_BUDGET when max_iter is exhausted
  * (x_out then holds the last iterate).                                                        */
 int lqg_solve_qp(int32_t n, int32_t mc, const double* D, const double* dvec, const double* A,

@@ -1102,7 +1102,9 @@ extern "C" int lqg_solve_qp(int32_t n, int32_t mc, const double* D, const double
     set_error("lqg_solve_qp: invalid argument (n=%d mc=%d)", n, mc);
     return LQG_ERR_INVALID;
   }
-  if (tol <= 0.0) tol = 1e-10;
+  const bool polish = tol >= 0.0;           // tol < 0: |tol| is the tolerance and the active-set polish is skipped
+  if (tol < 0.0) tol = -tol;
+  if (tol == 0.0) tol = 1e-10;
   if (max_iter <= 0) max_iter = 200;
   cudaStream_t st = (cudaStream_t)o.stream;
   DevBuf::cur_stream = st;
@@ -1136,9 +1138,11 @@ extern "C" int lqg_solve_qp(int32_t n, int32_t mc, const double* D, const double
   int it = 0;
   bool converged = mc == 0;
   const double* x_result = x;
-  DevBuf b_best;
+  DevBuf b_best, b_x0;
   if (mc > 0) {
-    LQG_CUDA_TRY(b_best.alloc(n * sizeof(double)));
+    LQG_CUDA_TRY(b_best.alloc(((size_t)n + 2 * (size_t)mc) * sizeof(double)));   // best x, s, lam
+    LQG_CUDA_TRY(b_x0.alloc(n * sizeof(double)));
+    LQG_CUDA_TRY(cudaMemcpyAsync(b_x0.p, x, n * sizeof(double), cudaMemcpyDeviceToDevice, st));   // x0 = solve(D, dvec)
     double best_phi = INFINITY;
     int stall = 0;
     LQG_CUDA_TRY(b_H.alloc(nn * sizeof(double)));
@@ -1187,6 +1191,7 @@ extern "C" int lqg_solve_qp(int32_t n, int32_t mc, const double* D, const double
       if (phi < best_phi) {
         best_phi = phi; stall = 0;
         LQG_CUDA_TRY(cudaMemcpyAsync(b_best.p, x, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        LQG_CUDA_TRY(cudaMemcpyAsync(b_best.as<double>() + n, s, 2 * (size_t)mc * sizeof(double), cudaMemcpyDeviceToDevice, st));
       } else if (++stall >= 5) {
         break;
       }
@@ -1217,9 +1222,81 @@ extern "C" int lqg_solve_qp(int32_t n, int32_t mc, const double* D, const double
       const double a = 0.995 * amax();
       LQG_CUDA_TRY(launch_qp_update(n, mc, a, x, rhs, s, ds, lam, dl, st));
     }
+    const double* s_fin = s; const double* lam_fin = lam;
     if (!converged && best_phi < 1e3 * tol) {                        // rounding floor reached: best iterate
       converged = true;
       x_result = b_best.as<double>();
+      s_fin = b_best.as<double>() + n; lam_fin = s_fin + mc;
+    }
+    // ---- active-set polish: quadprog returns the exact minimiser, an interior-point iterate is only
+    //      O(sqrt(mu)) close on weakly active rows.  Guess the active set (lam_i > s_i), solve the
+    //      equality-constrained problem through the Schur complement (A_a D^-1 A_a') lam_a = b_a - A_a x0,
+    //      x = x0 + D^-1 A_a' lam_a, check the KKT conditions of the full problem, adjust the set a few
+    //      times.  Without a consistent set the interior-point iterate stands.
+    if (converged && polish) {
+      std::vector<double> h_s(mc), h_lam(mc), h_r(mc), h_la;
+      LQG_CUDA_TRY(cudaMemcpyAsync(h_s.data(), s_fin, mc * sizeof(double), cudaMemcpyDeviceToHost, st));
+      LQG_CUDA_TRY(cudaMemcpyAsync(h_lam.data(), lam_fin, mc * sizeof(double), cudaMemcpyDeviceToHost, st));
+      LQG_CUDA_TRY(cudaStreamSynchronize(st));
+      std::vector<char> act(mc);
+      for (int i = 0; i < mc; ++i) act[i] = h_lam[i] > h_s[i];
+      if ((rc = chol_device(n, i_D.dev, 0, Lc, &bad, st))) return rc;          // Lc held the last KKT factor
+      DevBuf b_idx, b_AaT, b_Y, b_S, b_Ls, b_la, b_xp, b_rf;
+      LQG_CUDA_TRY(b_xp.alloc(n * sizeof(double)));
+      LQG_CUDA_TRY(b_rf.alloc(mc * sizeof(double)));
+      const double* x0 = b_x0.as<double>();
+      bool done = false;
+      for (int round = 0; round < 8 && !done && !bad; ++round) {
+        std::vector<int> idx;
+        for (int i = 0; i < mc; ++i) if (act[i]) idx.push_back(i);
+        const int k = (int)idx.size();
+        double* xp = b_xp.as<double>();
+        LQG_CUDA_TRY(cudaMemcpyAsync(xp, x0, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        h_la.assign(k, 0.0);
+        if (k > n) break;                                                      // more active rows than unknowns: dependent
+        if (k > 0) {
+          LQG_CUDA_TRY(b_idx.alloc(k * sizeof(int)));
+          LQG_CUDA_TRY(b_AaT.alloc((size_t)n * k * sizeof(double)));
+          LQG_CUDA_TRY(b_Y.alloc((size_t)n * k * sizeof(double)));
+          LQG_CUDA_TRY(b_S.alloc((size_t)k * k * sizeof(double)));
+          LQG_CUDA_TRY(b_Ls.alloc((size_t)k * k * sizeof(double)));
+          LQG_CUDA_TRY(b_la.alloc(k * sizeof(double)));
+          LQG_CUDA_TRY(cudaMemcpyAsync(b_idx.p, idx.data(), k * sizeof(int), cudaMemcpyHostToDevice, st));
+          double* AaT = b_AaT.as<double>(); double* Y = b_Y.as<double>(); double* la = b_la.as<double>();
+          LQG_CUDA_TRY(launch_qp_gather_rows(n, k, mc, Ad, b_idx.as<int>(), AaT, st));
+          LQG_CUDA_TRY(cudaMemcpyAsync(Y, AaT, (size_t)n * k * sizeof(double), cudaMemcpyDeviceToDevice, st));
+          LQG_CUDA_TRY(launch_chol_solve(n, Lc, n, Y, n, k, st));                                      // Y = D^-1 A_a'
+          LQG_CUDA_TRY(launch_gemm(true, false, k, k, n, 1.0, AaT, n, Y, n, 0.0, b_S.as<double>(), k, 0, st));
+          int bad_s = 0;
+          if ((rc = chol_device(k, b_S.as<double>(), 0, b_Ls.as<double>(), &bad_s, st))) return rc;
+          if (bad_s) break;                                                    // dependent active rows
+          // la = b_a - A_a x0, then solve
+          LQG_CUDA_TRY(launch_gemm(true, false, k, 1, n, 1.0, AaT, n, x0, n, 0.0, la, k, 0, st));
+          LQG_CUDA_TRY(cudaMemcpyAsync(h_la.data(), la, k * sizeof(double), cudaMemcpyDeviceToHost, st));
+          LQG_CUDA_TRY(cudaStreamSynchronize(st));
+          for (int q = 0; q < k; ++q) h_la[q] = h_b[idx[q]] - h_la[q];
+          LQG_CUDA_TRY(cudaMemcpyAsync(la, h_la.data(), k * sizeof(double), cudaMemcpyHostToDevice, st));
+          LQG_CUDA_TRY(launch_chol_solve(k, b_Ls.as<double>(), k, la, k, 1, st));
+          LQG_CUDA_TRY(launch_gemm(false, false, n, 1, k, 1.0, Y, n, la, k, 1.0, xp, n, 0, st));       // xp = x0 + Y la
+          LQG_CUDA_TRY(cudaMemcpyAsync(h_la.data(), la, k * sizeof(double), cudaMemcpyDeviceToHost, st));
+        }
+        LQG_CUDA_TRY(launch_gemm(false, false, mc, 1, n, 1.0, Ad, mc, xp, n, 0.0, b_rf.as<double>(), mc, 0, st));
+        LQG_CUDA_TRY(cudaMemcpyAsync(h_r.data(), b_rf.p, mc * sizeof(double), cudaMemcpyDeviceToHost, st));
+        LQG_CUDA_TRY(cudaStreamSynchronize(st));
+        double la_max = 1.0;
+        for (double v : h_la) la_max = std::max(la_max, std::fabs(v));
+        bool changed = false, ok = true;
+        for (int q = 0; q < k; ++q)
+          if (h_la[q] < -1e-10 * la_max) { act[idx[q]] = 0; changed = true; ok = false; }
+        for (int i = 0; i < mc; ++i)
+          if (h_r[i] - h_b[i] < -1e-12 * scale_p) { ok = false; if (!act[i]) { act[i] = 1; changed = true; } }
+        if (ok) {                                                              // b_xp dies with this block: keep the result in b_best
+          LQG_CUDA_TRY(cudaMemcpyAsync(b_best.p, xp, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+          x_result = b_best.as<double>();
+          done = true;
+        }
+        else if (!changed) break;
+      }
     }
   }
   if (iters) *iters = it;

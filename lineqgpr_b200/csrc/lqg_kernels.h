@@ -134,6 +134,7 @@ cudaError_t launch_qp_step(int mc, const double* s, const double* lam, const dou
                            double* dl, double* scal, cudaStream_t st);
 cudaError_t launch_qp_muaff(int mc, double a, const double* s, const double* lam, const double* ds,
                             const double* dl, double* scal, cudaStream_t st);
+cudaError_t launch_qp_gather_rows(int n, int k, int mc, const double* A, const int* idx, double* AaT, cudaStream_t st);
 cudaError_t launch_qp_update(int n, int mc, double a, double* x, const double* dx, double* s, const double* ds,
                              double* lam, const double* dl, cudaStream_t st);
 

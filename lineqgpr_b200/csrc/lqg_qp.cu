@@ -106,7 +106,26 @@ __global__ void qp_update_kernel(int n, int mc, double a, double* x, const doubl
   for (int i = threadIdx.x; i < mc; i += RT) { s[i] = fma(a, ds[i], s[i]); lam[i] = fma(a, dl[i], lam[i]); }
 }
 
+// AaT[j, q] = A[idx[q], j]: the active rows of A (mc x n), transposed into an n x k matrix
+__global__ void qp_gather_rows_kernel(int n, int k, int mc, const double* __restrict__ A, const int* __restrict__ idx,
+                                      double* __restrict__ AaT) {
+  const size_t total = (size_t)n * k;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(e % n), q = (int)(e / n);
+    AaT[e] = A[(size_t)j * mc + idx[q]];
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_qp_gather_rows(int n, int k, int mc, const double* A, const int* idx, double* AaT, cudaStream_t st) {
+  const size_t total = (size_t)n * k;
+  if (total == 0) return cudaSuccess;
+  const unsigned grid = (unsigned)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  qp_gather_rows_kernel<<<grid, 256, 0, st>>>(n, k, mc, A, idx, AaT);
+  ++launch_counter();
+  return cudaGetLastError();
+}
 
 #define LQG_QP_LAUNCH(call) do { call; ++launch_counter(); return cudaGetLastError(); } while (0)
 

@@ -184,7 +184,7 @@ def lineqGPSys(m, constrType="boundedness", l=-np.inf, u=np.inf, A=None, d=None,
 # --------------------------------------------------------------------------- QP (solve.QP stand-in)
 
 
-def solve_qp(D, dvec, A, b, tol=1e-10, max_iter=200):
+def solve_qp(D, dvec, A, b, tol=1e-10, max_iter=200, polish=True):
     """min 1/2 x'Dx - dvec'x  s.t.  A x >= b   (quadprog::solve.QP(Dmat, dvec, t(A), b) as used at
     R/lineqGP.R:530, R/lineqAGP.R:431).  quadprog is not available here; this is a Mehrotra
     predictor-corrector interior-point method (dense, O(m^3) per iteration).
@@ -192,7 +192,9 @@ def solve_qp(D, dvec, A, b, tol=1e-10, max_iter=200):
     With the normal-equations form the attainable dual residual grows like eps |A|^2 lam^2 / mu,
     so close to the solution phi can bottom out just above tol and then rise again: the best
     iterate is kept, and when phi has not improved for 5 iterations it is returned provided
-    phi_best < 1e3 tol (the rounding floor of this problem was reached)."""
+    phi_best < 1e3 tol (the rounding floor of this problem was reached).
+    polish: finish with an active-set solve (polish_qp) so that, like quadprog, the exact
+    minimiser is returned."""
     D = np.asarray(D, float); dvec = np.asarray(dvec, float).ravel()
     A = np.asarray(A, float); b = np.asarray(b, float).ravel()
     n, mc = D.shape[0], A.shape[0]
@@ -204,16 +206,17 @@ def solve_qp(D, dvec, A, b, tol=1e-10, max_iter=200):
     scale_d = max(1.0, np.abs(dvec).max())
     fin = np.isfinite(b)
     scale_p = max(1.0, np.abs(b[fin]).max() if fin.any() else 1.0)
-    best_phi, best_x, stall = np.inf, x, 0
+    best_phi, best_x, best_sl, stall = np.inf, x, (s, lam), 0
     for _ in range(max_iter):
         rd = D @ x - dvec - A.T @ lam
         rp = A @ x - s - b
         mu = s @ lam / mc
         phi = max(np.abs(rd).max() / (1e3 * scale_d), np.abs(rp).max() / scale_p, mu / scale_p)
         if phi < tol:
-            return x
+            xp = polish_qp(D, dvec, A, b, s, lam) if polish else None
+            return x if xp is None else xp
         if phi < best_phi:
-            best_phi, best_x, stall = phi, x.copy(), 0
+            best_phi, best_x, best_sl, stall = phi, x.copy(), (s.copy(), lam.copy()), 0
         else:
             stall += 1
             if stall >= 5:
@@ -243,7 +246,54 @@ def solve_qp(D, dvec, A, b, tol=1e-10, max_iter=200):
         dx, ds, dl = step(s * lam + ds * dl - sigma * mu)
         a = 0.995 * min(amax(s, ds), amax(lam, dl))
         x = x + a * dx; s = s + a * ds; lam = lam + a * dl
-    return best_x if best_phi < 1e3 * tol else x
+    if best_phi < 1e3 * tol:
+        xp = polish_qp(D, dvec, A, b, *best_sl) if polish else None
+        return best_x if xp is None else xp
+    return x
+
+
+def polish_qp(D, dvec, A, b, s, lam, max_rounds=8):
+    """Active-set polish of an interior-point iterate: quadprog::solve.QP is an active-set method
+    and returns the exact minimiser, an interior-point iterate is only O(sqrt(mu)) close on weakly
+    active rows.  Guess the active set (lam_i > s_i), solve the equality-constrained problem
+    through the Schur complement  (A_a D^-1 A_a') lam_a = b_a - A_a D^-1 dvec,
+    x = D^-1 (dvec + A_a' lam_a),  and check the KKT conditions of the full problem; rows that
+    are violated are added, rows with a negative multiplier dropped, a few times.  Returns the
+    exact minimiser, or None when no consistent active set was found (the caller keeps the
+    interior-point iterate)."""
+    D = np.asarray(D, float); A = np.asarray(A, float); b = np.asarray(b, float).ravel()
+    dvec = np.asarray(dvec, float).ravel()
+    Lc = np.linalg.cholesky(D)
+    solveD = lambda R: np.linalg.solve(Lc.T, np.linalg.solve(Lc, R))
+    x0 = solveD(dvec)
+    scale_p = max(1.0, np.abs(b).max(initial=0.0))
+    act = lam > s
+    for _ in range(max_rounds):
+        idx = np.flatnonzero(act)
+        if idx.size == 0:
+            xp, lam_a = x0, np.zeros(0)
+        else:
+            Aa = A[idx]
+            Y = solveD(Aa.T)                                   # n x k
+            S = Aa @ Y
+            try:
+                Ls = np.linalg.cholesky((S + S.T) / 2)
+            except np.linalg.LinAlgError:
+                return None                                    # dependent active rows
+            lam_a = np.linalg.solve(Ls.T, np.linalg.solve(Ls, b[idx] - Aa @ x0))
+            xp = x0 + Y @ lam_a
+        r = A @ xp - b
+        viol = r < -1e-12 * scale_p
+        neg = lam_a < -1e-10 * max(1.0, np.abs(lam_a).max(initial=0.0))
+        if not viol.any() and not neg.any():
+            return xp
+        new = act.copy()
+        new[idx[neg]] = False
+        new[viol] = True
+        if np.array_equal(new, act):
+            return None
+        act = new
+    return None
 
 
 def _chol2inv(S):

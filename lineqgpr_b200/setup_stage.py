@@ -90,9 +90,11 @@ def lambda_pinv_device(Lambda):
     return Lp
 
 
-def solve_qp_device(D, dvec, A, b, tol=1e-10, max_iter=200, return_iters=False):
+def solve_qp_device(D, dvec, A, b, tol=1e-10, max_iter=200, return_iters=False, polish=True):
     """quadprog::solve.QP(D, dvec, t(A), b)$solution (R/lineqGP.R:530, R/lineqAGP.R:431) on the
-    GPU: interior-point iteration with every O(n^2 c)/O(n^3) product on the FP64 tensor cores."""
+    GPU: interior-point iteration with every O(n^2 c)/O(n^3) product on the FP64 tensor cores,
+    finished by an active-set polish that returns the exact minimiser (polish=False: the
+    interior-point iterate)."""
     D = L.f64(D)
     n = D.shape[0]
     dvec = np.ascontiguousarray(np.ravel(dvec), dtype=np.float64)
@@ -101,7 +103,7 @@ def solve_qp_device(D, dvec, A, b, tol=1e-10, max_iter=200, return_iters=False):
     x = np.empty(n)
     it = C.c_int32(0)
     rc = L.lib().lqg_solve_qp(n, A.shape[0], L.ptr(D), L.ptr(dvec), L.ptr(A) if A.size else None,
-                              L.ptr(b) if b.size else None, float(tol), int(max_iter), L.make_opts(),
+                              L.ptr(b) if b.size else None, float(tol) if polish else -float(tol), int(max_iter), L.make_opts(),
                               L.ptr(x), C.byref(it))
     L.check(rc, "solve_qp")
     return (x, it.value) if return_iters else x
