@@ -10,7 +10,10 @@
 #include <mutex>
 #include <vector>
 
+#include <memory>
+
 #include "lqg_common.cuh"
+#include "lqg_hostcopy.h"
 #include "lqg_kernels.h"
 
 namespace lqg {
@@ -363,6 +366,20 @@ extern "C" int lqg_hmc_box(int32_t d, const double* mu, const double* U, int32_t
     }
     cudaStream_t copy_st = copy_guard.s;
     cudaEvent_t ev_round = round_guard.e;
+    // a pageable result matrix (R, numpy) is filled through the pinned staging ring and helper
+    // threads; a page-locked one (lqg_alloc_host) directly by the copy engine.  LQG_STAGED=0 disables.
+    std::unique_ptr<StagedCopier> staged;
+    static const char* env_staged = getenv("LQG_STAGED");
+    if (copy_st && !(env_staged && env_staged[0] == '0') && StagedCopier::is_pageable(out))
+      staged.reset(new StagedCopier(copy_st));
+    auto copy_out = [&](int from, int upto, cudaStream_t cs) -> int {
+      const size_t pitch = (size_t)n_per_chain * d * sizeof(double);
+      const size_t width = (size_t)(upto - from) * d * sizeof(double);
+      if (staged) LQG_CUDA_TRY(staged->copy2d(out + (size_t)from * d, pitch, d_out + (size_t)from * d, pitch, width, n_chains));
+      else LQG_CUDA_TRY(cudaMemcpy2DAsync(out + (size_t)from * d, pitch, d_out + (size_t)from * d, pitch, width, n_chains,
+                                          cudaMemcpyDeviceToHost, cs));
+      return LQG_OK;
+    };
     // every round consumes `attempts` momenta per active chain, so this terminates after at most
     // (total + restarts) / attempts rounds; max_restarts bounds the restarts of every transition
     while (n_active > 0) {
@@ -388,10 +405,7 @@ extern "C" int lqg_hmc_box(int32_t d, const double* mu, const double* U, int32_t
       if (copy_st && s_min - burn_in > copied) {
         const int upto = s_min - burn_in;
         LQG_CUDA_TRY(cudaStreamWaitEvent(copy_st, ev_round, 0));
-        const size_t pitch = (size_t)n_per_chain * d * sizeof(double);
-        LQG_CUDA_TRY(cudaMemcpy2DAsync(out + (size_t)copied * d, pitch, d_out + (size_t)copied * d, pitch,
-                                       (size_t)(upto - copied) * d * sizeof(double), n_chains,
-                                       cudaMemcpyDeviceToHost, copy_st));
+        if ((rc = copy_out(copied, upto, copy_st))) return rc;
         copied = upto;
       }
       // shrink the last rounds' pool to what the slowest chain can still need; when the samples
@@ -409,11 +423,11 @@ extern "C" int lqg_hmc_box(int32_t d, const double* mu, const double* U, int32_t
     if (copy_st) {
       // chains that failed never advance s_min: whatever is left is copied by the common tail below
       if (copied < n_per_chain) {
-        const size_t pitch = (size_t)n_per_chain * d * sizeof(double);
-        LQG_CUDA_TRY(cudaMemcpy2DAsync(out + (size_t)copied * d, pitch, d_out + (size_t)copied * d, pitch,
-                                       (size_t)(n_per_chain - copied) * d * sizeof(double), n_chains,
-                                       cudaMemcpyDeviceToHost, st));
+        LQG_CUDA_TRY(cudaEventRecord(ev_round, st));
+        LQG_CUDA_TRY(cudaStreamWaitEvent(copy_st, ev_round, 0));
+        if ((rc = copy_out(copied, n_per_chain, copy_st))) return rc;
       }
+      if (staged) LQG_CUDA_TRY(staged->finish());
       LQG_CUDA_TRY(cudaStreamSynchronize(copy_st));
       out_copied = true;
     }

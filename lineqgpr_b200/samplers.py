@@ -14,7 +14,7 @@ What stays on the host, exactly where the reference has it on the host: the one-
 whitening algebra (solve, chol, triangular inverse).  Everything per-sample runs on the GPU.
 Extensions (all optional keys of `control`): "n.chains" (independent chains; 1 reproduces the
 reference's single serial chain), "seed", "prepass", "injected", "max.restarts",
-"chain.offset", "U" (a precomputed factor), "whiten" ("ul" | "tmg" | "device", see whiten_box).
+"chain.offset", "U" (a precomputed factor), "whiten" ("device" (default) | "ul" | "tmg", see whiten_box).
 """
 from __future__ import annotations
 
@@ -104,8 +104,8 @@ def tmvrnorm_HMC(object, nsim, control=None, **kw):
     n_chains = max(1, min(n_chains, nsim))
     n_per = -(-nsim // n_chains)
     U = control.get("U")
-    if U is None and control.get("whiten", "ul") != "device":
-        U = whiten_box(mu, Sigma, control.get("whiten", "ul"))     # "device": lqg_hmc_box factors Sigma itself
+    if U is None and control.get("whiten", "device") != "device":
+        U = whiten_box(mu, Sigma, control["whiten"])               # default "device": lqg_hmc_box factors Sigma itself
     seed = control.get("seed")
     if seed is None:
         seed = int(np.random.randint(1, 10000000))                     # tmg:R/tmg.R:102
@@ -127,6 +127,8 @@ def tmvrnorm_HMC(object, nsim, control=None, **kw):
     rc = L.lib().lqg_hmc_box(d, L.ptr(mu_c), L.ptr(Uf), 1, L.ptr(Sf), L.ptr(lb_c), L.ptr(ub_c),
                              L.ptr(init_c), 0, n_per, int(control["burn.in"]), opts, L.ptr(out), None, stats)
     last_stats.clear(); last_stats.update(stats.asdict(), sampler="HMC", n_chains=n_chains, n_per_chain=n_per, seed=seed)
+    if rc == 8:
+        raise ValueError("Error: M must be positive definite.")        # tmg:R/tmg.R:17-20 (device whitening)
     L.check(rc, "tmvrnorm.HMC")
     return out[:, :nsim]                                               # :142  t(xi): d x nsim
 

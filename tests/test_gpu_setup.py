@@ -296,3 +296,35 @@ def test_factorization_is_as_robust_as_lapack_on_nearly_singular_input(lqg, d):
         X = S.solve_spd(A, A @ np.ones((d, 2)))
         assert np.linalg.norm(A @ X - A @ np.ones((d, 2))) <= 1e-9 * np.linalg.norm(A @ np.ones((d, 2))), shift
     assert not S.is_positive_definite(S0 - 1e-8 * nrm * np.eye(d))
+
+
+def test_tmvrnorm_default_whitens_on_device_and_reports_non_pd(lqg):
+    from lineqgpr_b200 import workloads as W
+    par, _ = W.cfg3()
+    par = dict(par, **{"class": "HMC"})
+    a = lqg.tmvrnorm(par, 32, {"burn.in": 2, "n.chains": 4, "seed": 5})                      # default: device
+    b = lqg.tmvrnorm(par, 32, {"burn.in": 2, "n.chains": 4, "seed": 5, "whiten": "device"})
+    assert np.array_equal(a, b)
+    S_bad = np.eye(par["mu"].size)
+    S_bad[0, 1] = S_bad[1, 0] = 2.0                                                          # positive diagonal, eigenvalues 1 +- 2
+    bad = dict(par, Sigma=S_bad)
+    with pytest.raises(ValueError, match="positive definite"):
+        lqg.tmvrnorm(bad, 8, {"burn.in": 1, "n.chains": 2, "seed": 1})
+
+
+def test_pageable_and_pinned_results_are_bit_identical(lqg):
+    """A pageable result matrix goes through the pinned staging ring and helper threads, a
+    page-locked one straight through the copy engine: same bytes, ragged chain counts and a
+    sample count that does not fill the last round."""
+    from lineqgpr_b200 import workloads as W, _lib as L
+    par, _ = W.cfg4(m=300)
+    par = dict(par, **{"class": "HMC"})
+    d = par["mu"].size
+    for n_chains, nsim in ((7, 7 * 150), (32, 32 * 41)):
+        ctl = {"burn.in": 3, "n.chains": n_chains, "seed": 2}
+        x_page = lqg.tmvrnorm(par, nsim, dict(ctl))
+        out = L.empty_result(d, nsim)
+        x_pin = lqg.tmvrnorm(par, nsim, dict(ctl, out=out))
+        assert x_page.shape == x_pin.shape == (d, nsim)
+        assert np.array_equal(x_page, x_pin)
+        assert np.all(x_page >= par["lb"][:, None]) and np.all(x_page <= par["ub"][:, None])
