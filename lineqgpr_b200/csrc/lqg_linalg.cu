@@ -153,6 +153,9 @@ __global__ void __launch_bounds__(256) chol_diag_kernel(int nbk, int k0, const d
     s[i * 65 + l] = v;
   }
   __syncthreads();
+  // thread -> (row i, column phase lq): column l = j+1+lq, j+5+lq, ... of row i; a warp shares l
+  // (broadcast read of s[l][j]) and walks 32 consecutive rows (stride 65: conflict-free)
+  const int ri = tid & (NB - 1), lq = tid >> 6;
   for (int j = 0; j < nbk; ++j) {
     if (tid == 0) {
       double piv = s[j * 65 + j];
@@ -163,11 +166,9 @@ __global__ void __launch_bounds__(256) chol_diag_kernel(int nbk, int k0, const d
     const double ljj = s[j * 65 + j];
     if (tid > j && tid < nbk) s[tid * 65 + j] /= ljj;
     __syncthreads();
-    // trailing update of the lower triangle: (i, l) with j < l <= i < nbk
-    const int rem = nbk - j - 1;
-    for (int e = tid; e < rem * rem; e += 256) {
-      const int i = j + 1 + e % rem, l = j + 1 + e / rem;
-      if (l <= i) s[i * 65 + l] = fma(-s[i * 65 + j], s[l * 65 + j], s[i * 65 + l]);
+    if (ri > j && ri < nbk) {
+      const double lij = s[ri * 65 + j];
+      for (int l = j + 1 + lq; l <= ri; l += 4) s[ri * 65 + l] = fma(-lij, s[l * 65 + j], s[ri * 65 + l]);
     }
     __syncthreads();
   }
@@ -181,16 +182,19 @@ __global__ void __launch_bounds__(256) chol_diag_kernel(int nbk, int k0, const d
 //   trans = 0:  L x = b   (forward substitution)      trans = 1:  L' x = b   (backward)
 // Right-hand side r has its element j at B[j * sj + r * sr]; the solution is written to
 // X[j * xj + r * xr] (may alias B).  Lane l owns elements l and l + 32; the pivot element is
-// divided by the diagonal in its owner lane and broadcast.
+// scaled by the reciprocal diagonal (computed once per CTA) in its owner lane and broadcast.
 __global__ void __launch_bounds__(256) tri_solve_kernel(int nbk, const double* __restrict__ Lkk, int64_t ldl, int trans,
                                                         int nrhs, const double* B, int64_t sj, int64_t sr,
                                                         double* X, int64_t xj, int64_t xr) {
   __shared__ double s[NB * 65];      // s[i * 65 + l] = L[i, l]
+  __shared__ double rdiag[NB];       // 1 / L[j, j]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int e = tid; e < NB * NB; e += 256) {
     const int i = e % NB, l = e / NB;
     s[i * 65 + l] = (i < nbk && l <= i) ? Lkk[(size_t)l * ldl + i] : (i == l ? 1.0 : 0.0);
   }
+  __syncthreads();
+  if (tid < NB) rdiag[tid] = 1.0 / s[tid * 65 + tid];
   __syncthreads();
   for (int r = blockIdx.x * 8 + warp; r < nrhs; r += gridDim.x * 8) {
     double b0 = lane < nbk ? B[(size_t)lane * sj + (size_t)r * sr] : 0.0;
@@ -198,14 +202,14 @@ __global__ void __launch_bounds__(256) tri_solve_kernel(int nbk, const double* _
     const int i0 = lane, i1 = lane + 32;
     if (!trans) {
       for (int j = 0; j < nbk; ++j) {
-        const double mine = (j < 32 ? b0 : b1) / s[j * 65 + j];
+        const double mine = (j < 32 ? b0 : b1) * rdiag[j];
         const double xv = __shfl_sync(0xffffffffu, mine, j & 31);
         if (i0 == j) b0 = xv; else if (i0 > j) b0 = fma(-s[i0 * 65 + j], xv, b0);
         if (i1 == j) b1 = xv; else if (i1 > j) b1 = fma(-s[i1 * 65 + j], xv, b1);
       }
     } else {
       for (int j = nbk - 1; j >= 0; --j) {                    // L'[i, j] = L[j, i]
-        const double mine = (j < 32 ? b0 : b1) / s[j * 65 + j];
+        const double mine = (j < 32 ? b0 : b1) * rdiag[j];
         const double xv = __shfl_sync(0xffffffffu, mine, j & 31);
         if (i0 == j) b0 = xv; else if (i0 < j) b0 = fma(-s[j * 65 + i0], xv, b0);
         if (i1 == j) b1 = xv; else if (i1 < j) b1 = fma(-s[j * 65 + i1], xv, b1);
