@@ -29,6 +29,7 @@ extern "C" {
 #define LQG_ERR_CUDA             4   /* no device / CUDA runtime error (see lqg_last_error)   */
 #define LQG_ERR_RESTART_CAP      5   /* a chain exceeded max_restarts in one transition        */
 #define LQG_ERR_DRAWS_EXHAUSTED  6   /* injected Gaussian stream too short                     */
+#define LQG_ERR_INTERNAL         9   /* host allocation failure or another internal exception  */
 #define LQG_ERR_NOT_PD           8   /* tmg:R/tmg.R:17-20 "M must be positive definite"        */
 #define LQG_ERR_BUDGET           7   /* RSM: proposal budget exhausted before nsim accepts     */
 

@@ -15,7 +15,7 @@ LIB_PATH = PKG / "liblineqgpr_b200.so"
 LQG_OK = 0
 STATUS = {0: "LQG_OK", 1: "LQG_ERR_INVALID", 2: "LQG_ERR_UNSUPPORTED", 3: "LQG_ERR_INIT_INFEASIBLE",
           4: "LQG_ERR_CUDA", 5: "LQG_ERR_RESTART_CAP", 6: "LQG_ERR_DRAWS_EXHAUSTED", 7: "LQG_ERR_BUDGET",
-          8: "LQG_ERR_NOT_PD"}
+          8: "LQG_ERR_NOT_PD", 9: "LQG_ERR_INTERNAL"}
 MEM_HOST, MEM_DEVICE = 0, 1
 
 # every symbol include/lineqgpr_b200.h declares

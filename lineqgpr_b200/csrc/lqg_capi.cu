@@ -10,6 +10,7 @@
 #include <mutex>
 #include <vector>
 
+#include <exception>
 #include <memory>
 
 #include "lqg_common.cuh"
@@ -205,6 +206,18 @@ static int chain_status_rc(const std::vector<int>& st, unsigned long long* faile
 
 using namespace lqg;
 
+// No exception crosses the C ABI: host-side allocation failures (std::bad_alloc), thread start-up
+// failures (std::system_error) and anything else thrown inside an entry point become a status.
+#define LQG_API_BEGIN try {
+#define LQG_API_END(name)                                                      \
+  } catch (const std::exception& e) {                                          \
+    set_error("%s: internal error: %s", name, e.what());                      \
+    return LQG_ERR_INTERNAL;                                                   \
+  } catch (...) {                                                              \
+    set_error("%s: internal error (unknown exception)", name);                \
+    return LQG_ERR_INTERNAL;                                                   \
+  }
+
 static int ul_factor_device(int d, const double* S_dev, double* U_dev, cudaStream_t st);
 
 // ===========================================================================================
@@ -213,6 +226,7 @@ extern "C" int lqg_hmc_box(int32_t d, const double* mu, const double* U, int32_t
                            const double* init, int64_t init_ld, int32_t n_per_chain,
                            int32_t burn_in, const lqg_opts* opts_, double* out,
                            double* state_out, lqg_hmc_stats* stats) {
+  LQG_API_BEGIN
   if (stats) memset(stats, 0, sizeof(*stats));
   if (!have_device()) return LQG_ERR_CUDA;
   Phase ph("hmc_box");
@@ -461,6 +475,7 @@ extern "C" int lqg_hmc_box(int32_t d, const double* mu, const double* U, int32_t
   if (rc == LQG_ERR_DRAWS_EXHAUSTED) set_error("lqg_hmc_box: injected Gaussian stream too short for %llu chain(s)", h_stats[7]);
   if (rc == LQG_OK && h_stats[6] != 0) { set_error("lqg_hmc_box: %llu emitted values violate the bounds", h_stats[6]); }
   return rc;
+  LQG_API_END("lqg_hmc_box")
 }
 
 // ===========================================================================================
@@ -573,24 +588,29 @@ extern "C" int lqg_hmc_canonical(int32_t d, int32_t c, const double* F, const do
                                  const double* initial, int64_t initial_ld, int32_t n_per_chain,
                                  int32_t burn_in, const lqg_opts* opts_, double* out,
                                  double* state_out, lqg_hmc_stats* stats) {
+  LQG_API_BEGIN
   return hmc_canonical_impl(d, c, F, g, initial, initial_ld, n_per_chain, burn_in, opts_, out, state_out, stats,
                             0, nullptr, nullptr, nullptr);
+  LQG_API_END("lqg_hmc_canonical")
 }
 
 extern "C" int lqg_hmc_canonical_trace(int32_t d, int32_t c, const double* F, const double* g,
                                        const double* initial, int64_t initial_ld, int32_t n_per_chain,
                                        const lqg_opts* opts_, double* out, int32_t trace_cap,
                                        double* trace_t, int32_t* trace_cn, int32_t* trace_n) {
+  LQG_API_BEGIN
   if (opts_ && opts_->mem != LQG_MEM_HOST) { set_error("lqg_hmc_canonical_trace: host pointers only"); return LQG_ERR_INVALID; }
   if (trace_cap <= 0 || !trace_t || !trace_cn || !trace_n) { set_error("lqg_hmc_canonical_trace: invalid trace buffers"); return LQG_ERR_INVALID; }
   return hmc_canonical_impl(d, c, F, g, initial, initial_ld, n_per_chain, 0, opts_, out, nullptr, nullptr,
                             trace_cap, trace_t, trace_cn, trace_n);
+  LQG_API_END("lqg_hmc_canonical_trace")
 }
 
 // ===========================================================================================
 extern "C" int lqg_rtmg(int32_t n, int32_t seed, const double* initial, int32_t d, int32_t numlin,
                         const double* F, const double* g, int32_t numquad, const double* quadratics,
                         double* out) {
+  LQG_API_BEGIN
   (void)quadratics;
   if (numquad != 0) {
     set_error("lqg_rtmg: quadratic constraints are not supported (lineqGPR always passes q=NULL)");
@@ -606,6 +626,7 @@ extern "C" int lqg_rtmg(int32_t n, int32_t seed, const double* initial, int32_t 
   for (int i = 0; i < n; ++i)                    // d x n (column = sample) -> n x d (row = sample)
     for (int j = 0; j < d; ++j) out[(size_t)i + (size_t)j * n] = cols[(size_t)i * d + j];
   return LQG_OK;
+  LQG_API_END("lqg_rtmg")
 }
 
 // ===========================================================================================
@@ -637,17 +658,20 @@ extern "C" int64_t lqg_launch_count(int32_t reset) {
   return v;
 }
 extern "C" int lqg_measure_fp64_peaks(double* dfma_tflops, double* dmma_tflops, const lqg_opts* opts) {
+  LQG_API_BEGIN
   if (!have_device()) return LQG_ERR_CUDA;
   cudaStream_t st = opts ? (cudaStream_t)opts->stream : nullptr;
   LQG_CUDA_TRY(measure_fp64_peaks(dfma_tflops, dmma_tflops, st));
   fold_launches();
   return LQG_OK;
+  LQG_API_END("lqg_measure_fp64_peaks")
 }
 
 // ===========================================================================================
 extern "C" int lqg_rsm(int32_t d, const double* map, const double* factor, const double* w,
                        const double* lb, const double* ub, int64_t nsim, int64_t max_proposals,
                        const lqg_opts* opts_, double* out, lqg_rsm_stats* stats) {
+  LQG_API_BEGIN
   if (stats) memset(stats, 0, sizeof(*stats));
   if (!have_device()) return LQG_ERR_CUDA;
   const lqg_opts o = opts_ ? *opts_ : default_opts();
@@ -737,12 +761,14 @@ extern "C" int lqg_rsm(int32_t d, const double* map, const double* factor, const
     return LQG_ERR_BUDGET;
   }
   return LQG_OK;
+  LQG_API_END("lqg_rsm")
 }
 
 // ===========================================================================================
 extern "C" int lqg_expt(int32_t d, const double* L0, const double* l, const double* u, const double* mu,
                         double psistar, int64_t nsim, int64_t max_proposals, const lqg_opts* opts_,
                         double* Z_out, lqg_expt_stats* stats) {
+  LQG_API_BEGIN
   if (stats) memset(stats, 0, sizeof(*stats));
   if (!have_device()) return LQG_ERR_CUDA;
   const lqg_opts o = opts_ ? *opts_ : default_opts();
@@ -812,12 +838,14 @@ extern "C" int lqg_expt(int32_t d, const double* L0, const double* l, const doub
     return LQG_ERR_BUDGET;
   }
   return LQG_OK;
+  LQG_API_END("lqg_expt")
 }
 
 // ===========================================================================================
 extern "C" int lqg_dgemm(int32_t m, int32_t n, int32_t k, const double* A, int64_t lda,
                          const double* B, int64_t ldb, double* C, int64_t ldc, double* row_sum,
                          const lqg_opts* opts_, double* kernel_ms) {
+  LQG_API_BEGIN
   if (!have_device()) return LQG_ERR_CUDA;
   const lqg_opts o = opts_ ? *opts_ : default_opts();
   if (m <= 0 || n <= 0 || k <= 0 || !A || !B || (!C && !row_sum) || lda < m || ldb < k || (C && ldc < m)) {
@@ -854,6 +882,7 @@ extern "C" int lqg_dgemm(int32_t m, int32_t n, int32_t k, const double* A, int64
   LQG_CUDA_TRY(cudaStreamSynchronize(st));
   fold_launches();
   return LQG_OK;
+  LQG_API_END("lqg_dgemm")
 }
 
 // ===========================================================================================
@@ -900,6 +929,7 @@ static int ul_factor_device(int d, const double* S_dev, double* U_dev, cudaStrea
 
 extern "C" int lqg_whiten_box(int32_t d, const double* Sigma, const lqg_opts* opts_, double* U_out,
                               double* kernel_ms) {
+  LQG_API_BEGIN
   if (!have_device()) return LQG_ERR_CUDA;
   const lqg_opts o = opts_ ? *opts_ : default_opts();
   if (d <= 0 || d > 32768 || !Sigma || !U_out) { set_error("lqg_whiten_box: invalid argument (d=%d)", d); return LQG_ERR_INVALID; }
@@ -921,9 +951,11 @@ extern "C" int lqg_whiten_box(int32_t d, const double* Sigma, const lqg_opts* op
   LQG_CUDA_TRY(cudaStreamSynchronize(st));
   fold_launches();
   return LQG_OK;
+  LQG_API_END("lqg_whiten_box")
 }
 
 extern "C" int lqg_chol(int32_t d, const double* A, const lqg_opts* opts_, double* L_out, int32_t* bad_pivot) {
+  LQG_API_BEGIN
   if (!have_device()) return LQG_ERR_CUDA;
   const lqg_opts o = opts_ ? *opts_ : default_opts();
   if (d <= 0 || d > 32768 || !A) { set_error("lqg_chol: invalid argument (d=%d)", d); return LQG_ERR_INVALID; }
@@ -943,10 +975,12 @@ extern "C" int lqg_chol(int32_t d, const double* A, const lqg_opts* opts_, doubl
   if ((rc = deliver(L_out, b_l.as<double>(), dd, o.mem, st))) return rc;
   LQG_CUDA_TRY(cudaStreamSynchronize(st));
   return LQG_OK;
+  LQG_API_END("lqg_chol")
 }
 
 extern "C" int lqg_solve_spd(int32_t d, int32_t nrhs, const double* A, const double* B, const lqg_opts* opts_,
                              double* X_out) {
+  LQG_API_BEGIN
   if (!have_device()) return LQG_ERR_CUDA;
   const lqg_opts o = opts_ ? *opts_ : default_opts();
   if (d <= 0 || d > 32768 || nrhs <= 0 || !A || !B || !X_out) {
@@ -971,11 +1005,13 @@ extern "C" int lqg_solve_spd(int32_t d, int32_t nrhs, const double* A, const dou
   LQG_CUDA_TRY(cudaStreamSynchronize(st));
   fold_launches();
   return LQG_OK;
+  LQG_API_END("lqg_solve_spd")
 }
 
 extern "C" int lqg_eta_params(int32_t d, int32_t m, const double* Lambda, const double* mu, const double* xi_map,
                               const double* Sigma, double nugget, const lqg_opts* opts_,
                               double* eta_mu, double* eta_map, double* Sigma_eta) {
+  LQG_API_BEGIN
   if (!have_device()) return LQG_ERR_CUDA;
   const lqg_opts o = opts_ ? *opts_ : default_opts();
   if (d <= 0 || m <= 0 || d > 32768 || m > 32768 || !Lambda || !Sigma || !Sigma_eta || (eta_mu && !mu) || (eta_map && !xi_map)) {
@@ -1013,9 +1049,11 @@ extern "C" int lqg_eta_params(int32_t d, int32_t m, const double* Lambda, const 
   LQG_CUDA_TRY(cudaStreamSynchronize(st));
   fold_launches();
   return LQG_OK;
+  LQG_API_END("lqg_eta_params")
 }
 
 extern "C" int lqg_lambda_pinv(int32_t d, int32_t m, const double* Lambda, const lqg_opts* opts_, double* Lp_out) {
+  LQG_API_BEGIN
   if (!have_device()) return LQG_ERR_CUDA;
   const lqg_opts o = opts_ ? *opts_ : default_opts();
   if (d <= 0 || m <= 0 || d < m || d > 32768 || !Lambda || !Lp_out) {
@@ -1059,10 +1097,12 @@ extern "C" int lqg_lambda_pinv(int32_t d, int32_t m, const double* Lambda, const
   LQG_CUDA_TRY(cudaStreamSynchronize(st));
   fold_launches();
   return LQG_OK;
+  LQG_API_END("lqg_lambda_pinv")
 }
 
 extern "C" int lqg_basis(int32_t n_t, int32_t D, const int32_t* m_k, const double* x, int64_t ldx, const double* u,
                          const lqg_opts* opts_, double* Phi, int64_t ld) {
+  LQG_API_BEGIN
   if (!have_device()) return LQG_ERR_CUDA;
   const lqg_opts o = opts_ ? *opts_ : default_opts();
   if (n_t <= 0 || D <= 0 || !m_k || !x || !u || !Phi || ldx < n_t || ld < n_t) {
@@ -1105,11 +1145,13 @@ extern "C" int lqg_basis(int32_t n_t, int32_t D, const int32_t* m_k, const doubl
     return LQG_ERR_INVALID;
   }
   return LQG_OK;
+  LQG_API_END("lqg_basis")
 }
 
 extern "C" int lqg_solve_qp(int32_t n, int32_t mc, const double* D, const double* dvec, const double* A,
                             const double* b, double tol, int32_t max_iter, const lqg_opts* opts_,
                             double* x_out, int32_t* iters) {
+  LQG_API_BEGIN
   if (!have_device()) return LQG_ERR_CUDA;
   const lqg_opts o = opts_ ? *opts_ : default_opts();
   if (n <= 0 || n > 32768 || mc < 0 || !D || !dvec || !x_out || (mc > 0 && (!A || !b))) {
@@ -1322,12 +1364,14 @@ extern "C" int lqg_solve_qp(int32_t n, int32_t mc, const double* D, const double
     return LQG_ERR_BUDGET;
   }
   return LQG_OK;
+  LQG_API_END("lqg_solve_qp")
 }
 
 // ===========================================================================================
 extern "C" int lqg_bands(int32_t n_t, int64_t N, const double* ysim, int64_t ld, const double* probs,
                          int32_t nprobs, double* mean, double* qtls, const lqg_opts* opts_,
                          double* kernel_ms) {
+  LQG_API_BEGIN
   if (!have_device()) return LQG_ERR_CUDA;
   const lqg_opts o = opts_ ? *opts_ : default_opts();
   if (n_t <= 0 || N <= 0 || !ysim || ld < n_t || nprobs < 0 || nprobs > 8 || (nprobs > 0 && (!probs || !qtls)) || !mean) {
@@ -1363,4 +1407,5 @@ extern "C" int lqg_bands(int32_t n_t, int64_t N, const double* ysim, int64_t ld,
   LQG_CUDA_TRY(cudaStreamSynchronize(st));
   fold_launches();
   return LQG_OK;
+  LQG_API_END("lqg_bands")
 }
