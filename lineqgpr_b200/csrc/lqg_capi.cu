@@ -137,6 +137,23 @@ struct Input {
   }
 };
 
+// Device -> host copy of a large result: a pageable destination (R / numpy matrix) goes through the
+// pinned staging ring and helper threads (lqg_hostcopy.cu), anything else through the copy engine.
+// Ordered after the work already enqueued on st; returns after the bytes are in place when staged.
+static cudaError_t d2h_result(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t rows,
+                              cudaStream_t st) {
+  static const char* env_staged = getenv("LQG_STAGED");
+  if (width * rows >= ((size_t)32 << 20) && !(env_staged && env_staged[0] == '0') && StagedCopier::is_pageable(dst)) {
+    StagedCopier sc(st);
+    cudaError_t e = sc.copy2d(dst, dpitch, src, spitch, width, rows);
+    if (e != cudaSuccess) return e;
+    return sc.finish();
+  }
+  if (rows == 1 || (dpitch == width && spitch == width))
+    return cudaMemcpyAsync(dst, src, width * rows, cudaMemcpyDeviceToHost, st);
+  return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, cudaMemcpyDeviceToHost, st);
+}
+
 static int have_device() {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
@@ -874,8 +891,8 @@ extern "C" int lqg_dgemm(int32_t m, int32_t n, int32_t k, const double* A, int64
   if (kernel_ms) *kernel_ms = tm.ms();
   if (mem == LQG_MEM_HOST) {
     if (C) {
-      if (ldc == m) LQG_CUDA_TRY(cudaMemcpyAsync(C, d_C, (size_t)m * n * sizeof(double), cudaMemcpyDeviceToHost, st));
-      else LQG_CUDA_TRY(cudaMemcpy2DAsync(C, ldc * sizeof(double), d_C, ldc * sizeof(double), m * sizeof(double), n, cudaMemcpyDeviceToHost, st));
+      if (ldc == m) LQG_CUDA_TRY(d2h_result(C, (size_t)m * n * sizeof(double), d_C, (size_t)m * n * sizeof(double), (size_t)m * n * sizeof(double), 1, st));
+      else LQG_CUDA_TRY(d2h_result(C, ldc * sizeof(double), d_C, ldc * sizeof(double), m * sizeof(double), n, st));
     }
     if (row_sum) LQG_CUDA_TRY(cudaMemcpyAsync(row_sum, d_rs, m * sizeof(double), cudaMemcpyDeviceToHost, st));
   }

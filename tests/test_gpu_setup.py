@@ -328,3 +328,14 @@ def test_pageable_and_pinned_results_are_bit_identical(lqg):
         assert x_page.shape == x_pin.shape == (d, nsim)
         assert np.array_equal(x_page, x_pin)
         assert np.all(x_page >= par["lb"][:, None]) and np.all(x_page <= par["ub"][:, None])
+
+
+def test_large_dgemm_result_through_staging_ring(lqg):
+    """A > 32 MB pageable GEMM result is delivered through the pinned staging ring (16 MB pieces,
+    helper threads): every byte must arrive, including the ragged last piece."""
+    rng = np.random.default_rng(4)
+    A = rng.standard_normal((701, 64))
+    B = rng.standard_normal((64, 9001))                     # C = 701 x 9001 doubles = 50.5 MB, not a multiple of 16 MB
+    C = lqg.dgemm(A, B)
+    assert np.allclose(C, A @ B, rtol=1e-12, atol=1e-12)
+    assert np.array_equal(C, lqg.dgemm(A, B))
