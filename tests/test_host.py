@@ -203,3 +203,23 @@ def test_solve_qp_stops_at_the_rounding_floor(lqg):
         lam = np.linalg.lstsq(A[act].T, g, rcond=None)[0] if act.any() else np.zeros(0)
         assert np.linalg.norm(A[act].T @ lam - g) <= 1e-6 * max(1.0, np.linalg.norm(g))
         assert lam.min(initial=0.0) >= -1e-6
+
+
+def test_r_shim_type_checks_against_the_header():
+    """R is not installed here, so rshim/lqg_rcall.c cannot be built; it is at least compiled
+    (syntax + types, -Wall -Wextra clean) against include/lineqgpr_b200.h with a minimal stand-in
+    for R's C API, so that every .Call wrapper matches the C ABI it forwards to."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    r = subprocess.run([gcc, "-fsyntax-only", "-Wall", "-Wextra", "-Werror", f"-I{ROOT / 'include'}",
+                        f"-I{ROOT / 'tests' / 'r_stub'}", str(ROOT / "rshim" / "lqg_rcall.c")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    # every wrapper the patched R methods call exists in the shim
+    shim = (ROOT / "rshim" / "lqg_rcall.c").read_text()
+    rfile = (ROOT / "rshim" / "lineqGPsamplers_b200.R").read_text()
+    for name in set(re.findall(r'\.Call\("(lqg_[a-z_]+)"', rfile)):
+        assert re.search(r"\bSEXP %s\(" % name, shim), name
