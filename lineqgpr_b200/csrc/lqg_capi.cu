@@ -1406,15 +1406,40 @@ extern "C" int lqg_bands(int32_t n_t, int64_t N, const double* ysim, int64_t ld,
   Input i_y;
   if ((rc = i_y.stage(ysim, (size_t)ld * (N - 1) + n_t, mem, st))) return rc;
   DevBuf b_scr, b_mean, b_q;
-  LQG_CUDA_TRY(b_scr.alloc((size_t)n_t * N * sizeof(double)));
   double* d_mean = mean; double* d_q = qtls;
   if (mem == LQG_MEM_HOST) {
     LQG_CUDA_TRY(b_mean.alloc(n_t * sizeof(double))); d_mean = b_mean.as<double>();
     LQG_CUDA_TRY(b_q.alloc((size_t)std::max(1, nprobs) * n_t * sizeof(double))); d_q = b_q.as<double>();
   }
+  // bracketed path (one coalesced pass over ysim); test points whose bracket missed or overflowed,
+  // and shapes it does not cover, go through the exact transpose + radix-select path
+  static const char* env_exact = getenv("LQG_BANDS_EXACT");              // tuning / test aid
+  const size_t fast_bytes = (env_exact && env_exact[0] == '1') ? 0 : bands_bracket_scratch_bytes(n_t, N, nprobs);
+  LQG_CUDA_TRY(b_scr.alloc(fast_bytes ? fast_bytes : (size_t)n_t * N * sizeof(double)));
   Timer tm(st);
   tm.start();
-  LQG_CUDA_TRY(launch_bands(n_t, N, i_y.dev, ld, h_probs.data(), nprobs, d_mean, d_q, b_scr.as<double>(), st));
+  if (fast_bytes) {
+    int* fail_dev = nullptr;
+    LQG_CUDA_TRY(launch_bands_bracketed(n_t, N, i_y.dev, ld, h_probs.data(), nprobs, d_mean, d_q, b_scr.p, &fail_dev, st));
+    std::vector<int> h_fail(n_t);
+    LQG_CUDA_TRY(cudaMemcpyAsync(h_fail.data(), fail_dev, n_t * sizeof(int), cudaMemcpyDeviceToHost, st));
+    LQG_CUDA_TRY(cudaStreamSynchronize(st));
+    std::vector<int> rows;
+    for (int r = 0; r < n_t; ++r) if (h_fail[r]) rows.push_back(r);
+    if (getenv("LQG_TRACE")) fprintf(stderr, "[lqg bands] bracketed path: %zu of %d test points go to the exact path (first %d)\n",
+                                     rows.size(), n_t, rows.empty() ? -1 : rows[0]);
+    if (rows.size() > 64) {
+      LQG_CUDA_TRY(b_scr.alloc((size_t)n_t * N * sizeof(double)));
+      LQG_CUDA_TRY(launch_bands_exact(n_t, N, i_y.dev, ld, h_probs.data(), nprobs, d_mean, d_q, b_scr.as<double>(), st));
+    } else if (!rows.empty()) {
+      LQG_CUDA_TRY(b_scr.alloc((size_t)N * sizeof(double)));
+      for (int r : rows)
+        LQG_CUDA_TRY(launch_bands_exact(1, N, i_y.dev + r, ld, h_probs.data(), nprobs, d_mean + r,
+                                        d_q + (size_t)r * nprobs, b_scr.as<double>(), st));
+    }
+  } else {
+    LQG_CUDA_TRY(launch_bands_exact(n_t, N, i_y.dev, ld, h_probs.data(), nprobs, d_mean, d_q, b_scr.as<double>(), st));
+  }
   tm.stop();
   if (kernel_ms) *kernel_ms = tm.ms();
   if (mem == LQG_MEM_HOST) {

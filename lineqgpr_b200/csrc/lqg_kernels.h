@@ -182,9 +182,15 @@ cudaError_t launch_add_colvec(int m, size_t n, double* out, int64_t ld, const do
 
 // ---- bands (lqg_bands.cu) ---------------------------------------------------------------
 // ysim n_t x N col-major (ld).  scratch: N x n_t doubles (transposed copy).
-cudaError_t launch_bands(int n_t, int64_t N, const double* ysim, int64_t ld, const double* probs_host,
-                         int nprobs, double* mean, double* qtls, double* scratch,
-                         cudaStream_t st);
+// exact path (fallback): scratch = n_t * N doubles (transposed copy)
+cudaError_t launch_bands_exact(int n_t, int64_t N, const double* ysim, int64_t ld, const double* probs_host,
+                               int nprobs, double* mean, double* qtls, double* scratch, cudaStream_t st);
+// bracketed path (one coalesced pass); scratch of bands_bracket_scratch_bytes() bytes (0: not applicable);
+// *fail_dev -> n_t flags (inside scratch): 1 = this test point must go through launch_bands_exact
+size_t bands_bracket_scratch_bytes(int n_t, int64_t N, int nprobs);
+cudaError_t launch_bands_bracketed(int n_t, int64_t N, const double* ysim, int64_t ld, const double* probs_host,
+                                   int nprobs, double* mean, double* qtls, void* scratch, int** fail_dev,
+                                   cudaStream_t st);
 
 // ---- peaks (lqg_peaks.cu) ---------------------------------------------------------------
 cudaError_t measure_fp64_peaks(double* dfma_tflops, double* dmma_tflops, cudaStream_t st);

@@ -126,3 +126,30 @@ def test_paths_bands_slabs_match_materialised(lqg, oracle):
     assert np.allclose(mean, mo, rtol=1e-11, atol=1e-13)
     assert np.allclose(q, qo, rtol=1e-11, atol=1e-13)       # GEMM rounding differs from numpy's, selection is exact
     assert info["gemm_ms"] > 0 and info["bands_ms"] > 0
+
+
+def test_bands_bracketed_path_is_exact(lqg, oracle):
+    """The one-pass bracketed path (sampled brackets -> collect -> select) against the oracle's
+    sort-based type-7 quantiles, bit for bit: ragged tile counts, heavy ties (bracket overflow ->
+    per-row exact fallback), an adversarial row whose systematic sample is unrepresentative
+    (bracket miss -> fallback), constant slabs (every row falls back -> whole-slab exact path),
+    extreme probabilities."""
+    rng = np.random.default_rng(21)
+    probs = np.array([0.0, 0.001, 0.025, 0.5, 0.75, 0.975, 0.9999, 1.0])
+    for (n_t, N) in [(70, 50000), (33, 8192), (1, 100001), (97, 20011)]:
+        y = rng.standard_normal((n_t, N)) * 10.0 ** rng.integers(-2, 3, size=(n_t, 1)) + rng.standard_normal((n_t, 1))
+        y[0, : N // 2] = y[0, 0]                                   # half the row tied
+        if n_t > 2:
+            y[1] = np.round(y[1])                                  # few distinct values: massive ties
+            stride = N / 2048.0                                    # the sampled positions see only huge values
+            idx = np.unique((np.arange(2048) * stride).astype(np.int64))
+            y[2, idx] = 1e6 + rng.standard_normal(idx.size)
+        mean, q = lqg.bands(y, probs)
+        mo, qo = oracle.bands(y, probs)
+        assert np.array_equal(q, qo), (n_t, N)
+        assert np.allclose(mean, mo, rtol=1e-12, atol=1e-300)
+    y = np.full((100, 9000), 3.25)                                 # every bracket overflows
+    mean, q = lqg.bands(y, probs[:3])
+    assert np.array_equal(q, np.full((3, 100), 3.25)) and np.array_equal(mean, np.full(100, 3.25))
+    mean, q = lqg.bands(rng.standard_normal((40, 30000)), np.zeros(0))   # means only
+    assert q.shape[0] == 0 and mean.shape == (40,)
