@@ -26,7 +26,10 @@ x = lqg.tmvrnorm(dict(W.cfg3()[0], **{"class": "ExpT"}), 300, {"seed": 2}); prin
 A = rng.standard_normal((130, 19)); B = rng.standard_normal((19, 67))
 C, rs = lqg.dgemm(A, B, row_sum=True); assert np.allclose(C, A @ B)
 y = rng.standard_normal((5, 300)); y[0, :100] = y[0, 0]
-m, q = lqg.bands(y, (0.025, 0.5, 0.975)); print("gemm/bands ok", flush=True)
+m, q = lqg.bands(y, (0.025, 0.5, 0.975))
+yb = rng.standard_normal((37, 9001)); yb[3, :5000] = 1.0          # sampled (bracketed) bands path + one overflowing row
+mb, qb = lqg.bands(yb, (0.0, 0.3, 1.0)); assert np.allclose(qb[1], np.quantile(yb, 0.3, axis=1), rtol=1e-12, atol=1e-12)
+print("gemm/bands ok", flush=True)
 # set-up stage: blocked Cholesky / solves / QP at ragged sizes (1, 64 +- 1, several blocks)
 from lineqgpr_b200 import setup_stage as S
 for n in (1, 63, 65, 130):
