@@ -55,11 +55,13 @@ def paths_bands(Phi_test, xi_sim, probs=(0.025, 0.975), slab_rows=None, return_y
     lqg_bands (exact type-7 quantiles + mean) and dropped.  xi.sim is uploaded once.
     With Phi_test = None and (xtest, ulist) given, each slab of the hat-basis matrix is built on
     the device from the test points (lqg_basis) instead of being computed on the host and
-    uploaded (config 5: 800 MB).
+    uploaded (config 5: 800 MB).  xi_sim may also be a CUDA tensor of shape (N, m) (= m x N
+    column-major) that is already on the device.
     Device buffers are torch tensors (plumbing); all compute goes through the C ABI.
     Returns (ymean[n_t], qtls[nprobs, n_t]) and timing info."""
     import torch
-    xi = np.asarray(xi_sim, float)
+    xi_dev = xi_sim if isinstance(xi_sim, torch.Tensor) else None      # already on the device: (N, m) contiguous = m x N column-major
+    xi = None if xi_dev is not None else np.asarray(xi_sim, float)
     if Phi_test is None:
         if xtest is None or ulist is None:
             raise ValueError("paths_bands needs Phi_test or (xtest, ulist)")
@@ -73,7 +75,7 @@ def paths_bands(Phi_test, xi_sim, probs=(0.025, 0.975), slab_rows=None, return_y
     else:
         Phi = np.asarray(Phi_test, float)
         n_t, m = Phi.shape
-    m2, N = xi.shape
+    m2, N = (xi_dev.shape[1], xi_dev.shape[0]) if xi_dev is not None else xi.shape
     if m != m2:
         raise ValueError("non-conformable arguments")
     probs = np.ascontiguousarray(probs, dtype=np.float64)
@@ -81,7 +83,14 @@ def paths_bands(Phi_test, xi_sim, probs=(0.025, 0.975), slab_rows=None, return_y
     st = torch.cuda.current_stream().cuda_stream
     if slab_rows is None:                                   # ysim slab + its transposed copy <= ~8 GB
         slab_rows = int(max(1, min(n_t, (4 << 30) // (8 * N))))
-    xi_d = torch.from_numpy(np.asfortranarray(xi).T.copy()).to(dev)               # column-major m x N
+        if 128 <= slab_rows < n_t:                          # whole 128-row GEMM tiles (no partly filled row block)
+            slab_rows -= slab_rows % 128
+    if xi_dev is not None:
+        if not (xi_dev.is_cuda and xi_dev.dtype == torch.float64 and xi_dev.is_contiguous()):
+            raise ValueError("xi_sim on the device must be a contiguous float64 CUDA tensor of shape (N, m)")
+        xi_d = xi_dev
+    else:
+        xi_d = torch.from_numpy(np.asfortranarray(xi).T.copy()).to(dev)           # column-major m x N
     y_d = torch.empty((N, slab_rows), dtype=torch.float64, device=dev)            # column-major slab x N
     mean_d = torch.empty(slab_rows, dtype=torch.float64, device=dev)
     q_d = torch.empty((slab_rows, probs.size), dtype=torch.float64, device=dev)   # column-major nprobs x slab
