@@ -192,6 +192,7 @@ constexpr int CW = 8;                // warps per collect CTA: 8 x 32 = 256 cons
 constexpr int CROWS = 32 * CW;
 constexpr int MAXSPLIT = 256;        // CTAs along the sample axis per 256-row tile (chosen at launch)
 constexpr int MAXP = MAXT / 2;       // probabilities
+constexpr int CUNR = 16;             // sample columns in flight per thread in the collect pass
 
 struct BandPlan {
   int nprobs;
@@ -271,12 +272,12 @@ bands_collect_kernel(int n_t, int64_t N, const double* __restrict__ ysim, int64_
   };
   const double* src = ysim + (size_t)n_begin * ld + row;
   int64_t n = n_begin;
-  for (; n + UNR <= n_end; n += UNR, src += (size_t)UNR * ld) {
-    double v[UNR];
+  for (; n + CUNR <= n_end; n += CUNR, src += (size_t)CUNR * ld) {
+    double v[CUNR];
 #pragma unroll
-    for (int q = 0; q < UNR; ++q) v[q] = __ldg(src + (size_t)q * ld);   // UNR sample columns in flight
+    for (int q = 0; q < CUNR; ++q) v[q] = __ldg(src + (size_t)q * ld);   // CUNR sample columns in flight
 #pragma unroll
-    for (int q = 0; q < UNR; ++q) consume(v[q]);
+    for (int q = 0; q < CUNR; ++q) consume(v[q]);
   }
   for (; n < n_end; ++n, src += ld) consume(__ldg(src));
   part_sum[((size_t)row * pl.splits + split) * 2 + 0] = sum;
