@@ -62,7 +62,9 @@ typedef struct lqg_opts {
   int32_t  prepass;        /* HMC box: 1 = batch the fresh momenta U*a of all transitions as one
                               FP64 tensor-core GEMM before the chain kernel, 0 = per-chain
                               in-kernel product, -1 = auto                                      */
-  int32_t  reserved1;
+  int32_t  canon_mode;     /* lqg_hmc_canonical: 0 = auto, 1 = one persistent CTA per chain (F in shared
+                              memory when it fits), 2 = lock-step rounds, the dot products of all
+                              chains as one FP64 tensor-core GEMM per round (large dense F)        */
 } lqg_opts;
 
 typedef struct lqg_hmc_stats {

@@ -570,10 +570,51 @@ static int hmc_canonical_impl(int32_t d, int32_t c, const double* F, const doubl
     LQG_CUDA_TRY(cudaMemsetAsync(b_tn.p, 0, b_tn.bytes, st));
     p.trace_t = b_tt.as<double>(); p.trace_cn = b_tc.as<int>(); p.trace_cap = trace_cap; p.trace_n = b_tn.as<int>();
   }
+  // large dense F (does not fit in shared memory) and enough chains: lock-step rounds whose dot
+  // products are one tensor-core GEMM per round (lqg_hmc_canonical_batched.cu); lqg_opts.canon_mode overrides
+  const bool batched = c > 0 && !p.trace_t &&
+                       (o.canon_mode == 2 || (o.canon_mode == 0 && !p.f_in_smem && n_chains >= 64 && (size_t)c * d >= ((size_t)1 << 20)));
   Timer t_chain(st);
-  t_chain.start();
-  LQG_CUDA_TRY(launch_hmc_canonical(p, 0, st));
-  t_chain.stop();
+  DevBuf b_ft, b_ab, b_fab, b_dbl, b_int;
+  if (batched) {
+    const int n = n_chains;
+    LQG_CUDA_TRY(b_ft.alloc(n_F * sizeof(double)));
+    LQG_CUDA_TRY(b_ab.alloc((size_t)d * 2 * n * sizeof(double)));
+    LQG_CUDA_TRY(b_fab.alloc((size_t)c * 2 * n * sizeof(double)));
+    LQG_CUDA_TRY(b_dbl.alloc((size_t)2 * n * sizeof(double)));
+    LQG_CUDA_TRY(b_int.alloc(((size_t)3 * n + 4) * sizeof(int)));
+    LQG_CUDA_TRY(cudaMemsetAsync(b_ab.p, 0, b_ab.bytes, st));
+    LQG_CUDA_TRY(cudaMemsetAsync(b_dbl.p, 0, b_dbl.bytes, st));
+    LQG_CUDA_TRY(cudaMemsetAsync(b_int.p, 0, b_int.bytes, st));
+    LQG_CUDA_TRY(launch_transpose(c, d, i_F.dev, c, b_ft.as<double>(), d, st));
+    CanonBatch q;
+    memset(&q, 0, sizeof(q));
+    q.d = d; q.c = c; q.n = n; q.Ft = b_ft.as<double>(); q.g = i_g.dev; q.frow2 = p.frow2; q.fnorm = p.fnorm;
+    q.AB = b_ab.as<double>(); q.Zlast = b_state.as<double>(); q.FAB = b_fab.as<double>();
+    q.tt = b_dbl.as<double>(); q.E = q.tt + n;
+    q.phase = b_int.as<int>(); q.s_done = q.phase + n; q.restart = q.s_done + n; q.n_unfinished = q.restart + n;
+    q.pos = b_injpos.as<int64_t>(); q.status = b_status.as<int>();
+    q.burn_in = burn_in; q.n_per_chain = n_per_chain; q.total = burn_in + n_per_chain; q.out = d_out;
+    q.seed = o.seed; q.chain_offset = o.chain_offset; q.injected = p.injected; q.n_injected = p.n_injected;
+    q.max_restarts = p.max_restarts; q.stats = p.stats;
+    t_chain.start();
+    for (long long round = 0;; ++round) {
+      LQG_CUDA_TRY(cudaMemsetAsync(q.n_unfinished, 0, sizeof(int), st));
+      LQG_CUDA_TRY(launch_canon_batch_round_begin(q, st));
+      LQG_CUDA_TRY(launch_dgemm(c, 2 * n, d, i_F.dev, c, q.AB, d, b_fab.as<double>(), c, nullptr, 0, st));
+      LQG_CUDA_TRY(launch_canon_batch_round_step(q, st));
+      int unfinished = 0;
+      LQG_CUDA_TRY(cudaMemcpyAsync(&unfinished, q.n_unfinished, sizeof(int), cudaMemcpyDeviceToHost, st));
+      LQG_CUDA_TRY(cudaStreamSynchronize(st));
+      if (unfinished == 0) break;
+      if (round > 100000000ll) { set_error("lqg_hmc_canonical: round limit reached"); return LQG_ERR_INTERNAL; }
+    }
+    t_chain.stop();
+  } else {
+    t_chain.start();
+    LQG_CUDA_TRY(launch_hmc_canonical(p, 0, st));
+    t_chain.stop();
+  }
   const double chain_ms = t_chain.ms();
   if (p.trace_t) {
     LQG_CUDA_TRY(cudaMemcpyAsync(trace_t, b_tt.p, (size_t)n_chains * trace_cap * sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -87,6 +87,28 @@ cudaError_t launch_canon_violations(int d, int c, size_t n_cols, const double* F
 size_t canon_smem_bytes(int d, int c, int f_in_smem);
 int canon_f_fits_smem(int d, int c);
 
+// ---- lock-step canonical HMC for large dense F (lqg_hmc_canonical_batched.cu) ----------------
+struct CanonBatch {
+  int d, c, n;                 // n chains
+  const double* Ft;            // d x c: row k of F contiguous
+  const double* g; const double* frow2; const double* fnorm;
+  double* AB;                  // d x 2n: velocities a (columns 0..n-1), positions b (columns n..2n-1)
+  double* Zlast;               // d x n: lastSample of every chain
+  const double* FAB;           // c x 2n: F [A | B] of this round (GEMM output)
+  double* tt; double* E;       // [n] remaining time, energy scale of the filter
+  int* phase;                  // [n] 0 = transition starts, 2 = retry (both need a momentum), 1 = moving
+  int* s_done; int* restart; int64_t* pos; int* status;
+  int burn_in, n_per_chain, total;
+  double* out;
+  uint64_t seed; int64_t chain_offset;
+  const double* injected; int64_t n_injected;
+  int max_restarts;
+  unsigned long long* stats;
+  int* n_unfinished;           // chains that still have work after this round
+};
+cudaError_t launch_canon_batch_round_begin(const CanonBatch& p, cudaStream_t st);
+cudaError_t launch_canon_batch_round_step(const CanonBatch& p, cudaStream_t st);
+
 // ---- momentum pre-pass + generic FP64 tensor-core GEMM (lqg_dgemm.cu) -------------------
 // Philox normals for the momentum pool: column a*attempts + j holds the d draws of
 // (chain = active[a] (or a), draw index = pos[chain] + j)

@@ -223,10 +223,10 @@ def tmvrnorm(object, nsim, control=None, method=None, **kw):
 
 
 # --------------------------------------------------------------------------- canonical-frame access
-def rtmg_canonical(n, seed, initial, F, g, n_chains=1, burn_in=0, injected=None, max_restarts=0):
+def rtmg_canonical(n, seed, initial, F, g, n_chains=1, burn_in=0, injected=None, max_restarts=0, mode=0):
     """The reference's native contract, .Call("rtmg", n, seed, initial, numlin, F, g, 0, NULL)
     (tmg:R/tmg.R:104), served by lqg_hmc_canonical.  Returns (d x (n_chains*n) samples in the
-    canonical frame, stats)."""
+    canonical frame, stats).  mode: 0 auto, 1 per-chain kernel, 2 lock-step GEMM rounds."""
     initial = np.asarray(initial, float)
     d = initial.shape[0]
     F = L.f64(np.asarray(F, float).reshape(-1, d))
@@ -239,7 +239,7 @@ def rtmg_canonical(n, seed, initial, F, g, n_chains=1, burn_in=0, injected=None,
     ld = 0 if initial.ndim == 1 else d
     init_c = np.ascontiguousarray(initial.T if initial.ndim == 2 else initial, dtype=np.float64)
     opts = L.make_opts(mem=L.MEM_HOST, seed=seed, n_chains=n_chains, max_restarts=max_restarts,
-                       injected=injected, n_injected=n_inj)
+                       injected=injected, n_injected=n_inj, canon_mode=mode)
     out = np.empty((d, n_chains * n), order="F")
     stats = L.HmcStats()
     rc = L.lib().lqg_hmc_canonical(d, c, L.ptr(F), L.ptr(g), L.ptr(init_c), ld, int(n), int(burn_in),

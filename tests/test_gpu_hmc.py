@@ -17,12 +17,14 @@ def rel_err(a, b):
     return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
 
 
+@pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("name", SMALL)
-def test_canonical_chain_matches_reference_golden(lqg, golden, name):
-    """Free-running chain, same injected draws as the compiled reference consumed."""
+def test_canonical_chain_matches_reference_golden(lqg, golden, name, mode):
+    """Free-running chain, same injected draws as the compiled reference consumed; both the
+    per-chain kernel (mode 1) and the lock-step GEMM rounds (mode 2)."""
     G = golden(name)
     n = int(G["n"])
-    z, st = lqg.rtmg_canonical(n, 0, G["z0"], G["F"], G["g"], injected=G["draws"])
+    z, st = lqg.rtmg_canonical(n, 0, G["z0"], G["F"], G["g"], injected=G["draws"], mode=mode)
     assert rel_err(z.T, G["z_ref"]) < RTOL
     assert st["bounces"] == int(G["bounces"])
     assert st["vel_restarts"] == int(G["vel_restarts"]) and st["chk_restarts"] == int(G["chk_restarts"])
@@ -430,3 +432,31 @@ def test_guard_band_mode_finds_no_out_of_bounds_writes():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "guard mode 1 violations 0" in r.stdout
     assert "[lqg guard]" not in r.stderr
+
+
+
+def test_canonical_lockstep_rounds_follow_the_per_chain_kernel(lqg):
+    """lqg_opts.canon_mode = 2 (one tensor-core GEMM per hit-search round for all chains) against
+    mode 1 (one persistent CTA per chain): same Philox draws -> the same chains up to the rounding
+    of the dot products, same event counts on short runs; many chains with different lengths
+    (burn-in, ragged finish), c < d and c > d, restart cap, injected-draw exhaustion."""
+    from lineqgpr_b200 import _lib
+    rng = np.random.default_rng(5)
+    for d, c, K, n in ((30, 12, 7, 5), (24, 90, 70, 4), (200, 450, 96, 3)):
+        F = rng.standard_normal((c, d)) / np.sqrt(d)
+        g = np.full(c, 1.5)
+        z0 = np.zeros(d)
+        z1, s1 = lqg.rtmg_canonical(n, 9, z0, F, g, n_chains=K, burn_in=2, mode=1)
+        z2, s2 = lqg.rtmg_canonical(n, 9, z0, F, g, n_chains=K, burn_in=2, mode=2)
+        assert s2["violations"] == 0 and s2["transitions"] == K * (n + 2) == s1["transitions"]
+        assert (F @ z2 + g[:, None]).min() >= -1e-12
+        assert abs(s1["bounces"] - s2["bounces"]) <= max(2, s1["bounces"] // 200), (s1["bounces"], s2["bounces"])
+        close = np.abs(z1 - z2).max(axis=0) <= 1e-8 * max(1.0, np.abs(z1).max())
+        assert close.mean() >= 0.97, close.mean()          # a rounding-level tie in a hit search may fork a chain
+        assert s2["hit_searches"] >= s2["bounces"] + s2["transitions"]
+    # errors are reported the same way
+    F = np.array([[1.0, 0.0], [-1.0, 0.0]]); g = np.array([-50.0, 60.0])        # start (40, 0) violates z0 >= 50
+    with pytest.raises(_lib.LqgError, match="RESTART_CAP"):
+        lqg.rtmg_canonical(2, 1, np.array([40.0, 0.0]), F, g, n_chains=3, max_restarts=20, mode=2)
+    with pytest.raises(_lib.LqgError, match="DRAWS_EXHAUSTED"):
+        lqg.rtmg_canonical(5, 1, np.zeros(4), np.eye(4), np.ones(4), n_chains=2, injected=np.zeros((2, 8)), mode=2)
