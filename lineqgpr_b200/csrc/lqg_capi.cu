@@ -603,6 +603,7 @@ static int hmc_canonical_impl(int32_t d, int32_t c, const double* F, const doubl
       LQG_CUDA_TRY(launch_canon_batch_round_begin(q, st));
       LQG_CUDA_TRY(launch_dgemm(c, 2 * n, d, i_F.dev, c, q.AB, d, b_fab.as<double>(), c, nullptr, 0, st));
       LQG_CUDA_TRY(launch_canon_batch_round_step(q, st));
+      if ((round & 3) != 3) continue;                    // completion is polled every 4th round (idle rounds are no-ops)
       int unfinished = 0;
       LQG_CUDA_TRY(cudaMemcpyAsync(&unfinished, q.n_unfinished, sizeof(int), cudaMemcpyDeviceToHost, st));
       LQG_CUDA_TRY(cudaStreamSynchronize(st));
