@@ -460,3 +460,31 @@ def test_canonical_lockstep_rounds_follow_the_per_chain_kernel(lqg):
         lqg.rtmg_canonical(2, 1, np.array([40.0, 0.0]), F, g, n_chains=3, max_restarts=20, mode=2)
     with pytest.raises(_lib.LqgError, match="DRAWS_EXHAUSTED"):
         lqg.rtmg_canonical(5, 1, np.zeros(4), np.eye(4), np.ones(4), n_chains=2, injected=np.zeros((2, 8)), mode=2)
+
+
+def test_packed_and_per_warp_exact_evaluation_are_bitwise_identical(lqg):
+    """The packed evaluation of the candidates of all warps (default from 4 warps per chain) and
+    the per-warp evaluation (LQG_BOX_VARIANT=n) select the same walls at the same times: the
+    arg-min with the first-index tie break does not depend on who evaluated what.  Compared in
+    two fresh processes (the variant is read once per process) at d = 300, 600 and 1100."""
+    import hashlib
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys, hashlib, numpy as np; sys.path.insert(0, '.');"
+            "import lineqgpr_b200 as lqg; from lineqgpr_b200 import workloads as W;"
+            "h = hashlib.sha256();"
+            "[h.update(np.ascontiguousarray(lqg.tmvrnorm(dict(W.cfg4(m=m)[0], **{'class': 'HMC'}), 96, "
+            "{'burn.in': 3, 'n.chains': 12, 'seed': 4, 'whiten': 'ul'})).tobytes()) for m in (150, 300, 550)];"
+            "print('HASH', h.hexdigest())")
+    out = {}
+    for variant in ("", "n"):
+        env = dict(os.environ)
+        env.pop("LQG_BOX_VARIANT", None)
+        if variant:
+            env["LQG_BOX_VARIANT"] = variant
+        r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out[variant] = [l for l in r.stdout.splitlines() if l.startswith("HASH")][0]
+    assert out[""] == out["n"]
