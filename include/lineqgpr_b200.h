@@ -205,6 +205,19 @@ int lqg_bands(int32_t n_t, int64_t N, const double* ysim, int64_t ld,
               const double* probs, int32_t nprobs, double* mean, double* qtls,
               const lqg_opts* opts, double* kernel_ms);
 
+/* Sample paths and their bands in one call:
+ *   ysim = Phi.test %*% xi.sim  (R/lineqGP.R:640, R/lineqAGP.R:509-512), then
+ *   apply(ysim, 1, mean) and apply(ysim, 1, quantile, probs)  (R/lineqGPutils.R:422-423).
+ * Phi n_t x m (ldphi >= n_t), xi m x N (ldxi >= m), column-major.  ysim is nullable: the n_t x N
+ * matrix is produced slab by slab on the device (row slabs of Phi of at most slab_rows rows,
+ * 0 = as many as fit ~4 GB), summarised exactly and dropped, so it never has to exist anywhere
+ * (config 5: 10^5 x 10^6 doubles); when ysim (ldy >= n_t) is given the slabs are also copied out.
+ * mean[n_t]; qtls nprobs x n_t (nullable when nprobs = 0).  gemm_ms / bands_ms nullable.          */
+int lqg_paths(int32_t n_t, int32_t m, int64_t N, const double* Phi, int64_t ldphi,
+              const double* xi, int64_t ldxi, const double* probs, int32_t nprobs,
+              double* ysim, int64_t ldy, double* mean, double* qtls, int32_t slab_rows,
+              const lqg_opts* opts, double* gemm_ms, double* bands_ms);
+
 /* ---- set-up stage on the device --------------------------- */
 /* All matrices column-major FP64; pointers host or device according to opts->mem; every
  * product runs on the FP64 tensor cores (blocked algorithms, lqg_linalg.cu).                 */

@@ -22,7 +22,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 SYMBOLS = ["lqg_rtmg", "lqg_hmc_canonical", "lqg_hmc_canonical_trace", "lqg_hmc_box", "lqg_hmc_box_slots", "lqg_rsm", "lqg_expt", "lqg_dgemm", "lqg_bands",
            "lqg_alloc_host", "lqg_free_host", "lqg_version", "lqg_last_error", "lqg_device_count", "lqg_measure_fp64_peaks",
            "lqg_launch_count", "lqg_guard_violations",
-           "lqg_whiten_box", "lqg_chol", "lqg_solve_spd", "lqg_eta_params", "lqg_lambda_pinv", "lqg_solve_qp", "lqg_basis"]
+           "lqg_whiten_box", "lqg_chol", "lqg_solve_spd", "lqg_eta_params", "lqg_lambda_pinv", "lqg_solve_qp", "lqg_basis", "lqg_paths"]
 
 _dp = C.POINTER(C.c_double)
 
@@ -123,6 +123,8 @@ def lib():
     L.lqg_eta_params.argtypes = [i32, i32, vp, vp, vp, vp, C.c_double, C.POINTER(Opts), vp, vp, vp]
     L.lqg_lambda_pinv.restype = C.c_int
     L.lqg_lambda_pinv.argtypes = [i32, i32, vp, C.POINTER(Opts), vp]
+    L.lqg_paths.restype = C.c_int
+    L.lqg_paths.argtypes = [i32, i32, i64, vp, i64, vp, i64, vp, i32, vp, i64, vp, vp, i32, C.POINTER(Opts), _dp, _dp]
     L.lqg_basis.restype = C.c_int
     L.lqg_basis.argtypes = [i32, i32, vp, vp, i64, vp, C.POINTER(Opts), vp, i64]
     L.lqg_solve_qp.restype = C.c_int

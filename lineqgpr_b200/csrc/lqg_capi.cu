@@ -1426,6 +1426,107 @@ extern "C" int lqg_solve_qp(int32_t n, int32_t mc, const double* D, const double
   LQG_API_END("lqg_solve_qp")
 }
 
+// mean and exact type-7 quantiles of a device-resident slab (ysim n_t x N, ld): bracketed one-pass
+// path, exact transpose + radix-select path for the test points it flags or the shapes it does not cover
+static int bands_on_device(int n_t, int64_t N, const double* y_dev, int64_t ld, const std::vector<double>& h_probs,
+                           int nprobs, double* d_mean, double* d_q, DevBuf& b_scr, double* ms_out, cudaStream_t st) {
+  static const char* env_exact = getenv("LQG_BANDS_EXACT");              // tuning / test aid
+  const size_t fast_bytes = (env_exact && env_exact[0] == '1') ? 0 : bands_bracket_scratch_bytes(n_t, N, nprobs);
+  const size_t need = fast_bytes ? fast_bytes : (size_t)n_t * N * sizeof(double);
+  if (!b_scr.p || b_scr.bytes < need) LQG_CUDA_TRY(b_scr.alloc(need));
+  Timer tm(st);
+  tm.start();
+  if (fast_bytes) {
+    int* fail_dev = nullptr;
+    LQG_CUDA_TRY(launch_bands_bracketed(n_t, N, y_dev, ld, h_probs.data(), nprobs, d_mean, d_q, b_scr.p, &fail_dev, st));
+    std::vector<int> h_fail(n_t);
+    LQG_CUDA_TRY(cudaMemcpyAsync(h_fail.data(), fail_dev, n_t * sizeof(int), cudaMemcpyDeviceToHost, st));
+    LQG_CUDA_TRY(cudaStreamSynchronize(st));
+    std::vector<int> rows;
+    for (int r = 0; r < n_t; ++r) if (h_fail[r]) rows.push_back(r);
+    if (getenv("LQG_TRACE")) fprintf(stderr, "[lqg bands] bracketed path: %zu of %d test points go to the exact path (first %d)\n",
+                                     rows.size(), n_t, rows.empty() ? -1 : rows[0]);
+    if (rows.size() > 64) {
+      LQG_CUDA_TRY(b_scr.alloc((size_t)n_t * N * sizeof(double)));
+      LQG_CUDA_TRY(launch_bands_exact(n_t, N, y_dev, ld, h_probs.data(), nprobs, d_mean, d_q, b_scr.as<double>(), st));
+    } else if (!rows.empty()) {
+      if (b_scr.bytes < (size_t)N * sizeof(double)) LQG_CUDA_TRY(b_scr.alloc((size_t)N * sizeof(double)));
+      for (int r : rows)
+        LQG_CUDA_TRY(launch_bands_exact(1, N, y_dev + r, ld, h_probs.data(), nprobs, d_mean + r,
+                                        d_q + (size_t)r * nprobs, b_scr.as<double>(), st));
+    }
+  } else {
+    LQG_CUDA_TRY(launch_bands_exact(n_t, N, y_dev, ld, h_probs.data(), nprobs, d_mean, d_q, b_scr.as<double>(), st));
+  }
+  tm.stop();
+  if (ms_out) *ms_out = tm.ms();
+  return LQG_OK;
+}
+
+// ===========================================================================================
+extern "C" int lqg_paths(int32_t n_t, int32_t m, int64_t N, const double* Phi, int64_t ldphi,
+                         const double* xi, int64_t ldxi, const double* probs, int32_t nprobs,
+                         double* ysim, int64_t ldy, double* mean, double* qtls, int32_t slab_rows,
+                         const lqg_opts* opts_, double* gemm_ms, double* bands_ms) {
+  LQG_API_BEGIN
+  if (!have_device()) return LQG_ERR_CUDA;
+  const lqg_opts o = opts_ ? *opts_ : default_opts();
+  if (n_t <= 0 || m <= 0 || N <= 0 || N > 0x7fffffff || !Phi || !xi || ldphi < n_t || ldxi < m || nprobs < 0 || nprobs > 8 ||
+      (nprobs > 0 && (!probs || !qtls)) || !mean || (ysim && ldy < n_t)) {
+    set_error("lqg_paths: invalid argument (n_t=%d m=%d N=%lld nprobs=%d)", n_t, m, (long long)N, nprobs);
+    return LQG_ERR_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)o.stream;
+  DevBuf::cur_stream = st;
+  const int mem = o.mem;
+  int rc;
+  std::vector<double> h_probs;
+  if (nprobs > 0 && (rc = fetch_host(h_probs, probs, nprobs, mem, st))) return rc;
+  for (int k = 0; k < nprobs; ++k)
+    if (!(h_probs[k] >= 0.0 && h_probs[k] <= 1.0)) { set_error("'probs' outside [0,1]"); return LQG_ERR_INVALID; }
+  Input i_phi, i_xi;
+  if ((rc = i_phi.stage(Phi, (size_t)ldphi * (m - 1) + n_t, mem, st)) || (rc = i_xi.stage(xi, (size_t)ldxi * (N - 1) + m, mem, st)))
+    return rc;
+  int rows = slab_rows > 0 ? slab_rows : (int)std::max<int64_t>(1, std::min<int64_t>(n_t, ((int64_t)4 << 30) / (8 * N)));
+  if (rows >= 128 && rows < n_t) rows -= rows % 128;              // whole 128-row GEMM tiles
+  if (rows > n_t) rows = n_t;
+  DevBuf b_y, b_scr, b_mean, b_q;
+  LQG_CUDA_TRY(b_y.alloc((size_t)rows * N * sizeof(double)));
+  double* d_mean = mean; double* d_q = qtls;
+  if (mem == LQG_MEM_HOST) {
+    LQG_CUDA_TRY(b_mean.alloc(n_t * sizeof(double))); d_mean = b_mean.as<double>();
+    LQG_CUDA_TRY(b_q.alloc((size_t)std::max(1, nprobs) * n_t * sizeof(double))); d_q = b_q.as<double>();
+  }
+  double t_gemm = 0.0, t_bands = 0.0;
+  for (int r0 = 0; r0 < n_t; r0 += rows) {
+    const int nr = std::min(rows, n_t - r0);
+    Timer tg(st);
+    tg.start();
+    LQG_CUDA_TRY(launch_dgemm(nr, (int)N, m, i_phi.dev + r0, ldphi, i_xi.dev, ldxi, b_y.as<double>(), nr, nullptr, 0, st));
+    tg.stop();
+    double ms = 0.0;
+    if ((rc = bands_on_device(nr, N, b_y.as<double>(), nr, h_probs, nprobs, d_mean + r0, d_q + (size_t)r0 * nprobs, b_scr, &ms, st)))
+      return rc;
+    t_gemm += tg.ms(); t_bands += ms;
+    if (ysim) {
+      if (mem == LQG_MEM_HOST) LQG_CUDA_TRY(d2h_result(ysim + r0, ldy * sizeof(double), b_y.p, (size_t)nr * sizeof(double), (size_t)nr * sizeof(double), N, st));
+      else LQG_CUDA_TRY(cudaMemcpy2DAsync(ysim + r0, ldy * sizeof(double), b_y.p, (size_t)nr * sizeof(double), (size_t)nr * sizeof(double), N,
+                                          cudaMemcpyDeviceToDevice, st));
+      LQG_CUDA_TRY(cudaStreamSynchronize(st));                     // the slab buffer is reused by the next GEMM
+    }
+  }
+  if (gemm_ms) *gemm_ms = t_gemm;
+  if (bands_ms) *bands_ms = t_bands;
+  if (mem == LQG_MEM_HOST) {
+    LQG_CUDA_TRY(cudaMemcpyAsync(mean, d_mean, n_t * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (nprobs > 0) LQG_CUDA_TRY(cudaMemcpyAsync(qtls, d_q, (size_t)nprobs * n_t * sizeof(double), cudaMemcpyDeviceToHost, st));
+  }
+  LQG_CUDA_TRY(cudaStreamSynchronize(st));
+  fold_launches();
+  return LQG_OK;
+  LQG_API_END("lqg_paths")
+}
+
 // ===========================================================================================
 extern "C" int lqg_bands(int32_t n_t, int64_t N, const double* ysim, int64_t ld, const double* probs,
                          int32_t nprobs, double* mean, double* qtls, const lqg_opts* opts_,
@@ -1453,37 +1554,9 @@ extern "C" int lqg_bands(int32_t n_t, int64_t N, const double* ysim, int64_t ld,
     LQG_CUDA_TRY(b_mean.alloc(n_t * sizeof(double))); d_mean = b_mean.as<double>();
     LQG_CUDA_TRY(b_q.alloc((size_t)std::max(1, nprobs) * n_t * sizeof(double))); d_q = b_q.as<double>();
   }
-  // bracketed path (one coalesced pass over ysim); test points whose bracket missed or overflowed,
-  // and shapes it does not cover, go through the exact transpose + radix-select path
-  static const char* env_exact = getenv("LQG_BANDS_EXACT");              // tuning / test aid
-  const size_t fast_bytes = (env_exact && env_exact[0] == '1') ? 0 : bands_bracket_scratch_bytes(n_t, N, nprobs);
-  LQG_CUDA_TRY(b_scr.alloc(fast_bytes ? fast_bytes : (size_t)n_t * N * sizeof(double)));
-  Timer tm(st);
-  tm.start();
-  if (fast_bytes) {
-    int* fail_dev = nullptr;
-    LQG_CUDA_TRY(launch_bands_bracketed(n_t, N, i_y.dev, ld, h_probs.data(), nprobs, d_mean, d_q, b_scr.p, &fail_dev, st));
-    std::vector<int> h_fail(n_t);
-    LQG_CUDA_TRY(cudaMemcpyAsync(h_fail.data(), fail_dev, n_t * sizeof(int), cudaMemcpyDeviceToHost, st));
-    LQG_CUDA_TRY(cudaStreamSynchronize(st));
-    std::vector<int> rows;
-    for (int r = 0; r < n_t; ++r) if (h_fail[r]) rows.push_back(r);
-    if (getenv("LQG_TRACE")) fprintf(stderr, "[lqg bands] bracketed path: %zu of %d test points go to the exact path (first %d)\n",
-                                     rows.size(), n_t, rows.empty() ? -1 : rows[0]);
-    if (rows.size() > 64) {
-      LQG_CUDA_TRY(b_scr.alloc((size_t)n_t * N * sizeof(double)));
-      LQG_CUDA_TRY(launch_bands_exact(n_t, N, i_y.dev, ld, h_probs.data(), nprobs, d_mean, d_q, b_scr.as<double>(), st));
-    } else if (!rows.empty()) {
-      LQG_CUDA_TRY(b_scr.alloc((size_t)N * sizeof(double)));
-      for (int r : rows)
-        LQG_CUDA_TRY(launch_bands_exact(1, N, i_y.dev + r, ld, h_probs.data(), nprobs, d_mean + r,
-                                        d_q + (size_t)r * nprobs, b_scr.as<double>(), st));
-    }
-  } else {
-    LQG_CUDA_TRY(launch_bands_exact(n_t, N, i_y.dev, ld, h_probs.data(), nprobs, d_mean, d_q, b_scr.as<double>(), st));
-  }
-  tm.stop();
-  if (kernel_ms) *kernel_ms = tm.ms();
+  double ms = 0.0;
+  if ((rc = bands_on_device(n_t, N, i_y.dev, ld, h_probs, nprobs, d_mean, d_q, b_scr, &ms, st))) return rc;
+  if (kernel_ms) *kernel_ms = ms;
   if (mem == LQG_MEM_HOST) {
     LQG_CUDA_TRY(cudaMemcpyAsync(mean, d_mean, n_t * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (nprobs > 0) LQG_CUDA_TRY(cudaMemcpyAsync(qtls, d_q, (size_t)nprobs * n_t * sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -48,6 +48,29 @@ def bands(ysim, probs=(0.025, 0.975)):
     return mean, q
 
 
+def paths(Phi_test, xi_sim, probs=(0.025, 0.975), return_ysim=False, slab_rows=0):
+    """ysim = Phi.test %*% xi.sim with its mean and quantile bands through ONE C-ABI call
+    (lqg_paths): the slab loop (tensor-core GEMM -> exact bands -> optional copy-out) runs inside
+    the library, host arrays in and out, no torch.  Returns (ymean, qtls[, ysim], info)."""
+    Phi = L.f64(np.atleast_2d(np.asarray(Phi_test, float)))
+    xi = L.f64(np.atleast_2d(np.asarray(xi_sim, float)))
+    n_t, m = Phi.shape
+    if xi.shape[0] != m:
+        raise ValueError("non-conformable arguments")
+    N = xi.shape[1]
+    probs = np.ascontiguousarray(probs, dtype=np.float64)
+    mean = np.empty(n_t)
+    q = np.empty((probs.size, n_t), order="F")
+    ysim = np.empty((n_t, N), order="F") if return_ysim else None
+    g_ms, b_ms = L.C.c_double(0.0), L.C.c_double(0.0)
+    rc = L.lib().lqg_paths(n_t, m, N, L.ptr(Phi), n_t, L.ptr(xi), m, L.ptr(probs), probs.size,
+                           L.ptr(ysim), n_t, L.ptr(mean), L.ptr(q), int(slab_rows), L.make_opts(mem=L.MEM_HOST),
+                           L.C.byref(g_ms), L.C.byref(b_ms))
+    L.check(rc, "lqg_paths")
+    info = dict(gemm_ms=g_ms.value, bands_ms=b_ms.value)
+    return (mean, q, ysim, info) if return_ysim else (mean, q, info)
+
+
 def paths_bands(Phi_test, xi_sim, probs=(0.025, 0.975), slab_rows=None, return_ysim=False, xtest=None, ulist=None):
     """Band summaries of ysim = Phi.test %*% xi.sim without materialising ysim (config 5:
     10^5 x 10^6 doubles = 800 GB).  Phi.test (n_t x m) is processed in row slabs: each slab's

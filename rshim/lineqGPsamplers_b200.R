@@ -82,5 +82,7 @@ tmvrnorm.ExpT <- function(object, nsim, control = NULL, ...) {
 #                                                                         -> .Call("lqg_solve_qp_call", invSigma, mu %*% invSigma, M, g)
 #   R/lineqGP.R:611-614  eta.mu / eta.map / Sigma.eta                     -> .Call("lqg_eta_params_call", Lambda, mu, xi.map, Sigma, nugget)
 #   R/lineqGP.R:639   qr.solve(pred$Lambda, eta)                          -> .Call("lqg_dgemm_call", .Call("lqg_lambda_pinv_call", pred$Lambda), eta)
+# paths and bands in one call, without keeping the n_t x N matrix (config 5):
+#   r <- .Call("lqg_paths_call", pred$Phi.test, simModel$xi.sim, probs, FALSE); ymean <- r[[2]]; qtls <- r[[3]]
 # plot.lineqGP bands (R/lineqGPutils.R:422-423):
 #   b <- .Call("lqg_bands_call", ysim, probs); qtls <- b[[2]]; ymean <- b[[1]]

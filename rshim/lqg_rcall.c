@@ -194,3 +194,25 @@ SEXP lqg_basis_call(SEXP x_, SEXP u_) {
   lqg_check(rc, "lqg_basis");
   return out;
 }
+
+/* simulate tail + bands in one call: list(ysim (or NULL), mean, qtls) with ysim = Phi.test %*% xi.sim
+ * (R/lineqGP.R:640), mean = apply(ysim,1,mean), qtls = apply(ysim,1,quantile,probs) (R/lineqGPutils.R:422-423);
+ * keep_ysim = FALSE never materialises the n_t x N matrix */
+SEXP lqg_paths_call(SEXP Phi_, SEXP xi_, SEXP probs_, SEXP keep_ysim_) {
+  const int n_t = Rf_nrows(Phi_), m = Rf_ncols(Phi_), np = Rf_length(probs_);
+  const long long N = Rf_ncols(xi_);
+  if (Rf_nrows(xi_) != m) Rf_error("non-conformable arguments");
+  const int keep = Rf_asInteger(keep_ysim_);
+  SEXP ysim = PROTECT(keep ? Rf_allocMatrix(REALSXP, n_t, (int)N) : Rf_allocVector(REALSXP, 0));
+  SEXP mean = PROTECT(Rf_allocVector(REALSXP, n_t));
+  SEXP q = PROTECT(Rf_allocMatrix(REALSXP, np, n_t));
+  int rc = lqg_paths(n_t, m, N, REAL(Phi_), n_t, REAL(xi_), m, REAL(probs_), np, keep ? REAL(ysim) : NULL, n_t,
+                     REAL(mean), REAL(q), 0, NULL, NULL, NULL);
+  SEXP res = PROTECT(Rf_allocVector(VECSXP, 3));
+  SET_VECTOR_ELT(res, 0, ysim);
+  SET_VECTOR_ELT(res, 1, mean);
+  SET_VECTOR_ELT(res, 2, q);
+  UNPROTECT(4);
+  lqg_check(rc, "lqg_paths");
+  return res;
+}

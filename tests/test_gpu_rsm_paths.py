@@ -153,3 +153,24 @@ def test_bands_bracketed_path_is_exact(lqg, oracle):
     assert np.array_equal(q, np.full((3, 100), 3.25)) and np.array_equal(mean, np.full(100, 3.25))
     mean, q = lqg.bands(rng.standard_normal((40, 30000)), np.zeros(0))   # means only
     assert q.shape[0] == 0 and mean.shape == (40,)
+
+
+def test_lqg_paths_one_call_matches_gemm_plus_bands(lqg, oracle):
+    """lqg_paths (native slab loop: GEMM -> exact bands -> optional ysim copy-out) against numpy + the
+    oracle's type-7 quantiles: several slabs with a ragged last one, with and without ysim."""
+    rng = np.random.default_rng(12)
+    Phi = rng.uniform(size=(301, 40)); xi = rng.standard_normal((40, 9000))
+    probs = np.array([0.025, 0.5, 0.975])
+    y = Phi @ xi
+    mo, qo = oracle.bands(y, probs)
+    for slab in (0, 128, 77):
+        mean, q, info = lqg.paths(Phi, xi, probs, slab_rows=slab)
+        assert np.allclose(mean, mo, rtol=1e-12, atol=1e-13)
+        assert np.allclose(q, qo, rtol=1e-12, atol=1e-12)        # GEMM summation order differs from numpy's by rounding
+        assert info["gemm_ms"] > 0 and info["bands_ms"] > 0
+    mean, q, ysim, _ = lqg.paths(Phi, xi, probs, return_ysim=True, slab_rows=100)
+    assert np.allclose(ysim, y, rtol=1e-12, atol=1e-12)
+    m2, q2 = lqg.bands(ysim, probs)
+    assert np.array_equal(q, q2) and np.allclose(mean, m2, rtol=1e-14)
+    mean0, q0, _ = lqg.paths(Phi, xi, np.zeros(0))
+    assert q0.shape == (0, 301) and np.allclose(mean0, mo, rtol=1e-12, atol=1e-13)
