@@ -284,6 +284,93 @@ int lqg_solve_qp(int32_t n, int32_t mc, const double* D, const double* dvec, con
  * matrices lineqGPR builds (cond(Lambda) <~ 1e4).  LQG_ERR_NOT_PD if Lambda is rank deficient.  */
 int lqg_lambda_pinv(int32_t d, int32_t m, const double* Lambda, const lqg_opts* opts, double* Lp_out);
 
+/* ---- the whole simulate tail in one call, device resident, optionally over several GPUs ----- */
+
+/* Communicator of a multi-GPU job: one process per GPU, this process's GPU = the current CUDA
+ * device.  Chains shard over the ranks with no data-path collective; lqg_simulate then performs
+ * the two exchanges of SURVEY.md par.8(e) option A with NCCL all-gathers over NVLink.  NCCL is
+ * resolved at run time (libnccl.so.2; LQG_NCCL_LIB overrides), so single-GPU use does not need it.
+ *   lqg_comm_unique_id  rank 0 fills 128 bytes that the host program hands to every rank
+ *                       (torch.distributed, MPI, a file ...)
+ *   lqg_comm_init       collective over the `world` ranks; world == 1 needs no id and no NCCL    */
+typedef struct lqg_comm lqg_comm;
+int lqg_comm_unique_id(void* id128);
+int lqg_comm_init(const void* id128, int32_t rank, int32_t world, lqg_comm** out);
+int lqg_comm_rank(const lqg_comm* c);
+int lqg_comm_world(const lqg_comm* c);
+int lqg_comm_destroy(lqg_comm* c);
+/* all-gather of `count` doubles per rank, DEVICE pointers, on `stream` (recv holds world*count
+ * doubles and may alias send at recv + rank*count) */
+int lqg_comm_allgather(const lqg_comm* c, const double* send, double* recv, int64_t count, void* stream);
+
+/* Arguments of lqg_simulate: the tail of simulate.lineqGP (R/lineqGP.R:611-640) and of
+ * simulate.lineqAGP (R/lineqAGP.R:558-575) plus the product the user applies to its result
+ * (R/lineqAGP.R:509-512) and the band summaries drawn from it (R/lineqGPutils.R:422-423).
+ * Pointers are host or device memory according to opts->mem.  Column-major FP64 throughout.     */
+typedef struct lqg_simulate_args {
+  int32_t d, m;              /* d = nrow(Lambda) = length(eta), m = ncol(Lambda) = length(xi)        */
+  /* tmvPar <- list(mu = eta.mu, map = eta.map, Sigma = Sigma.eta, lb, ub)   R/lineqGP.R:622        */
+  const double* mu;          /* [d]  eta.mu (lineqAGP passes eta.map here, R/lineqAGP.R:567)         */
+  const double* Sigma;       /* d x d  Lambda Sigma Lambda' + nugget I   R/lineqGP.R:613-614         */
+  const double* lb;          /* [d]                                                                  */
+  const double* ub;          /* [d]                                                                  */
+  const double* init;        /* [d]  eta.map clamped into the box   R/lineqGPsamplers.R:133-135      */
+  const double* U;           /* nullable d x d upper factor with U U' = Sigma (tmg's Ri); NULL = the
+                                device factors Sigma itself (lqg_whiten_box)                          */
+  /* xi.sim <- qr.solve(Lambda, eta)   R/lineqGP.R:639, R/lineqAGP.R:575                             */
+  const double* Lambda;      /* d x m; nullable when Lambda_pinv is given, or when d == m and
+                                xi = eta is wanted (both NULL)                                        */
+  const double* Lambda_pinv; /* nullable m x d: a precomputed lqg_lambda_pinv result                 */
+  /* ysim <- Phi.test %*% xi.sim   R/lineqGP.R:640, R/lineqAGP.R:509-512                             */
+  int32_t n_t;               /* test points; 0 = stop after xi                                       */
+  const double* Phi;         /* n_t x m (ldphi >= n_t), or NULL with the basis description below     */
+  int64_t ldphi;
+  int32_t basis_D;           /* Phi == NULL: Phi = [Phi_1 | ... | Phi_D], Phi_k = hat basis of        */
+  const int32_t* basis_mk;   /*   xtest[, k] on the knots of block k (lqg_basis; R/lineqGP.R:29-60,   */
+  const double* xtest;       /*   R/lineqAGP.R:341-348); basis_mk is a HOST array of D counts,        */
+  int64_t ldx;               /*   xtest n_t x D (ldx >= n_t), knots the concatenated knot vectors     */
+  const double* knots;
+  const double* probs;       /* [nprobs] quantile levels (R type 7), nprobs <= 8                      */
+  int32_t nprobs;
+  int32_t n_per_chain;       /* samples per chain; this rank draws opts->n_chains * n_per_chain       */
+  int32_t burn_in;           /* transitions every chain runs before it emits                          */
+  int32_t slab_rows;         /* rows of Phi per GEMM + summary slab, 0 = as many as fit ~4 GB         */
+  int32_t reserved0;
+  /* results (each nullable) */
+  double* eta_out;           /* d x N_local, chain-major columns like lqg_hmc_box                     */
+  double* xi_out;            /* m x N_local, same column order: this rank's share of xi.sim           */
+  double* ysim_out;          /* rows_local x N_total (ldy >= rows_local): this rank's rows of ysim,   */
+  int64_t ldy;               /*   columns in job order = [xi_out of rank 0 | xi_out of rank 1 | ...]  */
+  double* mean;              /* [n_t] on EVERY rank                                                   */
+  double* qtls;              /* nprobs x n_t on every rank                                            */
+} lqg_simulate_args;
+
+typedef struct lqg_simulate_stats {
+  lqg_hmc_stats hmc;
+  double xi_ms;              /* Lambda^+ eta products (device time, side stream)                      */
+  double gemm_ms;            /* Phi xi slabs                                                          */
+  double bands_ms;           /* mean + quantiles of the slabs                                         */
+  double total_ms;           /* whole call on the device (events on the caller's stream)              */
+  int64_t n_local, n_total;  /* samples drawn by this rank / by the job                               */
+  int32_t row_begin, row_end;/* rows of Phi this rank summarised                                      */
+  int32_t rank, world;
+  int32_t rounds;            /* sampling rounds = xi products = all-gather calls                      */
+  int32_t reserved0;
+} lqg_simulate_stats;
+
+/* sampler -> xi = Lambda^+ eta -> Phi xi -> bands, with eta, xi and ysim never leaving HBM unless an
+ * output pointer asks for them.  The box sampler is lqg_hmc_box (same chains, same Philox streams:
+ * eta_out equals what lqg_hmc_box returns for the same opts).  While later sampling rounds run, the
+ * samples every chain has finished are multiplied by Lambda^+ on a second stream, copied to xi_out
+ * and — with a communicator — all-gathered, so that after the last round every rank holds the xi of
+ * the whole job (m x N_total; column order: round, then rank, then chain, then sample).  Rank r then
+ * summarises rows [r ceil(n_t/world), (r+1) ceil(n_t/world)) of Phi over all N_total samples (exact
+ * mean and type-7 quantiles) and the band pieces are all-gathered: every rank returns the full
+ * mean[n_t], qtls[nprobs x n_t].  Global chain ids are opts->chain_offset + rank * n_chains + local
+ * id, so a job gives the same samples however many GPUs it runs on.  comm NULL = one GPU.          */
+int lqg_simulate(const lqg_simulate_args* args, const lqg_opts* opts, lqg_comm* comm,
+                 lqg_simulate_stats* stats);
+
 /* Page-locked host memory for large result matrices: with it the LQG_MEM_HOST entry points copy
  * samples out at full PCIe speed and concurrently with the sampling rounds; with ordinary
  * (pageable) memory — e.g. an R matrix — the copies are staged and serialised by the driver. */
@@ -296,6 +383,9 @@ const char* lqg_last_error(void);        /* thread-local text of the last non-OK
 int lqg_device_count(void);              /* number of CUDA devices, 0 when none               */
 /* measured peaks used as roofline denominators: DFMA and DMMA micro-benchmarks (Tflop/s) */
 int lqg_measure_fp64_peaks(double* dfma_tflops, double* dmma_tflops, const lqg_opts* opts);
+/* probe: even warps issue DFMA, odd warps DMMA; *tflops = their combined rate, *dfma_share = the
+ * DFMA fraction of the flops.  A sum above either peak would mean separate units. */
+int lqg_measure_fp64_mixed(double* tflops, double* dfma_share, const lqg_opts* opts);
 /* counts kernel launches made by this library since the last reset (bench gpu_launches) */
 int64_t lqg_launch_count(int32_t reset);
 /* debugging aid: with LQG_GUARD=1 in the environment every internal device buffer carries a

@@ -22,7 +22,9 @@ MEM_HOST, MEM_DEVICE = 0, 1
 SYMBOLS = ["lqg_rtmg", "lqg_hmc_canonical", "lqg_hmc_canonical_trace", "lqg_hmc_box", "lqg_hmc_box_slots", "lqg_rsm", "lqg_expt", "lqg_dgemm", "lqg_bands",
            "lqg_alloc_host", "lqg_free_host", "lqg_version", "lqg_last_error", "lqg_device_count", "lqg_measure_fp64_peaks",
            "lqg_launch_count", "lqg_guard_violations",
-           "lqg_whiten_box", "lqg_chol", "lqg_solve_spd", "lqg_eta_params", "lqg_lambda_pinv", "lqg_solve_qp", "lqg_basis", "lqg_paths"]
+           "lqg_whiten_box", "lqg_chol", "lqg_solve_spd", "lqg_eta_params", "lqg_lambda_pinv", "lqg_solve_qp", "lqg_basis", "lqg_paths",
+           "lqg_simulate", "lqg_comm_unique_id", "lqg_comm_init", "lqg_comm_rank", "lqg_comm_world", "lqg_comm_destroy",
+           "lqg_comm_allgather", "lqg_measure_fp64_mixed"]
 
 _dp = C.POINTER(C.c_double)
 
@@ -49,6 +51,31 @@ class HmcStats(C.Structure):
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class SimulateArgs(C.Structure):
+    """lqg_simulate_args (include/lineqgpr_b200.h)."""
+    _fields_ = [("d", C.c_int32), ("m", C.c_int32),
+                ("mu", C.c_void_p), ("Sigma", C.c_void_p), ("lb", C.c_void_p), ("ub", C.c_void_p), ("init", C.c_void_p),
+                ("U", C.c_void_p), ("Lambda", C.c_void_p), ("Lambda_pinv", C.c_void_p),
+                ("n_t", C.c_int32), ("Phi", C.c_void_p), ("ldphi", C.c_int64),
+                ("basis_D", C.c_int32), ("basis_mk", C.c_void_p), ("xtest", C.c_void_p), ("ldx", C.c_int64),
+                ("knots", C.c_void_p), ("probs", C.c_void_p), ("nprobs", C.c_int32),
+                ("n_per_chain", C.c_int32), ("burn_in", C.c_int32), ("slab_rows", C.c_int32), ("reserved0", C.c_int32),
+                ("eta_out", C.c_void_p), ("xi_out", C.c_void_p), ("ysim_out", C.c_void_p), ("ldy", C.c_int64),
+                ("mean", C.c_void_p), ("qtls", C.c_void_p)]
+
+
+class SimulateStats(C.Structure):
+    _fields_ = [("hmc", HmcStats), ("xi_ms", C.c_double), ("gemm_ms", C.c_double), ("bands_ms", C.c_double),
+                ("total_ms", C.c_double), ("n_local", C.c_int64), ("n_total", C.c_int64),
+                ("row_begin", C.c_int32), ("row_end", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
+                ("rounds", C.c_int32), ("reserved0", C.c_int32)]
+
+    def asdict(self):
+        d = self.hmc.asdict()
+        d.update({k: getattr(self, k) for k, _ in self._fields_ if k not in ("hmc", "reserved0")})
+        return d
 
 
 class ExptStats(C.Structure):
@@ -109,6 +136,8 @@ def lib():
     L.lqg_device_count.restype = C.c_int
     L.lqg_measure_fp64_peaks.restype = C.c_int
     L.lqg_measure_fp64_peaks.argtypes = [_dp, _dp, C.POINTER(Opts)]
+    L.lqg_measure_fp64_mixed.restype = C.c_int
+    L.lqg_measure_fp64_mixed.argtypes = [_dp, _dp, C.POINTER(Opts)]
     L.lqg_launch_count.restype = i64
     L.lqg_launch_count.argtypes = [i32]
     L.lqg_guard_violations.restype = C.c_int
@@ -129,6 +158,20 @@ def lib():
     L.lqg_basis.argtypes = [i32, i32, vp, vp, i64, vp, C.POINTER(Opts), vp, i64]
     L.lqg_solve_qp.restype = C.c_int
     L.lqg_solve_qp.argtypes = [i32, i32, vp, vp, vp, vp, C.c_double, i32, C.POINTER(Opts), vp, C.POINTER(i32)]
+    L.lqg_simulate.restype = C.c_int
+    L.lqg_simulate.argtypes = [C.POINTER(SimulateArgs), C.POINTER(Opts), vp, C.POINTER(SimulateStats)]
+    L.lqg_comm_unique_id.restype = C.c_int
+    L.lqg_comm_unique_id.argtypes = [vp]
+    L.lqg_comm_init.restype = C.c_int
+    L.lqg_comm_init.argtypes = [vp, i32, i32, C.POINTER(vp)]
+    L.lqg_comm_rank.restype = C.c_int
+    L.lqg_comm_rank.argtypes = [vp]
+    L.lqg_comm_world.restype = C.c_int
+    L.lqg_comm_world.argtypes = [vp]
+    L.lqg_comm_destroy.restype = C.c_int
+    L.lqg_comm_destroy.argtypes = [vp]
+    L.lqg_comm_allgather.restype = C.c_int
+    L.lqg_comm_allgather.argtypes = [vp, vp, vp, i64, vp]
     _lib = L
     return L
 

@@ -10,7 +10,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "liblineqgpr_b200.so"
 SOURCES = ["lqg_capi.cu", "lqg_hmc_box.cu", "lqg_hmc_canonical.cu", "lqg_dgemm.cu", "lqg_rsm.cu", "lqg_expt.cu",
-           "lqg_bands.cu", "lqg_peaks.cu", "lqg_linalg.cu", "lqg_qp.cu", "lqg_basis.cu", "lqg_hostcopy.cu", "lqg_hmc_canonical_batched.cu"]
+           "lqg_bands.cu", "lqg_peaks.cu", "lqg_linalg.cu", "lqg_qp.cu", "lqg_basis.cu", "lqg_hostcopy.cu", "lqg_hmc_canonical_batched.cu", "lqg_comm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
@@ -64,7 +64,7 @@ def _build_locked(verbose: bool) -> Path:
         if verbose and out.strip():
             print(out)
     tmp = LIB.with_suffix(".so.tmp")
-    cmd = [nvcc, "-shared", "-o", str(tmp), *objs, "-lcudart"]
+    cmd = [nvcc, "-shared", "-o", str(tmp), *objs, "-lcudart", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

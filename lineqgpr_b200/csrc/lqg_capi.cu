@@ -11,8 +11,10 @@
 #include <vector>
 
 #include <exception>
+#include <functional>
 #include <memory>
 
+#include "lqg_comm.h"
 #include "lqg_common.cuh"
 #include "lqg_hostcopy.h"
 #include "lqg_kernels.h"
@@ -238,6 +240,218 @@ using namespace lqg;
 static int ul_factor_device(int d, const double* S_dev, double* U_dev, cudaStream_t st);
 
 // ===========================================================================================
+// Box-form HMC with every operand resident on the device.  lqg_hmc_box (host or device pointers)
+// and lqg_simulate (which keeps eta on the device and feeds it to the xi / path stages) both end
+// up here.
+struct BoxRun {
+  int d = 0;
+  const double* mu = nullptr; const double* U = nullptr; int u_upper = 1;
+  const double* Sigma = nullptr; const double* lb = nullptr; const double* ub = nullptr;
+  const double* init = nullptr; int64_t init_ld = 0;
+  int n_chains = 1, n_per_chain = 0, burn_in = 0;
+  uint64_t seed = 0; int64_t chain_offset = 0; int prepass = -1; int max_restarts = 0;
+  const double* injected = nullptr; int64_t n_injected = 0;      // device pointer
+  double* out = nullptr;                                          // d x (n_chains*n_per_chain), chain-major columns
+  cudaStream_t st = nullptr;
+  // Called (host side) whenever samples [from, upto) of EVERY chain are final in `out`; `ready`
+  // has been recorded on st after the kernels that wrote them.  Lets a consumer (D2H copy, xi GEMM,
+  // all-gather) work on another stream while later rounds run.  Nullable.
+  std::function<int(int from, int upto, cudaEvent_t ready)> on_round;
+  bool short_tail = false;    // cut the last stretch into halving rounds (the consumer cannot overlap the last one)
+};
+struct BoxResult {
+  unsigned long long stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  std::vector<int> status;
+  double chain_ms = 0.0, pre_ms = 0.0;
+  DevBuf state;               // d x n_chains centred positions x_b of the last transition
+  int max_restarts = 0;
+};
+
+static int hmc_box_core(const BoxRun& r, BoxResult& res) {
+  Phase ph("hmc_box");
+  const int d = r.d, n_chains = r.n_chains, n_per_chain = r.n_per_chain, burn_in = r.burn_in;
+  cudaStream_t st = r.st;
+  const size_t n_cols = (size_t)n_chains * n_per_chain;
+  double* d_out = r.out;
+  DevBuf b_glo, b_ghi, b_sd, b_misc, b_status, b_sdone, b_pos, b_rcount, b_act;
+  DevBuf& b_state = res.state;
+  LQG_CUDA_TRY(b_state.alloc((size_t)d * n_chains * sizeof(double)));
+  LQG_CUDA_TRY(b_glo.alloc(d * sizeof(double)));
+  LQG_CUDA_TRY(b_ghi.alloc(d * sizeof(double)));
+  LQG_CUDA_TRY(b_sd.alloc(d * sizeof(double)));
+  LQG_CUDA_TRY(b_misc.alloc(16 * sizeof(unsigned long long)));      // [0..7] stats, [8] queue head, [9] n_active
+  LQG_CUDA_TRY(b_status.alloc((size_t)n_chains * sizeof(int)));
+  LQG_CUDA_TRY(b_sdone.alloc((size_t)n_chains * sizeof(int)));
+  LQG_CUDA_TRY(b_pos.alloc((size_t)n_chains * sizeof(int64_t)));
+  LQG_CUDA_TRY(b_rcount.alloc((size_t)n_chains * sizeof(int)));
+  LQG_CUDA_TRY(b_act.alloc((size_t)2 * n_chains * sizeof(int)));
+  LQG_CUDA_TRY(cudaMemsetAsync(b_misc.p, 0, b_misc.bytes, st));
+  LQG_CUDA_TRY(cudaMemsetAsync(b_status.p, 0, b_status.bytes, st));
+  LQG_CUDA_TRY(cudaMemsetAsync(b_sdone.p, 0, b_sdone.bytes, st));
+  LQG_CUDA_TRY(cudaMemsetAsync(b_pos.p, 0, b_pos.bytes, st));
+  LQG_CUDA_TRY(cudaMemsetAsync(b_rcount.p, 0, b_rcount.bytes, st));
+
+  ph.mark("alloc");
+  LQG_CUDA_TRY(launch_box_prep(d, r.mu, r.lb, r.ub, r.Sigma, b_glo.as<double>(), b_ghi.as<double>(), b_sd.as<double>(), st));
+  // x_b(0) = init - mu for every chain (init_ld == 0 broadcasts one shared start)
+  LQG_CUDA_TRY(launch_box_init_state(d, n_chains, r.init, r.init_ld, r.mu, b_state.as<double>(), st));
+  std::vector<double> h_sd(d);
+  LQG_CUDA_TRY(cudaMemcpyAsync(h_sd.data(), b_sd.p, d * sizeof(double), cudaMemcpyDeviceToHost, st));
+  LQG_CUDA_TRY(cudaStreamSynchronize(st));
+  double sd_max = 0.0;
+  for (int i = 0; i < d; ++i) {
+    if (!(h_sd[i] > 0.0)) { set_error("lqg_hmc_box: Sigma[%d,%d] = %g is not positive", i, i, h_sd[i]); return LQG_ERR_INVALID; }
+    sd_max = std::max(sd_max, h_sd[i]);
+  }
+
+  BoxParams p;
+  memset(&p, 0, sizeof(p));
+  p.d = d; p.mu = r.mu; p.lb = r.lb; p.ub = r.ub; p.U = r.U; p.u_upper = r.u_upper;
+  p.Sigma = r.Sigma; p.glo = b_glo.as<double>(); p.ghi = b_ghi.as<double>(); p.sdiag = b_sd.as<double>();
+  p.abs_eps = kFilterRel * std::sqrt(sd_max);
+  p.state = b_state.as<double>(); p.n_chains = n_chains;
+  p.s_done = b_sdone.as<int>(); p.pos = b_pos.as<int64_t>(); p.rcount = b_rcount.as<int>();
+  p.burn_in = burn_in; p.n_per_chain = n_per_chain; p.out = d_out; p.seed = r.seed;
+  p.chain_offset = r.chain_offset; p.injected = r.injected;
+  p.n_injected = r.n_injected;
+  p.max_restarts = r.max_restarts > 0 ? r.max_restarts : 100000;
+  res.max_restarts = p.max_restarts;
+  p.stats = b_misc.as<unsigned long long>();
+  p.next_chain = reinterpret_cast<int*>(b_misc.as<unsigned long long>() + 8);
+  int* d_nactive = reinterpret_cast<int*>(b_misc.as<unsigned long long>() + 9);
+  p.chain_status = b_status.as<int>();
+
+  ph.mark("prep");
+  const int total = burn_in + n_per_chain;
+  // ---- momentum pool: X_a = U A for the next `attempts` draws of every active chain, ONE GEMM ----
+  const bool use_pool = !r.injected && (r.prepass == 1 || (r.prepass == -1 && d >= 256));
+  double chain_ms = 0.0, pre_ms = 0.0;
+  Timer t_chain(st), t_pre(st);
+  EventGuard round_guard;
+  if (r.on_round) LQG_CUDA_TRY(cudaEventCreateWithFlags(&round_guard.e, cudaEventDisableTiming));
+  cudaEvent_t ev_round = round_guard.e;
+  int handed = 0;                        // samples per chain already handed to on_round
+  int rc;
+  if (!use_pool) {
+    p.active = nullptr; p.n_active = n_chains; p.attempts = 0x7fffffff; p.pool = nullptr;
+    t_chain.start();
+    LQG_CUDA_TRY(launch_hmc_box(p, 0, st));
+    t_chain.stop();
+    chain_ms = t_chain.ms();
+  } else {
+    // attempts per round: pool + draw buffers stay below ~2 GB each
+    const size_t budget = (size_t)2 << 30;
+    static const char* env_att = getenv("LQG_POOL_ATTEMPTS");          // tuning aid
+    const size_t att_cap = env_att ? (size_t)std::max(4, atoi(env_att)) : 64;
+    int attempts = (int)std::max<size_t>(4, std::min<size_t>(att_cap, budget / ((size_t)d * n_chains * sizeof(double))));
+    attempts = std::min(attempts, total + 8);
+    // the buffers hold max_attempts columns per chain; later rounds never ask for more (the
+    // short tail below wants at least 6, hence the floor here rather than there)
+    const int max_attempts = std::max(attempts, 6);
+    DevBuf b_pool, b_a;
+    LQG_CUDA_TRY(b_pool.alloc((size_t)d * n_chains * max_attempts * sizeof(double)));
+    LQG_CUDA_TRY(b_a.alloc((size_t)d * n_chains * max_attempts * sizeof(double)));
+    ph.mark("pool alloc");
+    int n_active = n_chains;
+    int* act[2] = {b_act.as<int>(), b_act.as<int>() + n_chains};
+    int cur = 0;
+    bool first = true;
+    // round counters come back through mapped pinned memory (allocated once per thread)
+    static thread_local volatile int* h_flags = nullptr;
+    static thread_local int* d_flags = nullptr;
+    if (!h_flags) {
+      void* hp = nullptr;
+      LQG_CUDA_TRY(cudaHostAlloc(&hp, 64, cudaHostAllocMapped));
+      LQG_CUDA_TRY(cudaHostGetDevicePointer((void**)&d_flags, hp, 0));
+      h_flags = (volatile int*)hp;
+    }
+    // every round consumes `attempts` momenta per active chain, so this terminates after at most
+    // (total + restarts) / attempts rounds; max_restarts bounds the restarts of every transition
+    while (n_active > 0) {
+      NormalGen gen{r.seed, r.chain_offset, attempts, first ? nullptr : act[cur], p.pos};
+      t_pre.start();
+      LQG_CUDA_TRY(launch_fill_normals(d, (size_t)n_active * attempts, b_a.as<double>(), gen, st));
+      LQG_CUDA_TRY(launch_dgemm(d, n_active * attempts, d, r.U, d, b_a.as<double>(), d,
+                                b_pool.as<double>(), d, nullptr, r.u_upper, st));
+      t_pre.stop();
+      p.active = first ? nullptr : act[cur]; p.n_active = n_active; p.attempts = attempts;
+      p.pool = b_pool.as<double>();
+      // queue head = 0, n_active = 0, min s_done = 0x7f7f7f7f  (memsets: no copy-engine traffic)
+      LQG_CUDA_TRY(cudaMemsetAsync(p.next_chain, 0, 3 * sizeof(int), st));
+      LQG_CUDA_TRY(cudaMemsetAsync(d_nactive + 1, 0x7f, sizeof(int), st));
+      t_chain.start();
+      LQG_CUDA_TRY(launch_hmc_box(p, 0, st));
+      t_chain.stop();
+      LQG_CUDA_TRY(launch_box_compact(n_chains, total, p.s_done, p.chain_status, act[cur ^ 1], d_nactive, d_flags, st));
+      if (ev_round) LQG_CUDA_TRY(cudaEventRecord(ev_round, st));
+      LQG_CUDA_TRY(cudaStreamSynchronize(st));
+      n_active = h_flags[0];
+      const int s_min = std::min((int)h_flags[1], total);
+      if (r.on_round && s_min - burn_in > handed) {
+        const int upto = s_min - burn_in;
+        if ((rc = r.on_round(handed, upto, ev_round))) return rc;
+        handed = upto;
+      }
+      // shrink the last rounds' pool to what the slowest chain can still need; with a consumer
+      // that works round by round, the last stretch is additionally cut into halving rounds so that
+      // the part that cannot overlap any compute (the final round's samples) is a few columns per chain
+      const int rem = total - s_min;
+      attempts = std::max(4, std::min(max_attempts, (int)(rem * 1.25) + 4));
+      if (r.short_tail && rem <= 2 * max_attempts) attempts = std::max(6, std::min(attempts, (int)(rem * 0.55) + 2));
+      attempts = std::min(attempts, max_attempts);                 // never past the pool allocation
+      pre_ms += t_pre.ms();
+      chain_ms += t_chain.ms();
+      cur ^= 1;
+      first = false;
+      ph.mark("round");
+    }
+  }
+  // chains that failed never advance s_min, and the one-launch path has no rounds: whatever is left
+  // is handed over here
+  if (r.on_round && handed < n_per_chain) {
+    LQG_CUDA_TRY(cudaEventRecord(ev_round, st));
+    if ((rc = r.on_round(handed, n_per_chain, ev_round))) return rc;
+  }
+
+  // ---- audit, stats ----
+  LQG_CUDA_TRY(launch_box_violations(d, n_cols, d_out, r.lb, r.ub, p.stats + 6, st));
+  res.status.assign(n_chains, 0);
+  LQG_CUDA_TRY(cudaMemcpyAsync(res.stats, p.stats, sizeof(res.stats), cudaMemcpyDeviceToHost, st));
+  LQG_CUDA_TRY(cudaMemcpyAsync(res.status.data(), b_status.p, n_chains * sizeof(int), cudaMemcpyDeviceToHost, st));
+  LQG_CUDA_TRY(cudaStreamSynchronize(st));
+  res.chain_ms = chain_ms; res.pre_ms = pre_ms;
+  ph.mark("audit");
+  return LQG_OK;
+}
+
+// status of a finished run -> return code + message (shared by lqg_hmc_box and lqg_simulate)
+static int box_result_rc(BoxResult& res, const char* who) {
+  const int rc = chain_status_rc(res.status, &res.stats[7]);
+  if (rc == LQG_ERR_RESTART_CAP) set_error("%s: %llu chain(s) exceeded max_restarts=%d in one transition", who, res.stats[7], res.max_restarts);
+  if (rc == LQG_ERR_DRAWS_EXHAUSTED) set_error("%s: injected Gaussian stream too short for %llu chain(s)", who, res.stats[7]);
+  if (rc == LQG_OK && res.stats[6] != 0) { set_error("%s: %llu emitted values violate the bounds", who, res.stats[6]); }
+  return rc;
+}
+
+// host-side validation of the box problem, as the R layers do it
+static int validate_box(int d, const std::vector<double>& h_lb, const std::vector<double>& h_ub,
+                        const std::vector<double>& h_init, int64_t init_ld, int n_chains) {
+  for (int i = 0; i < d; ++i)
+    if (!(h_lb[i] < h_ub[i])) {                            // R/lineqGPutils.R:359-360
+      set_error("The elements from \"u\" has to be greater than the elements from \"l\" (i=%d)", i);
+      return LQG_ERR_INVALID;
+    }
+  for (int ch = 0; ch < (init_ld == 0 ? 1 : n_chains); ++ch)
+    for (int i = 0; i < d; ++i) {
+      const double x = h_init[(size_t)ch * init_ld + i];
+      if (!(x - h_lb[i] > 0.0) || !(h_ub[i] - x > 0.0)) {  // tmg:R/tmg.R:44-47
+        set_error("Error: initial point violates linear constraints. (chain %d, coordinate %d)", ch, i);
+        return LQG_ERR_INIT_INFEASIBLE;
+      }
+    }
+  return LQG_OK;
+}
+
 extern "C" int lqg_hmc_box(int32_t d, const double* mu, const double* U, int32_t u_upper,
                            const double* Sigma, const double* lb, const double* ub,
                            const double* init, int64_t init_ld, int32_t n_per_chain,
@@ -246,7 +460,7 @@ extern "C" int lqg_hmc_box(int32_t d, const double* mu, const double* U, int32_t
   LQG_API_BEGIN
   if (stats) memset(stats, 0, sizeof(*stats));
   if (!have_device()) return LQG_ERR_CUDA;
-  Phase ph("hmc_box");
+  Phase ph("hmc_box api");
   const lqg_opts o = opts_ ? *opts_ : default_opts();
   const int n_chains = o.n_chains > 0 ? o.n_chains : 1;
   if (d <= 0 || d > 8192 || !mu || !Sigma || !lb || !ub || !init || !out || n_per_chain <= 0 ||
@@ -261,25 +475,12 @@ extern "C" int lqg_hmc_box(int32_t d, const double* mu, const double* U, int32_t
   const size_t dd = (size_t)d * d;
   const size_t n_init = init_ld == 0 ? (size_t)d : (size_t)init_ld * (n_chains - 1) + d;
 
-  // ---- host-side validation, as the R layers do it ----
   std::vector<double> h_lb, h_ub, h_init;
   int rc;
   if ((rc = fetch_host(h_lb, lb, d, mem, st)) || (rc = fetch_host(h_ub, ub, d, mem, st)) ||
       (rc = fetch_host(h_init, init, n_init, mem, st)))
     return rc;
-  for (int i = 0; i < d; ++i)
-    if (!(h_lb[i] < h_ub[i])) {                            // R/lineqGPutils.R:359-360
-      set_error("The elements from \"u\" has to be greater than the elements from \"l\" (i=%d)", i);
-      return LQG_ERR_INVALID;
-    }
-  for (int ch = 0; ch < (init_ld == 0 ? 1 : n_chains); ++ch)
-    for (int i = 0; i < d; ++i) {
-      const double x = h_init[(size_t)ch * init_ld + i];
-      if (!(x - h_lb[i] > 0.0) || !(h_ub[i] - x > 0.0)) {  // tmg:R/tmg.R:44-47
-        set_error("Error: initial point violates linear constraints. (chain %d, coordinate %d)", ch, i);
-        return LQG_ERR_INIT_INFEASIBLE;
-      }
-    }
+  if ((rc = validate_box(d, h_lb, h_ub, h_init, init_ld, n_chains))) return rc;
 
   ph.mark("validate");
   // ---- stage inputs ----
@@ -299,198 +500,62 @@ extern "C" int lqg_hmc_box(int32_t d, const double* mu, const double* U, int32_t
   }
 
   const size_t n_cols = (size_t)n_chains * n_per_chain;
-  DevBuf b_out, b_state, b_glo, b_ghi, b_sd, b_misc, b_status, b_sdone, b_pos, b_rcount, b_act;
+  DevBuf b_out;
   double* d_out = out;
   if (mem == LQG_MEM_HOST) { LQG_CUDA_TRY(b_out.alloc(n_cols * d * sizeof(double))); d_out = b_out.as<double>(); }
-  LQG_CUDA_TRY(b_state.alloc((size_t)d * n_chains * sizeof(double)));
-  LQG_CUDA_TRY(b_glo.alloc(d * sizeof(double)));
-  LQG_CUDA_TRY(b_ghi.alloc(d * sizeof(double)));
-  LQG_CUDA_TRY(b_sd.alloc(d * sizeof(double)));
-  LQG_CUDA_TRY(b_misc.alloc(16 * sizeof(unsigned long long)));      // [0..7] stats, [8] queue head, [9] n_active
-  LQG_CUDA_TRY(b_status.alloc((size_t)n_chains * sizeof(int)));
-  LQG_CUDA_TRY(b_sdone.alloc((size_t)n_chains * sizeof(int)));
-  LQG_CUDA_TRY(b_pos.alloc((size_t)n_chains * sizeof(int64_t)));
-  LQG_CUDA_TRY(b_rcount.alloc((size_t)n_chains * sizeof(int)));
-  LQG_CUDA_TRY(b_act.alloc((size_t)2 * n_chains * sizeof(int)));
-  LQG_CUDA_TRY(cudaMemsetAsync(b_misc.p, 0, b_misc.bytes, st));
-  LQG_CUDA_TRY(cudaMemsetAsync(b_status.p, 0, b_status.bytes, st));
-  LQG_CUDA_TRY(cudaMemsetAsync(b_sdone.p, 0, b_sdone.bytes, st));
-  LQG_CUDA_TRY(cudaMemsetAsync(b_pos.p, 0, b_pos.bytes, st));
-  LQG_CUDA_TRY(cudaMemsetAsync(b_rcount.p, 0, b_rcount.bytes, st));
+  ph.mark("stage");
 
-  ph.mark("stage+alloc");
-  LQG_CUDA_TRY(launch_box_prep(d, i_mu.dev, i_lb.dev, i_ub.dev, i_S.dev, b_glo.as<double>(),
-                               b_ghi.as<double>(), b_sd.as<double>(), st));
-  // x_b(0) = init - mu for every chain (init_ld == 0 broadcasts one shared start)
-  LQG_CUDA_TRY(launch_box_init_state(d, n_chains, i_init.dev, init_ld, i_mu.dev, b_state.as<double>(), st));
-  std::vector<double> h_sd(d);
-  LQG_CUDA_TRY(cudaMemcpyAsync(h_sd.data(), b_sd.p, d * sizeof(double), cudaMemcpyDeviceToHost, st));
-  LQG_CUDA_TRY(cudaStreamSynchronize(st));
-  double sd_max = 0.0;
-  for (int i = 0; i < d; ++i) {
-    if (!(h_sd[i] > 0.0)) { set_error("lqg_hmc_box: Sigma[%d,%d] = %g is not positive", i, i, h_sd[i]); return LQG_ERR_INVALID; }
-    sd_max = std::max(sd_max, h_sd[i]);
-  }
+  BoxRun r;
+  r.d = d; r.mu = i_mu.dev; r.U = i_U.dev; r.u_upper = u_upper; r.Sigma = i_S.dev; r.lb = i_lb.dev; r.ub = i_ub.dev;
+  r.init = i_init.dev; r.init_ld = init_ld; r.n_chains = n_chains; r.n_per_chain = n_per_chain; r.burn_in = burn_in;
+  r.seed = o.seed; r.chain_offset = o.chain_offset; r.prepass = o.prepass; r.max_restarts = o.max_restarts;
+  r.injected = o.injected ? i_inj.dev : nullptr; r.n_injected = o.n_injected;
+  r.out = d_out; r.st = st;
 
-  BoxParams p;
-  memset(&p, 0, sizeof(p));
-  p.d = d; p.mu = i_mu.dev; p.lb = i_lb.dev; p.ub = i_ub.dev; p.U = i_U.dev; p.u_upper = u_upper;
-  p.Sigma = i_S.dev; p.glo = b_glo.as<double>(); p.ghi = b_ghi.as<double>(); p.sdiag = b_sd.as<double>();
-  p.abs_eps = kFilterRel * std::sqrt(sd_max);
-  p.state = b_state.as<double>(); p.n_chains = n_chains;
-  p.s_done = b_sdone.as<int>(); p.pos = b_pos.as<int64_t>(); p.rcount = b_rcount.as<int>();
-  p.burn_in = burn_in; p.n_per_chain = n_per_chain; p.out = d_out; p.seed = o.seed;
-  p.chain_offset = o.chain_offset; p.injected = o.injected ? i_inj.dev : nullptr;
-  p.n_injected = o.n_injected;
-  p.max_restarts = o.max_restarts > 0 ? o.max_restarts : 100000;
-  p.stats = b_misc.as<unsigned long long>();
-  p.next_chain = reinterpret_cast<int*>(b_misc.as<unsigned long long>() + 8);
-  int* d_nactive = reinterpret_cast<int*>(b_misc.as<unsigned long long>() + 9);
-  p.chain_status = b_status.as<int>();
-
-  ph.mark("prep");
-  const int total = burn_in + n_per_chain;
-  // ---- momentum pool: X_a = U A for the next `attempts` draws of every active chain, ONE GEMM ----
-  const bool use_pool = !o.injected && (o.prepass == 1 || (o.prepass == -1 && d >= 256));
-  double chain_ms = 0.0, pre_ms = 0.0;
-  bool out_copied = false;
-  Timer t_chain(st), t_pre(st);
-  if (!use_pool) {
-    p.active = nullptr; p.n_active = n_chains; p.attempts = 0x7fffffff; p.pool = nullptr;
-    t_chain.start();
-    LQG_CUDA_TRY(launch_hmc_box(p, 0, st));
-    t_chain.stop();
-    chain_ms = t_chain.ms();
-  } else {
-    // attempts per round: pool + draw buffers stay below ~2 GB each
-    const size_t budget = (size_t)2 << 30;
-    static const char* env_att = getenv("LQG_POOL_ATTEMPTS");          // tuning aid
-    const size_t att_cap = env_att ? (size_t)std::max(4, atoi(env_att)) : 64;
-    int attempts = (int)std::max<size_t>(4, std::min<size_t>(att_cap, budget / ((size_t)d * n_chains * sizeof(double))));
-    attempts = std::min(attempts, total + 8);
-    DevBuf b_pool, b_a;
-    LQG_CUDA_TRY(b_pool.alloc((size_t)d * n_chains * attempts * sizeof(double)));
-    LQG_CUDA_TRY(b_a.alloc((size_t)d * n_chains * attempts * sizeof(double)));
-    ph.mark("pool alloc");
-    int n_active = n_chains;
-    int* act[2] = {b_act.as<int>(), b_act.as<int>() + n_chains};
-    int cur = 0;
-    bool first = true;
-    const int max_attempts = attempts;
-    // round counters come back through mapped pinned memory (allocated once per thread)
-    static thread_local volatile int* h_flags = nullptr;
-    static thread_local int* d_flags = nullptr;
-    if (!h_flags) {
-      void* hp = nullptr;
-      LQG_CUDA_TRY(cudaHostAlloc(&hp, 64, cudaHostAllocMapped));
-      LQG_CUDA_TRY(cudaHostGetDevicePointer((void**)&d_flags, hp, 0));
-      h_flags = (volatile int*)hp;
-    }
-    // HOST mode: samples every chain has already emitted are copied out while later rounds run
-    // (one strided 2-D copy per round: chain-major columns, pitch = n_per_chain * d doubles)
-    StreamGuard copy_guard;
-    EventGuard round_guard;
-    int copied = 0;                      // samples per chain already on their way to the host
-    if (mem == LQG_MEM_HOST) {
-      LQG_CUDA_TRY(cudaStreamCreateWithFlags(&copy_guard.s, cudaStreamNonBlocking));
-      LQG_CUDA_TRY(cudaEventCreateWithFlags(&round_guard.e, cudaEventDisableTiming));
-    }
-    cudaStream_t copy_st = copy_guard.s;
-    cudaEvent_t ev_round = round_guard.e;
-    // a pageable result matrix (R, numpy) is filled through the pinned staging ring and helper
-    // threads; a page-locked one (lqg_alloc_host) directly by the copy engine.  LQG_STAGED=0 disables.
-    std::unique_ptr<StagedCopier> staged;
+  // HOST mode: samples every chain has already emitted are copied out while later rounds run
+  // (one strided 2-D copy per round: chain-major columns, pitch = n_per_chain * d doubles).
+  // A pageable result matrix (R, numpy) is filled through the pinned staging ring and helper
+  // threads; a page-locked one (lqg_alloc_host) directly by the copy engine.  LQG_STAGED=0 disables.
+  StreamGuard copy_guard;
+  std::unique_ptr<StagedCopier> staged;
+  if (mem == LQG_MEM_HOST) {
+    LQG_CUDA_TRY(cudaStreamCreateWithFlags(&copy_guard.s, cudaStreamNonBlocking));
     static const char* env_staged = getenv("LQG_STAGED");
-    if (copy_st && !(env_staged && env_staged[0] == '0') && StagedCopier::is_pageable(out))
-      staged.reset(new StagedCopier(copy_st));
-    auto copy_out = [&](int from, int upto, cudaStream_t cs) -> int {
+    if (!(env_staged && env_staged[0] == '0') && StagedCopier::is_pageable(out)) staged.reset(new StagedCopier(copy_guard.s));
+    cudaStream_t copy_st = copy_guard.s;
+    r.short_tail = true;
+    r.on_round = [&, copy_st](int from, int upto, cudaEvent_t ready) -> int {
+      LQG_CUDA_TRY(cudaStreamWaitEvent(copy_st, ready, 0));
       const size_t pitch = (size_t)n_per_chain * d * sizeof(double);
       const size_t width = (size_t)(upto - from) * d * sizeof(double);
       if (staged) LQG_CUDA_TRY(staged->copy2d(out + (size_t)from * d, pitch, d_out + (size_t)from * d, pitch, width, n_chains));
       else LQG_CUDA_TRY(cudaMemcpy2DAsync(out + (size_t)from * d, pitch, d_out + (size_t)from * d, pitch, width, n_chains,
-                                          cudaMemcpyDeviceToHost, cs));
+                                          cudaMemcpyDeviceToHost, copy_st));
       return LQG_OK;
     };
-    // every round consumes `attempts` momenta per active chain, so this terminates after at most
-    // (total + restarts) / attempts rounds; max_restarts bounds the restarts of every transition
-    while (n_active > 0) {
-      NormalGen gen{o.seed, o.chain_offset, attempts, first ? nullptr : act[cur], p.pos};
-      t_pre.start();
-      LQG_CUDA_TRY(launch_fill_normals(d, (size_t)n_active * attempts, b_a.as<double>(), gen, st));
-      LQG_CUDA_TRY(launch_dgemm(d, n_active * attempts, d, i_U.dev, d, b_a.as<double>(), d,
-                                b_pool.as<double>(), d, nullptr, u_upper, st));
-      t_pre.stop();
-      p.active = first ? nullptr : act[cur]; p.n_active = n_active; p.attempts = attempts;
-      p.pool = b_pool.as<double>();
-      // queue head = 0, n_active = 0, min s_done = 0x7f7f7f7f  (memsets: no copy-engine traffic)
-      LQG_CUDA_TRY(cudaMemsetAsync(p.next_chain, 0, 3 * sizeof(int), st));
-      LQG_CUDA_TRY(cudaMemsetAsync(d_nactive + 1, 0x7f, sizeof(int), st));
-      t_chain.start();
-      LQG_CUDA_TRY(launch_hmc_box(p, 0, st));
-      t_chain.stop();
-      LQG_CUDA_TRY(launch_box_compact(n_chains, total, p.s_done, p.chain_status, act[cur ^ 1], d_nactive, d_flags, st));
-      if (ev_round) LQG_CUDA_TRY(cudaEventRecord(ev_round, st));
-      LQG_CUDA_TRY(cudaStreamSynchronize(st));
-      n_active = h_flags[0];
-      const int s_min = std::min((int)h_flags[1], total);
-      if (copy_st && s_min - burn_in > copied) {
-        const int upto = s_min - burn_in;
-        LQG_CUDA_TRY(cudaStreamWaitEvent(copy_st, ev_round, 0));
-        if ((rc = copy_out(copied, upto, copy_st))) return rc;
-        copied = upto;
-      }
-      // shrink the last rounds' pool to what the slowest chain can still need; when the samples
-      // go to the host, the last stretch is additionally cut into halving rounds so that the copy
-      // that cannot overlap any compute (the final round's samples) is a few columns per chain
-      const int rem = total - s_min;
-      attempts = std::max(4, std::min(max_attempts, (int)(rem * 1.25) + 4));
-      if (copy_st && rem <= 2 * max_attempts) attempts = std::max(6, std::min(attempts, (int)(rem * 0.55) + 2));
-      pre_ms += t_pre.ms();
-      chain_ms += t_chain.ms();
-      cur ^= 1;
-      first = false;
-      ph.mark("round");
-    }
-    if (copy_st) {
-      // chains that failed never advance s_min: whatever is left is copied by the common tail below
-      if (copied < n_per_chain) {
-        LQG_CUDA_TRY(cudaEventRecord(ev_round, st));
-        LQG_CUDA_TRY(cudaStreamWaitEvent(copy_st, ev_round, 0));
-        if ((rc = copy_out(copied, n_per_chain, copy_st))) return rc;
-      }
-      if (staged) LQG_CUDA_TRY(staged->finish());
-      LQG_CUDA_TRY(cudaStreamSynchronize(copy_st));
-      out_copied = true;
-    }
   }
-
-  // ---- audit, stats, results ----
-  LQG_CUDA_TRY(launch_box_violations(d, n_cols, d_out, i_lb.dev, i_ub.dev, p.stats + 6, st));
-  unsigned long long h_stats[8];
-  std::vector<int> h_status(n_chains);
-  LQG_CUDA_TRY(cudaMemcpyAsync(h_stats, p.stats, sizeof(h_stats), cudaMemcpyDeviceToHost, st));
-  LQG_CUDA_TRY(cudaMemcpyAsync(h_status.data(), b_status.p, n_chains * sizeof(int), cudaMemcpyDeviceToHost, st));
-  if (mem == LQG_MEM_HOST && !out_copied)
-    LQG_CUDA_TRY(cudaMemcpyAsync(out, d_out, n_cols * d * sizeof(double), cudaMemcpyDeviceToHost, st));
+  BoxResult res;
+  if ((rc = hmc_box_core(r, res))) return rc;
+  if (copy_guard.s) {
+    if (staged) LQG_CUDA_TRY(staged->finish());
+    LQG_CUDA_TRY(cudaStreamSynchronize(copy_guard.s));
+  }
   if (state_out) {
     // state_out holds positions in the ORIGINAL frame: mu + x_b, chain by chain
     std::vector<double> h_state((size_t)d * n_chains), h_mu;
-    LQG_CUDA_TRY(cudaMemcpyAsync(h_state.data(), b_state.p, h_state.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    LQG_CUDA_TRY(cudaMemcpyAsync(h_state.data(), res.state.p, h_state.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
     if ((rc = fetch_host(h_mu, mu, d, mem, st))) return rc;
     LQG_CUDA_TRY(cudaStreamSynchronize(st));
     for (int ch = 0; ch < n_chains; ++ch)
       for (int i = 0; i < d; ++i) h_state[(size_t)ch * d + i] += h_mu[i];
     if (mem == LQG_MEM_HOST) memcpy(state_out, h_state.data(), h_state.size() * sizeof(double));
     else LQG_CUDA_TRY(cudaMemcpyAsync(state_out, h_state.data(), h_state.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    LQG_CUDA_TRY(cudaStreamSynchronize(st));
   }
-  LQG_CUDA_TRY(cudaStreamSynchronize(st));
-  ph.mark("audit+copy out");
-  rc = chain_status_rc(h_status, &h_stats[7]);
-  fill_stats(stats, h_stats, chain_ms, pre_ms);
+  ph.mark("copy out");
+  rc = box_result_rc(res, "lqg_hmc_box");
+  fill_stats(stats, res.stats, res.chain_ms, res.pre_ms);
   fold_launches();
-  if (rc == LQG_ERR_RESTART_CAP) set_error("lqg_hmc_box: %llu chain(s) exceeded max_restarts=%d in one transition", h_stats[7], p.max_restarts);
-  if (rc == LQG_ERR_DRAWS_EXHAUSTED) set_error("lqg_hmc_box: injected Gaussian stream too short for %llu chain(s)", h_stats[7]);
-  if (rc == LQG_OK && h_stats[6] != 0) { set_error("lqg_hmc_box: %llu emitted values violate the bounds", h_stats[6]); }
   return rc;
   LQG_API_END("lqg_hmc_box")
 }
@@ -726,6 +791,17 @@ extern "C" int lqg_measure_fp64_peaks(double* dfma_tflops, double* dmma_tflops, 
   LQG_API_END("lqg_measure_fp64_peaks")
 }
 
+// probe: DFMA warps and DMMA warps side by side (are the two FP64 paths separate units?)
+extern "C" int lqg_measure_fp64_mixed(double* tflops, double* dfma_share, const lqg_opts* opts) {
+  LQG_API_BEGIN
+  if (!have_device()) return LQG_ERR_CUDA;
+  cudaStream_t st = opts ? (cudaStream_t)opts->stream : nullptr;
+  LQG_CUDA_TRY(measure_fp64_mixed(tflops, dfma_share, st));
+  fold_launches();
+  return LQG_OK;
+  LQG_API_END("lqg_measure_fp64_mixed")
+}
+
 // ===========================================================================================
 extern "C" int lqg_rsm(int32_t d, const double* map, const double* factor, const double* w,
                        const double* lb, const double* ub, int64_t nsim, int64_t max_proposals,
@@ -734,9 +810,17 @@ extern "C" int lqg_rsm(int32_t d, const double* map, const double* factor, const
   if (stats) memset(stats, 0, sizeof(*stats));
   if (!have_device()) return LQG_ERR_CUDA;
   const lqg_opts o = opts_ ? *opts_ : default_opts();
-  if (d <= 0 || d > 4096 || !map || !factor || !w || !lb || !ub || !out || nsim <= 0) {
+  if (d <= 0 || !map || !factor || !w || !lb || !ub || !out || nsim <= 0) {
     set_error("lqg_rsm: invalid argument (d=%d, nsim=%lld)", d, (long long)nsim);
     return LQG_ERR_INVALID;
+  }
+  // rsm_eval/rsm_emit keep one proposal vector per warp in shared memory: 8 warps x d doubles
+  // must fit the 227 KB a CTA can opt into (rejection from the mode is hopeless long before that:
+  // the acceptance rate falls geometrically with d)
+  if ((size_t)d * 64 > (size_t)227 * 1024) {
+    set_error("lqg_rsm: d=%d exceeds the supported maximum of %d (8 proposal vectors per CTA in shared memory)", d,
+              (int)((size_t)227 * 1024 / 64));
+    return LQG_ERR_UNSUPPORTED;
   }
   cudaStream_t st = (cudaStream_t)o.stream;
   DevBuf::cur_stream = st;
@@ -1111,6 +1195,37 @@ extern "C" int lqg_eta_params(int32_t d, int32_t m, const double* Lambda, const 
   LQG_API_END("lqg_eta_params")
 }
 
+// X (m x d, device) <- Lambda^+ for a device-resident Lambda (d x m, d >= m).  Synchronises the stream.
+static int lambda_pinv_device(int d, int m, const double* L_dev, double* X, cudaStream_t st) {
+  const size_t dd = (size_t)d * d, dm = (size_t)d * m, mm = (size_t)m * m;
+  int rc;
+  DevBuf b_g, b_l, b_r, b_y;
+  LQG_CUDA_TRY(b_g.alloc(mm * sizeof(double)));
+  LQG_CUDA_TRY(b_l.alloc(mm * sizeof(double)));
+  LQG_CUDA_TRY(b_r.alloc(dd * sizeof(double)));
+  LQG_CUDA_TRY(b_y.alloc(dm * sizeof(double)));
+  double *G = b_g.as<double>(), *Lc = b_l.as<double>(), *R = b_r.as<double>(), *Y = b_y.as<double>();
+  // G = Lambda' Lambda;  G = Lc Lc'
+  LQG_CUDA_TRY(launch_gemm(true, false, m, m, d, 1.0, L_dev, d, L_dev, d, 0.0, G, m, 0, st));
+  int bad = 0;
+  if ((rc = chol_device(m, G, 0, Lc, &bad, st))) return rc;
+  if (bad) {
+    set_error("lqg_lambda_pinv: Lambda is rank deficient (pivot %d of Lambda'Lambda is not positive)", bad);
+    return LQG_ERR_NOT_PD;
+  }
+  // X0 = G^-1 Lambda'
+  LQG_CUDA_TRY(launch_transpose(d, m, L_dev, d, X, m, st));
+  LQG_CUDA_TRY(launch_chol_solve(m, Lc, m, X, m, d, st));
+  // one refinement step: X += G^-1 Lambda' (I - Lambda X0)
+  LQG_CUDA_TRY(launch_gemm(false, false, d, d, m, -1.0, L_dev, d, X, m, 0.0, R, d, 0, st));
+  LQG_CUDA_TRY(launch_add_diag(d, R, d, 1.0, st));
+  LQG_CUDA_TRY(launch_gemm(true, false, m, d, d, 1.0, L_dev, d, R, d, 0.0, Y, m, 0, st));
+  LQG_CUDA_TRY(launch_chol_solve(m, Lc, m, Y, m, d, st));
+  LQG_CUDA_TRY(launch_axpy(dm, 1.0, Y, X, st));
+  LQG_CUDA_TRY(cudaStreamSynchronize(st));                   // the scratch above dies with this frame
+  return LQG_OK;
+}
+
 extern "C" int lqg_lambda_pinv(int32_t d, int32_t m, const double* Lambda, const lqg_opts* opts_, double* Lp_out) {
   LQG_API_BEGIN
   if (!have_device()) return LQG_ERR_CUDA;
@@ -1122,39 +1237,17 @@ extern "C" int lqg_lambda_pinv(int32_t d, int32_t m, const double* Lambda, const
   cudaStream_t st = (cudaStream_t)o.stream;
   DevBuf::cur_stream = st;
   const int mem = o.mem;
-  const size_t dd = (size_t)d * d, dm = (size_t)d * m, mm = (size_t)m * m;
+  const size_t dm = (size_t)d * m;
   int rc;
   Input i_L;
   if ((rc = i_L.stage(Lambda, dm, mem, st))) return rc;
-  DevBuf b_g, b_l, b_x, b_r, b_y;
-  LQG_CUDA_TRY(b_g.alloc(mm * sizeof(double)));
-  LQG_CUDA_TRY(b_l.alloc(mm * sizeof(double)));
+  DevBuf b_x;
   LQG_CUDA_TRY(b_x.alloc(dm * sizeof(double)));
-  LQG_CUDA_TRY(b_r.alloc(dd * sizeof(double)));
-  LQG_CUDA_TRY(b_y.alloc(dm * sizeof(double)));
-  double *G = b_g.as<double>(), *Lc = b_l.as<double>(), *X = b_x.as<double>(), *R = b_r.as<double>(),
-         *Y = b_y.as<double>();
-  // G = Lambda' Lambda;  G = Lc Lc'
-  LQG_CUDA_TRY(launch_gemm(true, false, m, m, d, 1.0, i_L.dev, d, i_L.dev, d, 0.0, G, m, 0, st));
-  int bad = 0;
-  if ((rc = chol_device(m, G, 0, Lc, &bad, st))) return rc;
-  if (bad) {
-    set_error("lqg_lambda_pinv: Lambda is rank deficient (pivot %d of Lambda'Lambda is not positive)", bad);
-    fold_launches();
-    return LQG_ERR_NOT_PD;
-  }
-  // X0 = G^-1 Lambda'
-  LQG_CUDA_TRY(launch_transpose(d, m, i_L.dev, d, X, m, st));
-  LQG_CUDA_TRY(launch_chol_solve(m, Lc, m, X, m, d, st));
-  // one refinement step: X += G^-1 Lambda' (I - Lambda X0)
-  LQG_CUDA_TRY(launch_gemm(false, false, d, d, m, -1.0, i_L.dev, d, X, m, 0.0, R, d, 0, st));
-  LQG_CUDA_TRY(launch_add_diag(d, R, d, 1.0, st));
-  LQG_CUDA_TRY(launch_gemm(true, false, m, d, d, 1.0, i_L.dev, d, R, d, 0.0, Y, m, 0, st));
-  LQG_CUDA_TRY(launch_chol_solve(m, Lc, m, Y, m, d, st));
-  LQG_CUDA_TRY(launch_axpy(dm, 1.0, Y, X, st));
-  if ((rc = deliver(Lp_out, X, dm, mem, st))) return rc;
-  LQG_CUDA_TRY(cudaStreamSynchronize(st));
+  rc = lambda_pinv_device(d, m, i_L.dev, b_x.as<double>(), st);
   fold_launches();
+  if (rc) return rc;
+  if ((rc = deliver(Lp_out, b_x.as<double>(), dm, mem, st))) return rc;
+  LQG_CUDA_TRY(cudaStreamSynchronize(st));
   return LQG_OK;
   LQG_API_END("lqg_lambda_pinv")
 }
@@ -1565,4 +1658,340 @@ extern "C" int lqg_bands(int32_t n_t, int64_t N, const double* ysim, int64_t ld,
   fold_launches();
   return LQG_OK;
   LQG_API_END("lqg_bands")
+}
+
+// ===========================================================================================
+// lqg_simulate: sampler -> xi -> Phi xi -> bands in one call, device resident, optionally sharded
+// over the GPUs of a communicator (include/lineqgpr_b200.h)
+namespace {
+
+// dst[:, g] = src[:, perm[g]]: puts a slab of sample paths, whose columns follow the gathered order of
+// xi (round, rank, chain, sample), into job order (rank, chain, sample) = [xi_out(rank 0) | xi_out(rank 1) | ...]
+__global__ void permute_cols_kernel(int rows, int64_t n_cols, const double* __restrict__ src, int64_t lds,
+                                    const int* __restrict__ perm, double* __restrict__ dst, int64_t ldd) {
+  const size_t total = (size_t)rows * n_cols;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t g = idx / rows;
+    const int i = (int)(idx - g * rows);
+    dst[g * ldd + i] = src[(size_t)perm[g] * lds + i];
+  }
+}
+
+// 2-D device -> host copy of result columns on a copy stream: pinned destinations go through the
+// copy engine directly, pageable ones (R / numpy matrices) through the staging ring
+struct HostSink {
+  cudaStream_t st = nullptr;
+  std::unique_ptr<StagedCopier> staged;
+  void open(cudaStream_t copy_st, const void* dst) {
+    st = copy_st;
+    static const char* env_staged = getenv("LQG_STAGED");
+    if (!(env_staged && env_staged[0] == '0') && StagedCopier::is_pageable(dst)) staged.reset(new StagedCopier(copy_st));
+  }
+  cudaError_t copy2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t rows) {
+    if (staged) return staged->copy2d(dst, dpitch, src, spitch, width, rows);
+    return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, cudaMemcpyDeviceToHost, st);
+  }
+  cudaError_t finish() { return staged ? staged->finish() : cudaSuccess; }
+};
+
+}  // namespace
+
+extern "C" int lqg_simulate(const lqg_simulate_args* a_, const lqg_opts* opts_, lqg_comm* comm,
+                            lqg_simulate_stats* stats) {
+  LQG_API_BEGIN
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (!have_device()) return LQG_ERR_CUDA;
+  if (!a_) { set_error("lqg_simulate: NULL arguments"); return LQG_ERR_INVALID; }
+  const lqg_simulate_args a = *a_;
+  const lqg_opts o = opts_ ? *opts_ : default_opts();
+  const int d = a.d, m = a.m, n_t = a.n_t, nprobs = a.nprobs;
+  const int n_chains = o.n_chains > 0 ? o.n_chains : 1;
+  const int W = comm ? comm->world : 1, rank = comm ? comm->rank : 0;
+  const bool have_pinv = a.Lambda_pinv != nullptr, have_lambda = a.Lambda != nullptr;
+  if (d <= 0 || d > 8192 || m <= 0 || m > d || !a.mu || !a.Sigma || !a.lb || !a.ub || !a.init || a.n_per_chain <= 0 ||
+      a.burn_in < 0 || (!have_pinv && !have_lambda && d != m) || n_t < 0 || nprobs < 0 || nprobs > 8 ||
+      (nprobs > 0 && !a.probs) || (n_t > 0 && (!a.mean || (nprobs > 0 && !a.qtls))) ||
+      (n_t > 0 && !a.Phi && (a.basis_D <= 0 || !a.basis_mk || !a.xtest || !a.knots || a.ldx < n_t)) ||
+      (n_t > 0 && a.Phi && a.ldphi < n_t) || o.injected) {
+    set_error("lqg_simulate: invalid argument (d=%d m=%d n_t=%d nprobs=%d n_per_chain=%d burn_in=%d%s)", d, m, n_t, nprobs,
+              a.n_per_chain, a.burn_in, o.injected ? "; injected draws are a lqg_hmc_box feature" : "");
+    return LQG_ERR_INVALID;
+  }
+  const int n_per = a.n_per_chain;
+  const int64_t N_local = (int64_t)n_chains * n_per, N_total = N_local * W;
+  if (N_total > 0x7fffffff) { set_error("lqg_simulate: %lld samples exceed the 2^31-1 columns of one job", (long long)N_total); return LQG_ERR_INVALID; }
+  if (!a.Phi && n_t > 0) {
+    long long mt = 0;
+    for (int k = 0; k < a.basis_D; ++k) {
+      if (a.basis_mk[k] < 2) { set_error("lqg_simulate: basis block %d has %d knots (needs >= 2)", k, a.basis_mk[k]); return LQG_ERR_INVALID; }
+      mt += a.basis_mk[k];
+    }
+    if (mt != m) { set_error("lqg_simulate: the basis blocks have %lld knots in total, m = %d", mt, m); return LQG_ERR_INVALID; }
+  }
+  cudaStream_t st = (cudaStream_t)o.stream;
+  DevBuf::cur_stream = st;
+  const int mem = o.mem;
+  const size_t dd = (size_t)d * d, dm = (size_t)d * m;
+  int rc;
+  Timer t_total(st);
+  t_total.start();
+
+  // ---- validation and staging of the box problem (as lqg_hmc_box) ----
+  std::vector<double> h_lb, h_ub, h_init, h_probs;
+  if ((rc = fetch_host(h_lb, a.lb, d, mem, st)) || (rc = fetch_host(h_ub, a.ub, d, mem, st)) ||
+      (rc = fetch_host(h_init, a.init, d, mem, st)))
+    return rc;
+  if ((rc = validate_box(d, h_lb, h_ub, h_init, 0, 1))) return rc;
+  if (nprobs > 0 && (rc = fetch_host(h_probs, a.probs, nprobs, mem, st))) return rc;
+  for (int k = 0; k < nprobs; ++k)
+    if (!(h_probs[k] >= 0.0 && h_probs[k] <= 1.0)) { set_error("'probs' outside [0,1]"); return LQG_ERR_INVALID; }
+  Input i_mu, i_U, i_S, i_lb, i_ub, i_init, i_Lp;
+  if ((rc = i_mu.stage(a.mu, d, mem, st)) || (a.U && (rc = i_U.stage(a.U, dd, mem, st))) ||
+      (rc = i_S.stage(a.Sigma, dd, mem, st)) || (rc = i_lb.stage(a.lb, d, mem, st)) ||
+      (rc = i_ub.stage(a.ub, d, mem, st)) || (rc = i_init.stage(a.init, d, mem, st)))
+    return rc;
+  int u_upper = 1;
+  if (!a.U) {
+    LQG_CUDA_TRY(i_U.buf.alloc(dd * sizeof(double)));
+    if ((rc = ul_factor_device(d, i_S.dev, i_U.buf.as<double>(), st))) return rc;
+    i_U.dev = i_U.buf.as<double>();
+  }
+  // ---- Lambda^+ (m x d) ----
+  const bool identity = !have_pinv && !have_lambda;          // xi = eta
+  if (have_pinv) {
+    if ((rc = i_Lp.stage(a.Lambda_pinv, dm, mem, st))) return rc;
+  } else if (have_lambda) {
+    Input i_L;
+    if ((rc = i_L.stage(a.Lambda, dm, mem, st))) return rc;
+    LQG_CUDA_TRY(i_Lp.buf.alloc(dm * sizeof(double)));
+    if ((rc = lambda_pinv_device(d, m, i_L.dev, i_Lp.buf.as<double>(), st))) return rc;   // synchronises st
+    i_Lp.dev = i_Lp.buf.as<double>();
+  }
+
+  // ---- device-resident eta and the gathered xi of the whole job ----
+  DevBuf b_eta, b_xi;
+  double* d_eta = (mem == LQG_MEM_DEVICE && a.eta_out) ? a.eta_out : nullptr;
+  if (!d_eta) { LQG_CUDA_TRY(b_eta.alloc((size_t)d * N_local * sizeof(double))); d_eta = b_eta.as<double>(); }
+  LQG_CUDA_TRY(b_xi.alloc((size_t)m * N_total * sizeof(double)));
+  double* xi_all = b_xi.as<double>();
+
+  StreamGuard side_guard, copy_guard;
+  EventGuard ev_x_guard, ev_side_guard;
+  LQG_CUDA_TRY(cudaStreamCreateWithFlags(&side_guard.s, cudaStreamNonBlocking));
+  LQG_CUDA_TRY(cudaEventCreateWithFlags(&ev_x_guard.e, cudaEventDisableTiming));
+  LQG_CUDA_TRY(cudaEventCreateWithFlags(&ev_side_guard.e, cudaEventDisableTiming));
+  cudaStream_t s_side = side_guard.s;
+  HostSink sink_xi, sink_eta;
+  const bool host_out = mem == LQG_MEM_HOST && (a.xi_out || a.eta_out);
+  if (host_out) {
+    LQG_CUDA_TRY(cudaStreamCreateWithFlags(&copy_guard.s, cudaStreamNonBlocking));
+    if (a.xi_out) sink_xi.open(copy_guard.s, a.xi_out);
+    if (a.eta_out) sink_eta.open(copy_guard.s, a.eta_out);
+  }
+  cudaStream_t s_copy = copy_guard.s;
+
+  size_t round_off = 0;                   // doubles of xi_all filled by earlier rounds (all ranks)
+  int rounds = 0;
+  std::vector<std::pair<int, int>> round_span;                  // [from, upto) of every round
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> xi_timers;   // per-round device time of the xi product
+  struct EvList { std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& v; ~EvList() { for (auto& p : v) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); } } } ev_list{xi_timers};
+
+  BoxRun r;
+  r.d = d; r.mu = i_mu.dev; r.U = i_U.dev; r.u_upper = u_upper; r.Sigma = i_S.dev; r.lb = i_lb.dev; r.ub = i_ub.dev;
+  r.init = i_init.dev; r.init_ld = 0; r.n_chains = n_chains; r.n_per_chain = n_per; r.burn_in = a.burn_in;
+  r.seed = o.seed; r.chain_offset = o.chain_offset + (int64_t)rank * n_chains; r.prepass = o.prepass;
+  r.max_restarts = o.max_restarts; r.out = d_eta; r.st = st;
+  r.short_tail = host_out || W > 1;       // the last round's copy / gather cannot hide behind sampling
+  r.on_round = [&](int from, int upto, cudaEvent_t ready) -> int {
+    const int w = upto - from;
+    const size_t cols = (size_t)n_chains * w;
+    double* dst = xi_all + round_off + (size_t)rank * cols * m;
+    LQG_CUDA_TRY(cudaStreamWaitEvent(s_side, ready, 0));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    LQG_CUDA_TRY(cudaEventCreate(&e0));
+    LQG_CUDA_TRY(cudaEventCreate(&e1));
+    xi_timers.emplace_back(e0, e1);
+    LQG_CUDA_TRY(cudaEventRecord(e0, s_side));
+    if (identity)      // xi = eta: gather the round's columns into the contiguous round block
+      LQG_CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)w * m * sizeof(double), d_eta + (size_t)from * d, (size_t)n_per * d * sizeof(double),
+                                     (size_t)w * m * sizeof(double), n_chains, cudaMemcpyDeviceToDevice, s_side));
+    else               // xi = Lambda^+ eta on the FP64 tensor cores; B = the round's column blocks of eta
+      LQG_CUDA_TRY(launch_dgemm(m, (int)cols, d, i_Lp.dev, m, d_eta + (size_t)from * d, d, dst, m, nullptr, 0, s_side,
+                                w, (int64_t)n_per * d));
+    LQG_CUDA_TRY(cudaEventRecord(e1, s_side));
+    LQG_CUDA_TRY(cudaEventRecord(ev_x_guard.e, s_side));
+    int rcg;
+    if (W > 1 && (rcg = comm_allgather_f64(comm, dst, xi_all + round_off, cols * m, s_side))) return rcg;
+    const size_t spitch = (size_t)w * m * sizeof(double), dpitch = (size_t)n_per * m * sizeof(double);
+    if (a.xi_out) {
+      if (mem == LQG_MEM_HOST) {
+        LQG_CUDA_TRY(cudaStreamWaitEvent(s_copy, ev_x_guard.e, 0));
+        LQG_CUDA_TRY(sink_xi.copy2d(a.xi_out + (size_t)from * m, dpitch, dst, spitch, spitch, n_chains));
+      } else {
+        LQG_CUDA_TRY(cudaMemcpy2DAsync(a.xi_out + (size_t)from * m, dpitch, dst, spitch, spitch, n_chains, cudaMemcpyDeviceToDevice, s_side));
+      }
+    }
+    if (a.eta_out && mem == LQG_MEM_HOST) {
+      const size_t pe = (size_t)n_per * d * sizeof(double), we = (size_t)w * d * sizeof(double);
+      LQG_CUDA_TRY(cudaStreamWaitEvent(s_copy, ready, 0));
+      LQG_CUDA_TRY(sink_eta.copy2d(a.eta_out + (size_t)from * d, pe, d_eta + (size_t)from * d, pe, we, n_chains));
+    }
+    round_off += (size_t)W * cols * m;
+    round_span.emplace_back(from, upto);
+    ++rounds;
+    return LQG_OK;
+  };
+  BoxResult res;
+  if ((rc = hmc_box_core(r, res))) return rc;
+  // the path stage (caller's stream) starts when the last product / gather is done
+  LQG_CUDA_TRY(cudaEventRecord(ev_side_guard.e, s_side));
+  LQG_CUDA_TRY(cudaStreamWaitEvent(st, ev_side_guard.e, 0));
+  int rc_chain = box_result_rc(res, "lqg_simulate");
+  // a failed chain is an error on this rank, but the collectives below must still be entered by every
+  // rank of the job: carry on and report at the end
+
+  // ---- Phi xi slabs and their bands: rows [r0, r1) of Phi on this rank, all N_total samples ----
+  double t_gemm = 0.0, t_bands = 0.0;
+  const int rows_per = n_t > 0 ? (n_t + W - 1) / W : 0;
+  const int r0 = std::min(n_t, rank * rows_per), r1 = std::min(n_t, r0 + rows_per);
+  const int nr_local = r1 - r0;
+  if (n_t > 0) {
+    const int bw = 1 + nprobs;                                   // per test point: mean + nprobs quantiles
+    DevBuf b_band, b_y, b_scr, b_phi, b_x, b_u;
+    LQG_CUDA_TRY(b_band.alloc((size_t)W * rows_per * bw * sizeof(double)));
+    LQG_CUDA_TRY(cudaMemsetAsync(b_band.p, 0, b_band.bytes, st));
+    double* band_mine = b_band.as<double>() + (size_t)rank * rows_per * bw;   // [mean (rows_per) | qtls (nprobs x rows_per)]
+    if (nr_local > 0) {
+      int rows = a.slab_rows > 0 ? a.slab_rows : (int)std::max<int64_t>(1, std::min<int64_t>(nr_local, ((int64_t)4 << 30) / (8 * N_total)));
+      if (rows >= 128 && rows < nr_local) rows -= rows % 128;    // whole 128-row GEMM tiles
+      if (rows > nr_local) rows = nr_local;
+      LQG_CUDA_TRY(b_y.alloc((size_t)rows * N_total * sizeof(double)));
+      // this rank's rows of Phi: staged from the host (rows r0..r1 only), used in place on the device,
+      // or built slab by slab from the test points
+      const double* phi_dev = nullptr; int64_t phi_ld = 0;
+      if (a.Phi) {
+        if (mem == LQG_MEM_DEVICE) { phi_dev = a.Phi + r0; phi_ld = a.ldphi; }
+        else {
+          LQG_CUDA_TRY(b_phi.alloc((size_t)nr_local * m * sizeof(double)));
+          LQG_CUDA_TRY(cudaMemcpy2DAsync(b_phi.p, (size_t)nr_local * sizeof(double), a.Phi + r0, (size_t)a.ldphi * sizeof(double),
+                                         (size_t)nr_local * sizeof(double), m, cudaMemcpyHostToDevice, st));
+          phi_dev = b_phi.as<double>(); phi_ld = nr_local;
+        }
+      } else {
+        LQG_CUDA_TRY(b_phi.alloc((size_t)rows * m * sizeof(double)));
+        if (mem == LQG_MEM_HOST) {
+          LQG_CUDA_TRY(b_x.alloc((size_t)nr_local * a.basis_D * sizeof(double)));
+          LQG_CUDA_TRY(cudaMemcpy2DAsync(b_x.p, (size_t)nr_local * sizeof(double), a.xtest + r0, (size_t)a.ldx * sizeof(double),
+                                         (size_t)nr_local * sizeof(double), a.basis_D, cudaMemcpyHostToDevice, st));
+          LQG_CUDA_TRY(b_u.alloc((size_t)m * sizeof(double)));
+          LQG_CUDA_TRY(cudaMemcpyAsync(b_u.p, a.knots, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, st));
+        }
+      }
+      DevBuf b_flag, b_perm, b_yp;
+      LQG_CUDA_TRY(b_flag.alloc(sizeof(int)));
+      LQG_CUDA_TRY(cudaMemsetAsync(b_flag.p, 0, sizeof(int), st));
+      if (a.ysim_out) {
+        if (a.ldy < nr_local) { set_error("lqg_simulate: ldy=%lld < %d rows of this rank", (long long)a.ldy, nr_local); return LQG_ERR_INVALID; }
+        // job-order column g = (rank, chain, sample)  ->  its column in the gathered order
+        std::vector<int> perm((size_t)N_total);
+        size_t col_off = 0;
+        for (const auto& sp : round_span) {
+          const int w = sp.second - sp.first;
+          for (int rk = 0; rk < W; ++rk)
+            for (int c = 0; c < n_chains; ++c)
+              for (int s = sp.first; s < sp.second; ++s)
+                perm[(size_t)rk * N_local + (size_t)c * n_per + s] = (int)(col_off + ((size_t)rk * n_chains + c) * w + (s - sp.first));
+          col_off += (size_t)W * n_chains * w;
+        }
+        LQG_CUDA_TRY(b_perm.alloc(perm.size() * sizeof(int)));
+        LQG_CUDA_TRY(cudaMemcpyAsync(b_perm.p, perm.data(), perm.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        LQG_CUDA_TRY(cudaStreamSynchronize(st));               // perm is a local
+        if (mem == LQG_MEM_HOST) LQG_CUDA_TRY(b_yp.alloc((size_t)rows * N_total * sizeof(double)));
+      }
+      for (int s0 = 0; s0 < nr_local; s0 += rows) {
+        const int nr = std::min(rows, nr_local - s0);
+        const double* phi_slab; int64_t ld_slab;
+        if (a.Phi) { phi_slab = phi_dev + s0; ld_slab = phi_ld; }
+        else {
+          const double* x_dev = mem == LQG_MEM_HOST ? b_x.as<double>() + s0 : a.xtest + r0 + s0;
+          const int64_t x_ld = mem == LQG_MEM_HOST ? nr_local : a.ldx;
+          const double* u_dev = mem == LQG_MEM_HOST ? b_u.as<double>() : a.knots;
+          size_t off = 0;
+          for (int k = 0; k < a.basis_D; ++k) {
+            LQG_CUDA_TRY(launch_basis_hat(nr, a.basis_mk[k], x_dev + (size_t)k * x_ld, u_dev + off, b_phi.as<double>() + off * nr, nr,
+                                          b_flag.as<int>(), st));
+            off += (size_t)a.basis_mk[k];
+          }
+          phi_slab = b_phi.as<double>(); ld_slab = nr;
+        }
+        Timer tg(st);
+        tg.start();
+        LQG_CUDA_TRY(launch_dgemm(nr, (int)N_total, m, phi_slab, ld_slab, xi_all, m, b_y.as<double>(), nr, nullptr, 0, st));
+        tg.stop();
+        double ms = 0.0;
+        double* q_slab = nprobs > 0 ? band_mine + rows_per + (size_t)s0 * nprobs : nullptr;
+        // the slab's quantiles land in a (nprobs x rows_per) column-major block: column = test point
+        if ((rc = bands_on_device(nr, N_total, b_y.as<double>(), nr, h_probs, nprobs, band_mine + s0,
+                                  nprobs > 0 ? q_slab : band_mine + rows_per, b_scr, &ms, st)))
+          return rc;
+        t_gemm += tg.ms(); t_bands += ms;
+        if (a.ysim_out) {
+          double* yp = mem == LQG_MEM_HOST ? b_yp.as<double>() : a.ysim_out + s0;
+          const int64_t ldp = mem == LQG_MEM_HOST ? nr : a.ldy;
+          permute_cols_kernel<<<148 * 8, 256, 0, st>>>(nr, N_total, b_y.as<double>(), nr, b_perm.as<int>(), yp, ldp);
+          ++launch_counter();
+          LQG_CUDA_TRY(cudaGetLastError());
+          if (mem == LQG_MEM_HOST)
+            LQG_CUDA_TRY(d2h_result(a.ysim_out + s0, a.ldy * sizeof(double), yp, (size_t)nr * sizeof(double), (size_t)nr * sizeof(double), N_total, st));
+          LQG_CUDA_TRY(cudaStreamSynchronize(st));                 // the slab buffers are reused by the next GEMM
+        }
+      }
+      int flag = 0;
+      LQG_CUDA_TRY(cudaMemcpyAsync(&flag, b_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+      LQG_CUDA_TRY(cudaStreamSynchronize(st));
+      if (flag && rc_chain == LQG_OK) { set_error("basisCompute.lineqGP: x outside the knot range [u_1, u_m]"); rc_chain = LQG_ERR_INVALID; }
+    }
+    // ---- all-gather of the band pieces, unpacked on the host ----
+    if (W > 1 && (rc = comm_allgather_f64(comm, band_mine, b_band.as<double>(), (size_t)rows_per * bw, st))) return rc;
+    std::vector<double> h_band((size_t)W * rows_per * bw);
+    LQG_CUDA_TRY(cudaMemcpyAsync(h_band.data(), b_band.p, h_band.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    LQG_CUDA_TRY(cudaStreamSynchronize(st));
+    std::vector<double> h_mean(n_t), h_q((size_t)std::max(1, nprobs) * n_t);
+    for (int rk = 0; rk < W; ++rk) {
+      const int b0 = std::min(n_t, rk * rows_per), b1 = std::min(n_t, b0 + rows_per);
+      const double* blk = h_band.data() + (size_t)rk * rows_per * bw;
+      for (int i = b0; i < b1; ++i) {
+        h_mean[i] = blk[i - b0];
+        for (int k = 0; k < nprobs; ++k) h_q[(size_t)i * nprobs + k] = blk[rows_per + (size_t)(i - b0) * nprobs + k];
+      }
+    }
+    if (mem == LQG_MEM_HOST) {
+      memcpy(a.mean, h_mean.data(), n_t * sizeof(double));
+      if (nprobs > 0) memcpy(a.qtls, h_q.data(), (size_t)nprobs * n_t * sizeof(double));
+    } else {
+      LQG_CUDA_TRY(cudaMemcpyAsync(a.mean, h_mean.data(), n_t * sizeof(double), cudaMemcpyHostToDevice, st));
+      if (nprobs > 0) LQG_CUDA_TRY(cudaMemcpyAsync(a.qtls, h_q.data(), (size_t)nprobs * n_t * sizeof(double), cudaMemcpyHostToDevice, st));
+      LQG_CUDA_TRY(cudaStreamSynchronize(st));
+    }
+  }
+  // ---- outputs still in flight, timings ----
+  if (s_copy) {
+    if (a.xi_out) LQG_CUDA_TRY(sink_xi.finish());
+    if (a.eta_out) LQG_CUDA_TRY(sink_eta.finish());
+    LQG_CUDA_TRY(cudaStreamSynchronize(s_copy));
+  }
+  LQG_CUDA_TRY(cudaStreamSynchronize(s_side));
+  t_total.stop();
+  double xi_ms = 0.0;
+  for (auto& pr : xi_timers) { float f = 0; if (cudaEventElapsedTime(&f, pr.first, pr.second) == cudaSuccess) xi_ms += f; }
+  if (stats) {
+    fill_stats(&stats->hmc, res.stats, res.chain_ms, res.pre_ms);
+    stats->xi_ms = xi_ms; stats->gemm_ms = t_gemm; stats->bands_ms = t_bands; stats->total_ms = t_total.ms();
+    stats->n_local = N_local; stats->n_total = N_total; stats->row_begin = r0; stats->row_end = r1;
+    stats->rank = rank; stats->world = W; stats->rounds = rounds;
+  }
+  LQG_CUDA_TRY(cudaStreamSynchronize(st));
+  fold_launches();
+  return rc_chain;
+  LQG_API_END("lqg_simulate")
 }

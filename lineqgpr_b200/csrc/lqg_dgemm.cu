@@ -34,7 +34,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 __global__ void __launch_bounds__(NT)
 dgemm_dmma_kernel(int m, int n, int k, const double* __restrict__ A, int64_t lda,
                   const double* __restrict__ B, int64_t ldb, double* __restrict__ C, int64_t ldc,
-                  double* __restrict__ row_sum, int a_upper) {
+                  double* __restrict__ row_sum, int a_upper, int b_blk_w, int64_t b_blk_pitch) {
   extern __shared__ __align__(16) double dg_smem[];
   double (*As)[BK * A_LD] = reinterpret_cast<double (*)[BK * A_LD]>(dg_smem);
   double (*Bs)[BN * B_LD] = reinterpret_cast<double (*)[BN * B_LD]>(dg_smem + 2 * BK * A_LD);
@@ -50,6 +50,16 @@ dgemm_dmma_kernel(int m, int n, int k, const double* __restrict__ A, int64_t lda
   const int b_k = tid & (BK - 1), b_n = tid >> 4;
 
   double ra[8], rb[4];
+  // B columns may come in blocks (b_blk_w > 0): column j lives at B + (j / w) * pitch + (j % w) * ldb.
+  // That is how a round of chain-major samples looks: w finished columns of every chain.
+  const double* bcol[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int gc = col0 + b_n + 16 * q;
+    bcol[q] = gc >= n ? nullptr
+            : b_blk_w > 0 ? B + (size_t)(gc / b_blk_w) * b_blk_pitch + (size_t)(gc % b_blk_w) * ldb
+                          : B + (size_t)gc * ldb;
+  }
   const int kt_end = (k + BK - 1) / BK;
   // upper-triangular A: A[i, kk] = 0 for i > kk, so k-tiles entirely left of the row block vanish
   const int kt_begin = a_upper ? min(row0 / BK, kt_end) : 0;
@@ -64,9 +74,8 @@ dgemm_dmma_kernel(int m, int n, int k, const double* __restrict__ A, int64_t lda
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const int gc = col0 + b_n + 16 * q;
       const int kk = k0 + b_k;
-      rb[q] = (gc < n && kk < k) ? __ldg(B + (size_t)gc * ldb + kk) : 0.0;
+      rb[q] = (bcol[q] && kk < k) ? __ldg(bcol[q] + kk) : 0.0;
     }
   };
   auto store_tile = [&](int buf) {
@@ -155,18 +164,24 @@ __global__ void fill_normals_kernel(int d, size_t n_cols, double* __restrict__ A
 
 cudaError_t launch_dgemm(int m, int n, int k, const double* A, int64_t lda, const double* B,
                          int64_t ldb, double* C, int64_t ldc, double* row_sum, int a_upper,
-                         cudaStream_t st) {
+                         cudaStream_t st, int b_blk_w, int64_t b_blk_pitch) {
   if (m <= 0 || n <= 0) return cudaSuccess;
   // grid.y is limited to 65535 column tiles: slice very wide problems
-  const int max_cols = 65535 * BN;
+  int max_cols = 65535 * BN;
+  if (b_blk_w > 0) {                                  // column slices start on a block boundary
+    if (b_blk_w > max_cols) return cudaErrorInvalidValue;
+    max_cols -= max_cols % b_blk_w;
+  }
   const size_t smem = (size_t)(2 * BK * A_LD + 2 * BN * B_LD) * sizeof(double);
   cudaError_t e0 = cudaFuncSetAttribute(dgemm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e0 != cudaSuccess) return e0;
   for (int c0 = 0; c0 < n; c0 += max_cols) {
     const int nc = n - c0 < max_cols ? n - c0 : max_cols;
     dim3 grid((m + BM - 1) / BM, (nc + BN - 1) / BN);
-    dgemm_dmma_kernel<<<grid, NT, smem, st>>>(m, nc, k, A, lda, B + (size_t)c0 * ldb, ldb,
-                                            C ? C + (size_t)c0 * ldc : nullptr, ldc, row_sum, a_upper);
+    const double* Bs = b_blk_w > 0 ? B + (size_t)(c0 / b_blk_w) * b_blk_pitch : B + (size_t)c0 * ldb;
+    dgemm_dmma_kernel<<<grid, NT, smem, st>>>(m, nc, k, A, lda, Bs, ldb,
+                                            C ? C + (size_t)c0 * ldc : nullptr, ldc, row_sum, a_upper,
+                                            b_blk_w, b_blk_pitch);
     ++launch_counter();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;

@@ -16,18 +16,36 @@ constexpr size_t kSlotBytes = (size_t)16 << 20;
 constexpr int kSlots = 8;
 constexpr int kWorkers = 4;
 
-// process-wide pinned ring (allocated on first use, kept): one user at a time
+// pinned ring.  One process-wide instance is allocated on first use and kept; a copier that finds
+// it busy (another host thread is inside the library) works on a private ring of its own, so
+// concurrent callers do not serialise behind each other's sampling loops.
 struct Ring {
-  std::mutex owner;                       // held by the StagedCopier that is using the ring
+  std::mutex owner;                       // held by a StagedCopier only while it is moving bytes
   unsigned char* base = nullptr;
   cudaEvent_t ev[kSlots] = {};
+  bool ready = false;                     // base AND every event exist
+  // called with `owner` held.  A partial failure releases what was created, so that a later call
+  // starts from scratch instead of running with null events.
   cudaError_t init() {
-    if (base) return cudaSuccess;
+    if (ready) return cudaSuccess;
     cudaError_t e = cudaHostAlloc((void**)&base, kSlotBytes * kSlots, cudaHostAllocDefault);
     if (e != cudaSuccess) { base = nullptr; return e; }
     for (int i = 0; i < kSlots; ++i)
-      if ((e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming | cudaEventBlockingSync)) != cudaSuccess) return e;
+      if ((e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming | cudaEventBlockingSync)) != cudaSuccess) {
+        for (int j = 0; j < i; ++j) { cudaEventDestroy(ev[j]); ev[j] = nullptr; }
+        cudaFreeHost(base);
+        base = nullptr;
+        return e;
+      }
+    ready = true;
     return cudaSuccess;
+  }
+  void destroy() {
+    if (!ready) return;
+    for (int i = 0; i < kSlots; ++i) { cudaEventDestroy(ev[i]); ev[i] = nullptr; }
+    cudaFreeHost(base);
+    base = nullptr;
+    ready = false;
   }
 };
 Ring g_ring;
@@ -42,7 +60,9 @@ struct Task {
 struct StagedCopier::Impl {
   cudaStream_t st;
   int device = 0;
-  std::unique_lock<std::mutex> own;
+  std::unique_lock<std::mutex> own;       // engaged when `ring` is the process-wide ring
+  Ring* ring = nullptr;
+  Ring* private_ring = nullptr;
   std::mutex m;
   std::condition_variable cv_task, cv_free;
   std::deque<Task> tasks;
@@ -63,9 +83,9 @@ struct StagedCopier::Impl {
         t = tasks.front();
         tasks.pop_front();
       }
-      cudaError_t e = cudaEventSynchronize(g_ring.ev[t.slot]);
+      cudaError_t e = cudaEventSynchronize(ring->ev[t.slot]);
       if (e == cudaSuccess) {
-        const unsigned char* src = g_ring.base + (size_t)t.slot * kSlotBytes;
+        const unsigned char* src = ring->base + (size_t)t.slot * kSlotBytes;
         if (t.dpitch == t.width) memcpy(t.dst, src, t.width * t.rows);
         else for (size_t r = 0; r < t.rows; ++r) memcpy(t.dst + r * t.dpitch, src + r * t.width, t.width);
       }
@@ -89,8 +109,14 @@ bool StagedCopier::is_pageable(const void* p) {
 StagedCopier::StagedCopier(cudaStream_t copy_stream) : impl_(new Impl) {
   impl_->st = copy_stream;
   cudaGetDevice(&impl_->device);
-  impl_->own = std::unique_lock<std::mutex>(g_ring.owner);
-  impl_->err = g_ring.init();
+  impl_->own = std::unique_lock<std::mutex>(g_ring.owner, std::try_to_lock);
+  if (impl_->own.owns_lock()) {
+    impl_->ring = &g_ring;
+  } else {
+    impl_->private_ring = new Ring;
+    impl_->ring = impl_->private_ring;
+  }
+  impl_->err = impl_->ring->init();
   for (int i = 0; i < kSlots; ++i) impl_->free_slots.push_back(i);
   if (impl_->err == cudaSuccess)
     for (int i = 0; i < kWorkers; ++i) impl_->workers.emplace_back([this] { impl_->worker(); });
@@ -104,6 +130,7 @@ StagedCopier::~StagedCopier() {
   }
   impl_->cv_task.notify_all();
   for (auto& t : impl_->workers) t.join();
+  if (impl_->private_ring) { impl_->private_ring->destroy(); delete impl_->private_ring; }
   delete impl_;
 }
 
@@ -120,10 +147,10 @@ cudaError_t StagedCopier::copy2d(void* dst_, size_t dpitch, const void* src_, si
       impl_->free_slots.pop_back();
       ++impl_->in_flight;
     }
-    unsigned char* stage = g_ring.base + (size_t)slot * kSlotBytes;
+    unsigned char* stage = impl_->ring->base + (size_t)slot * kSlotBytes;
     cudaError_t e = (r == 1) ? cudaMemcpyAsync(stage, s, w, cudaMemcpyDeviceToHost, impl_->st)
                              : cudaMemcpy2DAsync(stage, w, s, sp, w, r, cudaMemcpyDeviceToHost, impl_->st);
-    if (e == cudaSuccess) e = cudaEventRecord(g_ring.ev[slot], impl_->st);
+    if (e == cudaSuccess) e = cudaEventRecord(impl_->ring->ev[slot], impl_->st);
     if (e != cudaSuccess) {
       std::lock_guard<std::mutex> lk(impl_->m);
       impl_->free_slots.push_back(slot);

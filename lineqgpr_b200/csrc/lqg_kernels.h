@@ -119,9 +119,11 @@ struct NormalGen {
   const int* active;       // nullable
   const int64_t* pos;      // [n_chains]
 };
+// b_blk_w > 0: the columns of B come in blocks of b_blk_w consecutive columns (stride ldb) that
+// start b_blk_pitch doubles apart (a round of chain-major samples: w finished columns per chain)
 cudaError_t launch_dgemm(int m, int n, int k, const double* A, int64_t lda, const double* B,
                          int64_t ldb, double* C, int64_t ldc, double* row_sum, int a_upper,
-                         cudaStream_t st);
+                         cudaStream_t st, int b_blk_w = 0, int64_t b_blk_pitch = 0);
 cudaError_t launch_fill_normals(int d, size_t n_cols, double* A, const NormalGen& g, cudaStream_t st);
 
 // ---- dense set-up algebra (lqg_linalg.cu) ---------------------------------------------------
@@ -216,5 +218,6 @@ cudaError_t launch_bands_bracketed(int n_t, int64_t N, const double* ysim, int64
 
 // ---- peaks (lqg_peaks.cu) ---------------------------------------------------------------
 cudaError_t measure_fp64_peaks(double* dfma_tflops, double* dmma_tflops, cudaStream_t st);
+cudaError_t measure_fp64_mixed(double* tflops, double* dfma_share, cudaStream_t st);
 
 }  // namespace lqg

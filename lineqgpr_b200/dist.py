@@ -23,6 +23,55 @@ def shard_rows(n_rows: int, rank: int, world: int):
     return shard_chains(n_rows, rank, world)
 
 
+def simulate_rows(n_rows: int, rank: int, world: int):
+    """Test-point range [lo, hi) that lqg_simulate summarises on `rank`: equal blocks of
+    ceil(n_rows / world) rows (the band all-gather moves equal-sized pieces), the last ranks may own
+    fewer rows or none."""
+    per = -(-n_rows // world) if n_rows > 0 else 0
+    lo = min(n_rows, rank * per)
+    return lo, min(n_rows, lo + per)
+
+
+class Comm:
+    """lqg_comm of the C ABI: the NCCL communicator lqg_simulate uses for its two exchanges (xi shards,
+    band pieces).  One process per GPU; the current CUDA device must be set before construction.
+    The 128-byte NCCL id is created on rank 0 and handed over by `exchange`, a callable that
+    broadcasts a bytes object from rank 0 (from_torch_distributed uses the default process group)."""
+
+    def __init__(self, rank: int, world: int, exchange=None):
+        from . import _lib as L
+        self.rank, self.world = int(rank), int(world)
+        idb = None
+        if self.world > 1:
+            buf = (L.C.c_char * 128)()
+            if self.rank == 0:
+                L.check(L.lib().lqg_comm_unique_id(buf), "lqg_comm_unique_id")
+            idb = exchange(bytes(buf.raw))
+            if len(idb) != 128:
+                raise ValueError("the exchanged NCCL id must be 128 bytes")
+        h = L.C.c_void_p()
+        keep = L.C.create_string_buffer(idb, 128) if idb is not None else None
+        L.check(L.lib().lqg_comm_init(keep, self.rank, self.world, L.C.byref(h)), "lqg_comm_init")
+        self.handle = h
+
+    @classmethod
+    def from_torch_distributed(cls, group=None):
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+
+        def exchange(b):
+            box = [b]
+            dist.broadcast_object_list(box, src=0, group=group)
+            return box[0]
+        return cls(rank, world, exchange)
+
+    def close(self):
+        from . import _lib as L
+        if getattr(self, "handle", None) is not None and self.handle.value:
+            L.lib().lqg_comm_destroy(self.handle)
+            self.handle = None
+
+
 def hmc_control_for_rank(control: dict, n_chains: int, rank: int, world: int) -> dict:
     """control list for this rank's tmvrnorm call: its share of the chains, global chain offset."""
     lo, hi = shard_chains(n_chains, rank, world)

@@ -13,7 +13,8 @@ argument meaning and error behaviour, with the bodies replaced by calls into the
 What stays on the host, exactly where the reference has it on the host: the one-off O(d^3)
 whitening algebra (solve, chol, triangular inverse).  Everything per-sample runs on the GPU.
 Extensions (all optional keys of `control`): "n.chains" (independent chains; 1 reproduces the
-reference's single serial chain), "seed", "prepass", "injected", "max.restarts",
+reference's single serial chain; with several chains each one runs at least 100 burn-in
+transitions, see chain_burn_in), "burn.in.exact", "seed", "prepass", "injected", "max.restarts",
 "chain.offset", "U" (a precomputed factor), "whiten" ("device" (default) | "ul" | "tmg", see whiten_box).
 """
 from __future__ import annotations
@@ -84,6 +85,24 @@ def whiten_box(mu, Sigma, method="ul"):
     return np.triu(Ri)
 
 
+MULTI_CHAIN_BURN_IN = 100   # = the burn.in default of tmvrnorm.HMC (R/lineqGPsamplers.R:100-101)
+
+
+def chain_burn_in(burn_in, n_chains, control=None):
+    """Burn-in per chain.  The reference runs ONE chain of nsim + burn.in transitions from the
+    clamped MAP, and simulate.* hands it burn.in = 1 (R/lineqGP.R:264,617): its samples are spread
+    along a long chain.  With n.chains > 1 every chain starts at that same point, so a burn-in of 1
+    would make every column the second transition after the MAP — not the reference's chain
+    distribution under active constraints.  Several chains therefore never run fewer than
+    MULTI_CHAIN_BURN_IN transitions each before emitting (control["burn.in.exact"] = True, or an
+    injected draw stream, keeps the caller's value: parity tests); n.chains = 1 is the reference
+    chain and keeps burn.in as given."""
+    control = control or {}
+    if n_chains > 1 and not control.get("burn.in.exact") and control.get("injected") is None:
+        return max(int(burn_in), MULTI_CHAIN_BURN_IN)
+    return int(burn_in)
+
+
 def tmvrnorm_HMC(object, nsim, control=None, **kw):
     """tmvrnorm.HMC (R/lineqGPsamplers.R:99-143) on the GPU: box-form exact HMC, lqg_hmc_box."""
     control = dict(control or {})
@@ -123,10 +142,15 @@ def tmvrnorm_HMC(object, nsim, control=None, **kw):
     out = control.get("out")                                            # optional caller-owned d x (n_chains*n_per) F-array
     if out is None:                                                    # (e.g. _lib.empty_result(): page-locked, reusable)
         out = np.empty((d, n_chains * n_per), order="F")
+    elif not (isinstance(out, np.ndarray) and out.dtype == np.float64 and out.flags.f_contiguous
+              and out.flags.writeable and out.shape == (d, n_chains * n_per)):
+        raise ValueError(f'control["out"] must be a writable Fortran-ordered float64 array of shape ({d}, {n_chains * n_per})')
+    burn = chain_burn_in(int(control["burn.in"]), n_chains, control)
     stats = L.HmcStats()
     rc = L.lib().lqg_hmc_box(d, L.ptr(mu_c), L.ptr(Uf), 1, L.ptr(Sf), L.ptr(lb_c), L.ptr(ub_c),
-                             L.ptr(init_c), 0, n_per, int(control["burn.in"]), opts, L.ptr(out), None, stats)
-    last_stats.clear(); last_stats.update(stats.asdict(), sampler="HMC", n_chains=n_chains, n_per_chain=n_per, seed=seed)
+                             L.ptr(init_c), 0, n_per, burn, opts, L.ptr(out), None, stats)
+    last_stats.clear(); last_stats.update(stats.asdict(), sampler="HMC", n_chains=n_chains, n_per_chain=n_per, seed=seed,
+                                          burn_in_per_chain=burn)
     if rc == 8:
         raise ValueError("Error: M must be positive definite.")        # tmg:R/tmg.R:17-20 (device whitening)
     L.check(rc, "tmvrnorm.HMC")

@@ -149,6 +149,113 @@ def paths_bands(Phi_test, xi_sim, probs=(0.025, 0.975), slab_rows=None, return_y
     return mean, q, info
 
 
+def simulate_pipeline(tmvPar, nsim, Lambda=None, Phi_test=None, xtest=None, ulist=None, probs=(0.025, 0.975),
+                      control=None, comm=None, Lambda_pinv=None, return_eta=False, return_ysim=False, slab_rows=0):
+    """The whole simulate tail in ONE C-ABI call (lqg_simulate): box HMC -> xi = Lambda^+ eta ->
+    ysim = Phi.test xi -> mean / type-7 quantile bands, with eta, xi and ysim resident in HBM and
+    only the requested results copied out (R/lineqGP.R:611-640; R/lineqAGP.R:558-575, 509-512;
+    R/lineqGPutils.R:422-423).
+
+    tmvPar: dict(mu, [map], Sigma, lb, ub) in eta space, as simulate.* builds it.  nsim = samples drawn
+    by THIS rank; with `comm` (lineqgpr_b200.dist.Comm, one process per GPU) the job draws
+    world * nsim samples, every rank ends up with the bands of all test points over all samples, and
+    xi.sim holds this rank's columns.  Phi_test (n_t x m) or (xtest, ulist) to build the hat basis on
+    the device; neither = stop after xi.  control keys as tmvrnorm.HMC ("n.chains", "burn.in", "seed",
+    "chain.offset", "prepass", "max.restarts", "U").
+    Returns a dict: xi.sim (m x nsim), ymean, qtls, [eta], [ysim], stats."""
+    from .samplers import _as_par, EPSILON, chain_burn_in
+    control = dict(control or {})
+    control.setdefault("burn.in", 100)
+    par = _as_par(tmvPar)
+    mu, Sigma, lb, ub = par["mu"], par["Sigma"], par["lb"], par["ub"]
+    d = mu.size
+    if lb.size != d or ub.size != d:
+        raise ValueError("The bounds have to be d-dimensionals")
+    if np.any(lb >= ub):
+        raise ValueError('The elements from "u" has to be greater than the elements from "l"')
+    init = np.minimum(np.maximum(par["map"], lb + EPSILON), ub - EPSILON)
+    nsim = int(nsim)
+    slots = L.lib().lqg_hmc_box_slots(d) or 1024
+    n_chains = max(1, min(int(control.get("n.chains", min(nsim, slots))), nsim))
+    n_per = -(-nsim // n_chains)
+    N_local = n_chains * n_per
+    world = comm.world if comm is not None else 1
+    N_total = N_local * world
+    if Lambda is not None:
+        Lambda = L.f64(np.asarray(Lambda, float)); m = Lambda.shape[1]
+    elif Lambda_pinv is not None:
+        Lambda_pinv = L.f64(np.asarray(Lambda_pinv, float)); m = Lambda_pinv.shape[0]
+    else:
+        m = d
+    probs = np.ascontiguousarray(probs, dtype=np.float64)
+    a = L.SimulateArgs()
+    keep = []                                   # arrays that must outlive the call
+
+    def P(x):
+        if x is None:
+            return None
+        keep.append(x)
+        return L.ptr(x)
+
+    a.d, a.m = d, m
+    a.mu, a.lb, a.ub, a.init = (P(np.ascontiguousarray(v, dtype=np.float64)) for v in (mu, lb, ub, init))
+    a.Sigma = P(L.f64(Sigma))
+    U = control.get("U")
+    a.U = P(L.f64(U)) if U is not None else None
+    a.Lambda, a.Lambda_pinv = P(Lambda), P(Lambda_pinv)
+    n_t = 0
+    if Phi_test is not None:
+        Phi = L.f64(np.atleast_2d(np.asarray(Phi_test, float)))
+        n_t = Phi.shape[0]
+        if Phi.shape[1] != m:
+            raise ValueError("non-conformable arguments")
+        a.Phi, a.ldphi = P(Phi), n_t
+    elif xtest is not None:
+        if not isinstance(ulist, (list, tuple)):
+            ulist = [ulist]
+        D = len(ulist)
+        xt = L.f64(np.asarray(xtest, float).reshape(-1, D))
+        n_t = xt.shape[0]
+        m_k = np.ascontiguousarray([np.size(u) for u in ulist], dtype=np.int32)
+        knots = np.ascontiguousarray(np.concatenate([np.ravel(u) for u in ulist]), dtype=np.float64)
+        a.basis_D, a.basis_mk, a.xtest, a.ldx, a.knots = D, P(m_k), P(xt), n_t, P(knots)
+    a.n_t = n_t
+    a.probs, a.nprobs = P(probs), probs.size
+    a.n_per_chain = n_per
+    a.burn_in = chain_burn_in(int(control["burn.in"]), n_chains * world, control)
+    a.slab_rows = int(slab_rows)
+    xi = control.get("out")
+    if xi is None:
+        xi = np.empty((m, N_local), order="F")
+    eta = np.empty((d, N_local), order="F") if return_eta else None
+    mean = np.empty(n_t) if n_t else None
+    q = np.empty((probs.size, n_t), order="F") if n_t else None
+    rows_per = -(-n_t // world) if n_t else 0
+    rank = comm.rank if comm is not None else 0
+    r0 = min(n_t, rank * rows_per); r1 = min(n_t, r0 + rows_per)
+    ysim = np.empty((r1 - r0, N_total), order="F") if (return_ysim and n_t) else None
+    a.eta_out, a.xi_out, a.ysim_out, a.ldy, a.mean, a.qtls = P(eta), P(xi), P(ysim), max(1, r1 - r0), P(mean), P(q)
+    seed = control.get("seed")
+    if seed is None:
+        seed = int(np.random.randint(1, 10000000))                     # tmg:R/tmg.R:102
+    opts = L.make_opts(mem=L.MEM_HOST, seed=seed, n_chains=n_chains, max_restarts=int(control.get("max.restarts", 0)),
+                       chain_offset=int(control.get("chain.offset", 0)), prepass=int(control.get("prepass", -1)))
+    st = L.SimulateStats()
+    rc = L.lib().lqg_simulate(L.C.byref(a), opts, comm.handle if comm is not None else None, st)
+    last_stats.clear(); last_stats.update(st.asdict(), sampler="HMC", n_chains=n_chains, n_per_chain=n_per, seed=seed,
+                                          burn_in_per_chain=int(a.burn_in))
+    if rc == 8:
+        raise ValueError("Error: M must be positive definite.")        # tmg:R/tmg.R:17-20 (device whitening)
+    L.check(rc, "lqg_simulate")
+    out = {"xi.sim": xi[:, :nsim] if world == 1 else xi, "ymean": mean, "qtls": q, "stats": dict(last_stats),
+           "rows": (r0, r1)}
+    if return_eta:
+        out["eta"] = eta[:, :nsim] if world == 1 else eta
+    if ysim is not None:
+        out["ysim"] = ysim
+    return out
+
+
 def lambda_pinv(Lambda):
     """The operator of qr.solve(Lambda, .) (R/lineqGP.R:639): inverse for a square Lambda, the
     least-squares pseudo-inverse for a tall full-column-rank Lambda (Q8).  O(d m^2), once."""
@@ -201,14 +308,23 @@ def simulate_lineqGP(model, nsim=1, seed=None, xtest=None, control=None):
         ctl.setdefault("seed", int(seed))                               # set.seed(seed) :624
     tmvPar = {"mu": eta_mu, "map": eta_map, "Sigma": Sigma_eta, "lb": pred["lb"], "ub": pred["ub"],
               "class": mdl["localParam"]["sampler"]}                    # :622-623
+    extra = {}
     t0 = time.perf_counter()
-    eta = tmvrnorm(tmvPar, nsim, ctl)                                   # :626
-    simtime = time.perf_counter() - t0
-    xi_sim = dgemm(_pinv(Lam, setup), eta)                              # :639
-    ysim = dgemm(pred["Phi.test"], xi_sim)                              # :640
+    if tmvPar["class"] == "HMC" and ctl.get("pipeline", "device") == "device" and ctl.get("injected") is None:
+        # :626, :639, :640 in one device-resident call; the bands plot.lineqGP draws come with it
+        r = simulate_pipeline(tmvPar, nsim, Lambda=Lam, Phi_test=pred["Phi.test"], control=ctl,
+                              probs=ctl.get("probs", (0.025, 0.975)), return_eta=True, return_ysim=True)
+        simtime = time.perf_counter() - t0
+        eta, xi_sim, ysim = r["eta"], r["xi.sim"], r["ysim"][:, :nsim]
+        extra = {"ymean": r["ymean"], "qtls": r["qtls"]}
+    else:
+        eta = tmvrnorm(tmvPar, nsim, ctl)                               # :626
+        simtime = time.perf_counter() - t0
+        xi_sim = dgemm(_pinv(Lam, setup), eta)                          # :639
+        ysim = dgemm(pred["Phi.test"], xi_sim)                          # :640
     return dict(cls="lineqGP", x=mdl["x"], y=mdl["y"], xtest=xtest, **{"Phi.test": pred["Phi.test"]},
                 predtime=predtime, simtime=simtime, **{"xi.map": pred["xi.map"], "xi.sim": xi_sim},
-                ysim=ysim, eta=eta, stats=dict(last_stats))
+                ysim=ysim, eta=eta, stats=dict(last_stats), **extra)
 
 
 def simulate_lineqAGP(model, nsim=1, seed=None, xtest=None, control=None):
@@ -237,9 +353,14 @@ def simulate_lineqAGP(model, nsim=1, seed=None, xtest=None, control=None):
     tmvPar = {"mu": eta_map, "Sigma": Sigma_eta, "lb": mdl["lineqSys"]["lb"], "ub": mdl["lineqSys"]["ub"],
               "class": mdl["localParam"]["sampler"]}                    # :567-570 (mean := MAP, Q4)
     t0 = time.perf_counter()
-    etaAll = tmvrnorm(tmvPar, nsim, ctl)                                # :573
-    simtime = time.perf_counter() - t0
-    xiAll_sim = dgemm(_pinv(LamAll, setup), etaAll)                     # :575
+    if tmvPar["class"] == "HMC" and ctl.get("pipeline", "device") == "device" and ctl.get("injected") is None:
+        r = simulate_pipeline(tmvPar, nsim, Lambda=LamAll, control=ctl, return_eta=True)    # :573, :575 in one call
+        simtime = time.perf_counter() - t0
+        etaAll, xiAll_sim = r["eta"], r["xi.sim"]
+    else:
+        etaAll = tmvrnorm(tmvPar, nsim, ctl)                            # :573
+        simtime = time.perf_counter() - t0
+        xiAll_sim = dgemm(_pinv(LamAll, setup), etaAll)                 # :575
     return dict(cls="lineqAGP", x=mdl["x"], y=mdl["y"], xtest=xtest, **{"Phi.test": pred["Phi.test"]},
                 predtime=predtime, simtime=simtime, muAll=pred["muAll"],
                 **{"xiAll.map": pred["xiAll.map"], "xiAll.sim": xiAll_sim, "PhiAll.test": pred["PhiAll.test"]},
