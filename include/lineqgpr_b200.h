@@ -354,7 +354,7 @@ typedef struct lqg_simulate_stats {
   int64_t n_local, n_total;  /* samples drawn by this rank / by the job                               */
   int32_t row_begin, row_end;/* rows of Phi this rank summarised                                      */
   int32_t rank, world;
-  int32_t rounds;            /* sampling rounds = xi products = all-gather calls                      */
+  int32_t rounds;            /* units of samples processed = xi products = xi all-gather calls        */
   int32_t reserved0;
 } lqg_simulate_stats;
 
@@ -363,7 +363,8 @@ typedef struct lqg_simulate_stats {
  * eta_out equals what lqg_hmc_box returns for the same opts).  While later sampling rounds run, the
  * samples every chain has finished are multiplied by Lambda^+ on a second stream, copied to xi_out
  * and — with a communicator — all-gathered, so that after the last round every rank holds the xi of
- * the whole job (m x N_total; column order: round, then rank, then chain, then sample).  Rank r then
+ * the whole job (m x N_total; the work proceeds in units of 32 samples per chain, the same on every
+ * rank, and the gathered columns are ordered unit, rank, chain, sample).  Rank r then
  * summarises rows [r ceil(n_t/world), (r+1) ceil(n_t/world)) of Phi over all N_total samples (exact
  * mean and type-7 quantiles) and the band pieces are all-gathered: every rank returns the full
  * mean[n_t], qtls[nprobs x n_t].  Global chain ids are opts->chain_offset + rank * n_chains + local

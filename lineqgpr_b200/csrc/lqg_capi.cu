@@ -1792,7 +1792,7 @@ extern "C" int lqg_simulate(const lqg_simulate_args* a_, const lqg_opts* opts_, 
 
   size_t round_off = 0;                   // doubles of xi_all filled by earlier rounds (all ranks)
   int rounds = 0;
-  std::vector<std::pair<int, int>> round_span;                  // [from, upto) of every round
+  std::vector<std::pair<int, int>> round_span;                  // [from, upto) of every processed unit
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> xi_timers;   // per-round device time of the xi product
   struct EvList { std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& v; ~EvList() { for (auto& p : v) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); } } } ev_list{xi_timers};
 
@@ -1802,7 +1802,18 @@ extern "C" int lqg_simulate(const lqg_simulate_args* a_, const lqg_opts* opts_, 
   r.seed = o.seed; r.chain_offset = o.chain_offset + (int64_t)rank * n_chains; r.prepass = o.prepass;
   r.max_restarts = o.max_restarts; r.out = d_eta; r.st = st;
   r.short_tail = host_out || W > 1;       // the last round's copy / gather cannot hide behind sampling
-  r.on_round = [&](int from, int upto, cudaEvent_t ready) -> int {
+  // The xi products, the all-gathers and the copies work on UNITS of `unit` samples per chain, not on
+  // the sampling rounds themselves: how far a round gets depends on the chains, i.e. differs from
+  // rank to rank, while the sequence of all-gather calls (and their sizes) must be the same on every
+  // rank.  Unit u = samples [u*unit, (u+1)*unit) of every chain is processed as soon as the local
+  // chains have all passed it; NCCL pairs unit u of one rank with unit u of the others whenever
+  // each of them gets there.  The column order of the gathered xi is therefore fixed: unit, rank,
+  // chain, sample.
+  static const char* env_unit = getenv("LQG_GATHER_UNIT");            // tuning aid
+  const int unit = std::max(1, env_unit ? atoi(env_unit) : 32);
+  const int n_units = (n_per + unit - 1) / unit;
+  int next_unit = 0;
+  auto process_unit = [&](int from, int upto, cudaEvent_t ready) -> int {
     const int w = upto - from;
     const size_t cols = (size_t)n_chains * w;
     double* dst = xi_all + round_off + (size_t)rank * cols * m;
@@ -1839,6 +1850,16 @@ extern "C" int lqg_simulate(const lqg_simulate_args* a_, const lqg_opts* opts_, 
     round_off += (size_t)W * cols * m;
     round_span.emplace_back(from, upto);
     ++rounds;
+    return LQG_OK;
+  };
+  r.on_round = [&](int /*from*/, int upto, cudaEvent_t ready) -> int {
+    while (next_unit < n_units) {
+      const int u0 = next_unit * unit, u1 = std::min(n_per, u0 + unit);
+      if (u1 > upto) break;
+      const int rcu = process_unit(u0, u1, ready);
+      if (rcu) return rcu;
+      ++next_unit;
+    }
     return LQG_OK;
   };
   BoxResult res;

@@ -363,7 +363,7 @@ def test_full_size_m1000_properties(lqg):
     properties — every emitted value inside the box, counters consistent, finite output."""
     from lineqgpr_b200 import workloads as W
     for par, n_chains, n in ((W.cfg4()[0], 296, 592), (W.cfg5(n_test=10)[0], 296, 592)):
-        x = lqg.tmvrnorm(dict(par, **{"class": "HMC"}), n, {"burn.in": 3, "n.chains": n_chains, "seed": 1})
+        x = lqg.tmvrnorm(dict(par, **{"class": "HMC"}), n, {"burn.in": 3, "n.chains": n_chains, "seed": 1, "burn.in.exact": True})
         st = dict(lqg.last_stats)
         lb, ub = np.asarray(par["lb"]), np.asarray(par["ub"])
         assert np.isfinite(x).all()

@@ -108,7 +108,7 @@ def test_hmc_box_whitens_on_device_when_U_is_null(lqg):
     from lineqgpr_b200 import workloads as W
     par, _ = W.cfg3()
     par = dict(par, **{"class": "HMC"})
-    ctl = {"burn.in": 2, "n.chains": 8, "seed": 11}
+    ctl = {"burn.in": 2, "n.chains": 8, "seed": 11, "burn.in.exact": True}
     a = lqg.tmvrnorm(par, 64, dict(ctl))
     b = lqg.tmvrnorm(par, 64, dict(ctl, whiten="device"))
     assert lqg.last_stats["violations"] == 0
