@@ -42,7 +42,10 @@ typedef struct lqg_opts {
   int32_t  mem;            /* LQG_MEM_HOST: all pointers are host memory, the call copies in/out
                               (this is what the .Call shim uses); LQG_MEM_DEVICE: all array
                               pointers are device memory on the current device                */
-  int32_t  reserved0;
+  int32_t  hmc_search;     /* lqg_hmc_box / lqg_simulate hit search: 0 = default (walls ranked by
+                              tan(t/2) of their hit time, tmg's own acos/atan2 arithmetic only where a
+                              discrete threshold, a near-tie or the end of the trajectory is close),
+                              1 = every search with tmg's arithmetic (tmg:src/HmcSampler.cpp:157-181)  */
   void*    stream;         /* cudaStream_t to launch on (NULL = legacy default stream)         */
   uint64_t seed;           /* Philox key; replaces sample(1:1e7,1) of tmg:R/tmg.R:102          */
   int32_t  n_chains;       /* HMC: independent chains. 1 = the reference's single serial chain */
@@ -73,11 +76,12 @@ typedef struct lqg_hmc_stats {
   int64_t hit_searches;    /* _getNextLinearHitTime calls (tmg:src/HmcSampler.cpp:152)         */
   int64_t vel_restarts;    /* velsign < 0 restarts (tmg:src/HmcSampler.cpp:112,117)            */
   int64_t chk_restarts;    /* end-point infeasible restarts (tmg:src/HmcSampler.cpp:121-130)   */
-  int64_t exact_evals;     /* constraints whose hit time was evaluated with sqrt/atan2/acos    */
+  int64_t exact_evals;     /* constraints that survived the filter and had their hit time evaluated */
   int64_t violations;      /* emitted samples outside the constraints: always 0                */
   int64_t failed_chains;   /* chains stopped by max_restarts / exhausted injected draws        */
   double  chain_ms;        /* device time of the chain kernel(s)                               */
   double  prepass_ms;      /* device time of the momentum GEMM pre-pass (0 when off)           */
+  int64_t slow_searches;   /* box kernel: hit searches that were re-run with tmg's exact arithmetic */
 } lqg_hmc_stats;
 
 typedef struct lqg_rsm_stats {

@@ -36,7 +36,7 @@ class LqgError(RuntimeError):
 
 
 class Opts(C.Structure):
-    _fields_ = [("mem", C.c_int32), ("reserved0", C.c_int32), ("stream", C.c_void_p),
+    _fields_ = [("mem", C.c_int32), ("hmc_search", C.c_int32), ("stream", C.c_void_p),
                 ("seed", C.c_uint64), ("n_chains", C.c_int32), ("max_restarts", C.c_int32),
                 ("chain_offset", C.c_int64), ("injected", C.c_void_p), ("n_injected", C.c_int64),
                 ("injected_u", C.c_void_p), ("n_injected_u", C.c_int64), ("prepass", C.c_int32),
@@ -47,7 +47,7 @@ class HmcStats(C.Structure):
     _fields_ = [("transitions", C.c_int64), ("bounces", C.c_int64), ("hit_searches", C.c_int64),
                 ("vel_restarts", C.c_int64), ("chk_restarts", C.c_int64), ("exact_evals", C.c_int64),
                 ("violations", C.c_int64), ("failed_chains", C.c_int64), ("chain_ms", C.c_double),
-                ("prepass_ms", C.c_double)]
+                ("prepass_ms", C.c_double), ("slow_searches", C.c_int64)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -200,9 +200,10 @@ def ptr(a):
 
 
 def make_opts(mem=MEM_HOST, stream=None, seed=0, n_chains=1, max_restarts=0, chain_offset=0,
-              injected=None, n_injected=0, injected_u=None, n_injected_u=0, prepass=-1, canon_mode=0) -> Opts:
+              injected=None, n_injected=0, injected_u=None, n_injected_u=0, prepass=-1, canon_mode=0, hmc_search=0) -> Opts:
     o = Opts()
     o.mem = mem
+    o.hmc_search = int(hmc_search)
     o.stream = stream
     o.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     o.n_chains = int(n_chains)

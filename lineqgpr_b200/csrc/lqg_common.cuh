@@ -123,6 +123,56 @@ static __device__ __noinline__ double hit_time_exact(double fa, double fb, doubl
   return t > kMinT ? t : 0.0;                                           // :183 (first half)
 }
 
+// ---------------------------------------------------------------------------------------
+// The same hit time without inverse trigonometry.  With u = |(fa, fb)|, w = sqrt(u^2 - g^2) the two
+// zero crossings of y(s) = fa sin s + fb cos s + g are the angles of
+//     exit   (t1 of tmg):  (-g + i w)(fb + i fa) / u^2
+//     entry  (t2 of tmg):  (-g - i w)(fb + i fa) / u^2
+// (tmg:src/HmcSampler.cpp:161-162,170 written as complex products), so cos t and sin t of either are
+// four products and one square root away, and for t in (0, pi) the value tan(t/2) = sin t / (1 + cos t)
+// orders like t with uniform resolution.  A sampleNext step only ever needs: WHICH wall is hit first,
+// whether that is before the remaining time tt, and sin t / cos t of that hit for the rotation
+// (:82, :91-92).  hit_fast returns, for one wall, the key tan(t/2) of tmg's hit time t with its cos and
+// sin (all scaled by u^2 = `u2`), or says that the wall cannot be hit within the remaining time
+// (key > klim), or that the case is too close to one of tmg's discrete thresholds to be decided
+// without its own arithmetic: u ~ |g| (:160), t1 or t2 within 1e-6 relative of the 1e-5 dead zone
+// (:166-167, :174-175).  Callers resolve those (and near-ties between walls, and hits within 1e-9 of
+// tt) with hit_time_exact, so every discrete event is still decided by tmg's formula; the exact t of
+// the walls that were hit is evaluated later, off the critical path, to keep tt = tt - t (:90) exact.
+constexpr int kFastNone = 0, kFastHit = 1, kFastSlow = 2;
+constexpr double kSinMinT = 9.9999999998333333e-06;                     // sin(min_t)
+struct FastHit { double key, c, s, u2; };
+__device__ __forceinline__ int hit_fast(double fa, double fb, double g, double klim, FastHit& h) {
+  const double u2 = fma(fa, fa, fb * fb);
+  const double w2 = fma(-g, g, u2);
+  if (!(w2 > 1e-6 * u2)) return (w2 < -1e-6 * u2) ? kFastNone : kFastSlow;   // out of reach (:160) | grazing
+  const double w = sqrt(w2);
+  const double gb = g * fb, ga = g * fa, wa = w * fa, wb = w * fb;
+  const double c1 = -gb - wa, s1 = wb - ga;                             // exit crossing, t1
+  double c2 = -gb + wa, s2 = -wb - ga;                                  // entry crossing, t2 = -t1 - 2 phi
+  const double dz = kSinMinT * u2, band = 1e-6 * dz;
+  bool amb = (c1 > 0.0) & (fabs(fabs(s1) - dz) <= band);
+  const bool dead1 = (c1 > 0.0) & (fabs(s1) < dz);                      // |t1| or |t1 - 2 pi| < min_t (:166-167)
+  if (dead1) {                                                          // t1 := 0  =>  t2 = -2 phi (:170, Q6)
+    c2 = fma(fb, fb, -fa * fa);
+    s2 = 2.0 * fa * fb;
+  }
+  amb |= (c2 > 0.0) & (fabs(fabs(s2) - dz) <= band);
+  const bool dead2 = (c2 > 0.0) & (fabs(s2) < dz);                      // (:174-175)
+  // a crossing matters when it is alive, in (0, pi) and not later than the remaining time:
+  // tan(t/2) = s / (u2 + c) <= klim
+  const bool ok1 = !dead1 & (s1 > 0.0) & (s1 <= klim * (u2 + c1));
+  const bool ok2 = !dead2 & (s2 > 0.0) & (s2 <= klim * (u2 + c2));
+  if (amb) return kFastSlow;
+  if (!(ok1 | ok2)) return kFastNone;
+  const bool use1 = ok1 & (!ok2 | (c1 >= c2));                          // the earlier one: larger cosine (:178-181)
+  h.c = use1 ? c1 : c2;
+  h.s = use1 ? s1 : s2;
+  h.u2 = u2;
+  h.key = h.s / (u2 + h.c);
+  return kFastHit;
+}
+
 // Conservative filter in front of hit_time_exact.  y(t) = fa sin t + fb cos t + g is the
 // constraint value along the trajectory; u = sqrt(fa^2 + fb^2) its amplitude.
 //  (1) tmg only considers a wall when u > |g| (tmg:src/HmcSampler.cpp:160): if u < g - margin

@@ -29,6 +29,7 @@
 // the host loops rounds until every chain has finished.  Draws are Philox-addressed by
 // (chain, draw index), so the samples do not depend on the round size or on the pool.
 #include <limits.h>
+#include <type_traits>
 #include <stdlib.h>
 #include <string.h>
 
@@ -36,10 +37,6 @@
 #include "lqg_kernels.h"
 
 namespace lqg {
-
-struct RedSlot {
-  unsigned long long tb; double xa; double xb; int key; int pad;
-};
 
 // Survivors of the filter are compacted into a per-warp queue and evaluated 32 at a time:
 // hit_time_exact (sqrt, atan2, acos) then runs once per ~32 candidates instead of once per
@@ -51,25 +48,6 @@ constexpr int QCAP = 64;
 struct Cand {
   double fa[QCAP]; double fb[QCAP]; int key[QCAP];
 };
-struct LaneBest {                    // best candidate seen by this lane
-  unsigned long long tb; double xa, xb; int key;
-};
-// evaluates queue entries [0, qn) with tmg's exact formula, 32 at a time (one per lane)
-static __device__ __noinline__ void flush_queue(const Cand* q, int qn, int lane, int d,
-                                                const double* glo, const double* ghi, LaneBest& b) {
-  for (int e = lane; e < qn; e += 32) {
-    const int key = q->key[e];
-    const double fa = q->fa[e], fb = q->fb[e];
-    const double g = __ldg(key < d ? glo + key : ghi + (key - d));
-    const unsigned long long tb = hit_bits(hit_time_exact(fa, fb, g));
-    if (tb < b.tb || (tb == b.tb && key < b.key)) {
-      b.tb = tb; b.key = key;
-      const double sgn = key < d ? 1.0 : -1.0;                   // stored (fa, fb) = sgn * (x_a, x_b)
-      b.xa = sgn * fa; b.xb = sgn * fb;
-    }
-  }
-}
-
 // fresh momentum x_a = U a for this chain, computed by the CTA itself (restarts, injected
 // draws, or when the GEMM pre-pass is off).  a ~ N(0, I_d) drawn like tmg:src/HmcSampler.cpp:54-55.
 template <int G, int CPT>
@@ -127,18 +105,31 @@ __device__ __forceinline__ bool draw_momentum(const BoxParams& p, int chain, int
   return true;
 }
 
+// One slot per warp for the cross-warp stage of the arg-min.  `tb` orders the candidates: bits of the
+// hit time (exact search) or of tan(t/2) (fast search); hi2 = high word of the warp's runner-up.
+struct WinSlot {
+  unsigned long long tb; double xa, xb, st, ct; int key; unsigned hi2; int slow; int pad;
+};
+// Bounces whose exact hit time is still owed to tt (see hit_fast): wall id and the (f.a, f.b) it was hit with
+constexpr int DCAP = 128;
+struct Deferred {
+  double fa[DCAP]; double fb[DCAP]; int key[DCAP];
+};
+
 template <int G, int CPT, bool GSM, int MINB, bool PACK = false>
 __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p) {
   constexpr int T = 32 * G;
   extern __shared__ double a_sm[];                 // d doubles: staging of a fresh draw
                                                    // (+ 2d doubles of bound offsets when GSM)
-  __shared__ RedSlot red[2][G];
+  __shared__ WinSlot red[2][G];
   __shared__ Cand queue[G];
   __shared__ int qcnt[G];                          // PACK: candidates left in every warp's queue after the filter
+  __shared__ Deferred dl;
   __shared__ int chain_sm;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int d = p.d;
+  const bool fast_on = p.fast != 0;
 
   // Per-coordinate filter thresholds h = g - m, with g the bound offset (mu - lb or ub - mu) and
   // m = 3e-9 |g| + abs_eps the safety margin (orders of magnitude above any rounding difference
@@ -186,51 +177,88 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
     int64_t draw = p.pos[chain];                   // momenta consumed so far
     int rcount = p.rcount[chain];                  // restarts inside the current transition
     int status = p.chain_status[chain];
-    unsigned long long n_bounce = 0, n_search = 0, n_vel = 0, n_chk = 0, n_exact = 0, n_trans = 0;
+    unsigned n_bounce = 0, n_search = 0, n_vel = 0, n_chk = 0, n_exact = 0, n_trans = 0, n_slow = 0;
     int parity = 0;
 
     for (int att = 0; att < p.attempts && s < total && status == 0; ++att) {   // while(2), HmcSampler.cpp:51
-      {
-        if (p.pool != nullptr) {
-          const double* src = p.pool + ((size_t)aidx * p.attempts + att) * d;
+      if (p.pool != nullptr) {
+        const double* src = p.pool + ((size_t)aidx * p.attempts + att) * d;
 #pragma unroll
-          for (int k = 0; k < CPT; ++k) {
-            const int i = tid + k * T;
-            xa[k] = i < d ? src[i] : 0.0;
-          }
-        } else if (!draw_momentum<G, CPT>(p, chain, draw, a_sm, xa)) {
-          status = LQG_ERR_DRAWS_EXHAUSTED;
-          break;
+        for (int k = 0; k < CPT; ++k) {
+          const int i = tid + k * T;
+          xa[k] = i < d ? src[i] : 0.0;
         }
-        ++draw;
-        double tt = kHalfPi;                                       // :57
-        double velsign = 0.0;                                      // :53
-        // sin/cos of the remaining time.  Inside the loop they only feed the filter, so after a
-        // bounce they are advanced by angle subtraction; the final move recomputes them exactly.
-        double S = 1.0, C = 6.123233995736766e-17;                 // sin(M_PI/2), cos(M_PI/2)
-        for (;;) {                                                 // while(1), :64
-          // ---- hit search over this thread's coordinates (both sides) ----
-          LaneBest best;
-          best.tb = kNoHitBits; best.xa = 0.0; best.xb = 0.0; best.key = INT_MAX;
+      } else if (!draw_momentum<G, CPT>(p, chain, draw, a_sm, xa)) {
+        status = LQG_ERR_DRAWS_EXHAUSTED;
+        break;
+      }
+      ++draw;
+      double tt = kHalfPi;                                       // :57; exact up to the hit times still owed (n_dl)
+      double velsign = 0.0;                                      // :53
+      // sin/cos of the remaining time, advanced by angle subtraction after every bounce.  They feed
+      // the filter and the fast search's comparison with the remaining time (both with margins); the
+      // final move recomputes them from the exact tt.
+      double S = 1.0, C = 6.123233995736766e-17;                 // sin(M_PI/2), cos(M_PI/2)
+      int n_dl = 0;                                              // bounces whose exact t is still owed to tt
+
+      // tt -= t for every owed bounce, in order, with tmg's own hit-time formula (one lane per bounce)
+      auto settle = [&]() {
+        if (n_dl == 0) return;
+        __syncthreads();                                         // entries written by thread 0 are visible
+        for (int e = tid; e < n_dl; e += T) {
+          const int key = dl.key[e];
+          const double g = __ldg(key < d ? p.glo + key : p.ghi + (key - d));
+          dl.fa[e] = hit_time_exact(dl.fa[e], dl.fb[e], g);
+        }
+        __syncthreads();
+        for (int e = 0; e < n_dl; ++e) tt = tt - dl.fa[e];       // :90, same order, same operands
+        n_dl = 0;
+        sincos(tt, &S, &C);
+        __syncthreads();                                         // dl is reused by the next bounce
+      };
+
+      for (;;) {                                                 // while(1), :64
+        // ---- one hit search.  FASTS: candidates ranked by tan(t/2) (hit_fast), EXACT otherwise ----
+        unsigned long long wtb = kNoHitBits; int wkey = INT_MAX;
+        double wxa = 0.0, wxb = 0.0, wst = 0.0, wct = 0.0;
+        bool need_exact = !fast_on;
+        auto search = [&](auto fast_tag) {
+          constexpr bool FASTS = decltype(fast_tag)::value;
+          // lane state: best candidate, high word of its runner-up, "some wall needs tmg's arithmetic"
+          unsigned long long btb = kNoHitBits; int bkey = INT_MAX;
+          double bxa = 0.0, bxb = 0.0, bc = 0.0, bs = 0.0, bu2 = 1.0;
+          unsigned bhi2 = 0xffffffffu;
+          bool bslow = false;
+          const double ktt = S / (1.0 + C);                      // tan(tt/2) of the remaining time
+          const double klim = fma(ktt, 1e-9, ktt) + 1e-12;
+          auto consider = [&](double fa, double fb, int key) {
+            const double g = __ldg(key < d ? p.glo + key : p.ghi + (key - d));
+            unsigned long long tb;
+            FastHit h;
+            if (FASTS) {
+              const int cls = hit_fast(fa, fb, g, klim, h);
+              bslow |= cls == kFastSlow;
+              tb = cls == kFastHit ? (unsigned long long)__double_as_longlong(h.key) : kNoHitBits;
+            } else {
+              tb = hit_bits(hit_time_exact(fa, fb, g));
+            }
+            if (tb < btb || (tb == btb && key < bkey)) {
+              if (FASTS) { bhi2 = min(bhi2, (unsigned)(btb >> 32)); bc = h.c; bs = h.s; bu2 = h.u2; }
+              btb = tb; bkey = key;
+              const double sgn = key < d ? 1.0 : -1.0;           // stored (fa, fb) = sgn * (x_a, x_b)
+              bxa = sgn * fa; bxb = sgn * fb;
+            } else if (FASTS) {
+              bhi2 = min(bhi2, (unsigned)(tb >> 32));
+            }
+          };
           Cand* q = &queue[warp];
-          int qn = 0;                                              // warp-uniform queue length
-          const unsigned lt_mask = (1u << lane) - 1u;
+          int qn = 0;                                            // warp-uniform queue length
           auto flush = [&]() {
-            __syncwarp();                                          // queue writes visible to every lane
-            flush_queue(q, qn, lane, d, p.glo, p.ghi, best);
-            __syncwarp();                                          // entries consumed before they are overwritten
+            __syncwarp();                                        // queue writes visible to every lane
+            for (int e = lane; e < qn; e += 32) consider(q->fa[e], q->fb[e], q->key[e]);
+            __syncwarp();                                        // entries consumed before they are overwritten
             n_exact += (lane == 0) ? qn : 0;
             qn = 0;
-          };
-          auto push = [&](bool need, double fa, double fb, int key) {
-            const unsigned m = __ballot_sync(0xffffffffu, need);
-            if (m == 0u) return;
-            if (qn + __popc(m) > QCAP) flush();
-            if (need) {
-              const int e = qn + __popc(m & lt_mask);
-              q->fa[e] = fa; q->fb[e] = fb; q->key[e] = key;
-            }
-            qn += __popc(m);
           };
           // Filter (see may_hit in lqg_common.cuh).  With y = position at time tt, dy = velocity
           // at time tt, u^2 = a^2 + b^2 and the threshold h = g - margin:
@@ -238,6 +266,9 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
           //                          (a < 0 and dy > 0) AND reaches the wall (u^2 >= h^2)
           //   upper row (f = -e_i):  mirrored.
           // h |h| compares like h^2 for h > 0 and is negative (always reachable) for h <= 0.
+          // Phase 1 is straight-line code over the thread's coordinates (no votes, no branches: the
+          // CPT coordinates overlap in the pipeline) and leaves one bit per wall in `mask`.
+          unsigned mask = 0u;
 #pragma unroll
           for (int k = 0; k < CPT; ++k) {
             const int i = tid + k * T;
@@ -255,132 +286,202 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
             const bool dip_hi = (a_ > 0.0) & (dy < 0.0) & (u2 >= hh * fabs(hh));
             const bool need_lo = !safe_lo | dip_lo;
             const bool need_hi = !safe_hi | dip_hi;
-            push(need_lo, a_, b_, i);
-            push(need_hi, -a_, -b_, d + i);
+            mask |= (need_lo ? 1u : 0u) << (2 * k);
+            mask |= (need_hi ? 1u : 0u) << (2 * k + 1);
+          }
+          // Phase 2: the survivors are compacted into the warp's queue: exclusive prefix sum of the
+          // per-lane counts, then every lane stores its walls at consecutive positions.
+          const int cnt = __popc(mask);
+          int incl = cnt;
+#pragma unroll
+          for (int off = 1; off < 32; off <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, off);
+            incl += lane >= off ? v : 0;
+          }
+          const int wtotal = __shfl_sync(0xffffffffu, incl, 31);
+          // more survivors than queue slots (tight boxes in the one- and two-warp variants): rounds of
+          // QCAP walls, each evaluated by the warp itself before the next round overwrites the queue
+          for (int base = 0; base < wtotal; base += QCAP) {
+            int pos = incl - cnt - base;
+            if (base > 0) __syncwarp();
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) {
+              const int i = tid + k * T;
+              if ((mask >> (2 * k)) & 1u) {
+                if ((unsigned)pos < (unsigned)QCAP) { q->fa[pos] = xa[k]; q->fb[pos] = xb[k]; q->key[pos] = i; }
+                ++pos;
+              }
+              if ((mask >> (2 * k + 1)) & 1u) {
+                if ((unsigned)pos < (unsigned)QCAP) { q->fa[pos] = -xa[k]; q->fb[pos] = -xb[k]; q->key[pos] = d + i; }
+                ++pos;
+              }
+            }
+            qn = min(QCAP, wtotal - base);
+            if (wtotal > QCAP) flush();
           }
           if (PACK && G > 1) {
             // Candidates of all warps are evaluated together, 32 per warp from the front: with ~13 per
-            // warp, 8 partly filled passes of the exact formula become ~4 full ones.
+            // warp, 8 partly filled passes become ~4 full ones.
             if (lane == 0) qcnt[warp] = qn;
             __syncthreads();
-            int total = 0, off[G + 1];
+            int ntot = 0;
 #pragma unroll
-            for (int w = 0; w < G; ++w) { off[w] = total; total += qcnt[w]; }
-            off[G] = total;
-            for (int e = tid; e < total; e += T) {
-              int w = 0;
+            for (int w = 0; w < G; ++w) ntot += qcnt[w];
+            for (int e = tid; e < ntot; e += T) {
+              int w = 0, le = e;
 #pragma unroll
-              for (int u = 1; u < G; ++u) w += (e >= off[u]) ? 1 : 0;
-              const int le = e - off[w];
-              const int key = queue[w].key[le];
-              const double fa = queue[w].fa[le], fb = queue[w].fb[le];
-              const double g = __ldg(key < d ? p.glo + key : p.ghi + (key - d));
-              const unsigned long long tb = hit_bits(hit_time_exact(fa, fb, g));
-              if (tb < best.tb || (tb == best.tb && key < best.key)) {
-                best.tb = tb; best.key = key;
-                const double sgn = key < d ? 1.0 : -1.0;
-                best.xa = sgn * fa; best.xb = sgn * fb;
+              for (int u = 0; u < G - 1; ++u) {                  // queue that holds entry e (static indexing only)
+                const int cw = qcnt[u];
+                const bool past = (w == u) & (le >= cw);
+                le -= past ? cw : 0;
+                w += past ? 1 : 0;
               }
+              consider(queue[w].fa[le], queue[w].fb[le], queue[w].key[le]);
             }
-            if (tid == 0) n_exact += total;
-            qn = 0;
+            if (tid == 0) n_exact += ntot;
             // the slot exchange below has its own barrier, which also protects the queues from the
             // next search's pushes
           } else {
             flush();
           }
-          // ---- arg-min: hardware warp-reduce, one slot per warp, warp-reduce over the slots ----
-          unsigned long long wtb; int wkey;
-          int src = warp_argmin_hit(best.tb, best.key, wtb, wkey);
-          double wxa = __shfl_sync(0xffffffffu, best.xa, src);
-          double wxb = __shfl_sync(0xffffffffu, best.xb, src);
+          // ---- arg-min: hardware warp-reduce, the owner lane fills the warp's slot, warp-reduce over the slots ----
+          unsigned long long mtb; int mkey;
+          const int src = warp_argmin_hit(btb, bkey, mtb, mkey);
+          unsigned whi2 = 0xffffffffu;
+          bool wslow = false;
+          if (FASTS) {
+            whi2 = __reduce_min_sync(0xffffffffu, lane == src ? bhi2 : (unsigned)(btb >> 32));
+            wslow = __any_sync(0xffffffffu, bslow);
+          }
           if (G > 1) {
-            if (lane == 0) {
-              RedSlot& r = red[parity][warp];
-              r.tb = wtb; r.key = wkey; r.xa = wxa; r.xb = wxb;
+            if (lane == src) {
+              WinSlot& r = red[parity][warp];
+              r.tb = mtb; r.key = mkey; r.xa = bxa; r.xb = bxb; r.hi2 = whi2; r.slow = wslow ? 1 : 0;
+              if (FASTS) { const double ru = 1.0 / bu2; r.st = bs * ru; r.ct = bc * ru; }
             }
             __syncthreads();
-            // lane l < G holds warp l's candidate; every warp reduces the G slots redundantly
-            RedSlot r;
-            r.tb = kNoHitBits; r.key = INT_MAX; r.xa = 0.0; r.xb = 0.0;
-            if (lane < G) r = red[parity][lane];
-            src = warp_argmin_hit(r.tb, r.key, wtb, wkey);
-            wxa = __shfl_sync(0xffffffffu, r.xa, src);
-            wxb = __shfl_sync(0xffffffffu, r.xb, src);
+            // lane l < G holds warp l's slot key; every warp reduces the G slots redundantly
+            unsigned long long stb = kNoHitBits; int skey = INT_MAX;
+            if (lane < G) { stb = red[parity][lane].tb; skey = red[parity][lane].key; }
+            const int ws = warp_argmin_hit(stb, skey, wtb, wkey);
+            const WinSlot& r = red[parity][ws];
+            wxa = r.xa; wxb = r.xb;
+            if (FASTS) {
+              wst = r.st; wct = r.ct;
+              const unsigned shi2 = lane < G ? (lane == ws ? red[parity][lane].hi2 : (unsigned)(stb >> 32)) : 0xffffffffu;
+              whi2 = __reduce_min_sync(0xffffffffu, shi2);
+              wslow = __any_sync(0xffffffffu, lane < G && red[parity][lane].slow != 0);
+            }
             parity ^= 1;
+          } else {
+            wtb = mtb; wkey = mkey;
+            wxa = __shfl_sync(0xffffffffu, bxa, src);
+            wxb = __shfl_sync(0xffffffffu, bxb, src);
+            if (FASTS) {
+              const double ru = 1.0 / bu2;
+              wst = __shfl_sync(0xffffffffu, bs * ru, src);
+              wct = __shfl_sync(0xffffffffu, bc * ru, src);
+            }
           }
-          ++n_search;
+          if (FASTS) {
+            // tmg's arithmetic decides whenever a wall sits on one of its thresholds, two walls are hit
+            // within ~1e-6 relative of each other, or the first hit is within 1e-9 of the remaining time
+            const bool tie = wtb != kNoHitBits && whi2 <= (unsigned)(wtb >> 32) + 1u;
+            bool close = false;
+            if (wtb != kNoHitBits) {
+              const double kw = __longlong_as_double((long long)wtb);
+              close = fabs(kw - ktt) <= fma(ktt, 1e-9, 1e-12);
+            }
+            need_exact = wslow | tie | close;
+          }
+        };
+        if (fast_on) search(std::true_type{});
+        if (need_exact) {
+          if (fast_on) ++n_slow;
+          settle();                                              // the exact comparison tt < t needs the exact tt
+          search(std::false_type{});
+        }
+        ++n_search;
+        double st, ct;
+        if (need_exact) {
           const double t = hit_from_bits(wtb);
-          if (t == 0.0 || tt < t) break;                           // :82
-          // ---- bounce: rotate to the wall, reflect (:90-110) ----
-          ++n_bounce;
-          tt = tt - t;                                             // :90
-          const int j = wkey < d ? wkey : wkey - d;
-          const double side = wkey < d ? 1.0 : -1.0;
-          const double* scol = p.Sigma + (size_t)j * d;
-          // column j of Sigma is requested first so its L2 latency overlaps sincos(t)
-          double sc[CPT];
-#pragma unroll
-          for (int k = 0; k < CPT; ++k) {
-            const int i = tid + k * T;
-            sc[k] = i < d ? __ldg(scol + i) : 0.0;
-          }
-          const double sjj = __ldg(p.sdiag + j);
-          double st, ct;
+          if (t == 0.0 || tt < t) break;                         // :82
+          tt = tt - t;                                           // :90
           sincos(t, &st, &ct);
-          const double vj = __dsub_rn(__dmul_rn(ct, wxa), __dmul_rn(st, wxb));   // hit_vel[j]
-          const double alpha2 = 2.0 * (vj / sjj);                  // 2*alpha, alpha = f.v / f.f
-#pragma unroll
-          for (int k = 0; k < CPT; ++k) {
-            const double a_ = xa[k], b_ = xb[k];
-            xb[k] = fma(st, a_, ct * b_);                          // new_b  (:91)
-            const double v = fma(ct, a_, -st * b_);                // hit_vel (:92)
-            xa[k] = fma(-alpha2, sc[k], v);                        // reflected velocity (:109)
+        } else {
+          if (wtb == kNoHitBits) break;                          // no wall within the remaining time (:82)
+          st = wst; ct = wct;
+          if (n_dl == DCAP) settle();
+          if (tid == 0) {                                        // the exact t of this hit is owed to tt
+            const double sgn = wkey < d ? 1.0 : -1.0;
+            dl.fa[n_dl] = sgn * wxa; dl.fb[n_dl] = sgn * wxb; dl.key[n_dl] = wkey;
           }
-          velsign = side * __dsub_rn(vj, __dmul_rn(alpha2, sjj));  // a.f (:110)
-          if (velsign < 0.0) break;                                // :112
-          const double Sn = fma(S, ct, -C * st), Cn = fma(C, ct, S * st);   // sin/cos(tt - t)
-          S = Sn; C = Cn;
+          ++n_dl;
         }
-        if (velsign < 0.0) {                                       // :117
-          ++n_vel;
-          if (++rcount > p.max_restarts) status = LQG_ERR_RESTART_CAP;
-          continue;
-        }
-        // ---- end point: bb = sin(tt) a + cos(tt) b (:119), tmg's check min(F bb + g) >= 0 (:121)
-        //      in its eta form, and the exact check of the value that would be emitted ----
-        sincos(tt, &S, &C);
-        bool fine = true;
+        // ---- bounce: rotate to the wall, reflect (:90-110) ----
+        ++n_bounce;
+        const int j = wkey < d ? wkey : wkey - d;
+        const double side = wkey < d ? 1.0 : -1.0;
+        const double* scol = p.Sigma + (size_t)j * d;
+        double sc[CPT];
 #pragma unroll
         for (int k = 0; k < CPT; ++k) {
           const int i = tid + k * T;
-          if (i < d) {
-            const double bb = fma(xa[k], S, xb[k] * C);
-            const double e = __ldg(p.mu + i) + bb;
-            fine = fine && (bb + __ldg(p.glo + i) >= 0.0) && (__ldg(p.ghi + i) - bb >= 0.0) &&
-                   (e >= __ldg(p.lb + i)) && (e <= __ldg(p.ub + i));
-          }
+          sc[k] = i < d ? __ldg(scol + i) : 0.0;
         }
-        fine = (G > 1) ? (__syncthreads_and(fine) != 0) : __all_sync(0xffffffffu, fine);
-        if (!fine) {                                               // :130
-          ++n_chk;
-          if (++rcount > p.max_restarts) status = LQG_ERR_RESTART_CAP;
-          continue;
-        }
+        const double sjj = __ldg(p.sdiag + j);
+        const double vj = __dsub_rn(__dmul_rn(ct, wxa), __dmul_rn(st, wxb));   // hit_vel[j]
+        const double alpha2 = 2.0 * (vj / sjj);                  // 2*alpha, alpha = f.v / f.f
 #pragma unroll
-        for (int k = 0; k < CPT; ++k) xb[k] = fma(xa[k], S, xb[k] * C);   // lastSample = bb (:123)
-        rcount = 0;
-        ++n_trans;
-        if (s >= p.burn_in) {                                      // tmg:R/tmg.R:105 drops burn-in
-          double* dst = p.out + ((size_t)chain * p.n_per_chain + (s - p.burn_in)) * d;
-#pragma unroll
-          for (int k = 0; k < CPT; ++k) {
-            const int i = tid + k * T;
-            if (i < d) dst[i] = __ldg(p.mu + i) + xb[k];           // tmg:R/tmg.R:106
-          }
+        for (int k = 0; k < CPT; ++k) {
+          const double a_ = xa[k], b_ = xb[k];
+          xb[k] = fma(st, a_, ct * b_);                          // new_b  (:91)
+          const double v = fma(ct, a_, -st * b_);                // hit_vel (:92)
+          xa[k] = fma(-alpha2, sc[k], v);                        // reflected velocity (:109)
         }
-        ++s;
+        velsign = side * __dsub_rn(vj, __dmul_rn(alpha2, sjj));  // a.f (:110)
+        if (velsign < 0.0) break;                                // :112
+        const double Sn = fma(S, ct, -C * st), Cn = fma(C, ct, S * st);   // sin/cos(tt - t)
+        S = Sn; C = Cn;
       }
+      if (velsign < 0.0) {                                       // :117
+        ++n_vel;
+        if (++rcount > p.max_restarts) status = LQG_ERR_RESTART_CAP;
+        continue;
+      }
+      // ---- end point: bb = sin(tt) a + cos(tt) b (:119), tmg's check min(F bb + g) >= 0 (:121)
+      //      in its eta form, and the exact check of the value that would be emitted ----
+      if (n_dl > 0) settle(); else sincos(tt, &S, &C);
+      bool fine = true;
+#pragma unroll
+      for (int k = 0; k < CPT; ++k) {
+        const int i = tid + k * T;
+        if (i < d) {
+          const double bb = fma(xa[k], S, xb[k] * C);
+          const double e = __ldg(p.mu + i) + bb;
+          fine = fine && (bb + __ldg(p.glo + i) >= 0.0) && (__ldg(p.ghi + i) - bb >= 0.0) &&
+                 (e >= __ldg(p.lb + i)) && (e <= __ldg(p.ub + i));
+        }
+      }
+      fine = (G > 1) ? (__syncthreads_and(fine) != 0) : __all_sync(0xffffffffu, fine);
+      if (!fine) {                                               // :130
+        ++n_chk;
+        if (++rcount > p.max_restarts) status = LQG_ERR_RESTART_CAP;
+        continue;
+      }
+#pragma unroll
+      for (int k = 0; k < CPT; ++k) xb[k] = fma(xa[k], S, xb[k] * C);   // lastSample = bb (:123)
+      rcount = 0;
+      ++n_trans;
+      if (s >= p.burn_in) {                                      // tmg:R/tmg.R:105 drops burn-in
+        double* dst = p.out + ((size_t)chain * p.n_per_chain + (s - p.burn_in)) * d;
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) {
+          const int i = tid + k * T;
+          if (i < d) dst[i] = __ldg(p.mu + i) + xb[k];           // tmg:R/tmg.R:106
+        }
+      }
+      ++s;
     }
 
     // ---- persist chain state and counters ----
@@ -389,15 +490,16 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
       const int i = tid + k * T;
       if (i < d) p.state[(size_t)chain * d + i] = xb[k];
     }
-    if (lane == 0) atomicAdd(p.stats + 5, n_exact);
+    if (lane == 0) atomicAdd(p.stats + 5, (unsigned long long)n_exact);
     if (tid == 0) {
       p.s_done[chain] = s; p.pos[chain] = draw; p.rcount[chain] = rcount;
       p.chain_status[chain] = status;
-      atomicAdd(p.stats + 0, n_trans);
-      atomicAdd(p.stats + 1, n_bounce);
-      atomicAdd(p.stats + 2, n_search);
-      atomicAdd(p.stats + 3, n_vel);
-      atomicAdd(p.stats + 4, n_chk);
+      atomicAdd(p.stats + 0, (unsigned long long)n_trans);
+      atomicAdd(p.stats + 1, (unsigned long long)n_bounce);
+      atomicAdd(p.stats + 2, (unsigned long long)n_search);
+      atomicAdd(p.stats + 3, (unsigned long long)n_vel);
+      atomicAdd(p.stats + 4, (unsigned long long)n_chk);
+      atomicAdd(p.stats + 10, (unsigned long long)n_slow);
     }
   }
 }

@@ -36,8 +36,10 @@ struct BoxParams {
   int64_t n_injected;
   int max_restarts;
   int* next_chain;         // work queue head (zeroed before launch)
-  unsigned long long* stats;  // [8]: transitions,bounces,searches,vel,chk,exact,violations,failed
+  unsigned long long* stats;  // [0..7]: transitions,bounces,searches,vel,chk,evaluated,violations,failed;
+                              // [10]: searches that fell back to tmg's exact hit-time arithmetic
   int* chain_status;       // [n_chains]
+  int fast;                // 1: rank walls by tan(t/2) (hit_fast), exact arithmetic only near a threshold
 };
 
 cudaError_t launch_hmc_box(const BoxParams& p, int grid, cudaStream_t st);
