@@ -9,8 +9,10 @@ from pathlib import Path
 
 import numpy as np
 
+import os
+
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "liblineqgpr_b200.so"
+LIB_PATH = Path(os.environ["LQG_LIB_PATH"]) if os.environ.get("LQG_LIB_PATH") else PKG / "liblineqgpr_b200.so"   # override: diagnostic builds
 
 LQG_OK = 0
 STATUS = {0: "LQG_OK", 1: "LQG_ERR_INVALID", 2: "LQG_ERR_UNSUPPORTED", 3: "LQG_ERR_INIT_INFEASIBLE",

@@ -31,6 +31,32 @@ def needs_build() -> bool:
     return any(p.stat().st_mtime > t for p in deps)
 
 
+def build_variant(name: str, extra_flags, verbose: bool = False) -> Path:
+    """A diagnostic build of the same sources with extra nvcc flags (e.g. -DLQG_BOX_TIMING) into
+    lineqgpr_b200/liblineqgpr_b200_<name>.so; load it with LQG_LIB_PATH=<that file>."""
+    lib = PKG / f"liblineqgpr_b200_{name}.so"
+    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [PKG.parent / "include" / "lineqgpr_b200.h"]
+    if lib.exists() and all(p.stat().st_mtime <= lib.stat().st_mtime for p in deps):
+        return lib
+    nvcc = _nvcc()
+    objdir = PKG.parent / "build" / name
+    objdir.mkdir(parents=True, exist_ok=True)
+    objs, procs = [], []
+    for src in SOURCES:
+        obj = objdir / (Path(src).stem + ".o")
+        procs.append((src, subprocess.Popen([nvcc, *NVCC_FLAGS, *extra_flags, "-c", str(CSRC / src), "-o", str(obj)],
+                                            stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(str(obj))
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{out}")
+    r = subprocess.run([nvcc, "-shared", "-o", str(lib), *objs, "-lcudart", "-ldl"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return lib
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not needs_build():
         return LIB

@@ -779,6 +779,13 @@ extern "C" int lqg_device_count(void) {
   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
   return n;
 }
+// diagnostic: per-phase SM-clock sums of the box kernel's hit search since the last call (zeros unless
+// the library was built with -DLQG_BOX_TIMING; scripts/probe_box_phases.py).  Not part of the public header.
+extern "C" int lqg_debug_box_phases(unsigned long long* out16) {
+  if (!out16) return LQG_ERR_INVALID;
+  LQG_CUDA_TRY(box_phase_cycles(out16));
+  return LQG_OK;
+}
 extern "C" int lqg_guard_violations(void) { return g_guard_violations.load(); }
 extern "C" int64_t lqg_launch_count(int32_t reset) {
   fold_launches();

@@ -141,12 +141,13 @@ static __device__ __noinline__ double hit_time_exact(double fa, double fb, doubl
 // the walls that were hit is evaluated later, off the critical path, to keep tt = tt - t (:90) exact.
 constexpr int kFastNone = 0, kFastHit = 1, kFastSlow = 2;
 constexpr double kSinMinT = 9.9999999998333333e-06;                     // sin(min_t)
-struct FastHit { double key, c, s, u2; };
+struct FastHit { double key, st, ct; };                                 // tan(t/2), sin t, cos t
 __device__ __forceinline__ int hit_fast(double fa, double fb, double g, double klim, FastHit& h) {
   const double u2 = fma(fa, fa, fb * fb);
   const double w2 = fma(-g, g, u2);
   if (!(w2 > 1e-6 * u2)) return (w2 < -1e-6 * u2) ? kFastNone : kFastSlow;   // out of reach (:160) | grazing
   const double w = sqrt(w2);
+  const double ru = 1.0 / u2;                                           // independent of the sqrt: overlaps it
   const double gb = g * fb, ga = g * fa, wa = w * fa, wb = w * fb;
   const double c1 = -gb - wa, s1 = wb - ga;                             // exit crossing, t1
   double c2 = -gb + wa, s2 = -wb - ga;                                  // entry crossing, t2 = -t1 - 2 phi
@@ -166,10 +167,10 @@ __device__ __forceinline__ int hit_fast(double fa, double fb, double g, double k
   if (amb) return kFastSlow;
   if (!(ok1 | ok2)) return kFastNone;
   const bool use1 = ok1 & (!ok2 | (c1 >= c2));                          // the earlier one: larger cosine (:178-181)
-  h.c = use1 ? c1 : c2;
-  h.s = use1 ? s1 : s2;
-  h.u2 = u2;
-  h.key = h.s / (u2 + h.c);
+  const double c = use1 ? c1 : c2, sn = use1 ? s1 : s2;
+  h.key = sn / (u2 + c);
+  h.st = sn * ru;
+  h.ct = c * ru;
   return kFastHit;
 }
 

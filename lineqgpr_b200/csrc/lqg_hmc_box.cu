@@ -29,6 +29,7 @@
 // the host loops rounds until every chain has finished.  Draws are Philox-addressed by
 // (chain, draw index), so the samples do not depend on the round size or on the pool.
 #include <limits.h>
+#include <algorithm>
 #include <type_traits>
 #include <stdlib.h>
 #include <string.h>
@@ -38,24 +39,38 @@
 
 namespace lqg {
 
-// Survivors of the filter are compacted into a per-warp queue and evaluated 32 at a time:
-// hit_time_exact (sqrt, atan2, acos) then runs once per ~32 candidates instead of once per
-// call site with one or two active lanes.
-// The queue is a structure of arrays (8-byte lanes -> conflict-free stores) and holds only what
-// the filter already has in registers; the bound offset g is fetched once per candidate at
-// evaluation time, 32 lanes in parallel, instead of inside the (divergent) push.
+// Phase timing of the hit search (diagnostic build only: -DLQG_BOX_TIMING, scripts/probe_box_phases.py):
+// lane 0 of warp 0 reads the SM clock at the phase boundaries and the per-phase sums of all chains are
+// added into a global table.
+#ifdef LQG_BOX_TIMING
+__device__ unsigned long long g_box_phase[16];
+#define LQG_TICK(idx)                                                   \
+  do {                                                                  \
+    if (tid == 0) { const long long _t = clock64(); ph_acc[idx] += (unsigned long long)(_t - ph_last); ph_last = _t; } \
+  } while (0)
+#else
+#define LQG_TICK(idx) do { } while (0)
+#endif
+
+// Survivors of the filter are compacted into a per-warp queue of wall ids and evaluated 32 at a time.
+// A queue entry is just the wall id: the CTA keeps a copy of the chain state (x_a, x_b) and of the
+// bound offsets (glo, ghi) in shared memory, so whoever evaluates a wall reads its three operands from
+// there — the thread that owns the coordinate never has to move register values through a queue.
 constexpr int QCAP = 64;
 struct Cand {
-  double fa[QCAP]; double fb[QCAP]; int key[QCAP];
+  int key[QCAP];
 };
 // fresh momentum x_a = U a for this chain, computed by the CTA itself (restarts, injected
 // draws, or when the GEMM pre-pass is off).  a ~ N(0, I_d) drawn like tmg:src/HmcSampler.cpp:54-55.
+// `xs` (shared, CPT*T doubles) first stages a, then receives x_a.  Out of line on purpose: its
+// accumulators must not count against the register budget of the hit-search loop.
 template <int G, int CPT>
-__device__ __forceinline__ bool draw_momentum(const BoxParams& p, int chain, int64_t draw,
-                                              double* a_sm, double (&xa)[CPT]) {
+static __device__ __noinline__ bool draw_momentum(const BoxParams& p, int chain, int64_t draw, double* xs) {
   constexpr int T = 32 * G;
   const int tid = threadIdx.x;
   const int d = p.d;
+  double* a_sm = xs;
+  __syncthreads();                                                 // nobody reads the old x_a copy any more
   if (p.injected) {
     if ((draw + 1) * d > p.n_injected) return false;              // uniform across the CTA
     const double* src = p.injected + (size_t)chain * p.n_injected + (size_t)draw * d;
@@ -99,9 +114,10 @@ __device__ __forceinline__ bool draw_momentum(const BoxParams& p, int chain, int
       for (int k = 0; k < CPT; ++k) acc[k] = fma(u[c][k], av, acc[k]);
     }
   }
+  __syncthreads();                                                 // a is consumed: the area now receives x_a
 #pragma unroll
-  for (int k = 0; k < CPT; ++k) xa[k] = acc[k];
-  __syncthreads();                                                 // a_sm is reused
+  for (int k = 0; k < CPT; ++k) xs[tid + k * T] = (tid + k * T < d) ? acc[k] : 0.0;
+  __syncthreads();
   return true;
 }
 
@@ -116,11 +132,81 @@ struct Deferred {
   double fa[DCAP]; double fb[DCAP]; int key[DCAP];
 };
 
-template <int G, int CPT, bool GSM, int MINB, bool PACK = false>
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// What the rarely taken paths need from the kernel: all of it lives in shared or global memory, so
+// they can be out-of-line functions that do not compete for the registers of the search loop.
+struct BoxShared {
+  const double* xa_s; const double* xb_s;         // state copy, padded to NS entries
+  const double* glo; const double* ghi;            // bound offsets: shared copy when available, else global
+  int d, ns;
+};
+
+// One hit search with tmg's own arithmetic (tmg:src/HmcSampler.cpp:152-189): every wall is evaluated
+// with hit_time_exact, arg-min with the lowest index winning ties.  Taken when the fast search meets
+// a wall on one of tmg's thresholds, a near-tie, or a hit within 1e-9 of the remaining time, and for
+// every search with lqg_opts.hmc_search = 1.  The winner is left in red[0].
+template <int G>
+static __device__ __noinline__ void exact_search(const BoxShared sh, WinSlot* red, unsigned* n_eval) {
+  constexpr int T = 32 * G;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int d = sh.d;
+  unsigned long long btb = kNoHitBits; int bkey = INT_MAX;
+  double bxa = 0.0, bxb = 0.0;
+  unsigned cnt = 0;
+  for (int key = tid; key < 2 * d; key += T) {
+    const int i = key < d ? key : key - d;
+    const double g = key < d ? sh.glo[i] : sh.ghi[i];
+    if (g >= 0.5 * kBigG) continue;                               // dropped (infinite) bound: no row in f
+    const double sgn = key < d ? 1.0 : -1.0;
+    const double a_ = sh.xa_s[i], b_ = sh.xb_s[i];
+    const unsigned long long tb = hit_bits(hit_time_exact(sgn * a_, sgn * b_, g));
+    ++cnt;
+    if (tb < btb || (tb == btb && key < bkey)) { btb = tb; bkey = key; bxa = a_; bxb = b_; }
+  }
+  unsigned long long mtb; int mkey;
+  const int src = warp_argmin_hit(btb, bkey, mtb, mkey);
+  __syncthreads();                                                // red[] may still be read from the fast search
+  if (lane == src) { WinSlot& r = red[warp]; r.tb = mtb; r.key = mkey; r.xa = bxa; r.xb = bxb; }
+  __syncthreads();
+  if (tid == 0) {
+    int ws = 0;
+    for (int w = 1; w < G; ++w)
+      if (red[w].tb < red[ws].tb || (red[w].tb == red[ws].tb && red[w].key < red[ws].key)) ws = w;
+    if (ws != 0) red[0] = red[ws];
+  }
+  *n_eval += cnt;
+  __syncthreads();
+}
+
+// exact hit times of the bounces still owed to tt (see hit_fast), one lane per bounce; the caller
+// subtracts them in order
+template <int G>
+static __device__ __noinline__ void settle_times(const BoxShared sh, Deferred* dl, int n_dl) {
+  constexpr int T = 32 * G;
+  __syncthreads();                                                // entries written by thread 0 are visible
+  for (int e = threadIdx.x; e < n_dl; e += T) {
+    const int key = dl->key[e];
+    const double g = key < sh.d ? sh.glo[key] : sh.ghi[key - sh.d];
+    dl->fa[e] = hit_time_exact(dl->fa[e], dl->fb[e], g);
+  }
+  __syncthreads();
+}
+
+// THR: where the filter thresholds live: 0 = registers, 1 = shared memory, 2 = recomputed from the
+//      bound offsets.   GS: bound offsets (glo, ghi) in shared memory (else read through L1).
+template <int G, int CPT, int THR, bool GS, int MINB, bool PACK = false>
 __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p) {
   constexpr int T = 32 * G;
-  extern __shared__ double a_sm[];                 // d doubles: staging of a fresh draw
-                                                   // (+ 2d doubles of bound offsets when GSM)
+  constexpr int NS = CPT * T;                      // padded dimension: one slot per (thread, k)
+  extern __shared__ double dyn_sm[];
+  // xa_s doubles as the staging area of a fresh draw (draw_momentum): x_a is being replaced then
+  double* xa_s = dyn_sm;                           // [NS] copy of x_a
+  double* xb_s = xa_s + NS;                        // [NS] copy of x_b
+  double* glo_s = xb_s + NS;                       // [NS] if GS
+  double* ghi_s = glo_s + NS;
+  double* hlo_s = GS ? ghi_s + NS : glo_s;         // [NS] if THR == 1
+  double* hhi_s = hlo_s + NS;
   __shared__ WinSlot red[2][G];
   __shared__ Cand queue[G];
   __shared__ int qcnt[G];                          // PACK: candidates left in every warp's queue after the filter
@@ -133,22 +219,17 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
 
   // Per-coordinate filter thresholds h = g - m, with g the bound offset (mu - lb or ub - mu) and
   // m = 3e-9 |g| + abs_eps the safety margin (orders of magnitude above any rounding difference
-  // between this eta-frame recursion and tmg's whitened dot products).  Registers for small
-  // CPT, shared memory (padded to CPT*T entries, conflict-free) when the register budget is
-  // better spent on occupancy.
-  constexpr int NG = GSM ? 1 : CPT;
+  // between this eta-frame recursion and tmg's whitened dot products).
+  constexpr int NG = THR == 0 ? CPT : 1;
   double hlo_r[NG], hhi_r[NG];
-  double* hlo_s = a_sm + d;
-  double* hhi_s = hlo_s + CPT * T;
   const double abs_eps = p.abs_eps;
   auto thr = [&](double g) { return g - fma(3.0 * kFilterRel, fabs(g), abs_eps); };
-  if (GSM) {
-    for (int i = tid; i < CPT * T; i += T) {
-      hlo_s[i] = thr(i < d ? p.glo[i] : kBigG);
-      hhi_s[i] = thr(i < d ? p.ghi[i] : kBigG);
-    }
-    __syncthreads();
-  } else {
+  for (int i = tid; i < NS; i += T) {
+    const double gl = i < d ? p.glo[i] : kBigG, gh = i < d ? p.ghi[i] : kBigG;
+    if (GS) { glo_s[i] = gl; ghi_s[i] = gh; }
+    if (THR == 1) { hlo_s[i] = thr(gl); hhi_s[i] = thr(gh); }
+  }
+  if (THR == 0) {
 #pragma unroll
     for (int k = 0; k < NG; ++k) {
       const int i = tid + k * T;
@@ -156,6 +237,13 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
       hhi_r[k] = thr(i < d ? p.ghi[i] : kBigG);
     }
   }
+  __syncthreads();
+  BoxShared sh;
+  sh.xa_s = xa_s; sh.xb_s = xb_s; sh.glo = GS ? glo_s : p.glo; sh.ghi = GS ? ghi_s : p.ghi; sh.d = d; sh.ns = NS;
+  auto g_of = [&](int key) -> double {             // bound offset of wall `key` (lower walls 0..d-1, upper d..2d-1)
+    if (GS) return key < d ? glo_s[key] : ghi_s[key - d];
+    return __ldg(key < d ? p.glo + key : p.ghi + (key - d));
+  };
 
   const int total = p.burn_in + p.n_per_chain;
   for (;;) {
@@ -172,6 +260,7 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
       const int i = tid + k * T;
       xb[k] = i < d ? p.state[(size_t)chain * d + i] : 0.0;
       xa[k] = 0.0;
+      xb_s[i] = xb[k];
     }
     int s = p.s_done[chain];                       // transitions completed so far
     int64_t draw = p.pos[chain];                   // momenta consumed so far
@@ -179,6 +268,10 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
     int status = p.chain_status[chain];
     unsigned n_bounce = 0, n_search = 0, n_vel = 0, n_chk = 0, n_exact = 0, n_trans = 0, n_slow = 0;
     int parity = 0;
+#ifdef LQG_BOX_TIMING
+    unsigned long long ph_acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long ph_last = clock64();
+#endif
 
     for (int att = 0; att < p.attempts && s < total && status == 0; ++att) {   // while(2), HmcSampler.cpp:51
       if (p.pool != nullptr) {
@@ -186,31 +279,38 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
 #pragma unroll
         for (int k = 0; k < CPT; ++k) {
           const int i = tid + k * T;
-          xa[k] = i < d ? src[i] : 0.0;
+          xa[k] = i < d ? __ldcs(src + i) : 0.0;                 // streamed once: keep Sigma in L2 instead
+          xa_s[i] = xa[k];
         }
-      } else if (!draw_momentum<G, CPT>(p, chain, draw, a_sm, xa)) {
-        status = LQG_ERR_DRAWS_EXHAUSTED;
-        break;
+        // the next momentum of this chain is on its way to L2 while this attempt runs (one request per line)
+        if (att + 1 < p.attempts && (tid & 15) == 0) {
+#pragma unroll
+          for (int k = 0; k < CPT; ++k) {
+            const int i = tid + k * T;
+            if (i < d) prefetch_l2(src + d + i);
+          }
+        }
+      } else {
+        if (!draw_momentum<G, CPT>(p, chain, draw, xa_s)) {
+          status = LQG_ERR_DRAWS_EXHAUSTED;
+          break;
+        }
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) xa[k] = xa_s[tid + k * T];
       }
       ++draw;
       double tt = kHalfPi;                                       // :57; exact up to the hit times still owed (n_dl)
       double velsign = 0.0;                                      // :53
       // sin/cos of the remaining time, advanced by angle subtraction after every bounce.  They feed
-      // the filter and the fast search's comparison with the remaining time (both with margins); the
-      // final move recomputes them from the exact tt.
+      // the filter, the fast search's comparison with the remaining time (both with margins) and,
+      // after fast bounces, the final rotation; settling re-bases them on the exact tt.
       double S = 1.0, C = 6.123233995736766e-17;                 // sin(M_PI/2), cos(M_PI/2)
       int n_dl = 0;                                              // bounces whose exact t is still owed to tt
 
-      // tt -= t for every owed bounce, in order, with tmg's own hit-time formula (one lane per bounce)
+      // tt -= t for every owed bounce, in order, with tmg's own hit-time formula
       auto settle = [&]() {
         if (n_dl == 0) return;
-        __syncthreads();                                         // entries written by thread 0 are visible
-        for (int e = tid; e < n_dl; e += T) {
-          const int key = dl.key[e];
-          const double g = __ldg(key < d ? p.glo + key : p.ghi + (key - d));
-          dl.fa[e] = hit_time_exact(dl.fa[e], dl.fb[e], g);
-        }
-        __syncthreads();
+        settle_times<G>(sh, &dl, n_dl);
         for (int e = 0; e < n_dl; ++e) tt = tt - dl.fa[e];       // :90, same order, same operands
         n_dl = 0;
         sincos(tt, &S, &C);
@@ -218,36 +318,32 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
       };
 
       for (;;) {                                                 // while(1), :64
-        // ---- one hit search.  FASTS: candidates ranked by tan(t/2) (hit_fast), EXACT otherwise ----
         unsigned long long wtb = kNoHitBits; int wkey = INT_MAX;
         double wxa = 0.0, wxb = 0.0, wst = 0.0, wct = 0.0;
         bool need_exact = !fast_on;
-        auto search = [&](auto fast_tag) {
-          constexpr bool FASTS = decltype(fast_tag)::value;
+        if (fast_on) {
+          // ---- fast hit search: walls that survive the filter are ranked by tan(t/2) (hit_fast) ----
           // lane state: best candidate, high word of its runner-up, "some wall needs tmg's arithmetic"
           unsigned long long btb = kNoHitBits; int bkey = INT_MAX;
-          double bxa = 0.0, bxb = 0.0, bc = 0.0, bs = 0.0, bu2 = 1.0;
+          double bxa = 0.0, bxb = 0.0, bst = 0.0, bct = 0.0;
           unsigned bhi2 = 0xffffffffu;
           bool bslow = false;
           const double ktt = S / (1.0 + C);                      // tan(tt/2) of the remaining time
           const double klim = fma(ktt, 1e-9, ktt) + 1e-12;
-          auto consider = [&](double fa, double fb, int key) {
-            const double g = __ldg(key < d ? p.glo + key : p.ghi + (key - d));
-            unsigned long long tb;
+          auto consider = [&](int key) {
+            const int i = key < d ? key : key - d;
+            const double sgn = key < d ? 1.0 : -1.0;             // wall row f = sgn e_i
+            const double a_ = xa_s[i], b_ = xb_s[i];
+            const double g = g_of(key);
             FastHit h;
-            if (FASTS) {
-              const int cls = hit_fast(fa, fb, g, klim, h);
-              bslow |= cls == kFastSlow;
-              tb = cls == kFastHit ? (unsigned long long)__double_as_longlong(h.key) : kNoHitBits;
-            } else {
-              tb = hit_bits(hit_time_exact(fa, fb, g));
-            }
+            h.st = 0.0; h.ct = 0.0;
+            const int cls = hit_fast(sgn * a_, sgn * b_, g, klim, h);
+            bslow |= cls == kFastSlow;
+            const unsigned long long tb = cls == kFastHit ? (unsigned long long)__double_as_longlong(h.key) : kNoHitBits;
             if (tb < btb || (tb == btb && key < bkey)) {
-              if (FASTS) { bhi2 = min(bhi2, (unsigned)(btb >> 32)); bc = h.c; bs = h.s; bu2 = h.u2; }
-              btb = tb; bkey = key;
-              const double sgn = key < d ? 1.0 : -1.0;           // stored (fa, fb) = sgn * (x_a, x_b)
-              bxa = sgn * fa; bxb = sgn * fb;
-            } else if (FASTS) {
+              bhi2 = min(bhi2, (unsigned)(btb >> 32));
+              btb = tb; bkey = key; bxa = a_; bxb = b_; bst = h.st; bct = h.ct;
+            } else {
               bhi2 = min(bhi2, (unsigned)(tb >> 32));
             }
           };
@@ -255,7 +351,7 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
           int qn = 0;                                            // warp-uniform queue length
           auto flush = [&]() {
             __syncwarp();                                        // queue writes visible to every lane
-            for (int e = lane; e < qn; e += 32) consider(q->fa[e], q->fb[e], q->key[e]);
+            for (int e = lane; e < qn; e += 32) consider(q->key[e]);
             __syncwarp();                                        // entries consumed before they are overwritten
             n_exact += (lane == 0) ? qn : 0;
             qn = 0;
@@ -268,6 +364,7 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
           // h |h| compares like h^2 for h > 0 and is negative (always reachable) for h <= 0.
           // Phase 1 is straight-line code over the thread's coordinates (no votes, no branches: the
           // CPT coordinates overlap in the pipeline) and leaves one bit per wall in `mask`.
+          LQG_TICK(0);                                           // 0: everything since the last bounce update
           unsigned mask = 0u;
 #pragma unroll
           for (int k = 0; k < CPT; ++k) {
@@ -276,8 +373,10 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
             const double y = fma(a_, S, b_ * C);
             const double dy = fma(a_, C, -b_ * S);
             const double u2 = fma(a_, a_, b_ * b_);
-            const double hl = GSM ? hlo_s[i] : hlo_r[GSM ? 0 : k];
-            const double hh = GSM ? hhi_s[i] : hhi_r[GSM ? 0 : k];
+            double hl, hh;
+            if (THR == 0) { hl = hlo_r[THR == 0 ? k : 0]; hh = hhi_r[THR == 0 ? k : 0]; }
+            else if (THR == 1) { hl = hlo_s[i]; hh = hhi_s[i]; }
+            else { hl = thr(g_of(i < d ? i : 0)); hh = thr(g_of(i < d ? d + i : d)); if (i >= d) { hl = kBigG; hh = kBigG; } }
             // straight-line predicates (bitwise & |: no short-circuit branches, no fmin/fmax NaN fix-ups)
             const double nhl = -hl;
             const bool safe_lo = (b_ > nhl) & (y > nhl);
@@ -289,8 +388,9 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
             mask |= (need_lo ? 1u : 0u) << (2 * k);
             mask |= (need_hi ? 1u : 0u) << (2 * k + 1);
           }
-          // Phase 2: the survivors are compacted into the warp's queue: exclusive prefix sum of the
-          // per-lane counts, then every lane stores its walls at consecutive positions.
+          LQG_TICK(1);                                           // 1: filter masks
+          // Phase 2: the survivors' wall ids are compacted into the warp's queue: exclusive prefix sum of
+          // the per-lane counts, then every lane walks its set bits (most lanes have none).
           const int cnt = __popc(mask);
           int incl = cnt;
 #pragma unroll
@@ -303,27 +403,21 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
           // QCAP walls, each evaluated by the warp itself before the next round overwrites the queue
           for (int base = 0; base < wtotal; base += QCAP) {
             int pos = incl - cnt - base;
-            if (base > 0) __syncwarp();
-#pragma unroll
-            for (int k = 0; k < CPT; ++k) {
-              const int i = tid + k * T;
-              if ((mask >> (2 * k)) & 1u) {
-                if ((unsigned)pos < (unsigned)QCAP) { q->fa[pos] = xa[k]; q->fb[pos] = xb[k]; q->key[pos] = i; }
-                ++pos;
-              }
-              if ((mask >> (2 * k + 1)) & 1u) {
-                if ((unsigned)pos < (unsigned)QCAP) { q->fa[pos] = -xa[k]; q->fb[pos] = -xb[k]; q->key[pos] = d + i; }
-                ++pos;
-              }
+            for (unsigned mm = mask; mm != 0u; mm &= mm - 1u) {
+              const int b = __ffs(mm) - 1;
+              if ((unsigned)pos < (unsigned)QCAP) q->key[pos] = ((b & 1) ? d : 0) + tid + (b >> 1) * T;
+              ++pos;
             }
             qn = min(QCAP, wtotal - base);
             if (wtotal > QCAP) flush();
           }
+          LQG_TICK(2);                                           // 2: compaction
           if (PACK && G > 1) {
             // Candidates of all warps are evaluated together, 32 per warp from the front: with ~13 per
             // warp, 8 partly filled passes become ~4 full ones.
             if (lane == 0) qcnt[warp] = qn;
             __syncthreads();
+            LQG_TICK(3);                                         // 3: barrier after the pushes
             int ntot = 0;
 #pragma unroll
             for (int w = 0; w < G; ++w) ntot += qcnt[w];
@@ -336,7 +430,7 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
                 le -= past ? cw : 0;
                 w += past ? 1 : 0;
               }
-              consider(queue[w].fa[le], queue[w].fb[le], queue[w].key[le]);
+              consider(queue[w].key[le]);
             }
             if (tid == 0) n_exact += ntot;
             // the slot exchange below has its own barrier, which also protects the queues from the
@@ -344,71 +438,75 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
           } else {
             flush();
           }
-          // ---- arg-min: hardware warp-reduce, the owner lane fills the warp's slot, warp-reduce over the slots ----
+          LQG_TICK(4);                                           // 4: candidate evaluation
+          // ---- arg-min: hardware warp-reduce, the owner lane fills the warp's slot, then every thread
+          //      scans the G slots ----
           unsigned long long mtb; int mkey;
           const int src = warp_argmin_hit(btb, bkey, mtb, mkey);
-          unsigned whi2 = 0xffffffffu;
-          bool wslow = false;
-          if (FASTS) {
-            whi2 = __reduce_min_sync(0xffffffffu, lane == src ? bhi2 : (unsigned)(btb >> 32));
-            wslow = __any_sync(0xffffffffu, bslow);
-          }
+          unsigned whi2 = __reduce_min_sync(0xffffffffu, lane == src ? bhi2 : (unsigned)(btb >> 32));
+          bool wslow = __any_sync(0xffffffffu, bslow);
           if (G > 1) {
             if (lane == src) {
               WinSlot& r = red[parity][warp];
               r.tb = mtb; r.key = mkey; r.xa = bxa; r.xb = bxb; r.hi2 = whi2; r.slow = wslow ? 1 : 0;
-              if (FASTS) { const double ru = 1.0 / bu2; r.st = bs * ru; r.ct = bc * ru; }
+              r.st = bst; r.ct = bct;
             }
+            LQG_TICK(5);                                         // 5: warp arg-min + slot
             __syncthreads();
-            // lane l < G holds warp l's slot key; every warp reduces the G slots redundantly
-            unsigned long long stb = kNoHitBits; int skey = INT_MAX;
-            if (lane < G) { stb = red[parity][lane].tb; skey = red[parity][lane].key; }
-            const int ws = warp_argmin_hit(stb, skey, wtb, wkey);
-            const WinSlot& r = red[parity][ws];
-            wxa = r.xa; wxb = r.xb;
-            if (FASTS) {
-              wst = r.st; wct = r.ct;
-              const unsigned shi2 = lane < G ? (lane == ws ? red[parity][lane].hi2 : (unsigned)(stb >> 32)) : 0xffffffffu;
-              whi2 = __reduce_min_sync(0xffffffffu, shi2);
-              wslow = __any_sync(0xffffffffu, lane < G && red[parity][lane].slow != 0);
+            LQG_TICK(6);                                         // 6: barrier of the slot exchange
+            int ws = 0;
+            wtb = red[parity][0].tb; wkey = red[parity][0].key;
+            whi2 = 0xffffffffu;
+            int anyslow = red[parity][0].slow;
+#pragma unroll
+            for (int w = 1; w < G; ++w) {                        // broadcast reads: G is at most 16
+              const unsigned long long tb_w = red[parity][w].tb;
+              const int key_w = red[parity][w].key;
+              anyslow |= red[parity][w].slow;
+              if (tb_w < wtb || (tb_w == wtb && key_w < wkey)) {
+                whi2 = min(whi2, (unsigned)(wtb >> 32));
+                wtb = tb_w; wkey = key_w; ws = w;
+              } else {
+                whi2 = min(whi2, (unsigned)(tb_w >> 32));
+              }
             }
+            const WinSlot& r = red[parity][ws];
+            wxa = r.xa; wxb = r.xb; wst = r.st; wct = r.ct;
+            whi2 = min(whi2, r.hi2); wslow = anyslow != 0;
             parity ^= 1;
           } else {
             wtb = mtb; wkey = mkey;
             wxa = __shfl_sync(0xffffffffu, bxa, src);
             wxb = __shfl_sync(0xffffffffu, bxb, src);
-            if (FASTS) {
-              const double ru = 1.0 / bu2;
-              wst = __shfl_sync(0xffffffffu, bs * ru, src);
-              wct = __shfl_sync(0xffffffffu, bc * ru, src);
-            }
+            wst = __shfl_sync(0xffffffffu, bst, src);
+            wct = __shfl_sync(0xffffffffu, bct, src);
           }
-          if (FASTS) {
-            // tmg's arithmetic decides whenever a wall sits on one of its thresholds, two walls are hit
-            // within ~1e-6 relative of each other, or the first hit is within 1e-9 of the remaining time
-            const bool tie = wtb != kNoHitBits && whi2 <= (unsigned)(wtb >> 32) + 1u;
-            bool close = false;
-            if (wtb != kNoHitBits) {
-              const double kw = __longlong_as_double((long long)wtb);
-              close = fabs(kw - ktt) <= fma(ktt, 1e-9, 1e-12);
-            }
-            need_exact = wslow | tie | close;
+          // tmg's arithmetic decides whenever a wall sits on one of its thresholds, two walls are hit
+          // within ~1e-6 relative of each other, or the first hit is within 1e-9 of the remaining time
+          const bool tie = wtb != kNoHitBits && whi2 <= (unsigned)(wtb >> 32) + 1u;
+          bool close = false;
+          if (wtb != kNoHitBits) {
+            const double kw = __longlong_as_double((long long)wtb);
+            close = fabs(kw - ktt) <= fma(ktt, 1e-9, 1e-12);
           }
-        };
-        if (fast_on) search(std::true_type{});
+          need_exact = wslow | tie | close;
+        }
+        LQG_TICK(7);                                             // 7: slot scan + decision
+        double st, ct;
         if (need_exact) {
           if (fast_on) ++n_slow;
           settle();                                              // the exact comparison tt < t needs the exact tt
-          search(std::false_type{});
-        }
-        ++n_search;
-        double st, ct;
-        if (need_exact) {
+          exact_search<G>(sh, red[parity], &n_exact);
+          const WinSlot& r = red[parity][0];
+          wtb = r.tb; wkey = r.key; wxa = r.xa; wxb = r.xb;
+          __syncthreads();                                       // the slot is free for the next search
+          ++n_search;
           const double t = hit_from_bits(wtb);
           if (t == 0.0 || tt < t) break;                         // :82
           tt = tt - t;                                           // :90
           sincos(t, &st, &ct);
         } else {
+          ++n_search;
           if (wtb == kNoHitBits) break;                          // no wall within the remaining time (:82)
           st = wst; ct = wct;
           if (n_dl == DCAP) settle();
@@ -430,6 +528,10 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
           sc[k] = i < d ? __ldg(scol + i) : 0.0;
         }
         const double sjj = __ldg(p.sdiag + j);
+#ifdef LQG_BOX_TIMING
+        if (tid == 0) { double acc_ = 0; _Pragma("unroll") for (int k = 0; k < CPT; ++k) acc_ += sc[k]; if (acc_ == 1.2345e300) ph_acc[15] += 1; }
+        LQG_TICK(8);                                             // 8: Sigma column arrives (L2 latency)
+#endif
         const double vj = __dsub_rn(__dmul_rn(ct, wxa), __dmul_rn(st, wxb));   // hit_vel[j]
         const double alpha2 = 2.0 * (vj / sjj);                  // 2*alpha, alpha = f.v / f.f
 #pragma unroll
@@ -438,11 +540,13 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
           xb[k] = fma(st, a_, ct * b_);                          // new_b  (:91)
           const double v = fma(ct, a_, -st * b_);                // hit_vel (:92)
           xa[k] = fma(-alpha2, sc[k], v);                        // reflected velocity (:109)
+          xa_s[tid + k * T] = xa[k]; xb_s[tid + k * T] = xb[k];  // the copy the next search evaluates from
         }
         velsign = side * __dsub_rn(vj, __dmul_rn(alpha2, sjj));  // a.f (:110)
         if (velsign < 0.0) break;                                // :112
         const double Sn = fma(S, ct, -C * st), Cn = fma(C, ct, S * st);   // sin/cos(tt - t)
         S = Sn; C = Cn;
+        LQG_TICK(9);                                             // 9: rotate + reflect
       }
       if (velsign < 0.0) {                                       // :117
         ++n_vel;
@@ -450,8 +554,10 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
         continue;
       }
       // ---- end point: bb = sin(tt) a + cos(tt) b (:119), tmg's check min(F bb + g) >= 0 (:121)
-      //      in its eta form, and the exact check of the value that would be emitted ----
-      if (n_dl > 0) settle(); else sincos(tt, &S, &C);
+      //      in its eta form, and the exact check of the value that would be emitted.  After fast
+      //      bounces (S, C) are the angle-subtracted values (at most DCAP steps since the last exact
+      //      re-basing: ~1e-14); otherwise tt is exact and they are recomputed from it ----
+      if (n_dl == 0) sincos(tt, &S, &C);
       bool fine = true;
 #pragma unroll
       for (int k = 0; k < CPT; ++k) {
@@ -459,8 +565,8 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
         if (i < d) {
           const double bb = fma(xa[k], S, xb[k] * C);
           const double e = __ldg(p.mu + i) + bb;
-          fine = fine && (bb + __ldg(p.glo + i) >= 0.0) && (__ldg(p.ghi + i) - bb >= 0.0) &&
-                 (e >= __ldg(p.lb + i)) && (e <= __ldg(p.ub + i));
+          const double gl = GS ? glo_s[i] : __ldg(p.glo + i), gh = GS ? ghi_s[i] : __ldg(p.ghi + i);
+          fine = fine && (bb + gl >= 0.0) && (gh - bb >= 0.0) && (e >= __ldg(p.lb + i)) && (e <= __ldg(p.ub + i));
         }
       }
       fine = (G > 1) ? (__syncthreads_and(fine) != 0) : __all_sync(0xffffffffu, fine);
@@ -470,7 +576,10 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
         continue;
       }
 #pragma unroll
-      for (int k = 0; k < CPT; ++k) xb[k] = fma(xa[k], S, xb[k] * C);   // lastSample = bb (:123)
+      for (int k = 0; k < CPT; ++k) {
+        xb[k] = fma(xa[k], S, xb[k] * C);                        // lastSample = bb (:123)
+        xb_s[tid + k * T] = xb[k];
+      }
       rcount = 0;
       ++n_trans;
       if (s >= p.burn_in) {                                      // tmg:R/tmg.R:105 drops burn-in
@@ -478,11 +587,15 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
 #pragma unroll
         for (int k = 0; k < CPT; ++k) {
           const int i = tid + k * T;
-          if (i < d) dst[i] = __ldg(p.mu + i) + xb[k];           // tmg:R/tmg.R:106
+          if (i < d) __stcs(dst + i, __ldg(p.mu + i) + xb[k]);   // tmg:R/tmg.R:106; written once, read by later stages
         }
       }
       ++s;
+      LQG_TICK(10);                                              // 10: end of the transition (check, emit)
     }
+#ifdef LQG_BOX_TIMING
+    if (tid == 0) for (int q_ = 0; q_ < 16; ++q_) atomicAdd(&g_box_phase[q_], ph_acc[q_]);
+#endif
 
     // ---- persist chain state and counters ----
 #pragma unroll
@@ -501,6 +614,7 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
       atomicAdd(p.stats + 4, (unsigned long long)n_chk);
       atomicAdd(p.stats + 10, (unsigned long long)n_slow);
     }
+    __syncthreads();                                             // the state copy is rewritten by the next chain
   }
 }
 
@@ -559,67 +673,95 @@ __global__ void box_violation_kernel(int d, size_t n_cols, const double* out, co
 }
 
 // grid == -1: query only, *slots_out = resident CTAs on the device
-template <int G, int CPT, bool GSM, int MINB, bool PACK = false>
+template <int G, int CPT, int THR, bool GS, int MINB, bool PACK = false>
 static cudaError_t launch_box_t(const BoxParams& p, int grid, cudaStream_t st, int* slots_out = nullptr) {
-  const size_t smem = ((size_t)p.d + (GSM ? 2 * CPT * 32 * G : 0)) * sizeof(double);
-  auto kern = hmc_box_kernel<G, CPT, GSM, MINB, PACK>;
+  constexpr size_t NS = (size_t)CPT * 32 * G;
+  const size_t smem = NS * (2 + (GS ? 2 : 0) + (THR == 1 ? 2 : 0)) * sizeof(double);
+  auto kern = hmc_box_kernel<G, CPT, THR, GS, MINB, PACK>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
+  int per_sm = 0, dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * G, smem);
   if (slots_out) {
-    int per_sm = 0, dev = 0, sms = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * G, smem);
     *slots_out = sms * (per_sm > 0 ? per_sm : 1);
     return e;
   }
-  if (grid <= 0) {
-    int per_sm = 0, dev = 0, sms = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * G, smem);
-    if (e != cudaSuccess) return e;
-    grid = sms * (per_sm > 0 ? per_sm : 1);          // persistent: every resident slot, once
-  }
+  if (e != cudaSuccess) return e;
+  if (grid <= 0) grid = sms * (per_sm > 0 ? per_sm : 1);     // persistent: every resident slot, once
   if (grid > p.n_active) grid = p.n_active;
   if (grid <= 0) return cudaSuccess;
-  kern<<<grid, 32 * G, smem, st>>>(p);
+  // Sigma (one column per bounce, 32 MB at d = 2000) should stay in L2 while the momentum pool and the
+  // samples stream through it: persisting access-policy window on this launch
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(32 * G); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  int n_attr = 0;
+  static const size_t persist_max = [] {
+    int dev_ = 0, v = 0;
+    cudaGetDevice(&dev_);
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxPersistingL2CacheSize, dev_) != cudaSuccess) { cudaGetLastError(); return (size_t)0; }
+    if (v > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)v) != cudaSuccess) { cudaGetLastError(); return (size_t)0; }
+    return (size_t)v;
+  }();
+  static const char* env_l2 = getenv("LQG_L2_PERSIST");             // tuning aid: 0 disables
+  const size_t sig_bytes = (size_t)p.d * p.d * sizeof(double);
+  if (persist_max > 0 && sig_bytes >= ((size_t)4 << 20) && !(env_l2 && env_l2[0] == '0')) {
+    int max_win = 0;
+    cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+    attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[0].val.accessPolicyWindow.base_ptr = const_cast<double*>(p.Sigma);
+    attr[0].val.accessPolicyWindow.num_bytes = std::min(sig_bytes, (size_t)(max_win > 0 ? max_win : 0));
+    attr[0].val.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)persist_max / (double)sig_bytes);
+    attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (attr[0].val.accessPolicyWindow.num_bytes > 0) n_attr = 1;
+  }
+  cfg.attrs = attr; cfg.numAttrs = n_attr;
+  e = cudaLaunchKernelEx(&cfg, kern, p);
   ++launch_counter();
-  return cudaGetLastError();
+  return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 // picks (warps per chain, coordinates per thread) from d
 static cudaError_t dispatch_box(const BoxParams& p, int grid, cudaStream_t st, int* slots) {
   const int d = p.d;
-  if (d <= 32)   return launch_box_t<1, 1, false, 16>(p, grid, st, slots);
-  if (d <= 64)   return launch_box_t<1, 2, false, 16>(p, grid, st, slots);
-  if (d <= 128)  return launch_box_t<1, 4, false, 16>(p, grid, st, slots);
-  if (d <= 256)  return launch_box_t<2, 4, false, 8>(p, grid, st, slots);
+  if (d <= 32)   return launch_box_t<1, 1, 0, true, 16>(p, grid, st, slots);
+  if (d <= 64)   return launch_box_t<1, 2, 0, true, 16>(p, grid, st, slots);
+  if (d <= 128)  return launch_box_t<1, 4, 0, true, 16>(p, grid, st, slots);
+  if (d <= 256)  return launch_box_t<2, 4, 0, true, 8>(p, grid, st, slots);
   static const char* v = getenv("LQG_BOX_VARIANT");            // tuning aid, see below
   // From 4 warps per chain on, the candidates of all warps are evaluated together (PACK): with ~13
-  // survivors per warp, 8 partly filled passes of the exact formula become ~4 full ones
-  // (measured: cfg4 39.0 -> 38.3 ms, cfg5 35.9 -> 33.8 ms per step; "n" = per-warp evaluation).
+  // survivors per warp, 8 partly filled evaluation passes become ~4 full ones ("n" = per-warp evaluation).
   const bool pack = !(v && v[0] == 'n');
-  if (d <= 512)  return pack ? launch_box_t<4, 4, false, 4, true>(p, grid, st, slots) : launch_box_t<4, 4, false, 4>(p, grid, st, slots);
-  if (d <= 1024) {
-    if (v && v[0] == 'a') return launch_box_t<4, 8, true, 4>(p, grid, st, slots);     // 4 warps x 8, 4 CTAs/SM, per-warp evaluation
-    if (v && v[0] == 'b') return launch_box_t<4, 8, true, 2>(p, grid, st, slots);     // 4 warps x 8, 2 CTAs/SM
-    if (v && v[0] == 'c') return launch_box_t<8, 4, true, 2>(p, grid, st, slots);     // 8 warps x 4, 2 CTAs/SM
-    if (v && v[0] == 'd') return launch_box_t<8, 4, true, 3>(p, grid, st, slots);     // 8 warps x 4, 3 CTAs/SM
-    return pack ? launch_box_t<4, 8, true, 4, true>(p, grid, st, slots) : launch_box_t<4, 8, true, 4>(p, grid, st, slots);
-  }
+  if (d <= 512)  return pack ? launch_box_t<4, 4, 0, true, 4, true>(p, grid, st, slots) : launch_box_t<4, 4, 0, true, 4>(p, grid, st, slots);
+  if (d <= 1024) return pack ? launch_box_t<4, 8, 1, true, 4, true>(p, grid, st, slots) : launch_box_t<4, 8, 1, true, 4>(p, grid, st, slots);
   if (d <= 2048) {
-    // Fewer, longer chains do less burn-in work for the same number of samples, and the measured
-    // per-transition throughput of 2 and 3 resident CTAs per SM is the same: 2 CTAs/SM
-    // (128 registers) is the default.  "3" = 3 CTAs/SM (80 registers), "4" = 4 warps x 16.
-    if (v && v[0] == '4') return launch_box_t<4, 16, true, 4>(p, grid, st, slots);
-    if (v && v[0] == '3') return launch_box_t<8, 8, true, 3>(p, grid, st, slots);
-    if (v && v[0] == '5') return launch_box_t<8, 8, true, 4>(p, grid, st, slots);
-    return pack ? launch_box_t<8, 8, true, 2, true>(p, grid, st, slots) : launch_box_t<8, 8, true, 2>(p, grid, st, slots);
+    // Fewer, longer chains do less burn-in work for the same number of samples: 2 CTAs/SM
+    // (128 registers) is the default.  "3" = 3 CTAs/SM (80 registers, thresholds recomputed from
+    // the bound offsets instead of a second pair of shared-memory arrays).
+    if (v && v[0] == '3') return launch_box_t<8, 8, 2, true, 3, true>(p, grid, st, slots);
+    if (v && v[0] == 'w') return launch_box_t<16, 4, 1, true, 2, true>(p, grid, st, slots);     // 16 warps x 4 coordinates, 2 CTAs/SM (64 registers)
+    if (v && v[0] == 'x') return launch_box_t<16, 4, 1, true, 1, true>(p, grid, st, slots);     // 16 warps x 4 coordinates, 1 CTA/SM
+    return pack ? launch_box_t<8, 8, 1, true, 2, true>(p, grid, st, slots) : launch_box_t<8, 8, 1, true, 2>(p, grid, st, slots);
   }
-  if (d <= 4096) return pack ? launch_box_t<8, 16, true, 1, true>(p, grid, st, slots) : launch_box_t<8, 16, true, 1>(p, grid, st, slots);
-  if (d <= 8192) return pack ? launch_box_t<16, 16, true, 1, true>(p, grid, st, slots) : launch_box_t<16, 16, true, 1>(p, grid, st, slots);
+  if (d <= 4096) return pack ? launch_box_t<8, 16, 1, true, 1, true>(p, grid, st, slots) : launch_box_t<8, 16, 1, true, 1>(p, grid, st, slots);
+  if (d <= 8192) return pack ? launch_box_t<16, 16, 2, false, 1, true>(p, grid, st, slots) : launch_box_t<16, 16, 2, false, 1>(p, grid, st, slots);
   return cudaErrorInvalidValue;
+}
+// diagnostic build: reads (and clears) the phase table; a normal build reports zeros
+cudaError_t box_phase_cycles(unsigned long long* out16) {
+#ifdef LQG_BOX_TIMING
+  cudaError_t e = cudaMemcpyFromSymbol(out16, g_box_phase, 16 * sizeof(unsigned long long));
+  if (e != cudaSuccess) return e;
+  unsigned long long z[16] = {0};
+  return cudaMemcpyToSymbol(g_box_phase, z, sizeof(z));
+#else
+  for (int i = 0; i < 16; ++i) out16[i] = 0;
+  return cudaSuccess;
+#endif
 }
 cudaError_t launch_hmc_box(const BoxParams& p, int grid, cudaStream_t st) { return dispatch_box(p, grid, st, nullptr); }
 int hmc_box_slots(int d) {
