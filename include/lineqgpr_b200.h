@@ -133,6 +133,15 @@ int lqg_hmc_canonical_trace(int32_t d, int32_t c, const double* F, const double*
                             const lqg_opts* opts, double* out, int32_t trace_cap,
                             double* trace_t, int32_t* trace_cn, int32_t* trace_n);
 
+/* Parity tooling: the two device-side hit-time functions over n independent (f.a, f.b, g) triples
+ * (host pointers).  t_exact[n] (nullable) = tmg's hit time of one constraint,
+ * tmg:src/HmcSampler.cpp:157-181, 0 = none — compared with the oracle's scalar restatement on
+ * randomised inputs.  fast_class[n] (nullable) = verdict of the trig-free ranking the box kernel
+ * uses (0 = cannot be hit within tan(t/2) <= klim, 1 = hit: fast_key = tan(t/2), fast_sin / fast_cos
+ * of that t, 2 = too close to one of tmg's thresholds: decided by the exact function).            */
+int lqg_hit_time_batch(int64_t n, const double* fa, const double* fb, const double* g, double klim,
+                       double* t_exact, int32_t* fast_class, double* fast_key, double* fast_sin, double* fast_cos);
+
 /* Box-constrained form: what tmvrnorm.HMC always builds (R/lineqGPsamplers.R:128-141:
  * f = [I; -I] rows with finite bounds, g = c(-lb, ub)), sampled directly in the eta frame.
  * With U = Ri of tmg:R/tmg.R:27 (so U U' = Sigma) the chain is algebraically the reference's

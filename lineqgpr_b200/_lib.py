@@ -26,7 +26,7 @@ SYMBOLS = ["lqg_rtmg", "lqg_hmc_canonical", "lqg_hmc_canonical_trace", "lqg_hmc_
            "lqg_launch_count", "lqg_guard_violations",
            "lqg_whiten_box", "lqg_chol", "lqg_solve_spd", "lqg_eta_params", "lqg_lambda_pinv", "lqg_solve_qp", "lqg_basis", "lqg_paths",
            "lqg_simulate", "lqg_comm_unique_id", "lqg_comm_init", "lqg_comm_rank", "lqg_comm_world", "lqg_comm_destroy",
-           "lqg_comm_allgather", "lqg_measure_fp64_mixed"]
+           "lqg_comm_allgather", "lqg_measure_fp64_mixed", "lqg_hit_time_batch"]
 
 _dp = C.POINTER(C.c_double)
 
@@ -140,6 +140,8 @@ def lib():
     L.lqg_measure_fp64_peaks.argtypes = [_dp, _dp, C.POINTER(Opts)]
     L.lqg_measure_fp64_mixed.restype = C.c_int
     L.lqg_measure_fp64_mixed.argtypes = [_dp, _dp, C.POINTER(Opts)]
+    L.lqg_hit_time_batch.restype = C.c_int
+    L.lqg_hit_time_batch.argtypes = [i64, vp, vp, vp, C.c_double, vp, vp, vp, vp, vp]
     L.lqg_launch_count.restype = i64
     L.lqg_launch_count.argtypes = [i32]
     L.lqg_guard_violations.restype = C.c_int

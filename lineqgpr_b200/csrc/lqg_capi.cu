@@ -779,6 +779,38 @@ extern "C" int lqg_device_count(void) {
   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
   return n;
 }
+// Parity tooling (see the header): the device hit-time functions over arrays, host pointers
+extern "C" int lqg_hit_time_batch(int64_t n, const double* fa, const double* fb, const double* g, double klim,
+                                  double* t_exact, int32_t* fast_class, double* fast_key, double* fast_sin, double* fast_cos) {
+  LQG_API_BEGIN
+  if (!have_device()) return LQG_ERR_CUDA;
+  if (n <= 0 || !fa || !fb || !g || (!t_exact && !fast_class)) { set_error("lqg_hit_time_batch: invalid argument"); return LQG_ERR_INVALID; }
+  cudaStream_t st = nullptr;
+  DevBuf::cur_stream = st;
+  const size_t nb = (size_t)n * sizeof(double);
+  DevBuf b_fa, b_fb, b_g, b_t, b_c, b_k, b_s, b_co;
+  LQG_CUDA_TRY(b_fa.alloc(nb)); LQG_CUDA_TRY(b_fb.alloc(nb)); LQG_CUDA_TRY(b_g.alloc(nb));
+  LQG_CUDA_TRY(cudaMemcpyAsync(b_fa.p, fa, nb, cudaMemcpyHostToDevice, st));
+  LQG_CUDA_TRY(cudaMemcpyAsync(b_fb.p, fb, nb, cudaMemcpyHostToDevice, st));
+  LQG_CUDA_TRY(cudaMemcpyAsync(b_g.p, g, nb, cudaMemcpyHostToDevice, st));
+  if (t_exact) LQG_CUDA_TRY(b_t.alloc(nb));
+  if (fast_class) { LQG_CUDA_TRY(b_c.alloc((size_t)n * sizeof(int))); LQG_CUDA_TRY(b_k.alloc(nb)); LQG_CUDA_TRY(b_s.alloc(nb)); LQG_CUDA_TRY(b_co.alloc(nb)); }
+  LQG_CUDA_TRY(launch_hit_time_batch((size_t)n, b_fa.as<double>(), b_fb.as<double>(), b_g.as<double>(), klim,
+                                     t_exact ? b_t.as<double>() : nullptr, fast_class ? b_c.as<int>() : nullptr,
+                                     b_k.as<double>(), b_s.as<double>(), b_co.as<double>(), st));
+  if (t_exact) LQG_CUDA_TRY(cudaMemcpyAsync(t_exact, b_t.p, nb, cudaMemcpyDeviceToHost, st));
+  if (fast_class) {
+    LQG_CUDA_TRY(cudaMemcpyAsync(fast_class, b_c.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (fast_key) LQG_CUDA_TRY(cudaMemcpyAsync(fast_key, b_k.p, nb, cudaMemcpyDeviceToHost, st));
+    if (fast_sin) LQG_CUDA_TRY(cudaMemcpyAsync(fast_sin, b_s.p, nb, cudaMemcpyDeviceToHost, st));
+    if (fast_cos) LQG_CUDA_TRY(cudaMemcpyAsync(fast_cos, b_co.p, nb, cudaMemcpyDeviceToHost, st));
+  }
+  LQG_CUDA_TRY(cudaStreamSynchronize(st));
+  fold_launches();
+  return LQG_OK;
+  LQG_API_END("lqg_hit_time_batch")
+}
+
 // diagnostic: per-phase SM-clock sums of the box kernel's hit search since the last call (zeros unless
 // the library was built with -DLQG_BOX_TIMING; scripts/probe_box_phases.py).  Not part of the public header.
 extern "C" int lqg_debug_box_phases(unsigned long long* out16) {

@@ -751,6 +751,29 @@ static cudaError_t dispatch_box(const BoxParams& p, int grid, cudaStream_t st, i
   if (d <= 8192) return pack ? launch_box_t<16, 16, 2, false, 1, true>(p, grid, st, slots) : launch_box_t<16, 16, 2, false, 1>(p, grid, st, slots);
   return cudaErrorInvalidValue;
 }
+// parity tooling: the two device hit-time functions over arrays of (f.a, f.b, g)
+__global__ void hit_time_batch_kernel(size_t n, const double* fa, const double* fb, const double* g, double klim,
+                                      double* t_exact, int* cls, double* key, double* st, double* ct) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    if (t_exact) t_exact[i] = hit_time_exact(fa[i], fb[i], g[i]);
+    if (cls) {
+      FastHit h;
+      h.key = 0.0; h.st = 0.0; h.ct = 0.0;
+      const int c = hit_fast(fa[i], fb[i], g[i], klim, h);
+      cls[i] = c;
+      if (key) key[i] = c == kFastHit ? h.key : 0.0;
+      if (st) st[i] = c == kFastHit ? h.st : 0.0;
+      if (ct) ct[i] = c == kFastHit ? h.ct : 0.0;
+    }
+  }
+}
+cudaError_t launch_hit_time_batch(size_t n, const double* fa, const double* fb, const double* g, double klim,
+                                  double* t_exact, int* cls, double* key, double* st, double* ct, cudaStream_t stream) {
+  hit_time_batch_kernel<<<148 * 8, 256, 0, stream>>>(n, fa, fb, g, klim, t_exact, cls, key, st, ct);
+  ++launch_counter();
+  return cudaGetLastError();
+}
+
 // diagnostic build: reads (and clears) the phase table; a normal build reports zeros
 cudaError_t box_phase_cycles(unsigned long long* out16) {
 #ifdef LQG_BOX_TIMING

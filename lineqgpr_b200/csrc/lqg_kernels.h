@@ -43,6 +43,8 @@ struct BoxParams {
 };
 
 cudaError_t launch_hmc_box(const BoxParams& p, int grid, cudaStream_t st);
+cudaError_t launch_hit_time_batch(size_t n, const double* fa, const double* fb, const double* g, double klim,
+                                  double* t_exact, int* cls, double* key, double* st, double* ct, cudaStream_t stream);
 cudaError_t box_phase_cycles(unsigned long long* out16);   // diagnostic build (-DLQG_BOX_TIMING) only
 int hmc_box_slots(int d);        // resident CTAs (= chains in flight) for dimension d, current device
 cudaError_t launch_box_prep(int d, const double* mu, const double* lb, const double* ub,

@@ -63,6 +63,11 @@ def lib():
         _lib.oracle_normal_stream.argtypes = [ctypes.c_int, ctypes.c_int64, _dp]
         _lib.oracle_hit_time.restype = ctypes.c_double
         _lib.oracle_hit_time.argtypes = [ctypes.c_double] * 3
+        _lib.oracle_hit_time_batch.restype = None
+        _lib.oracle_hit_time_batch.argtypes = [ctypes.c_int64, _dp, _dp, _dp, _dp]
+        _lib.oracle_rtmg_ext.restype = ctypes.c_int
+        _lib.oracle_rtmg_ext.argtypes = [ctypes.c_int, ctypes.c_int, _dp, ctypes.c_int, _dp, _dp, _dp, ctypes.c_int64,
+                                         ctypes.c_int64, _dp, _dp, _dp, _i64p]
     return _lib
 
 
@@ -91,6 +96,34 @@ def normal_stream(seed: int, n: int) -> np.ndarray:
 def hit_time(fa: float, fb: float, g: float) -> float:
     """tmg:src/HmcSampler.cpp:157-181 for one constraint."""
     return lib().oracle_hit_time(float(fa), float(fb), float(g))
+
+
+def hit_time_batch(fa, fb, g):
+    """oracle_hit_time over arrays (tmg:src/HmcSampler.cpp:157-181 per element)."""
+    fa, fb, g = (np.ascontiguousarray(v, dtype=np.float64) for v in (fa, fb, g))
+    out = np.empty_like(fa)
+    lib().oracle_hit_time_batch(fa.size, _P(fa), _P(fb), _P(g), _P(out))
+    return out
+
+
+def rtmg_canonical_ext(n, initial, F, g, injected, unwhiten=None, shift=None, max_restarts=0):
+    """The canonical chain in EXTENDED precision (oracle/tmg_hmc_ext.cpp), injected draws.  With
+    `unwhiten` (= Ri) and `shift` (= mu) the result is Ri z + mu evaluated in extended precision
+    (tmg:R/tmg.R:106).  Returns (samples n x d rounded to double, info)."""
+    initial = np.ascontiguousarray(initial, dtype=np.float64)
+    d = initial.size
+    F = np.asfortranarray(np.asarray(F, dtype=np.float64).reshape(-1, d))
+    g = np.ascontiguousarray(g, dtype=np.float64)
+    inj = np.ascontiguousarray(injected, dtype=np.float64)
+    out = np.zeros((n, d), order="F")
+    stats = np.zeros(5, dtype=np.int64)
+    uw = np.asfortranarray(unwhiten, dtype=np.float64) if unwhiten is not None else None
+    sh = np.ascontiguousarray(shift, dtype=np.float64) if shift is not None else None
+    rc = lib().oracle_rtmg_ext(int(n), d, _P(initial), F.shape[0], _P(F), _P(g), _P(inj), inj.size, int(max_restarts),
+                               _P(uw) if uw is not None else None, _P(sh) if sh is not None else None, _P(out),
+                               stats.ctypes.data_as(_i64p))
+    return out, dict(rc=rc, bounces=int(stats[0]), vel_restarts=int(stats[1]), chk_restarts=int(stats[2]),
+                     draws=int(stats[3]), hit_searches=int(stats[4]))
 
 
 def rtmg_canonical(n, seed, initial, F, g, injected=None, faithful_copy=False,

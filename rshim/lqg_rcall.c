@@ -49,13 +49,71 @@ SEXP lqg_hmc_box_call(SEXP mu_, SEXP U_, SEXP Sigma_, SEXP lb_, SEXP ub_, SEXP i
   o.seed = (uint64_t)Rf_asInteger(seed_);
   o.prepass = -1;
   lqg_hmc_stats st;
-  SEXP out = PROTECT(Rf_allocMatrix(REALSXP, d, o.n_chains * n_per));
-  int rc = lqg_hmc_box(d, REAL(mu_), REAL(U_), 1, REAL(Sigma_), REAL(lb_), REAL(ub_), REAL(init_), 0,
+  /* Rf_allocMatrix takes int dimensions: n.chains * n.per is formed in 64 bits and refused when it
+   * does not fit (the element count d * ncol itself may exceed 2^31: R long vectors hold it) */
+  const long long ncol = (long long)o.n_chains * (long long)n_per;
+  if (o.n_chains <= 0 || n_per <= 0 || ncol > 2147483647LL)
+    Rf_error("lqg_hmc_box: n.chains * n.per = %lld columns do not fit an R matrix dimension", ncol);
+  SEXP out = PROTECT(Rf_allocMatrix(REALSXP, d, (int)ncol));
+  int rc = lqg_hmc_box(d, REAL(mu_), Rf_isNull(U_) ? NULL : REAL(U_), 1, REAL(Sigma_), REAL(lb_), REAL(ub_), REAL(init_), 0,
                        n_per, burn, &o, REAL(out), NULL, &st);
   UNPROTECT(1);
   lqg_check(rc, "lqg_hmc_box");
   if (st.violations != 0) Rf_error("lqg_hmc_box: %lld emitted values outside the bounds", (long long)st.violations);
   return out;
+}
+
+/* chains lqg_hmc_box keeps resident for dimension d: the default of control$n.chains */
+SEXP lqg_hmc_box_slots_call(SEXP d_) {
+  return Rf_ScalarInteger(lqg_hmc_box_slots(Rf_asInteger(d_)));
+}
+
+/* The tail of simulate.lineqGP / simulate.lineqAGP in ONE call (R/lineqGP.R:611-640, R/lineqAGP.R:558-575):
+ * tmvrnorm.HMC -> xi.sim = qr.solve(Lambda, eta) -> ysim = Phi.test %*% xi.sim -> bands, with eta, xi and
+ * ysim resident on the GPU.  Phi_ may be NULL (lineqAGP returns xiAll.sim only); keep_ysim = FALSE never
+ * materialises ysim.  Returns list(xi.sim, ysim | NULL, mean | NULL, qtls | NULL). */
+SEXP lqg_simulate_call(SEXP mu_, SEXP Sigma_, SEXP lb_, SEXP ub_, SEXP init_, SEXP Lambda_, SEXP Phi_, SEXP probs_,
+                       SEXP n_per_chain_, SEXP burn_in_, SEXP n_chains_, SEXP seed_, SEXP keep_ysim_) {
+  const int d = Rf_length(mu_), m = Rf_ncols(Lambda_);
+  const int n_per = Rf_asInteger(n_per_chain_);
+  const int have_phi = !Rf_isNull(Phi_), keep = have_phi && Rf_asInteger(keep_ysim_);
+  const int n_t = have_phi ? Rf_nrows(Phi_) : 0, np = have_phi ? Rf_length(probs_) : 0;
+  if (Rf_nrows(Lambda_) != d) Rf_error("non-conformable arguments");
+  if (have_phi && Rf_ncols(Phi_) != m) Rf_error("non-conformable arguments");
+  lqg_opts o;
+  memset(&o, 0, sizeof(o));
+  o.mem = LQG_MEM_HOST;
+  o.n_chains = Rf_asInteger(n_chains_);
+  o.seed = (uint64_t)Rf_asInteger(seed_);
+  o.prepass = -1;
+  const long long ncol = (long long)o.n_chains * (long long)n_per;
+  if (o.n_chains <= 0 || n_per <= 0 || ncol > 2147483647LL)
+    Rf_error("lqg_simulate: n.chains * n.per = %lld columns do not fit an R matrix dimension", ncol);
+  SEXP xi = PROTECT(Rf_allocMatrix(REALSXP, m, (int)ncol));
+  SEXP ysim = PROTECT(keep ? Rf_allocMatrix(REALSXP, n_t, (int)ncol) : R_NilValue);
+  SEXP mean = PROTECT(have_phi ? Rf_allocVector(REALSXP, n_t) : R_NilValue);
+  SEXP q = PROTECT(have_phi ? Rf_allocMatrix(REALSXP, np, n_t) : R_NilValue);
+  lqg_simulate_args a;
+  memset(&a, 0, sizeof(a));
+  a.d = d; a.m = m;
+  a.mu = REAL(mu_); a.Sigma = REAL(Sigma_); a.lb = REAL(lb_); a.ub = REAL(ub_); a.init = REAL(init_);
+  a.Lambda = REAL(Lambda_);
+  a.n_t = n_t;
+  if (have_phi) { a.Phi = REAL(Phi_); a.ldphi = n_t; a.probs = REAL(probs_); a.nprobs = np; a.mean = REAL(mean); a.qtls = REAL(q); }
+  if (keep) { a.ysim_out = REAL(ysim); a.ldy = n_t; }
+  a.n_per_chain = n_per; a.burn_in = Rf_asInteger(burn_in_);
+  a.xi_out = REAL(xi);
+  lqg_simulate_stats st;
+  int rc = lqg_simulate(&a, &o, NULL, &st);
+  SEXP res = PROTECT(Rf_allocVector(VECSXP, 4));
+  SET_VECTOR_ELT(res, 0, xi);
+  SET_VECTOR_ELT(res, 1, ysim);
+  SET_VECTOR_ELT(res, 2, mean);
+  SET_VECTOR_ELT(res, 3, q);
+  UNPROTECT(5);
+  lqg_check(rc, "lqg_simulate");
+  if (st.hmc.violations != 0) Rf_error("lqg_simulate: %lld emitted values outside the bounds", (long long)st.hmc.violations);
+  return res;
 }
 
 /* tmvrnorm.RSM body */

@@ -25,6 +25,9 @@ int Rf_isMatrix(SEXP);
 SEXP Rf_allocMatrix(SEXPTYPE, int, int);
 SEXP Rf_allocVector(SEXPTYPE, R_xlen_t);
 SEXP Rf_ScalarLogical(int);
+SEXP Rf_ScalarInteger(int);
+int Rf_isNull(SEXP);
+extern SEXP R_NilValue;
 SEXP SET_VECTOR_ELT(SEXP, R_xlen_t, SEXP);
 void Rf_error(const char*, ...) __attribute__((noreturn));
 #endif
