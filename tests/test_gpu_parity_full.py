@@ -74,13 +74,18 @@ def test_full_size_statistics_vs_reference_chains(lqg, oracle, cfg):
 # ------------------------------------------------------------------- who carries the 1e-7 at full size
 @pytest.mark.parametrize("cfg", ["cfg4", "cfg5"])
 def test_full_size_transition_against_extended_precision(lqg, oracle, cfg):
-    """K teacher-forced transitions at full size, three ways: GPU (eta frame, FP64), oracle
-    (whitened frame, FP64, the reference's arithmetic) and the oracle in extended precision with the
-    un-whitening x = Ri z + mu also in extended precision.  The eta-frame recursion never forms
-    Ri z, so it does not pay cond(Ri): the GPU must be closer to the extended result than the FP64
-    oracle is, and within 1e-10 of it (north_star's trajectory bound) whenever the discrete events
-    agree; the FP64 oracle's own distance to the extended result is what test_full_size_teacher_forced_parity
-    has to tolerate."""
+    """K teacher-forced transitions at full size against the SAME transitions in extended precision
+    (oracle/tmg_hmc_ext.cpp, un-whitening x = Ri z + mu in extended precision too).
+
+    What it establishes: (1) the FP64 oracle is within 1e-13 of the extended chain — the reference's
+    whitened recursion itself is accurate; (2) the GPU's eta-frame recursion, given the inputs the
+    whitened chain ACTUALLY samples from — centre Mir = M^-1 r and covariance Ri Ri' as tmg's whitening
+    produced them (tmg:R/tmg.R:15-28,51) — is within north_star's 1e-10 of the extended chain;
+    (3) with the CALLER's (mu, Sigma) the distance grows to ~cond(Sigma) eps, and that is the size of
+    |Mir - mu| and |Ri Ri' - Sigma|: tmg's whitening (solve, chol, solve on a Sigma_eta of condition
+    ~1e7 at config 4) moves the target by that much, while the eta-frame kernel takes mu and the columns
+    of Sigma as given.  The 1e-7 of test_full_size_teacher_forced_parity is this difference between the
+    two statements of the target, not kernel rounding."""
     from lineqgpr_b200 import _lib as L
     par, w = _problem(oracle, cfg)
     d = w["initial2"].size
@@ -99,24 +104,39 @@ def test_full_size_transition_against_extended_precision(lqg, oracle, cfg):
         x_ext[k] = xe[0]; nb_ext[k] = ie["bounces"]
     starts_x = starts_z @ w["Ri"].T + w["Mir"][None, :]
     starts_x = np.ascontiguousarray(np.minimum(np.maximum(starts_x, lbv + 1e-13), ubv - 1e-13))
-    out = np.empty((d, K), order="F")
-    hs = L.HmcStats()
-    opts = L.make_opts(n_chains=K, injected=np.ascontiguousarray(dr), n_injected=dr.shape[1], prepass=0)
-    Uf, Sf = L.f64(w["Ri"]), L.f64(par["Sigma"])
-    rc = L.lib().lqg_hmc_box(d, L.ptr(mu), L.ptr(Uf), 1, L.ptr(Sf), L.ptr(lbv), L.ptr(ubv), L.ptr(starts_x), d,
-                             1, 0, opts, L.ptr(out), None, hs)
-    L.check(rc, "lqg_hmc_box")
+    Sigma = np.asarray(par["Sigma"], float)
+    Sigma_c = w["Ri"] @ w["Ri"].T                          # the matrix the whitened chain actually samples from
+    resid = np.abs(Sigma_c - Sigma).max() / np.abs(Sigma).max()
+
+    Mir = np.ascontiguousarray(w["Mir"], dtype=np.float64)
+    shift = np.abs(Mir - mu).max() / np.abs(mu).max()
+
+    def gpu(centre, S):
+        out = np.empty((d, K), order="F")
+        hs = L.HmcStats()
+        opts = L.make_opts(n_chains=K, injected=np.ascontiguousarray(dr), n_injected=dr.shape[1], prepass=0)
+        Uf, Sf = L.f64(w["Ri"]), L.f64(S)
+        rc = L.lib().lqg_hmc_box(d, L.ptr(centre), L.ptr(Uf), 1, L.ptr(Sf), L.ptr(lbv), L.ptr(ubv), L.ptr(starts_x), d,
+                                 1, 0, opts, L.ptr(out), None, hs)
+        L.check(rc, "lqg_hmc_box")
+        assert hs.violations == 0
+        return out.T, hs.bounces
+
     same = nb == nb_ext                                   # discrete events of FP64 and extended chains agree
-    assert same.sum() >= K - 1 and hs.bounces == nb.sum()
+    assert same.sum() >= K - 1
     scale = np.abs(x_ext).max()
-    e_gpu = np.abs(out.T - x_ext).max(axis=1) / scale
     e_dbl = np.abs(x_dbl - x_ext).max(axis=1) / scale
-    print(f"{cfg}: max rel. distance to the extended-precision transition: GPU {e_gpu[same].max():.2e}, FP64 oracle {e_dbl[same].max():.2e}")
-    # the start itself is only known through Ri z0 in FP64 (clamped into the box): that rounding is common
-    # to the GPU input, not to the extended chain, and bounds what the comparison can resolve
-    e_start = np.abs(starts_x - (starts_z @ w["Ri"].T + w["Mir"][None, :])).max() / scale
-    assert e_gpu[same].max() < max(1e-10, 50 * e_dbl[same].max()), (e_gpu, e_dbl, e_start)
-    assert e_dbl[same].max() < 1e-7
+    x_c, b_c = gpu(Mir, Sigma_c)
+    x_o, b_o = gpu(mu, Sigma)
+    e_c = np.abs(x_c - x_ext).max(axis=1) / scale
+    e_o = np.abs(x_o - x_ext).max(axis=1) / scale
+    print(f"{cfg}: |Ri Ri' - Sigma|/|Sigma| = {resid:.2e}, |Mir - mu|/|mu| = {shift:.2e}; distance to the extended-precision "
+          f"transition: FP64 oracle {e_dbl[same].max():.2e}, GPU with (Mir, Ri Ri') {e_c[same].max():.2e}, "
+          f"GPU with the caller's (mu, Sigma) {e_o[same].max():.2e}")
+    assert b_c == nb.sum() and b_o == nb.sum()
+    assert e_dbl[same].max() < 1e-13                      # (1)
+    assert e_c[same].max() < 1e-10                        # (2) north_star's bound
+    assert e_o[same].max() < 1e-7 and e_o[same].max() < 1e3 * max(resid, shift, 1e-13)   # (3) bounded by the whitening residuals
 
 
 # --------------------------------------------------------------- general-F kernel, lock-step mode, full size
@@ -131,7 +151,7 @@ def test_canonical_mode2_full_size_against_oracle(lqg, oracle):
     base = np.vstack([w["initial2"][None, :], z])          # 8 distinct reference states
     starts = base[np.arange(K) % base.shape[0]]
     rng = np.random.default_rng(21)
-    dr = rng.standard_normal((K, 12 * d))
+    dr = rng.standard_normal((K, 80 * d))                  # restarts are frequent from the clamped-MAP start
     n_chk = 8
     want = np.zeros((n_chk, d)); nb = np.zeros(n_chk, int)
     for k in range(n_chk):
