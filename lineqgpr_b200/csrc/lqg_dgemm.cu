@@ -11,6 +11,10 @@
 // warp tile 32 x 32 = 4 x 4 DMMA fragments; operands staged through padded shared memory
 // (conflict-free fragment reads), register-prefetch double buffering, one barrier per k-tile.
 // For an upper-triangular A (tmg's Ri) the all-zero k-tiles below the diagonal are skipped.
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "lqg_common.cuh"
 #include "lqg_kernels.h"
 
@@ -34,14 +38,23 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 __global__ void __launch_bounds__(NT)
 dgemm_dmma_kernel(int m, int n, int k, const double* __restrict__ A, int64_t lda,
                   const double* __restrict__ B, int64_t ldb, double* __restrict__ C, int64_t ldc,
-                  double* __restrict__ row_sum, int a_upper, int b_blk_w, int64_t b_blk_pitch) {
+                  double* __restrict__ row_sum, int a_upper, int b_blk_w, int64_t b_blk_pitch, int tail_cb) {
   extern __shared__ __align__(16) double dg_smem[];
   double (*As)[BK * A_LD] = reinterpret_cast<double (*)[BK * A_LD]>(dg_smem);
   double (*Bs)[BN * B_LD] = reinterpret_cast<double (*)[BN * B_LD]>(dg_smem + 2 * BK * A_LD);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp & 3, wn = warp >> 2;
-  const int bm = blockIdx.x, bn = blockIdx.y;
+  // Tile order (1-D grid): row block fastest, so that the CTAs running side by side share one B tile
+  // and differ in length (their prologues and epilogues do not line up).  With an upper-triangular A a
+  // top row block has 25 x the k-tiles of a bottom one: if the last column blocks were issued in that
+  // order too, a few long tiles would be left running alone at the end of the launch (~9 % of it).
+  // The last `tail_cb` column blocks are therefore issued row block by row block, longest first.
+  const int MB = (m + BM - 1) / BM, NB = (n + BN - 1) / BN;
+  const int NBh = NB - tail_cb;
+  int bm, bn;
+  if ((int)blockIdx.x < MB * NBh) { bn = blockIdx.x / MB; bm = blockIdx.x - bn * MB; }
+  else { const int r = blockIdx.x - MB * NBh; bm = r / tail_cb; bn = NBh + (r - bm * tail_cb); }
   const int row0 = bm * BM, col0 = bn * BN;
 
   // A tile loader: thread -> (row = tid % 128, k in {kh*8 .. kh*8+7})
@@ -166,26 +179,29 @@ cudaError_t launch_dgemm(int m, int n, int k, const double* A, int64_t lda, cons
                          int64_t ldb, double* C, int64_t ldc, double* row_sum, int a_upper,
                          cudaStream_t st, int b_blk_w, int64_t b_blk_pitch) {
   if (m <= 0 || n <= 0) return cudaSuccess;
-  // grid.y is limited to 65535 column tiles: slice very wide problems
-  int max_cols = 65535 * BN;
-  if (b_blk_w > 0) {                                  // column slices start on a block boundary
-    if (b_blk_w > max_cols) return cudaErrorInvalidValue;
-    max_cols -= max_cols % b_blk_w;
-  }
   const size_t smem = (size_t)(2 * BK * A_LD + 2 * BN * B_LD) * sizeof(double);
   cudaError_t e0 = cudaFuncSetAttribute(dgemm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e0 != cudaSuccess) return e0;
-  for (int c0 = 0; c0 < n; c0 += max_cols) {
-    const int nc = n - c0 < max_cols ? n - c0 : max_cols;
-    dim3 grid((m + BM - 1) / BM, (nc + BN - 1) / BN);
-    const double* Bs = b_blk_w > 0 ? B + (size_t)(c0 / b_blk_w) * b_blk_pitch : B + (size_t)c0 * ldb;
-    dgemm_dmma_kernel<<<grid, NT, smem, st>>>(m, nc, k, A, lda, Bs, ldb,
-                                            C ? C + (size_t)c0 * ldc : nullptr, ldc, row_sum, a_upper,
-                                            b_blk_w, b_blk_pitch);
-    ++launch_counter();
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+  const long long tiles = (long long)((m + BM - 1) / BM) * ((n + BN - 1) / BN);
+  if (tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
+  int tail_cb = 0;
+  if (a_upper) {                       // four waves of resident CTAs' worth of column blocks, longest tiles first
+    static const int slots = [] {
+      int dev = 0, sms = 148, per_sm = 2;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dgemm_dmma_kernel, NT, (size_t)(2 * BK * A_LD + 2 * BN * B_LD) * sizeof(double));
+      return sms * (per_sm > 0 ? per_sm : 1);
+    }();
+    static const char* env_tail = getenv("LQG_GEMM_TAIL");           // tuning aid: waves of column blocks reordered (default 4)
+    const double waves = env_tail ? atof(env_tail) : 4.0;
+    const int MBc = (m + BM - 1) / BM, NBc = (n + BN - 1) / BN;
+    tail_cb = std::min(NBc, (int)(waves * slots / MBc));
   }
+  dgemm_dmma_kernel<<<(unsigned)tiles, NT, smem, st>>>(m, n, k, A, lda, B, ldb, C, ldc, row_sum, a_upper, b_blk_w, b_blk_pitch, tail_cb);
+  ++launch_counter();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
   return cudaSuccess;
 }
 
