@@ -239,7 +239,11 @@ def cpu_small_sample(P, a, budget_s=8.0):
     else:
         from oracle import expt_oracle as E
         mu = P["mu"]
-        su = E.setup(P["lb"] - mu, P["ub"] - mu, P["Sigma"])
+        try:
+            su = E.setup(P["lb"] - mu, P["ub"] - mu, P["Sigma"])
+        except ValueError:                     # the checker's own root finder gives up at d = 100: take the product's tilt
+            from lineqgpr_b200 import expt     # (host numpy set-up, excluded from the timing on both sides)
+            su = expt.setup(P["lb"] - mu, P["ub"] - mu, P["Sigma"])
         got, seed = 0, 0
         while time.perf_counter() - t0 < budget_s and got < 2000:
             x, _, _ = E.mvrandn(P["lb"] - mu, P["ub"] - mu, P["Sigma"], 50, seed, su=su)
