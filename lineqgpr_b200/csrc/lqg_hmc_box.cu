@@ -195,7 +195,10 @@ static __device__ __noinline__ void settle_times(const BoxShared sh, Deferred* d
 
 // THR: where the filter thresholds live: 0 = registers, 1 = shared memory, 2 = recomputed from the
 //      bound offsets.   GS: bound offsets (glo, ghi) in shared memory (else read through L1).
-template <int G, int CPT, int THR, bool GS, int MINB, bool PACK = false>
+//  RS: the thread also keeps its coordinates of (x_a, x_b) in registers (the filter and the update then
+//      work from registers and only mirror the result to shared memory); RS = false trades those 4 CPT
+//      registers for shared-memory traffic so that one more CTA fits on the SM.
+template <int G, int CPT, int THR, bool GS, int MINB, bool PACK = false, bool RS = true>
 __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p) {
   constexpr int T = 32 * G;
   constexpr int NS = CPT * T;                      // padded dimension: one slot per (thread, k)
@@ -254,13 +257,15 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
     if (aidx >= p.n_active) break;
     const int chain = p.active ? p.active[aidx] : aidx;
 
-    double xa[CPT], xb[CPT];
+    double xa[RS ? CPT : 1], xb[RS ? CPT : 1];
+    auto XA = [&](int k) -> double { return RS ? xa[RS ? k : 0] : xa_s[tid + k * T]; };
+    auto XB = [&](int k) -> double { return RS ? xb[RS ? k : 0] : xb_s[tid + k * T]; };
 #pragma unroll
     for (int k = 0; k < CPT; ++k) {
       const int i = tid + k * T;
-      xb[k] = i < d ? p.state[(size_t)chain * d + i] : 0.0;
-      xa[k] = 0.0;
-      xb_s[i] = xb[k];
+      const double b0 = i < d ? p.state[(size_t)chain * d + i] : 0.0;
+      if (RS) { xb[RS ? k : 0] = b0; xa[RS ? k : 0] = 0.0; }
+      xb_s[i] = b0;
     }
     int s = p.s_done[chain];                       // transitions completed so far
     int64_t draw = p.pos[chain];                   // momenta consumed so far
@@ -279,8 +284,9 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
 #pragma unroll
         for (int k = 0; k < CPT; ++k) {
           const int i = tid + k * T;
-          xa[k] = i < d ? __ldcs(src + i) : 0.0;                 // streamed once: keep Sigma in L2 instead
-          xa_s[i] = xa[k];
+          const double a0 = i < d ? __ldcs(src + i) : 0.0;       // streamed once: keep Sigma in L2 instead
+          if (RS) xa[RS ? k : 0] = a0;
+          xa_s[i] = a0;
         }
         // the next momentum of this chain is on its way to L2 while this attempt runs (one request per line)
         if (att + 1 < p.attempts && (tid & 15) == 0) {
@@ -296,7 +302,7 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
           break;
         }
 #pragma unroll
-        for (int k = 0; k < CPT; ++k) xa[k] = xa_s[tid + k * T];
+        for (int k = 0; k < CPT; ++k) if (RS) xa[RS ? k : 0] = xa_s[tid + k * T];
       }
       ++draw;
       double tt = kHalfPi;                                       // :57; exact up to the hit times still owed (n_dl)
@@ -369,7 +375,7 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
 #pragma unroll
           for (int k = 0; k < CPT; ++k) {
             const int i = tid + k * T;
-            const double a_ = xa[k], b_ = xb[k];
+            const double a_ = XA(k), b_ = XB(k);
             const double y = fma(a_, S, b_ * C);
             const double dy = fma(a_, C, -b_ * S);
             const double u2 = fma(a_, a_, b_ * b_);
@@ -536,11 +542,12 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
         const double alpha2 = 2.0 * (vj / sjj);                  // 2*alpha, alpha = f.v / f.f
 #pragma unroll
         for (int k = 0; k < CPT; ++k) {
-          const double a_ = xa[k], b_ = xb[k];
-          xb[k] = fma(st, a_, ct * b_);                          // new_b  (:91)
+          const double a_ = XA(k), b_ = XB(k);
+          const double nb = fma(st, a_, ct * b_);                // new_b  (:91)
           const double v = fma(ct, a_, -st * b_);                // hit_vel (:92)
-          xa[k] = fma(-alpha2, sc[k], v);                        // reflected velocity (:109)
-          xa_s[tid + k * T] = xa[k]; xb_s[tid + k * T] = xb[k];  // the copy the next search evaluates from
+          const double na = fma(-alpha2, sc[k], v);              // reflected velocity (:109)
+          if (RS) { xa[RS ? k : 0] = na; xb[RS ? k : 0] = nb; }
+          xa_s[tid + k * T] = na; xb_s[tid + k * T] = nb;        // the copy the next search evaluates from
         }
         velsign = side * __dsub_rn(vj, __dmul_rn(alpha2, sjj));  // a.f (:110)
         if (velsign < 0.0) break;                                // :112
@@ -563,7 +570,7 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
       for (int k = 0; k < CPT; ++k) {
         const int i = tid + k * T;
         if (i < d) {
-          const double bb = fma(xa[k], S, xb[k] * C);
+          const double bb = fma(XA(k), S, XB(k) * C);
           const double e = __ldg(p.mu + i) + bb;
           const double gl = GS ? glo_s[i] : __ldg(p.glo + i), gh = GS ? ghi_s[i] : __ldg(p.ghi + i);
           fine = fine && (bb + gl >= 0.0) && (gh - bb >= 0.0) && (e >= __ldg(p.lb + i)) && (e <= __ldg(p.ub + i));
@@ -577,8 +584,9 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
       }
 #pragma unroll
       for (int k = 0; k < CPT; ++k) {
-        xb[k] = fma(xa[k], S, xb[k] * C);                        // lastSample = bb (:123)
-        xb_s[tid + k * T] = xb[k];
+        const double nb = fma(XA(k), S, XB(k) * C);              // lastSample = bb (:123)
+        if (RS) xb[RS ? k : 0] = nb;
+        xb_s[tid + k * T] = nb;
       }
       rcount = 0;
       ++n_trans;
@@ -587,7 +595,7 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
 #pragma unroll
         for (int k = 0; k < CPT; ++k) {
           const int i = tid + k * T;
-          if (i < d) __stcs(dst + i, __ldg(p.mu + i) + xb[k]);   // tmg:R/tmg.R:106; written once, read by later stages
+          if (i < d) __stcs(dst + i, __ldg(p.mu + i) + XB(k));   // tmg:R/tmg.R:106; written once, read by later stages
         }
       }
       ++s;
@@ -601,7 +609,7 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
 #pragma unroll
     for (int k = 0; k < CPT; ++k) {
       const int i = tid + k * T;
-      if (i < d) p.state[(size_t)chain * d + i] = xb[k];
+      if (i < d) p.state[(size_t)chain * d + i] = XB(k);
     }
     if (lane == 0) atomicAdd(p.stats + 5, (unsigned long long)n_exact);
     if (tid == 0) {
@@ -673,11 +681,11 @@ __global__ void box_violation_kernel(int d, size_t n_cols, const double* out, co
 }
 
 // grid == -1: query only, *slots_out = resident CTAs on the device
-template <int G, int CPT, int THR, bool GS, int MINB, bool PACK = false>
+template <int G, int CPT, int THR, bool GS, int MINB, bool PACK = false, bool RS = true>
 static cudaError_t launch_box_t(const BoxParams& p, int grid, cudaStream_t st, int* slots_out = nullptr) {
   constexpr size_t NS = (size_t)CPT * 32 * G;
   const size_t smem = NS * (2 + (GS ? 2 : 0) + (THR == 1 ? 2 : 0)) * sizeof(double);
-  auto kern = hmc_box_kernel<G, CPT, THR, GS, MINB, PACK>;
+  auto kern = hmc_box_kernel<G, CPT, THR, GS, MINB, PACK, RS>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int per_sm = 0, dev = 0, sms = 0;
@@ -737,15 +745,22 @@ static cudaError_t dispatch_box(const BoxParams& p, int grid, cudaStream_t st, i
   // survivors per warp, 8 partly filled evaluation passes become ~4 full ones ("n" = per-warp evaluation).
   const bool pack = !(v && v[0] == 'n');
   if (d <= 512)  return pack ? launch_box_t<4, 4, 0, true, 4, true>(p, grid, st, slots) : launch_box_t<4, 4, 0, true, 4>(p, grid, st, slots);
-  if (d <= 1024) return pack ? launch_box_t<4, 8, 1, true, 4, true>(p, grid, st, slots) : launch_box_t<4, 8, 1, true, 4>(p, grid, st, slots);
+  // d in (512, 2048]: the state lives in shared memory only (RS = false).  The registers this frees
+  // remove most of the spills of the search loop: cfg4 36.0 -> 33.7 ms per step.  "r" = register state.
+  const bool rs = v && v[0] == 'r';
+  if (d <= 1024) {
+    if (!pack) return launch_box_t<4, 8, 1, true, 4>(p, grid, st, slots);
+    return rs ? launch_box_t<4, 8, 1, true, 4, true, true>(p, grid, st, slots) : launch_box_t<4, 8, 1, true, 4, true, false>(p, grid, st, slots);
+  }
   if (d <= 2048) {
-    // Fewer, longer chains do less burn-in work for the same number of samples: 2 CTAs/SM
-    // (128 registers) is the default.  "3" = 3 CTAs/SM (80 registers, thresholds recomputed from
-    // the bound offsets instead of a second pair of shared-memory arrays).
-    if (v && v[0] == '3') return launch_box_t<8, 8, 2, true, 3, true>(p, grid, st, slots);
-    if (v && v[0] == 'w') return launch_box_t<16, 4, 1, true, 2, true>(p, grid, st, slots);     // 16 warps x 4 coordinates, 2 CTAs/SM (64 registers)
-    if (v && v[0] == 'x') return launch_box_t<16, 4, 1, true, 1, true>(p, grid, st, slots);     // 16 warps x 4 coordinates, 1 CTA/SM
-    return pack ? launch_box_t<8, 8, 1, true, 2, true>(p, grid, st, slots) : launch_box_t<8, 8, 1, true, 2>(p, grid, st, slots);
+    // Fewer, longer chains do less burn-in work for the same number of samples: 2 CTAs/SM (128
+    // registers) is the default.  Measured alternatives: "3" = 3 CTAs/SM (80 registers, thresholds
+    // recomputed from the bound offsets: 38.4 ms for 444 chains, same work rate), "4" = 4 CTAs/SM
+    // (64 registers, bound offsets through L1: 49.3 ms).
+    if (v && v[0] == '3') return launch_box_t<8, 8, 2, true, 3, true, false>(p, grid, st, slots);
+    if (v && v[0] == '4') return launch_box_t<8, 8, 2, false, 4, true, false>(p, grid, st, slots);
+    if (!pack) return launch_box_t<8, 8, 1, true, 2>(p, grid, st, slots);
+    return rs ? launch_box_t<8, 8, 1, true, 2, true, true>(p, grid, st, slots) : launch_box_t<8, 8, 1, true, 2, true, false>(p, grid, st, slots);
   }
   if (d <= 4096) return pack ? launch_box_t<8, 16, 1, true, 1, true>(p, grid, st, slots) : launch_box_t<8, 16, 1, true, 1>(p, grid, st, slots);
   if (d <= 8192) return pack ? launch_box_t<16, 16, 2, false, 1, true>(p, grid, st, slots) : launch_box_t<16, 16, 2, false, 1>(p, grid, st, slots);
