@@ -11,6 +11,18 @@
 // warp tile 32 x 32 = 4 x 4 DMMA fragments; operands staged through padded shared memory
 // (conflict-free fragment reads), register-prefetch double buffering, one barrier per k-tile.
 // For an upper-triangular A (tmg's Ri) the all-zero k-tiles below the diagonal are skipped.
+//
+// Two kernels share the tile shape and the epilogue:
+//   * dgemm_ring_kernel (default): operands move global -> shared memory with bulk-async copies
+//     (cp.async.bulk, the TMA engine; SASS UBLKCP) into a 4-stage ring guarded by full/empty
+//     mbarriers.  There is no CTA-wide barrier in the k loop and no operand passes through
+//     registers: every warp issues its share of the copies two k-tiles ahead (2 columns of A,
+//     8 columns of B) and otherwise only reads fragments and issues DMMA.  Inside the diagonal
+//     block of an upper-triangular A the 8-row fragment groups that lie entirely below the
+//     diagonal are skipped as well.  Needs 16-byte aligned operand columns (even leading
+//     dimensions); partial k-tiles and odd row counts are staged by the threads themselves.
+//   * dgemm_dmma_kernel: LDG -> registers -> STS double buffering with one barrier per k-tile;
+//     kept for operands that are not 16-byte aligned (LQG_GEMM_RING=0 forces it).
 #include <stdlib.h>
 
 #include <algorithm>
@@ -154,6 +166,165 @@ dgemm_dmma_kernel(int m, int n, int k, const double* __restrict__ A, int64_t lda
   }
 }
 
+
+// ---- ring kernel -------------------------------------------------------------------------
+constexpr int ST = 4;                         // ring stages
+constexpr int PF = 2;                         // k-tiles in flight ahead of the one being multiplied
+constexpr int A_STAGE = BK * A_LD;            // doubles per stage: A tile, column kk at kk * A_LD
+constexpr int B_STAGE = BN * B_LD;            //                    B tile, column n at n * B_LD
+constexpr int STAGE = A_STAGE + B_STAGE;
+constexpr int NWARP = NT / 32;
+static_assert(BK == 2 * NWARP && BN == 8 * NWARP, "every warp stages 2 columns of A and 8 columns of B");
+static_assert((A_LD * 8) % 16 == 0 && (B_LD * 8) % 16 == 0 && (A_STAGE * 8) % 16 == 0 && (STAGE * 8) % 16 == 0,
+              "bulk copies need 16-byte aligned shared-memory destinations");
+
+__global__ void __launch_bounds__(NT, 2)
+dgemm_ring_kernel(int m, int n, int k, const double* __restrict__ A, int64_t lda,
+                  const double* __restrict__ B, int64_t ldb, double* __restrict__ C, int64_t ldc,
+                  double* __restrict__ row_sum, int a_upper, int b_blk_w, int64_t b_blk_pitch, int tail_cb) {
+  extern __shared__ __align__(128) double dg_ring[];
+  __shared__ __align__(8) uint64_t full_bar[ST], empty_bar[ST];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp & 3, wn = warp >> 2;
+  const int MB = (m + BM - 1) / BM, NB = (n + BN - 1) / BN;     // tile order: see dgemm_dmma_kernel
+  const int NBh = NB - tail_cb;
+  int bm, bn;
+  if ((int)blockIdx.x < MB * NBh) { bn = blockIdx.x / MB; bm = blockIdx.x - bn * MB; }
+  else { const int r = blockIdx.x - MB * NBh; bm = r / tail_cb; bn = NBh + (r - bm * tail_cb); }
+  const int row0 = bm * BM, col0 = bn * BN;
+  const int rows_valid = min(BM, m - row0);
+  const int kt_end = (k + BK - 1) / BK;
+  const int kt_begin = a_upper ? min(row0 / BK, kt_end) : 0;
+  const int nkt = kt_end - kt_begin;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < ST; ++s) { mbar_init(&full_bar[s], NWARP); mbar_init(&empty_bar[s], NWARP); }
+  }
+  __syncthreads();
+
+  auto b_col = [&](int gc) -> const double* {                   // global column gc of B (see b_blk_w)
+    return b_blk_w > 0 ? B + (size_t)(gc / b_blk_w) * b_blk_pitch + (size_t)(gc % b_blk_w) * ldb
+                       : B + (size_t)gc * ldb;
+  };
+  // the copies this lane issues for a full k-tile: lanes 0,1 one column of A each, lanes 2..9 one column of B each
+  const int my_b = col0 + 8 * warp + (lane - 2);
+  const double* my_src = lane < 2 ? A + (size_t)(2 * warp + lane) * lda + row0
+                       : (lane < 10 && my_b < n) ? b_col(my_b) : nullptr;
+  const int my_dst = lane < 2 ? (2 * warp + lane) * A_LD : A_STAGE + (8 * warp + (lane - 2)) * B_LD;
+  const uint32_t my_bytes = lane < 2 ? (uint32_t)rows_valid * 8u : (uint32_t)BK * 8u;
+  const int64_t my_kstride = lane < 2 ? lda : 1;                // elements per k step in this lane's source
+  const int b_valid = max(0, min(8, n - col0 - 8 * warp));      // valid columns among the warp's 8
+  const uint32_t warp_bytes = 2u * (uint32_t)rows_valid * 8u + (uint32_t)b_valid * BK * 8u;
+  const bool rows_even = (rows_valid & 1) == 0;
+
+  // stage k-tile `it` (counted from kt_begin) into ring slot it % ST
+  auto issue = [&](int it) {
+    const int s = it % ST;
+    const int k0 = (kt_begin + it) * BK;
+    double* stage = dg_ring + (size_t)s * STAGE;
+    if (it >= ST) mbar_wait(&empty_bar[s], (uint32_t)((it / ST) - 1) & 1u);   // every warp is done with the slot's previous tile
+    if (rows_even && k0 + BK <= k) {
+      if (lane == 0) mbar_expect_tx(&full_bar[s], warp_bytes);
+      __syncwarp();
+      if (my_src) bulk_g2s(stage + my_dst, my_src + (size_t)k0 * my_kstride, my_bytes, &full_bar[s]);
+    } else {
+      // partial k-tile (or an odd number of rows): plain loads, zero fill
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int kk = k0 + 2 * warp + c;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int r = lane + 32 * q;
+          stage[(2 * warp + c) * A_LD + r] = (row0 + r < m && kk < k) ? __ldg(A + (size_t)kk * lda + row0 + r) : 0.0;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int nn = 8 * warp + (lane >> 4) + 2 * q, kk = k0 + (lane & 15);
+        const int gc = col0 + nn;
+        stage[A_STAGE + nn * B_LD + (lane & 15)] = (gc < n && kk < k) ? __ldg(b_col(gc) + kk) : 0.0;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[s]);
+    }
+  };
+
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  for (int it = 0; it < PF && it < nkt; ++it) issue(it);
+
+  const int fr = lane >> 2, fk = lane & 3;
+  const int wrow = row0 + wm * 32;                                // first row of the warp tile
+  for (int it = 0; it < nkt; ++it) {
+    if (it + PF < nkt) issue(it + PF);
+    const int s = it % ST;
+    const int k0 = (kt_begin + it) * BK;
+    mbar_wait(&full_bar[s], (uint32_t)(it / ST) & 1u);
+    const double* as = dg_ring + (size_t)s * STAGE + wm * 32 + fr;
+    const double* bs = dg_ring + (size_t)s * STAGE + A_STAGE + (wn * 32 + fr) * B_LD + fk;
+    if (a_upper && k0 < wrow + 32) {
+      // diagonal block of an upper-triangular A: A[i, kk] = 0 for i > kk, so a fragment group of 8 rows
+      // starting at r contributes nothing to the 4 columns kk..kk+3 when r > kk + 3
+#pragma unroll
+      for (int k4 = 0; k4 < BK / 4; ++k4) {
+        const int kmax = k0 + k4 * 4 + 3;
+        if (wrow > kmax) continue;
+        double bf[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bf[j] = bs[j * 8 * B_LD + k4 * 4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (wrow + i * 8 > kmax) continue;
+          const double af = as[(k4 * 4 + fk) * A_LD + i * 8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af, bf[j]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int k4 = 0; k4 < BK / 4; ++k4) {
+        double af[4], bf[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) af[i] = as[(k4 * 4 + fk) * A_LD + i * 8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bf[j] = bs[j * 8 * B_LD + k4 * 4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+      }
+    }
+    __syncwarp();                                                 // every lane has read its fragments
+    if (lane == 0) mbar_arrive(&empty_bar[s]);
+  }
+
+  // ---- epilogue: C store and optional row sums (band mean numerator) ----
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = row0 + wm * 32 + i * 8 + fr;
+    double rs = 0.0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int cc = col0 + wn * 32 + j * 8 + 2 * fk;
+      if (r < m) {
+        if (cc < n)     { if (C) C[(size_t)cc * ldc + r] = acc[i][j][0];       rs += acc[i][j][0]; }
+        if (cc + 1 < n) { if (C) C[(size_t)(cc + 1) * ldc + r] = acc[i][j][1]; rs += acc[i][j][1]; }
+      }
+    }
+    if (row_sum) {
+      rs += __shfl_xor_sync(0xffffffffu, rs, 1);
+      rs += __shfl_xor_sync(0xffffffffu, rs, 2);
+      if (fk == 0 && r < m) atomicAdd(row_sum + r, rs);
+    }
+  }
+}
+
 // A[kk, col] = N(0,1) draw of (chain = active[col / attempts], draw index = pos[chain] + col % attempts,
 // coordinate kk) — the same Philox addressing the chain kernels use, so pool and in-kernel
 // draws agree.
@@ -179,30 +350,35 @@ cudaError_t launch_dgemm(int m, int n, int k, const double* A, int64_t lda, cons
                          int64_t ldb, double* C, int64_t ldc, double* row_sum, int a_upper,
                          cudaStream_t st, int b_blk_w, int64_t b_blk_pitch) {
   if (m <= 0 || n <= 0) return cudaSuccess;
-  const size_t smem = (size_t)(2 * BK * A_LD + 2 * BN * B_LD) * sizeof(double);
-  cudaError_t e0 = cudaFuncSetAttribute(dgemm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // the ring kernel's bulk copies need 16-byte aligned operand columns
+  static const char* env_ring = getenv("LQG_GEMM_RING");             // A/B aid: 0 = register-staged kernel
+  const bool aligned = ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && lda % 2 == 0 && ldb % 2 == 0 &&
+                       (b_blk_w <= 0 || b_blk_pitch % 2 == 0);
+  const bool ring = aligned && !(env_ring && env_ring[0] == '0');
+  const size_t smem = ring ? (size_t)ST * STAGE * sizeof(double) : (size_t)(2 * BK * A_LD + 2 * BN * B_LD) * sizeof(double);
+  auto kern = ring ? dgemm_ring_kernel : dgemm_dmma_kernel;
+  cudaError_t e0 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e0 != cudaSuccess) return e0;
   const long long tiles = (long long)((m + BM - 1) / BM) * ((n + BN - 1) / BN);
   if (tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
   int tail_cb = 0;
   if (a_upper) {                       // four waves of resident CTAs' worth of column blocks, longest tiles first
-    static const int slots = [] {
+    static int slots_of[2] = {0, 0};
+    if (slots_of[ring] == 0) {
       int dev = 0, sms = 148, per_sm = 2;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dgemm_dmma_kernel, NT, (size_t)(2 * BK * A_LD + 2 * BN * B_LD) * sizeof(double));
-      return sms * (per_sm > 0 ? per_sm : 1);
-    }();
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem);
+      slots_of[ring] = sms * (per_sm > 0 ? per_sm : 1);
+    }
     static const char* env_tail = getenv("LQG_GEMM_TAIL");           // tuning aid: waves of column blocks reordered (default 4)
     const double waves = env_tail ? atof(env_tail) : 4.0;
     const int MBc = (m + BM - 1) / BM, NBc = (n + BN - 1) / BN;
-    tail_cb = std::min(NBc, (int)(waves * slots / MBc));
+    tail_cb = std::min(NBc, (int)(waves * slots_of[ring] / MBc));
   }
-  dgemm_dmma_kernel<<<(unsigned)tiles, NT, smem, st>>>(m, n, k, A, lda, B, ldb, C, ldc, row_sum, a_upper, b_blk_w, b_blk_pitch, tail_cb);
+  kern<<<(unsigned)tiles, NT, smem, st>>>(m, n, k, A, lda, B, ldb, C, ldc, row_sum, a_upper, b_blk_w, b_blk_pitch, tail_cb);
   ++launch_counter();
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
-  return cudaSuccess;
+  return cudaGetLastError();
 }
 
 cudaError_t launch_fill_normals(int d, size_t n_cols, double* A, const NormalGen& g, cudaStream_t st) {

@@ -66,6 +66,28 @@ def test_dgemm_matches_numpy(lqg, shape):
     assert np.abs(rs - ref.sum(1)).max() < tol * n
 
 
+@pytest.mark.parametrize("shape", [(130, 67, 20, 130, 20), (129, 70, 40, 132, 44), (256, 130, 48, 256, 48),
+                                   (1000, 258, 1000, 1000, 1000), (333, 64, 16, 400, 18), (96, 8, 64, 96, 65)])
+def test_dgemm_leading_dimensions_and_ring_edges(lqg, shape):
+    """lqg_dgemm on sub-matrices (lda > m, ldb > k): even leading dimensions take the bulk-copy ring kernel
+    (full tiles by TMA, partial k-tiles / odd row counts staged by the threads), odd ones the
+    register-staged kernel; both must agree with numpy."""
+    from lineqgpr_b200 import _lib as L
+    m, n, k, lda, ldb = shape
+    rng = np.random.default_rng(m + 7 * n + k)
+    Abig = np.asfortranarray(rng.standard_normal((lda, k))); Bbig = np.asfortranarray(rng.standard_normal((ldb, n)))
+    Abig[m:, :] = np.nan; Bbig[k:, :] = np.nan            # rows outside the operands must never be used
+    ldc = m + 3
+    C = np.full((ldc, n), -7.0, order="F"); rs = np.zeros(m)
+    rc = L.lib().lqg_dgemm(m, n, k, L.ptr(Abig), lda, L.ptr(Bbig), ldb, L.ptr(C), ldc, L.ptr(rs),
+                           L.make_opts(mem=L.MEM_HOST), None)
+    L.check(rc, "lqg_dgemm")
+    ref = Abig[:m] @ Bbig[:k]
+    tol = 1e-13 * k * max(1.0, np.abs(ref).max())
+    assert np.abs(C[:m] - ref).max() < tol
+    assert np.abs(rs - ref.sum(1)).max() < tol * n
+
+
 def test_simulate_tail_matches_oracle(lqg, oracle):
     """xi.sim = qr.solve(Lambda, eta); ysim = Phi.test %*% xi.sim  (R/lineqGP.R:639-640)."""
     from lineqgpr_b200 import workloads as W
