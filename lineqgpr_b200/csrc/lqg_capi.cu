@@ -369,16 +369,20 @@ static int hmc_box_core(const BoxRun& r, BoxResult& res) {
       LQG_CUDA_TRY(cudaHostGetDevicePointer((void**)&d_flags, hp, 0));
       h_flags = (volatile int*)hp;
     }
-    // every round consumes `attempts` momenta per active chain, so this terminates after at most
-    // (total + restarts) / attempts rounds; max_restarts bounds the restarts of every transition
+    // every round hands each active chain at least 4 momenta, so this terminates after at most
+    // (total + restarts) / 4 rounds; max_restarts bounds the restarts of every transition
+    DevBuf b_off;
+    LQG_CUDA_TRY(b_off.alloc((size_t)(n_chains + 1) * sizeof(int)));
+    size_t round_cols = (size_t)n_chains * attempts;            // first round: `attempts` columns for every chain
     while (n_active > 0) {
-      NormalGen gen{r.seed, r.chain_offset, attempts, first ? nullptr : act[cur], p.pos};
+      NormalGen gen{r.seed, r.chain_offset, attempts, first ? nullptr : act[cur], p.pos, first ? nullptr : b_off.as<int>(), n_active};
       t_pre.start();
-      LQG_CUDA_TRY(launch_fill_normals(d, (size_t)n_active * attempts, b_a.as<double>(), gen, st));
-      LQG_CUDA_TRY(launch_dgemm(d, n_active * attempts, d, r.U, d, b_a.as<double>(), d,
+      LQG_CUDA_TRY(launch_fill_normals(d, round_cols, b_a.as<double>(), gen, st));
+      LQG_CUDA_TRY(launch_dgemm(d, (int)round_cols, d, r.U, d, b_a.as<double>(), d,
                                 b_pool.as<double>(), d, nullptr, r.u_upper, st));
       t_pre.stop();
       p.active = first ? nullptr : act[cur]; p.n_active = n_active; p.attempts = attempts;
+      p.col_off = first ? nullptr : b_off.as<int>();
       p.pool = b_pool.as<double>();
       // queue head = 0, n_active = 0, min s_done = 0x7f7f7f7f  (memsets: no copy-engine traffic)
       LQG_CUDA_TRY(cudaMemsetAsync(p.next_chain, 0, 3 * sizeof(int), st));
@@ -386,23 +390,20 @@ static int hmc_box_core(const BoxRun& r, BoxResult& res) {
       t_chain.start();
       LQG_CUDA_TRY(launch_hmc_box(p, 0, st));
       t_chain.stop();
-      LQG_CUDA_TRY(launch_box_compact(n_chains, total, p.s_done, p.chain_status, act[cur ^ 1], d_nactive, d_flags, st));
+      // unfinished chains -> next round's work list, and its plan: pool columns per chain (see box_plan_kernel)
+      LQG_CUDA_TRY(launch_box_compact(n_chains, total, p.s_done, p.chain_status, act[cur ^ 1], d_nactive, d_flags,
+                                      max_attempts, r.short_tail ? 1 : 0, b_off.as<int>(), st));
       if (ev_round) LQG_CUDA_TRY(cudaEventRecord(ev_round, st));
       LQG_CUDA_TRY(cudaStreamSynchronize(st));
       n_active = h_flags[0];
       const int s_min = std::min((int)h_flags[1], total);
+      round_cols = (size_t)h_flags[2];
+      attempts = h_flags[3];
       if (r.on_round && s_min - burn_in > handed) {
         const int upto = s_min - burn_in;
         if ((rc = r.on_round(handed, upto, ev_round))) return rc;
         handed = upto;
       }
-      // shrink the last rounds' pool to what the slowest chain can still need; with a consumer
-      // that works round by round, the last stretch is additionally cut into halving rounds so that
-      // the part that cannot overlap any compute (the final round's samples) is a few columns per chain
-      const int rem = total - s_min;
-      attempts = std::max(4, std::min(max_attempts, (int)(rem * 1.25) + 4));
-      if (r.short_tail && rem <= 2 * max_attempts) attempts = std::max(6, std::min(attempts, (int)(rem * 0.55) + 2));
-      attempts = std::min(attempts, max_attempts);                 // never past the pool allocation
       pre_ms += t_pre.ms();
       chain_ms += t_chain.ms();
       cur ^= 1;

@@ -326,7 +326,7 @@ dgemm_ring_kernel(int m, int n, int k, const double* __restrict__ A, int64_t lda
 }
 
 // A[kk, col] = N(0,1) draw of (chain = active[col / attempts], draw index = pos[chain] + col % attempts,
-// coordinate kk) — the same Philox addressing the chain kernels use, so pool and in-kernel
+// coordinate kk; with col_off the columns of active chain a are [col_off[a], col_off[a+1])) — the same Philox addressing the chain kernels use, so pool and in-kernel
 // draws agree.
 __global__ void fill_normals_kernel(int d, size_t n_cols, double* __restrict__ A, NormalGen g) {
   const int pairs = (d + 1) / 2;
@@ -335,9 +335,16 @@ __global__ void fill_normals_kernel(int d, size_t n_cols, double* __restrict__ A
        idx += (size_t)gridDim.x * blockDim.x) {
     const uint32_t pr = (uint32_t)(idx % pairs);
     const size_t col = idx / pairs;
-    const int a = (int)(col / g.attempts);
+    int a; int64_t j;
+    if (g.col_off) {                                   // per-chain column ranges: last a with col_off[a] <= col
+      int lo = 0, hi = g.n_active;
+      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if ((size_t)g.col_off[mid] <= col) lo = mid; else hi = mid; }
+      a = lo; j = (int64_t)(col - (size_t)g.col_off[lo]);
+    } else {
+      a = (int)(col / g.attempts); j = (int64_t)(col % g.attempts);
+    }
     const int chain = g.active ? g.active[a] : a;
-    const uint64_t draw = (uint64_t)(g.pos[chain] + (int64_t)(col % g.attempts));
+    const uint64_t draw = (uint64_t)(g.pos[chain] + j);
     double n0, n1;
     normal_pair(g.seed, (uint64_t)(g.chain_offset + chain), draw, pr, n0, n1);
     double* dst = A + col * d + 2 * (size_t)pr;

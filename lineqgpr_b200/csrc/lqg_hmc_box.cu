@@ -278,9 +278,12 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
     long long ph_last = clock64();
 #endif
 
-    for (int att = 0; att < p.attempts && s < total && status == 0; ++att) {   // while(2), HmcSampler.cpp:51
+    // this chain's momenta of the round: pool columns [col0, col0 + my_att)
+    const size_t col0 = p.pool == nullptr ? 0 : p.col_off ? (size_t)p.col_off[aidx] : (size_t)aidx * p.attempts;
+    const int my_att = (p.pool != nullptr && p.col_off) ? p.col_off[aidx + 1] - (int)col0 : p.attempts;
+    for (int att = 0; att < my_att && s < total && status == 0; ++att) {   // while(2), HmcSampler.cpp:51
       if (p.pool != nullptr) {
-        const double* src = p.pool + ((size_t)aidx * p.attempts + att) * d;
+        const double* src = p.pool + (col0 + att) * d;
 #pragma unroll
         for (int k = 0; k < CPT; ++k) {
           const int i = tid + k * T;
@@ -289,7 +292,7 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
           xa_s[i] = a0;
         }
         // the next momentum of this chain is on its way to L2 while this attempt runs (one request per line)
-        if (att + 1 < p.attempts && (tid & 15) == 0) {
+        if (att + 1 < my_att && (tid & 15) == 0) {
 #pragma unroll
           for (int k = 0; k < CPT; ++k) {
             const int i = tid + k * T;
@@ -656,13 +659,62 @@ __global__ void box_compact_kernel(int n_chains, int total, const int* s_done, c
   if (status[c] == 0) atomicMin(n_active_out + 1, s_done[c]);
 }
 
-// publishes the two round counters into mapped pinned host memory with plain stores, so the
-// host can read them after a stream sync without a D2H copy (which would queue behind the bulk
-// sample copies on the copy engine)
-__global__ void box_publish_kernel(const int* src, volatile int* host_mapped) {
-  host_mapped[0] = src[0];
-  host_mapped[1] = src[1];
-  __threadfence_system();
+// Plans the next round (one CTA) and publishes the round counters into mapped pinned host memory with
+// plain stores, so the host can read them after a stream sync without a D2H copy (which would queue
+// behind the bulk sample copies on the copy engine).
+//   cap   = momenta per chain of the round, from the slowest chain: the whole pool while it has more than
+//           a pool's worth of transitions left, then what it still needs (x1.25 + 4 for restarts); with a
+//           consumer that works round by round (short_tail) the last stretch is cut into halving rounds,
+//           so that the part no compute can overlap (the final round's samples) is a few columns per chain
+//   count = min(cap, transitions left + restart allowance) per chain: chains ahead of the slowest one
+//           do not get columns they cannot use
+__global__ void __launch_bounds__(1024) box_plan_kernel(int total, int max_attempts, int short_tail, const int* s_done,
+                                                        const int* active, const int* ctl, int* col_off,
+                                                        volatile int* host_mapped) {
+  __shared__ int wt[32];
+  __shared__ int carry;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_active = ctl[0];
+  const int s_min = min(ctl[1], total);
+  const int rem_min = total - s_min;
+  int cap = max(4, min(max_attempts, (int)(rem_min * 1.25) + 4));
+  if (short_tail && rem_min <= 2 * max_attempts) cap = max(6, min(cap, (int)(rem_min * 0.55) + 2));
+  cap = min(cap, max_attempts);                              // never past the pool allocation
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n_active; base += 1024) {
+    const int a = base + threadIdx.x;
+    int v = 0;
+    if (a < n_active) {
+      const int rem = total - s_done[active[a]];
+      // restart allowance: a straggler that runs out of momenta costs a whole extra round (~1 ms of serial
+      // transitions at d = 2000), a spare column per chain ~0.03 ms of GEMM: 6 + rem/6 makes that round rare
+      v = min(cap, rem + 6 + rem / 6);
+    }
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) wt[warp] = inc;
+    __syncthreads();
+    int wb = 0, tot = 0;
+    for (int w = 0; w < 32; ++w) { if (w < warp) wb += wt[w]; tot += wt[w]; }
+    const int c = carry;
+    if (a < n_active) col_off[a] = c + wb + inc - v;
+    __syncthreads();
+    if (threadIdx.x == 0) carry = c + tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    col_off[n_active] = carry;
+    host_mapped[0] = n_active;
+    host_mapped[1] = ctl[1];
+    host_mapped[2] = carry;
+    host_mapped[3] = cap;
+    __threadfence_system();
+  }
 }
 
 // independent audit of the emitted samples: counts entries outside [lb, ub]
@@ -812,9 +864,10 @@ int hmc_box_slots(int d) {
 }
 
 cudaError_t launch_box_compact(int n_chains, int total, const int* s_done, const int* status,
-                               int* active_out, int* n_active_out, int* host_mapped, cudaStream_t st) {
+                               int* active_out, int* n_active_out, int* host_mapped, int max_attempts,
+                               int short_tail, int* col_off, cudaStream_t st) {
   box_compact_kernel<<<(n_chains + 255) / 256, 256, 0, st>>>(n_chains, total, s_done, status, active_out, n_active_out);
-  box_publish_kernel<<<1, 1, 0, st>>>(n_active_out, host_mapped);
+  box_plan_kernel<<<1, 1024, 0, st>>>(total, max_attempts, short_tail, s_done, active_out, n_active_out, col_off, host_mapped);
   launch_counter() += 2;
   return cudaGetLastError();
 }

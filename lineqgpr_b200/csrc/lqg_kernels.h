@@ -23,8 +23,10 @@ struct BoxParams {
   const int* active;       // nullable: chain ids to run in this launch (NULL = 0..n_active-1)
   int n_active;
   int attempts;            // momenta each active chain may consume in this launch
-  const double* pool;      // nullable: d x (n_active * attempts) pre-computed momenta U a;
-                           // column a*attempts + j is draw pos[chain(a)] + j
+  const double* pool;      // nullable: pre-computed momenta U a, one column each;
+                           // column col_off[a] + j (a*attempts + j without col_off) is draw pos[chain(a)] + j
+  const int* col_off;      // nullable [n_active + 1]: first pool column of every active chain; chain a may
+                           // consume col_off[a+1] - col_off[a] momenta in this launch (instead of `attempts`)
   int* s_done;             // [n_chains] transitions completed
   int64_t* pos;            // [n_chains] momenta consumed (the chain's draw index)
   int* rcount;             // [n_chains] restarts inside the current transition
@@ -52,10 +54,15 @@ cudaError_t launch_box_prep(int d, const double* mu, const double* lb, const dou
                             cudaStream_t st);
 cudaError_t launch_box_init_state(int d, int n_chains, const double* init, int64_t init_ld,
                                   const double* mu, double* state, cudaStream_t st);
-// n_active_out[0] = number of unfinished chains, n_active_out[1] = min over healthy chains of s_done
-// host_mapped: device alias of 2 ints of mapped pinned host memory that receive n_active_out[0..1]
+// n_active_out[0] = number of unfinished chains, n_active_out[1] = min over healthy chains of s_done.
+// Then the next round is planned on the device: every unfinished chain gets as many pool columns as it
+// can still use (transitions left + a restart allowance, at most the round's cap, which follows the
+// slowest chain as before), col_off[0..n_active] = their exclusive prefix sums.
+// host_mapped: device alias of 4 ints of mapped pinned host memory that receive
+// {n_active, min s_done, pool columns of the next round, cap of the next round}
 cudaError_t launch_box_compact(int n_chains, int total, const int* s_done, const int* status,
-                               int* active_out, int* n_active_out, int* host_mapped, cudaStream_t st);
+                               int* active_out, int* n_active_out, int* host_mapped, int max_attempts,
+                               int short_tail, int* col_off, cudaStream_t st);
 cudaError_t launch_box_violations(int d, size_t n_cols, const double* out, const double* lb,
                                   const double* ub, unsigned long long* count, cudaStream_t st);
 
@@ -123,6 +130,8 @@ struct NormalGen {
   int attempts;
   const int* active;       // nullable
   const int64_t* pos;      // [n_chains]
+  const int* col_off;      // nullable [n_active + 1]: per-chain column ranges (see BoxParams::col_off)
+  int n_active;
 };
 // b_blk_w > 0: the columns of B come in blocks of b_blk_w consecutive columns (stride ldb) that
 // start b_blk_pitch doubles apart (a round of chain-major samples: w finished columns per chain)
