@@ -9,7 +9,7 @@
 Default workload (config.workload): BASELINE.json configs[3] — 1-D bounded + monotone lineqGP, m = 1000
 hat knots (d = 2000 eta coordinates, 2999 finite bound rows), HMC, 10^6 samples sharded over 8 GPUs,
 i.e. 125 000 samples per GPU (weak scaling: per-GPU work fixed).  tmvrnorm.HMC defaults: burn.in = 100
-per chain; one chain per resident CTA slot of the device (296 on a B200 at d = 2000) x 423 samples.
+per chain; one chain per resident chain slot of the device (444 on a B200 at d = 2000: 3 chains per SM) x 282 samples.
 One "step" = one full pass: every chain's burn-in + its samples.  Synthetic data, seeded
 (lineqgpr_b200.workloads).
 

@@ -45,7 +45,9 @@ typedef struct lqg_opts {
   int32_t  hmc_search;     /* lqg_hmc_box / lqg_simulate hit search: 0 = default (walls ranked by
                               tan(t/2) of their hit time, tmg's own acos/atan2 arithmetic only where a
                               discrete threshold, a near-tie or the end of the trajectory is close),
-                              1 = every search with tmg's arithmetic (tmg:src/HmcSampler.cpp:157-181)  */
+                              1 = every search with tmg's arithmetic (tmg:src/HmcSampler.cpp:157-181),
+                              2 = like 0 but every search looks at the whole remaining time (0 looks at a
+                              short time window first and widens it when it holds no hit)             */
   void*    stream;         /* cudaStream_t to launch on (NULL = legacy default stream)         */
   uint64_t seed;           /* Philox key; replaces sample(1:1e7,1) of tmg:R/tmg.R:102          */
   int32_t  n_chains;       /* HMC: independent chains. 1 = the reference's single serial chain */
@@ -82,6 +84,7 @@ typedef struct lqg_hmc_stats {
   double  chain_ms;        /* device time of the chain kernel(s)                               */
   double  prepass_ms;      /* device time of the momentum GEMM pre-pass (0 when off)           */
   int64_t slow_searches;   /* box kernel: hit searches that were re-run with tmg's exact arithmetic */
+  int64_t window_retries;  /* box kernel: time windows without a hit, searched again 4 x wider          */
 } lqg_hmc_stats;
 
 typedef struct lqg_rsm_stats {

@@ -179,9 +179,11 @@ static int fetch_host(std::vector<double>& dst, const double* src, size_t n, int
   return LQG_OK;
 }
 
-static void fill_stats(lqg_hmc_stats* s, const unsigned long long* h, double chain_ms, double pre_ms, unsigned long long slow = 0) {
+static void fill_stats(lqg_hmc_stats* s, const unsigned long long* h, double chain_ms, double pre_ms, unsigned long long slow = 0,
+                       unsigned long long widen = 0) {
   if (!s) return;
   s->slow_searches = (int64_t)slow;
+  s->window_retries = (int64_t)widen;
   s->transitions = (int64_t)h[0]; s->bounces = (int64_t)h[1]; s->hit_searches = (int64_t)h[2];
   s->vel_restarts = (int64_t)h[3]; s->chk_restarts = (int64_t)h[4]; s->exact_evals = (int64_t)h[5];
   s->violations = (int64_t)h[6]; s->failed_chains = (int64_t)h[7];
@@ -252,6 +254,7 @@ struct BoxRun {
   int n_chains = 1, n_per_chain = 0, burn_in = 0;
   uint64_t seed = 0; int64_t chain_offset = 0; int prepass = -1; int max_restarts = 0;
   int exact_search = 0;                                            // 1: every hit search with tmg's own arithmetic
+  int no_window = 0;                                               // 1: fast search over the whole remaining time
   const double* injected = nullptr; int64_t n_injected = 0;      // device pointer
   double* out = nullptr;                                          // d x (n_chains*n_per_chain), chain-major columns
   cudaStream_t st = nullptr;
@@ -262,7 +265,7 @@ struct BoxRun {
   bool short_tail = false;    // cut the last stretch into halving rounds (the consumer cannot overlap the last one)
 };
 struct BoxResult {
-  unsigned long long stats[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // device layout, see BoxParams::stats
+  unsigned long long stats[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // device layout, see BoxParams::stats
   std::vector<int> status;
   double chain_ms = 0.0, pre_ms = 0.0;
   DevBuf state;               // d x n_chains centred positions x_b of the last transition
@@ -324,6 +327,8 @@ static int hmc_box_core(const BoxRun& r, BoxResult& res) {
   p.chain_status = b_status.as<int>();
   static const char* env_fast = getenv("LQG_BOX_FAST");             // tuning / A-B aid: 0 = exact search only
   p.fast = (r.exact_search || (env_fast && env_fast[0] == '0')) ? 0 : 1;
+  static const char* env_win = getenv("LQG_BOX_WINDOW");            // tuning / A-B aid: 0 = always search the whole remaining time
+  p.window = (r.no_window || (env_win && env_win[0] == '0')) ? 0 : 1;
 
   ph.mark("prep");
   const int total = burn_in + n_per_chain;
@@ -514,7 +519,7 @@ extern "C" int lqg_hmc_box(int32_t d, const double* mu, const double* U, int32_t
   r.d = d; r.mu = i_mu.dev; r.U = i_U.dev; r.u_upper = u_upper; r.Sigma = i_S.dev; r.lb = i_lb.dev; r.ub = i_ub.dev;
   r.init = i_init.dev; r.init_ld = init_ld; r.n_chains = n_chains; r.n_per_chain = n_per_chain; r.burn_in = burn_in;
   r.seed = o.seed; r.chain_offset = o.chain_offset; r.prepass = o.prepass; r.max_restarts = o.max_restarts;
-  r.exact_search = o.hmc_search == 1;
+  r.exact_search = o.hmc_search == 1; r.no_window = o.hmc_search == 2;
   r.injected = o.injected ? i_inj.dev : nullptr; r.n_injected = o.n_injected;
   r.out = d_out; r.st = st;
 
@@ -560,7 +565,7 @@ extern "C" int lqg_hmc_box(int32_t d, const double* mu, const double* U, int32_t
   }
   ph.mark("copy out");
   rc = box_result_rc(res, "lqg_hmc_box");
-  fill_stats(stats, res.stats, res.chain_ms, res.pre_ms, res.stats[10]);
+  fill_stats(stats, res.stats, res.chain_ms, res.pre_ms, res.stats[10], res.stats[11]);
   fold_launches();
   return rc;
   LQG_API_END("lqg_hmc_box")
@@ -1845,7 +1850,7 @@ extern "C" int lqg_simulate(const lqg_simulate_args* a_, const lqg_opts* opts_, 
   r.d = d; r.mu = i_mu.dev; r.U = i_U.dev; r.u_upper = u_upper; r.Sigma = i_S.dev; r.lb = i_lb.dev; r.ub = i_ub.dev;
   r.init = i_init.dev; r.init_ld = 0; r.n_chains = n_chains; r.n_per_chain = n_per; r.burn_in = a.burn_in;
   r.seed = o.seed; r.chain_offset = o.chain_offset + (int64_t)rank * n_chains; r.prepass = o.prepass;
-  r.max_restarts = o.max_restarts; r.exact_search = o.hmc_search == 1; r.out = d_eta; r.st = st;
+  r.max_restarts = o.max_restarts; r.exact_search = o.hmc_search == 1; r.no_window = o.hmc_search == 2; r.out = d_eta; r.st = st;
   r.short_tail = host_out || W > 1;       // the last round's copy / gather cannot hide behind sampling
   // The xi products, the all-gathers and the copies work on UNITS of `unit` samples per chain, not on
   // the sampling rounds themselves: how far a round gets depends on the chains, i.e. differs from
@@ -2051,7 +2056,7 @@ extern "C" int lqg_simulate(const lqg_simulate_args* a_, const lqg_opts* opts_, 
   double xi_ms = 0.0;
   for (auto& pr : xi_timers) { float f = 0; if (cudaEventElapsedTime(&f, pr.first, pr.second) == cudaSuccess) xi_ms += f; }
   if (stats) {
-    fill_stats(&stats->hmc, res.stats, res.chain_ms, res.pre_ms, res.stats[10]);
+    fill_stats(&stats->hmc, res.stats, res.chain_ms, res.pre_ms, res.stats[10], res.stats[11]);
     stats->xi_ms = xi_ms; stats->gemm_ms = t_gemm; stats->bands_ms = t_bands; stats->total_ms = t_total.ms();
     stats->n_local = N_local; stats->n_total = N_total; stats->row_begin = r0; stats->row_end = r1;
     stats->rank = rank; stats->world = W; stats->rounds = rounds;

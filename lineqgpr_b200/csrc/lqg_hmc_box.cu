@@ -60,17 +60,46 @@ constexpr int QCAP = 64;
 struct Cand {
   int key[QCAP];
 };
+// Several chains may share one CTA (NCH > 1): a chain is then run by a GROUP of G warps with its own
+// named barrier (id 1 + group), its own state copy, queues and slots; what the groups share is the read-only
+// per-coordinate tables in shared memory.  With NCH == 1 the group is the CTA and the barrier is barrier 0.
+struct Grp {
+  int id;      // group (chain slot) inside the CTA
+  int tid;     // thread index inside the group
+};
+template <int NCH, int T>
+__device__ __forceinline__ void group_sync(int grp) {
+  if (NCH == 1) __syncthreads();
+  else asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(T) : "memory");
+}
+template <int NCH, int T>
+__device__ __forceinline__ bool group_and(int grp, bool v) {
+  if (NCH == 1) return __syncthreads_and(v) != 0;
+  unsigned r;
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      "setp.ne.u32 p, %1, 0;\n"
+      "bar.red.and.pred q, %2, %3, p;\n"
+      "selp.u32 %0, 1, 0, q;\n"
+      "}\n"
+      : "=r"(r)
+      : "r"((unsigned)v), "r"(grp + 1), "n"(T)
+      : "memory");
+  return r != 0;
+}
+
 // fresh momentum x_a = U a for this chain, computed by the CTA itself (restarts, injected
 // draws, or when the GEMM pre-pass is off).  a ~ N(0, I_d) drawn like tmg:src/HmcSampler.cpp:54-55.
 // `xs` (shared, CPT*T doubles) first stages a, then receives x_a.  Out of line on purpose: its
 // accumulators must not count against the register budget of the hit-search loop.
-template <int G, int CPT>
-static __device__ __noinline__ bool draw_momentum(const BoxParams& p, int chain, int64_t draw, double* xs) {
+template <int G, int CPT, int NCH>
+static __device__ __noinline__ bool draw_momentum(const BoxParams& p, int chain, int64_t draw, double* xs, const Grp gr) {
   constexpr int T = 32 * G;
-  const int tid = threadIdx.x;
+  const int tid = gr.tid;
   const int d = p.d;
   double* a_sm = xs;
-  __syncthreads();                                                 // nobody reads the old x_a copy any more
+  group_sync<NCH, T>(gr.id);                                       // nobody reads the old x_a copy any more
   if (p.injected) {
     if ((draw + 1) * d > p.n_injected) return false;              // uniform across the CTA
     const double* src = p.injected + (size_t)chain * p.n_injected + (size_t)draw * d;
@@ -84,7 +113,7 @@ static __device__ __noinline__ bool draw_momentum(const BoxParams& p, int chain,
       if (2 * pr + 1 < d) a_sm[2 * pr + 1] = n1;
     }
   }
-  __syncthreads();
+  group_sync<NCH, T>(gr.id);
   double acc[CPT];
 #pragma unroll
   for (int k = 0; k < CPT; ++k) acc[k] = 0.0;
@@ -114,12 +143,33 @@ static __device__ __noinline__ bool draw_momentum(const BoxParams& p, int chain,
       for (int k = 0; k < CPT; ++k) acc[k] = fma(u[c][k], av, acc[k]);
     }
   }
-  __syncthreads();                                                 // a is consumed: the area now receives x_a
+  group_sync<NCH, T>(gr.id);                                                 // a is consumed: the area now receives x_a
 #pragma unroll
   for (int k = 0; k < CPT; ++k) xs[tid + k * T] = (tid + k * T < d) ? acc[k] : 0.0;
-  __syncthreads();
+  group_sync<NCH, T>(gr.id);
   return true;
 }
+
+// Search windows.  A sampleNext step needs the FIRST wall hit; with ~16 bounces per transition at m = 1000
+// the walls that could be hit anywhere in the remaining time are ~100, the ones hit within a few mean gaps
+// a handful.  The fast search therefore looks at a window [0, tau] first, tau = (pi/2) 2^-l chosen from the
+// recent hit times of the transition (4 x their running mean): the filter runs with (sin tau, cos tau) and a
+// hit is accepted only strictly inside the window (tan(t/2) <= tan(tau/2) (1 - 4e-6), so that a wall the
+// window filter may have dropped is farther from the winner than the near-tie band that sends a search to
+// tmg's arithmetic).  A window without a hit is widened 4 x and searched again; a window that reaches the
+// remaining time IS the remaining-time search.  The policy depends on the chain's own hit times only, so
+// samples stay independent of kernel shape, round size and sharding.
+constexpr int kNLV = 12;
+__constant__ double c_winK[kNLV] = {1.0, 0.41421356237309503, 0.198912367379658, 0.09849140335716425, 0.049126849769467254,
+                                    0.024548622108925444, 0.012272462379566276, 0.006136000157623402, 0.003067971201422665,
+                                    0.0015339819910886664, 0.0007669905443430926, 0.000383495215771441};     // tan(tau/2)
+__constant__ double c_winS[kNLV] = {1.0, 0.7071067811865476, 0.3826834323650898, 0.19509032201612828, 0.0980171403295606,
+                                    0.049067674327418015, 0.024541228522912288, 0.012271538285719925, 0.006135884649154475,
+                                    0.003067956762965976, 0.0015339801862847657, 0.0007669903187427045};     // sin tau
+__constant__ double c_winC[kNLV] = {6.123233995736766e-17, 0.7071067811865476, 0.9238795325112867, 0.9807852804032304,
+                                    0.9951847266721969, 0.9987954562051724, 0.9996988186962042, 0.9999247018391445,
+                                    0.9999811752826011, 0.9999952938095762, 0.9999988234517019, 0.9999997058628822};  // cos tau
+constexpr double kWinKavg0 = 0.05;     // running mean of tan(t/2) at the start of a transition (~pi/32 between hits)
 
 // One slot per warp for the cross-warp stage of the arg-min.  `tb` orders the candidates: bits of the
 // hit time (exact search) or of tan(t/2) (fast search); hi2 = high word of the warp's runner-up.
@@ -146,10 +196,10 @@ struct BoxShared {
 // with hit_time_exact, arg-min with the lowest index winning ties.  Taken when the fast search meets
 // a wall on one of tmg's thresholds, a near-tie, or a hit within 1e-9 of the remaining time, and for
 // every search with lqg_opts.hmc_search = 1.  The winner is left in red[0].
-template <int G>
-static __device__ __noinline__ void exact_search(const BoxShared sh, WinSlot* red, unsigned* n_eval) {
+template <int G, int NCH>
+static __device__ __noinline__ void exact_search(const BoxShared sh, WinSlot* red, unsigned* n_eval, const Grp gr) {
   constexpr int T = 32 * G;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = gr.tid, lane = tid & 31, warp = tid >> 5;
   const int d = sh.d;
   unsigned long long btb = kNoHitBits; int bkey = INT_MAX;
   double bxa = 0.0, bxb = 0.0;
@@ -166,9 +216,9 @@ static __device__ __noinline__ void exact_search(const BoxShared sh, WinSlot* re
   }
   unsigned long long mtb; int mkey;
   const int src = warp_argmin_hit(btb, bkey, mtb, mkey);
-  __syncthreads();                                                // red[] may still be read from the fast search
+  group_sync<NCH, T>(gr.id);                                                // red[] may still be read from the fast search
   if (lane == src) { WinSlot& r = red[warp]; r.tb = mtb; r.key = mkey; r.xa = bxa; r.xb = bxb; }
-  __syncthreads();
+  group_sync<NCH, T>(gr.id);
   if (tid == 0) {
     int ws = 0;
     for (int w = 1; w < G; ++w)
@@ -176,21 +226,21 @@ static __device__ __noinline__ void exact_search(const BoxShared sh, WinSlot* re
     if (ws != 0) red[0] = red[ws];
   }
   *n_eval += cnt;
-  __syncthreads();
+  group_sync<NCH, T>(gr.id);
 }
 
 // exact hit times of the bounces still owed to tt (see hit_fast), one lane per bounce; the caller
 // subtracts them in order
-template <int G>
-static __device__ __noinline__ void settle_times(const BoxShared sh, Deferred* dl, int n_dl) {
+template <int G, int NCH>
+static __device__ __noinline__ void settle_times(const BoxShared sh, Deferred* dl, int n_dl, const Grp gr) {
   constexpr int T = 32 * G;
-  __syncthreads();                                                // entries written by thread 0 are visible
-  for (int e = threadIdx.x; e < n_dl; e += T) {
+  group_sync<NCH, T>(gr.id);                                      // entries written by thread 0 are visible
+  for (int e = gr.tid; e < n_dl; e += T) {
     const int key = dl->key[e];
     const double g = key < sh.d ? sh.glo[key] : sh.ghi[key - sh.d];
     dl->fa[e] = hit_time_exact(dl->fa[e], dl->fb[e], g);
   }
-  __syncthreads();
+  group_sync<NCH, T>(gr.id);
 }
 
 // THR: where the filter thresholds live: 0 = registers, 1 = shared memory, 2 = recomputed from the
@@ -198,25 +248,42 @@ static __device__ __noinline__ void settle_times(const BoxShared sh, Deferred* d
 //  RS: the thread also keeps its coordinates of (x_a, x_b) in registers (the filter and the update then
 //      work from registers and only mirror the result to shared memory); RS = false trades those 4 CPT
 //      registers for shared-memory traffic so that one more CTA fits on the SM.
-template <int G, int CPT, int THR, bool GS, int MINB, bool PACK = false, bool RS = true>
-__global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p) {
+//  NCH: chains per CTA (groups of G warps, see Grp).  Fewer warps per chain and more chains per SM: the
+//      per-search work that every warp of a chain repeats (slot scan, decisions, time bookkeeping) and the
+//      barriers shrink with G, and the chains of an SM hide each other's latency; the per-coordinate tables
+//      are shared by the groups, so a chain costs 2 NS doubles of shared memory.
+template <int G, int CPT, int THR, bool GS, int MINB, bool PACK = false, bool RS = true, int NCH = 1>
+__global__ void __launch_bounds__(32 * G * NCH, MINB) hmc_box_kernel(const BoxParams p) {
   constexpr int T = 32 * G;
   constexpr int NS = CPT * T;                      // padded dimension: one slot per (thread, k)
+  static_assert(NCH >= 1 && NCH <= 15, "one named barrier per chain group");
+  static_assert(CPT <= 32, "two filter bits per coordinate in a 64-bit mask");
   extern __shared__ double dyn_sm[];
-  // xa_s doubles as the staging area of a fresh draw (draw_momentum): x_a is being replaced then
-  double* xa_s = dyn_sm;                           // [NS] copy of x_a
-  double* xb_s = xa_s + NS;                        // [NS] copy of x_b
-  double* glo_s = xb_s + NS;                       // [NS] if GS
+  Grp gr;
+  gr.id = NCH > 1 ? (int)threadIdx.x / T : 0;
+  gr.tid = NCH > 1 ? (int)threadIdx.x - gr.id * T : (int)threadIdx.x;
+  // tables shared by the groups, then per group the state copy
+  double* glo_s = dyn_sm;                          // [NS] if GS
   double* ghi_s = glo_s + NS;
   double* hlo_s = GS ? ghi_s + NS : glo_s;         // [NS] if THR == 1
   double* hhi_s = hlo_s + NS;
-  __shared__ WinSlot red[2][G];
-  __shared__ Cand queue[G];
-  __shared__ int qcnt[G];                          // PACK: candidates left in every warp's queue after the filter
-  __shared__ Deferred dl;
-  __shared__ int chain_sm;
+  double* st_base = dyn_sm + (size_t)NS * ((GS ? 2 : 0) + (THR == 1 ? 2 : 0));
+  // xa_s doubles as the staging area of a fresh draw (draw_momentum): x_a is being replaced then
+  double* xa_s = st_base + (size_t)gr.id * 2 * NS; // [NS] copy of x_a
+  double* xb_s = xa_s + NS;                        // [NS] copy of x_b
+  __shared__ WinSlot red_[NCH][2][G];
+  __shared__ Cand queue_[NCH][G];
+  __shared__ int qcnt_[NCH][G];                    // PACK: candidates left in every warp's queue after the filter
+  __shared__ Deferred dl_[NCH];
+  __shared__ int chain_sm_[NCH];
+  WinSlot (*red)[G] = red_[gr.id];
+  Cand* queue = queue_[gr.id];
+  int* qcnt = qcnt_[gr.id];
+  Deferred& dl = dl_[gr.id];
+  int& chain_sm = chain_sm_[gr.id];
+  auto gsync = [&]() { group_sync<NCH, T>(gr.id); };
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = gr.tid, lane = tid & 31, warp = tid >> 5;
   const int d = p.d;
   const bool fast_on = p.fast != 0;
 
@@ -227,7 +294,7 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
   double hlo_r[NG], hhi_r[NG];
   const double abs_eps = p.abs_eps;
   auto thr = [&](double g) { return g - fma(3.0 * kFilterRel, fabs(g), abs_eps); };
-  for (int i = tid; i < NS; i += T) {
+  for (int i = threadIdx.x; i < NS; i += T * NCH) {
     const double gl = i < d ? p.glo[i] : kBigG, gh = i < d ? p.ghi[i] : kBigG;
     if (GS) { glo_s[i] = gl; ghi_s[i] = gh; }
     if (THR == 1) { hlo_s[i] = thr(gl); hhi_s[i] = thr(gh); }
@@ -249,11 +316,16 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
   };
 
   const int total = p.burn_in + p.n_per_chain;
+  // Work distribution: group g of CTA b starts with entry g * gridDim.x + b of the work list (a list shorter
+  // than the chain slots is spread over the SMs first), later entries come from the atomic queue.
+  bool first_pull = true;
   for (;;) {
-    if (tid == 0) chain_sm = atomicAdd(p.next_chain, 1);
-    __syncthreads();
+    if (tid == 0)
+      chain_sm = first_pull ? gr.id * (int)gridDim.x + (int)blockIdx.x : (int)gridDim.x * NCH + atomicAdd(p.next_chain, 1);
+    first_pull = false;
+    gsync();
     const int aidx = chain_sm;
-    __syncthreads();
+    gsync();
     if (aidx >= p.n_active) break;
     const int chain = p.active ? p.active[aidx] : aidx;
 
@@ -271,7 +343,7 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
     int64_t draw = p.pos[chain];                   // momenta consumed so far
     int rcount = p.rcount[chain];                  // restarts inside the current transition
     int status = p.chain_status[chain];
-    unsigned n_bounce = 0, n_search = 0, n_vel = 0, n_chk = 0, n_exact = 0, n_trans = 0, n_slow = 0;
+    unsigned n_bounce = 0, n_search = 0, n_vel = 0, n_chk = 0, n_exact = 0, n_trans = 0, n_slow = 0, n_widen = 0;
     int parity = 0;
 #ifdef LQG_BOX_TIMING
     unsigned long long ph_acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -300,7 +372,7 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
           }
         }
       } else {
-        if (!draw_momentum<G, CPT>(p, chain, draw, xa_s)) {
+        if (!draw_momentum<G, CPT, NCH>(p, chain, draw, xa_s, gr)) {
           status = LQG_ERR_DRAWS_EXHAUSTED;
           break;
         }
@@ -315,22 +387,24 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
       // after fast bounces, the final rotation; settling re-bases them on the exact tt.
       double S = 1.0, C = 6.123233995736766e-17;                 // sin(M_PI/2), cos(M_PI/2)
       int n_dl = 0;                                              // bounces whose exact t is still owed to tt
+      double kavg = kWinKavg0;                                   // running mean of tan(t/2) of this transition's hits
+      int wlvl = 3;                                              // current window level (see c_winK)
 
       // tt -= t for every owed bounce, in order, with tmg's own hit-time formula
       auto settle = [&]() {
         if (n_dl == 0) return;
-        settle_times<G>(sh, &dl, n_dl);
+        settle_times<G, NCH>(sh, &dl, n_dl, gr);
         for (int e = 0; e < n_dl; ++e) tt = tt - dl.fa[e];       // :90, same order, same operands
         n_dl = 0;
         sincos(tt, &S, &C);
-        __syncthreads();                                         // dl is reused by the next bounce
+        gsync();                                         // dl is reused by the next bounce
       };
 
       for (;;) {                                                 // while(1), :64
         unsigned long long wtb = kNoHitBits; int wkey = INT_MAX;
         double wxa = 0.0, wxb = 0.0, wst = 0.0, wct = 0.0;
         bool need_exact = !fast_on;
-        if (fast_on) {
+        if (fast_on) for (;;) {
           // ---- fast hit search: walls that survive the filter are ranked by tan(t/2) (hit_fast) ----
           // lane state: best candidate, high word of its runner-up, "some wall needs tmg's arithmetic"
           unsigned long long btb = kNoHitBits; int bkey = INT_MAX;
@@ -338,7 +412,18 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
           unsigned bhi2 = 0xffffffffu;
           bool bslow = false;
           const double ktt = S / (1.0 + C);                      // tan(tt/2) of the remaining time
-          const double klim = fma(ktt, 1e-9, ktt) + 1e-12;
+          // window of this pass (see c_winK): the smallest dyadic angle whose tan(tau/2) covers 4 x the running mean
+          bool win_full = !p.window;
+          double Sf = S, Cf = C;
+          double klim = fma(ktt, 1e-9, ktt) + 1e-12;
+          if (!win_full) {
+            const double target = 4.0 * kavg;
+            while (wlvl + 1 < kNLV && c_winK[wlvl + 1] >= target) ++wlvl;
+            while (wlvl > 0 && c_winK[wlvl] < target) --wlvl;
+            const double kwin = c_winK[wlvl];
+            win_full = kwin >= 0.999 * ktt;                      // reaches the remaining time: search all of it
+            if (!win_full) { Sf = c_winS[wlvl]; Cf = c_winC[wlvl]; klim = kwin * (1.0 - 4e-6); }
+          }
           auto consider = [&](int key) {
             const int i = key < d ? key : key - d;
             const double sgn = key < d ? 1.0 : -1.0;             // wall row f = sgn e_i
@@ -374,13 +459,15 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
           // Phase 1 is straight-line code over the thread's coordinates (no votes, no branches: the
           // CPT coordinates overlap in the pipeline) and leaves one bit per wall in `mask`.
           LQG_TICK(0);                                           // 0: everything since the last bounce update
-          unsigned mask = 0u;
-#pragma unroll
+          using Mask = typename std::conditional<(CPT > 16), unsigned long long, unsigned>::type;
+          Mask mask = 0;
+          // (with the state in shared memory nothing forces a full unroll: 8 coordinates in flight are enough)
+#pragma unroll (RS ? CPT : (CPT < 8 ? CPT : 8))
           for (int k = 0; k < CPT; ++k) {
             const int i = tid + k * T;
             const double a_ = XA(k), b_ = XB(k);
-            const double y = fma(a_, S, b_ * C);
-            const double dy = fma(a_, C, -b_ * S);
+            const double y = fma(a_, Sf, b_ * Cf);
+            const double dy = fma(a_, Cf, -b_ * Sf);
             const double u2 = fma(a_, a_, b_ * b_);
             double hl, hh;
             if (THR == 0) { hl = hlo_r[THR == 0 ? k : 0]; hh = hhi_r[THR == 0 ? k : 0]; }
@@ -394,13 +481,13 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
             const bool dip_hi = (a_ > 0.0) & (dy < 0.0) & (u2 >= hh * fabs(hh));
             const bool need_lo = !safe_lo | dip_lo;
             const bool need_hi = !safe_hi | dip_hi;
-            mask |= (need_lo ? 1u : 0u) << (2 * k);
-            mask |= (need_hi ? 1u : 0u) << (2 * k + 1);
+            mask |= (Mask)(need_lo ? 1u : 0u) << (2 * k);
+            mask |= (Mask)(need_hi ? 1u : 0u) << (2 * k + 1);
           }
           LQG_TICK(1);                                           // 1: filter masks
           // Phase 2: the survivors' wall ids are compacted into the warp's queue: exclusive prefix sum of
           // the per-lane counts, then every lane walks its set bits (most lanes have none).
-          const int cnt = __popc(mask);
+          const int cnt = (CPT > 16) ? __popcll((unsigned long long)mask) : __popc((unsigned)mask);
           int incl = cnt;
 #pragma unroll
           for (int off = 1; off < 32; off <<= 1) {
@@ -412,8 +499,8 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
           // QCAP walls, each evaluated by the warp itself before the next round overwrites the queue
           for (int base = 0; base < wtotal; base += QCAP) {
             int pos = incl - cnt - base;
-            for (unsigned mm = mask; mm != 0u; mm &= mm - 1u) {
-              const int b = __ffs(mm) - 1;
+            for (Mask mm = mask; mm != 0; mm &= mm - 1) {
+              const int b = (CPT > 16) ? __ffsll((long long)mm) - 1 : __ffs((int)mm) - 1;
               if ((unsigned)pos < (unsigned)QCAP) q->key[pos] = ((b & 1) ? d : 0) + tid + (b >> 1) * T;
               ++pos;
             }
@@ -425,7 +512,7 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
             // Candidates of all warps are evaluated together, 32 per warp from the front: with ~13 per
             // warp, 8 partly filled passes become ~4 full ones.
             if (lane == 0) qcnt[warp] = qn;
-            __syncthreads();
+            gsync();
             LQG_TICK(3);                                         // 3: barrier after the pushes
             int ntot = 0;
 #pragma unroll
@@ -461,7 +548,7 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
               r.st = bst; r.ct = bct;
             }
             LQG_TICK(5);                                         // 5: warp arg-min + slot
-            __syncthreads();
+            gsync();
             LQG_TICK(6);                                         // 6: barrier of the slot exchange
             int ws = 0;
             wtb = red[parity][0].tb; wkey = red[parity][0].key;
@@ -499,16 +586,22 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
             close = fabs(kw - ktt) <= fma(ktt, 1e-9, 1e-12);
           }
           need_exact = wslow | tie | close;
+          if (win_full || need_exact || wtb != kNoHitBits) {
+            if (!need_exact && wtb != kNoHitBits) kavg = 0.5 * (kavg + __longlong_as_double((long long)wtb));
+            break;
+          }
+          kavg *= 4.0;                                           // nothing inside the window: widen and search again
+          ++n_widen;
         }
         LQG_TICK(7);                                             // 7: slot scan + decision
         double st, ct;
         if (need_exact) {
           if (fast_on) ++n_slow;
           settle();                                              // the exact comparison tt < t needs the exact tt
-          exact_search<G>(sh, red[parity], &n_exact);
+          exact_search<G, NCH>(sh, red[parity], &n_exact, gr);
           const WinSlot& r = red[parity][0];
           wtb = r.tb; wkey = r.key; wxa = r.xa; wxb = r.xb;
-          __syncthreads();                                       // the slot is free for the next search
+          gsync();                                       // the slot is free for the next search
           ++n_search;
           const double t = hit_from_bits(wtb);
           if (t == 0.0 || tt < t) break;                         // :82
@@ -579,7 +672,7 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
           fine = fine && (bb + gl >= 0.0) && (gh - bb >= 0.0) && (e >= __ldg(p.lb + i)) && (e <= __ldg(p.ub + i));
         }
       }
-      fine = (G > 1) ? (__syncthreads_and(fine) != 0) : __all_sync(0xffffffffu, fine);
+      fine = (G > 1) ? group_and<NCH, T>(gr.id, fine) : __all_sync(0xffffffffu, fine);
       if (!fine) {                                               // :130
         ++n_chk;
         if (++rcount > p.max_restarts) status = LQG_ERR_RESTART_CAP;
@@ -624,8 +717,9 @@ __global__ void __launch_bounds__(32 * G, MINB) hmc_box_kernel(const BoxParams p
       atomicAdd(p.stats + 3, (unsigned long long)n_vel);
       atomicAdd(p.stats + 4, (unsigned long long)n_chk);
       atomicAdd(p.stats + 10, (unsigned long long)n_slow);
+      atomicAdd(p.stats + 11, (unsigned long long)n_widen);
     }
-    __syncthreads();                                             // the state copy is rewritten by the next chain
+    gsync();                                             // the state copy is rewritten by the next chain
   }
 }
 
@@ -733,30 +827,31 @@ __global__ void box_violation_kernel(int d, size_t n_cols, const double* out, co
 }
 
 // grid == -1: query only, *slots_out = resident CTAs on the device
-template <int G, int CPT, int THR, bool GS, int MINB, bool PACK = false, bool RS = true>
+template <int G, int CPT, int THR, bool GS, int MINB, bool PACK = false, bool RS = true, int NCH = 1>
 static cudaError_t launch_box_t(const BoxParams& p, int grid, cudaStream_t st, int* slots_out = nullptr) {
   constexpr size_t NS = (size_t)CPT * 32 * G;
-  const size_t smem = NS * (2 + (GS ? 2 : 0) + (THR == 1 ? 2 : 0)) * sizeof(double);
-  auto kern = hmc_box_kernel<G, CPT, THR, GS, MINB, PACK, RS>;
+  const size_t smem = NS * (2 * NCH + (GS ? 2 : 0) + (THR == 1 ? 2 : 0)) * sizeof(double);
+  auto kern = hmc_box_kernel<G, CPT, THR, GS, MINB, PACK, RS, NCH>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int per_sm = 0, dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * G, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * G * NCH, smem);
   if (slots_out) {
-    *slots_out = sms * (per_sm > 0 ? per_sm : 1);
+    *slots_out = sms * (per_sm > 0 ? per_sm : 1) * NCH;      // chains in flight
     return e;
   }
   if (e != cudaSuccess) return e;
   if (grid <= 0) grid = sms * (per_sm > 0 ? per_sm : 1);     // persistent: every resident slot, once
-  if (grid > p.n_active) grid = p.n_active;
-  if (grid <= 0) return cudaSuccess;
+  // fewer chains than chain slots: spread them over the SMs first (a CTA's groups pull from one queue)
+  if ((long long)grid * NCH > p.n_active) grid = std::max(1, std::min(grid, p.n_active));
+  if (p.n_active <= 0) return cudaSuccess;
   // Sigma (one column per bounce, 32 MB at d = 2000) should stay in L2 while the momentum pool and the
   // samples stream through it: persisting access-policy window on this launch
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(32 * G); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(32 * G * NCH); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   int n_attr = 0;
   static const size_t persist_max = [] {
@@ -801,6 +896,11 @@ static cudaError_t dispatch_box(const BoxParams& p, int grid, cudaStream_t st, i
   // remove most of the spills of the search loop: cfg4 36.0 -> 33.7 ms per step.  "r" = register state.
   const bool rs = v && v[0] == 'r';
   if (d <= 1024) {
+    // several chains per CTA (see NCH): "a" = 1 warp x 12 chains, "b" = 2 x 8, "c" = 2 x 10, "e" = 4 x 6
+    if (v && v[0] == 'a') return launch_box_t<1, 32, 2, true, 1, true, false, 12>(p, grid, st, slots);
+    if (v && v[0] == 'b') return launch_box_t<2, 16, 1, true, 1, true, false, 8>(p, grid, st, slots);
+    if (v && v[0] == 'c') return launch_box_t<2, 16, 2, true, 1, true, false, 10>(p, grid, st, slots);
+    if (v && v[0] == 'e') return launch_box_t<4, 8, 1, true, 1, true, false, 6>(p, grid, st, slots);
     if (!pack) return launch_box_t<4, 8, 1, true, 4>(p, grid, st, slots);
     return rs ? launch_box_t<4, 8, 1, true, 4, true, true>(p, grid, st, slots) : launch_box_t<4, 8, 1, true, 4, true, false>(p, grid, st, slots);
   }
@@ -809,10 +909,20 @@ static cudaError_t dispatch_box(const BoxParams& p, int grid, cudaStream_t st, i
     // registers) is the default.  Measured alternatives: "3" = 3 CTAs/SM (80 registers, thresholds
     // recomputed from the bound offsets: 38.4 ms for 444 chains, same work rate), "4" = 4 CTAs/SM
     // (64 registers, bound offsets through L1: 49.3 ms).
+    // several chains per CTA (see NCH): "a" = 2 warps x 5 chains, "b" = 4 x 5, "c" = 2 x 4 (threshold tables), "e" = 4 x 4, "f" = 4 x 3
+    if (v && v[0] == 'a') return launch_box_t<2, 32, 2, true, 1, true, false, 5>(p, grid, st, slots);
+    if (v && v[0] == 'b') return launch_box_t<4, 16, 2, true, 1, true, false, 5>(p, grid, st, slots);
+    if (v && v[0] == 'c') return launch_box_t<2, 32, 1, true, 1, true, false, 4>(p, grid, st, slots);
+    if (v && v[0] == 'e') return launch_box_t<4, 16, 1, true, 1, true, false, 4>(p, grid, st, slots);
     if (v && v[0] == '3') return launch_box_t<8, 8, 2, true, 3, true, false>(p, grid, st, slots);
     if (v && v[0] == '4') return launch_box_t<8, 8, 2, false, 4, true, false>(p, grid, st, slots);
     if (!pack) return launch_box_t<8, 8, 1, true, 2>(p, grid, st, slots);
-    return rs ? launch_box_t<8, 8, 1, true, 2, true, true>(p, grid, st, slots) : launch_box_t<8, 8, 1, true, 2, true, false>(p, grid, st, slots);
+    if (rs) return launch_box_t<8, 8, 1, true, 2, true, true>(p, grid, st, slots);
+    if (v && v[0] == 'g') return launch_box_t<8, 8, 1, true, 2, true, false>(p, grid, st, slots);   // one chain per CTA of 8 warps, 2 CTAs/SM (296 chains)
+    // default: 3 chains per CTA, 4 warps each (444 chains in flight): 27 % more hit searches per second
+    // than 2 x 8 warps; with 100 burn-in transitions per chain and 125 000 samples per GPU that is
+    // 57.2 vs 58.5 ms per step (4 and 5 chains per CTA search faster still, but their burn-in costs more)
+    return launch_box_t<4, 16, 1, true, 1, true, false, 3>(p, grid, st, slots);
   }
   if (d <= 4096) return pack ? launch_box_t<8, 16, 1, true, 1, true>(p, grid, st, slots) : launch_box_t<8, 16, 1, true, 1>(p, grid, st, slots);
   if (d <= 8192) return pack ? launch_box_t<16, 16, 2, false, 1, true>(p, grid, st, slots) : launch_box_t<16, 16, 2, false, 1>(p, grid, st, slots);

@@ -39,9 +39,11 @@ struct BoxParams {
   int max_restarts;
   int* next_chain;         // work queue head (zeroed before launch)
   unsigned long long* stats;  // [0..7]: transitions,bounces,searches,vel,chk,evaluated,violations,failed;
+                              // [11]: window passes without a hit (searched again 4 x wider);
                               // [10]: searches that fell back to tmg's exact hit-time arithmetic
   int* chain_status;       // [n_chains]
   int fast;                // 1: rank walls by tan(t/2) (hit_fast), exact arithmetic only near a threshold
+  int window;              // 1: the fast search looks at a short time window first (see c_winK in lqg_hmc_box.cu)
 };
 
 cudaError_t launch_hmc_box(const BoxParams& p, int grid, cudaStream_t st);

@@ -14,7 +14,7 @@ What stays on the host, exactly where the reference has it on the host: the one-
 whitening algebra (solve, chol, triangular inverse).  Everything per-sample runs on the GPU.
 Extensions (all optional keys of `control`): "n.chains" (independent chains; 1 reproduces the
 reference's single serial chain; with several chains each one runs at least 100 burn-in
-transitions, see chain_burn_in), "burn.in.exact", "seed", "prepass", "injected", "max.restarts",
+transitions, see chain_burn_in), "burn.in.exact", "seed", "prepass", "injected", "max.restarts", "hmc.search" (lqg_opts.hmc_search),
 "chain.offset", "U" (a precomputed factor), "whiten" ("device" (default) | "ul" | "tmg", see whiten_box).
 """
 from __future__ import annotations
@@ -136,7 +136,8 @@ def tmvrnorm_HMC(object, nsim, control=None, **kw):
     opts = L.make_opts(mem=L.MEM_HOST, seed=seed, n_chains=n_chains,
                        max_restarts=int(control.get("max.restarts", 0)),
                        chain_offset=int(control.get("chain.offset", 0)),
-                       injected=injected, n_injected=n_inj, prepass=int(control.get("prepass", -1)))
+                       injected=injected, n_injected=n_inj, prepass=int(control.get("prepass", -1)),
+                       hmc_search=int(control.get("hmc.search", 0)))
     Uf, Sf = (L.f64(U) if U is not None else None), L.f64(Sigma)
     mu_c, lb_c, ub_c, init_c = (np.ascontiguousarray(v, dtype=np.float64) for v in (mu, lb, ub, init))
     out = control.get("out")                                            # optional caller-owned d x (n_chains*n_per) F-array

@@ -8,7 +8,7 @@
 tmvrnorm.HMC <- function(object, nsim, control = list(burn.in = 1e2), ...) {
   if (!("burn.in" %in% names(control))) control$burn.in <- 1e2
   # extension: independent chains.  Default = one chain per resident CTA slot of the device for this
-  # dimension (296 on a B200 at d = 2000): every wave full, least burn-in work.  Several chains all
+  # dimension (444 on a B200 at d = 2000): every wave full, least burn-in work.  Several chains all
   # start at the clamped MAP, so each of them runs at least the tmvrnorm.HMC default of 100 burn-in
   # transitions before it emits (simulate.* passes burn.in = 1, R/lineqGP.R:264,617, which is meant
   # for ONE long chain); n.chains = 1 is the reference chain and keeps burn.in as given.

@@ -214,7 +214,7 @@ def test_box_queue_overflow_is_bitwise_neutral(lqg):
     U = whiten_box(mu, S)
     n, chains = 2, 3
     draws = rng.standard_normal((chains, 400, d))                        # 400 momenta per chain (restarts are frequent here)
-    ctl = {"burn.in": 0, "n.chains": chains, "max.restarts": 1000}
+    ctl = {"burn.in": 0, "n.chains": chains, "max.restarts": 1000, "hmc.search": 2}   # 2: no time windows, every search sees ~85 walls
     x1 = lqg.tmvrnorm(dict(mu=mu, Sigma=S, lb=lb, ub=ub), n * chains, dict(ctl, U=U, injected=draws.reshape(chains, -1)), method="HMC")
     s1 = dict(lqg.last_stats)
     S2 = np.eye(d + pad); S2[:d, :d] = S
