@@ -15,8 +15,8 @@ One "step" = one full pass: every chain's burn-in + its samples.  Synthetic data
 
 value   = samples/s with all inputs resident in HBM (lqg_hmc_box, LQG_MEM_DEVICE), CUDA events.
 e2e     = samples/s through ONE reference-facing call of the simulate tail, lqg_simulate, with pinned
-          HOST buffers: H2D of mu, U, Sigma, lb, ub, init, Lambda^+ and Phi (or the test points), the
-          sampler, xi = Lambda^+ eta, Phi xi and its mean / quantile bands on the device, D2H of
+          HOST buffers: H2D of mu, U, Sigma, lb, ub, init, Lambda and Phi (or the test points), the
+          sampler, xi = qr.solve(Lambda, eta), Phi xi and its mean / quantile bands on the device, D2H of
           xi (m x N) and the bands — all inside the timed region.  With N > 1 GPUs the xi shards and the
           band pieces are all-gathered by NCCL inside the call (lqg_comm).
 e2e_tmvrnorm = the round-1 end-to-end number: lqg_hmc_box with host buffers, i.e. the d x N matrix of
@@ -404,7 +404,7 @@ def run_ours(a):
     # ---- e2e: ONE lqg_simulate call per step, pinned host buffers, copies inside the timed region ----
     pin = lambda x: torch.from_numpy(np.ascontiguousarray(x)).pin_memory()
     pinF = lambda x: torch.from_numpy(np.asfortranarray(x).T.copy()).pin_memory()      # column-major bytes
-    hU, hS, hLp = pinF(P["U"]), pinF(P["Sigma"]), pinF(P["Lp"])
+    hU, hS, hLam = pinF(P["U"]), pinF(P["Sigma"]), pinF(P["Lambda"])
     hmu, hlb, hub, hinit = pin(P["mu"]), pin(P["lb"]), pin(P["ub"]), pin(P["init"])
     hxt, hknots = pinF(xt), pin(np.concatenate(ulist))
     m_k = np.ascontiguousarray([u.size for u in ulist], dtype=np.int32)
@@ -415,7 +415,7 @@ def run_ours(a):
     sa = L.SimulateArgs()
     sa.d, sa.m = d, m
     sa.mu, sa.Sigma, sa.lb, sa.ub, sa.init, sa.U = (t.data_ptr() for t in (hmu, hS, hlb, hub, hinit, hU))
-    sa.Lambda_pinv = hLp.data_ptr()
+    sa.Lambda = hLam.data_ptr()            # qr.solve(Lambda, eta), R/lineqGP.R:639: the call probes Lambda's structure itself
     sa.n_t = n_t
     sa.basis_D, sa.basis_mk, sa.xtest, sa.ldx, sa.knots = len(ulist), m_k.ctypes.data, hxt.data_ptr(), n_t, hknots.data_ptr()
     sa.probs, sa.nprobs = hprobs.data_ptr(), len(PROBS)

@@ -1727,6 +1727,53 @@ __global__ void permute_cols_kernel(int rows, int64_t n_cols, const double* __re
   }
 }
 
+// Plan of xi = qr.solve(Lambda, eta) for a Lambda whose rows have their non-zeros in short windows (what
+// lineqGPR builds): banded normal equations, see lqg_sparse.cu.  ok = false: use the dense Lambda^+ product.
+struct LsqPlan {
+  bool ok = false;
+  LsqPlanDev dev{};
+  DevBuf rstart, rval, cidx, cval, lband, fw, bw, info, gersh;
+};
+static bool sparse_paths_enabled() {
+  static const char* env = getenv("LQG_SPARSE");                     // A/B aid: 0 = always the dense DMMA products
+  return !(env && env[0] == '0');
+}
+static int lsq_plan_build(int d, int m, const double* L_dev, LsqPlan& P, cudaStream_t st) {
+  P.ok = false;
+  if (!sparse_paths_enabled()) return LQG_OK;
+  LQG_CUDA_TRY(P.rstart.alloc((size_t)d * sizeof(int)));
+  LQG_CUDA_TRY(P.info.alloc(4 * sizeof(int)));
+  LQG_CUDA_TRY(cudaMemsetAsync(P.info.p, 0, 4 * sizeof(int), st));
+  LQG_CUDA_TRY(launch_lsq_profile(d, m, L_dev, P.rstart.as<int>(), P.info.as<int>(), st));
+  int h[4] = {0, 0, 0, 0};
+  LQG_CUDA_TRY(cudaMemcpyAsync(h, P.info.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+  LQG_CUDA_TRY(cudaStreamSynchronize(st));
+  if (h[0] > kLsqMaxBand || h[1] > kLsqMaxColNnz || h[1] < 1) return LQG_OK;   // wide rows: dense path
+  const int W = h[0] + 1, Wc = h[1], b = std::max(1, h[0]);
+  LQG_CUDA_TRY(P.rval.alloc((size_t)W * d * sizeof(double)));
+  LQG_CUDA_TRY(P.cidx.alloc((size_t)Wc * m * sizeof(int)));
+  LQG_CUDA_TRY(P.cval.alloc((size_t)Wc * m * sizeof(double)));
+  LQG_CUDA_TRY(P.lband.alloc((size_t)(b + 1) * m * sizeof(double)));
+  LQG_CUDA_TRY(P.fw.alloc((size_t)(b + 1) * m * sizeof(double)));
+  LQG_CUDA_TRY(P.bw.alloc((size_t)(b + 1) * m * sizeof(double)));
+  LQG_CUDA_TRY(P.gersh.alloc(2 * sizeof(double)));
+  LQG_CUDA_TRY(launch_lsq_build(d, m, W, Wc, b, L_dev, P.rstart.as<int>(), P.rval.as<double>(), P.cidx.as<int>(),
+                                P.cval.as<double>(), P.lband.as<double>(), P.fw.as<double>(), P.bw.as<double>(),
+                                P.info.as<int>(), P.gersh.as<double>(), st));
+  double g[2] = {0.0, 0.0};
+  LQG_CUDA_TRY(cudaMemcpyAsync(h, P.info.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+  LQG_CUDA_TRY(cudaMemcpyAsync(g, P.gersh.p, sizeof(g), cudaMemcpyDeviceToHost, st));
+  LQG_CUDA_TRY(cudaStreamSynchronize(st));
+  if (h[2] != 0) return LQG_OK;                                      // G not positive definite: let the dense path report it
+  // normal equations lose cond(G) eps: with a proven cond(G) <= 1e3 that is below 1e-12 and the refinement
+  // step (a second sparse product and solve) buys nothing
+  const int refine = (g[0] > 0.0 && g[1] <= 1e3 * g[0]) ? 0 : 1;
+  P.dev = LsqPlanDev{d, m, W, Wc, b, P.rstart.as<int>(), P.rval.as<double>(), P.cidx.as<int>(), P.cval.as<double>(),
+                     P.fw.as<double>(), P.bw.as<double>(), refine};
+  P.ok = true;
+  return LQG_OK;
+}
+
 // 2-D device -> host copy of result columns on a copy stream: pinned destinations go through the
 // copy engine directly, pageable ones (R / numpy matrices) through the staging ring
 struct HostSink {
@@ -1808,14 +1855,23 @@ extern "C" int lqg_simulate(const lqg_simulate_args* a_, const lqg_opts* opts_, 
   }
   // ---- Lambda^+ (m x d) ----
   const bool identity = !have_pinv && !have_lambda;          // xi = eta
-  if (have_pinv) {
-    if ((rc = i_Lp.stage(a.Lambda_pinv, dm, mem, st))) return rc;
-  } else if (have_lambda) {
-    Input i_L;
+  // Lambda itself given: its rows are probed for short non-zero windows (identity / difference / block
+  // diagonal constraint matrices); then xi comes from banded normal equations per sample (lqg_sparse.cu),
+  // otherwise from the dense product with Lambda^+ (given, or computed here)
+  LsqPlan lsq;
+  Input i_L;
+  if (have_lambda) {
     if ((rc = i_L.stage(a.Lambda, dm, mem, st))) return rc;
-    LQG_CUDA_TRY(i_Lp.buf.alloc(dm * sizeof(double)));
-    if ((rc = lambda_pinv_device(d, m, i_L.dev, i_Lp.buf.as<double>(), st))) return rc;   // synchronises st
-    i_Lp.dev = i_Lp.buf.as<double>();
+    if ((rc = lsq_plan_build(d, m, i_L.dev, lsq, st))) return rc;
+  }
+  if (!lsq.ok) {
+    if (have_pinv) {
+      if ((rc = i_Lp.stage(a.Lambda_pinv, dm, mem, st))) return rc;
+    } else if (have_lambda) {
+      LQG_CUDA_TRY(i_Lp.buf.alloc(dm * sizeof(double)));
+      if ((rc = lambda_pinv_device(d, m, i_L.dev, i_Lp.buf.as<double>(), st))) return rc;   // synchronises st
+      i_Lp.dev = i_Lp.buf.as<double>();
+    }
   }
 
   // ---- device-resident eta and the gathered xi of the whole job ----
@@ -1827,7 +1883,13 @@ extern "C" int lqg_simulate(const lqg_simulate_args* a_, const lqg_opts* opts_, 
 
   StreamGuard side_guard, copy_guard;
   EventGuard ev_x_guard, ev_side_guard;
-  LQG_CUDA_TRY(cudaStreamCreateWithFlags(&side_guard.s, cudaStreamNonBlocking));
+  {
+    // the xi stage runs beside the sampling rounds, whose kernels fill every SM: with the highest priority its
+    // (short) CTAs are placed as soon as anything retires instead of queueing behind a whole GEMM
+    int prio_lo = 0, prio_hi = 0;
+    LQG_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    LQG_CUDA_TRY(cudaStreamCreateWithPriority(&side_guard.s, cudaStreamNonBlocking, prio_hi));
+  }
   LQG_CUDA_TRY(cudaEventCreateWithFlags(&ev_x_guard.e, cudaEventDisableTiming));
   LQG_CUDA_TRY(cudaEventCreateWithFlags(&ev_side_guard.e, cudaEventDisableTiming));
   cudaStream_t s_side = side_guard.s;
@@ -1851,7 +1913,8 @@ extern "C" int lqg_simulate(const lqg_simulate_args* a_, const lqg_opts* opts_, 
   r.init = i_init.dev; r.init_ld = 0; r.n_chains = n_chains; r.n_per_chain = n_per; r.burn_in = a.burn_in;
   r.seed = o.seed; r.chain_offset = o.chain_offset + (int64_t)rank * n_chains; r.prepass = o.prepass;
   r.max_restarts = o.max_restarts; r.exact_search = o.hmc_search == 1; r.no_window = o.hmc_search == 2; r.out = d_eta; r.st = st;
-  r.short_tail = host_out || W > 1;       // the last round's copy / gather cannot hide behind sampling
+  static const char* env_tail = getenv("LQG_SIM_SHORT_TAIL");          // A/B aid
+  r.short_tail = env_tail ? env_tail[0] != '0' : (host_out || W > 1);  // the last round's copy / gather cannot hide behind sampling
   // The xi products, the all-gathers and the copies work on UNITS of `unit` samples per chain, not on
   // the sampling rounds themselves: how far a round gets depends on the chains, i.e. differs from
   // rank to rank, while the sequence of all-gather calls (and their sizes) must be the same on every
@@ -1863,6 +1926,8 @@ extern "C" int lqg_simulate(const lqg_simulate_args* a_, const lqg_opts* opts_, 
   const int unit = std::max(1, env_unit ? atoi(env_unit) : 32);
   const int n_units = (n_per + unit - 1) / unit;
   int next_unit = 0;
+  DevBuf b_lsq_scr;                          // refinement right-hand sides of one unit (banded path)
+  if (lsq.ok) LQG_CUDA_TRY(b_lsq_scr.alloc((size_t)m * n_chains * std::min(unit, n_per) * sizeof(double)));
   auto process_unit = [&](int from, int upto, cudaEvent_t ready) -> int {
     const int w = upto - from;
     const size_t cols = (size_t)n_chains * w;
@@ -1876,6 +1941,9 @@ extern "C" int lqg_simulate(const lqg_simulate_args* a_, const lqg_opts* opts_, 
     if (identity)      // xi = eta: gather the round's columns into the contiguous round block
       LQG_CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)w * m * sizeof(double), d_eta + (size_t)from * d, (size_t)n_per * d * sizeof(double),
                                      (size_t)w * m * sizeof(double), n_chains, cudaMemcpyDeviceToDevice, s_side));
+    else if (lsq.ok)   // banded least squares per sample (HBM-bound, leaves the tensor pipe to the momentum GEMM)
+      LQG_CUDA_TRY(launch_lsq_apply(lsq.dev, ColBlocks{d_eta + (size_t)from * d, d, w, (int64_t)n_per * d}, (int64_t)cols, dst,
+                                    b_lsq_scr.as<double>(), s_side));
     else               // xi = Lambda^+ eta on the FP64 tensor cores; B = the round's column blocks of eta
       LQG_CUDA_TRY(launch_dgemm(m, (int)cols, d, i_Lp.dev, m, d_eta + (size_t)from * d, d, dst, m, nullptr, 0, s_side,
                                 w, (int64_t)n_per * d));
@@ -1979,6 +2047,9 @@ extern "C" int lqg_simulate(const lqg_simulate_args* a_, const lqg_opts* opts_, 
         LQG_CUDA_TRY(cudaStreamSynchronize(st));               // perm is a local
         if (mem == LQG_MEM_HOST) LQG_CUDA_TRY(b_yp.alloc((size_t)rows * N_total * sizeof(double)));
       }
+      DevBuf b_pidx, b_pval, b_pinfo;
+      bool phi_sparse_probe = sparse_paths_enabled();
+      int ell_k = 0;
       for (int s0 = 0; s0 < nr_local; s0 += rows) {
         const int nr = std::min(rows, nr_local - s0);
         const double* phi_slab; int64_t ld_slab;
@@ -1995,9 +2066,28 @@ extern "C" int lqg_simulate(const lqg_simulate_args* a_, const lqg_opts* opts_, 
           }
           phi_slab = b_phi.as<double>(); ld_slab = nr;
         }
+        // a slab whose rows hold at most kEllMaxNnz non-zeros (1-D hat basis: 2) is multiplied in ELL form:
+        // bound by writing ysim instead of an nr x m x N GEMM; the first dense slab ends the probing
+        bool ell = false;
+        if (phi_sparse_probe) {
+          if (!b_pidx.p) {
+            LQG_CUDA_TRY(b_pidx.alloc((size_t)kEllMaxNnz * rows * sizeof(int)));
+            LQG_CUDA_TRY(b_pval.alloc((size_t)kEllMaxNnz * rows * sizeof(double)));
+            LQG_CUDA_TRY(b_pinfo.alloc(sizeof(int)));
+          }
+          LQG_CUDA_TRY(cudaMemsetAsync(b_pinfo.p, 0, sizeof(int), st));
+          LQG_CUDA_TRY(launch_ell_from_dense(nr, m, kEllMaxNnz, phi_slab, ld_slab, b_pidx.as<int>(), b_pval.as<double>(), b_pinfo.as<int>(), st));
+          int mx = 0;
+          LQG_CUDA_TRY(cudaMemcpyAsync(&mx, b_pinfo.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+          LQG_CUDA_TRY(cudaStreamSynchronize(st));
+          ell = mx <= kEllMaxNnz;
+          ell_k = mx;
+          if (!ell) phi_sparse_probe = false;
+        }
         Timer tg(st);
         tg.start();
-        LQG_CUDA_TRY(launch_dgemm(nr, (int)N_total, m, phi_slab, ld_slab, xi_all, m, b_y.as<double>(), nr, nullptr, 0, st));
+        if (ell) LQG_CUDA_TRY(launch_ell_spmm(nr, m, std::max(1, ell_k), b_pidx.as<int>(), b_pval.as<double>(), xi_all, N_total, b_y.as<double>(), nr, st));
+        else LQG_CUDA_TRY(launch_dgemm(nr, (int)N_total, m, phi_slab, ld_slab, xi_all, m, b_y.as<double>(), nr, nullptr, 0, st));
         tg.stop();
         double ms = 0.0;
         double* q_slab = nprobs > 0 ? band_mine + rows_per + (size_t)s0 * nprobs : nullptr;

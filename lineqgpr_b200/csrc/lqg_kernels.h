@@ -68,6 +68,44 @@ cudaError_t launch_box_compact(int n_chains, int total, const int* s_done, const
 cudaError_t launch_box_violations(int d, size_t n_cols, const double* out, const double* lb,
                                   const double* ub, unsigned long long* count, cudaStream_t st);
 
+// ---- structure-aware products of the simulate tail (lqg_sparse.cu) ------------------------------
+// column c of a matrix whose columns come in blocks of w consecutive columns (stride ld) that start `pitch`
+// doubles apart (a unit of chain-major samples); w = 0: plain columns with stride ld
+struct ColBlocks {
+  const double* base; int64_t ld; int w; int64_t pitch;
+  __host__ __device__ const double* col(int64_t c) const {
+    return w > 0 ? base + (size_t)(c / w) * pitch + (size_t)(c % w) * ld : base + (size_t)c * ld;
+  }
+};
+// device-resident plan of xi = argmin |Lambda xi - eta| for a Lambda with short row windows
+struct LsqPlanDev {
+  int d, m;
+  int W;                   // row window: non-zeros of row i lie in columns [rstart[i], rstart[i] + W)
+  int Wc;                  // most non-zeros in a column
+  int b;                   // half bandwidth of G = Lambda' Lambda
+  const int* rstart;       // [d]
+  const double* rval;      // [W x d]   rval[l*d + i] = Lambda[i, rstart[i] + l]
+  const int* cidx;         // [Wc x m]  cidx[k*m + j] = k-th non-zero row of column j (-1: none)
+  const double* cval;      // [Wc x m]
+  const double* fw;        // [m x (b+1)] coefficients of the forward / backward recurrences of the banded
+  const double* bw;        //             Cholesky factor of G (see lsq_band_chol_kernel)
+  int refine;              // 1: one step of iterative refinement (cond(G) not provably small)
+};
+constexpr int kLsqMaxBand = 8, kLsqMaxColNnz = 32, kEllMaxNnz = 8;
+// info[0] = widest row window - 1, info[1] = most non-zeros in a column (both atomicMax: zero them first)
+cudaError_t launch_lsq_profile(int d, int m, const double* L, int* rstart, int* info, cudaStream_t st);
+// fills the plan's arrays; info[2] = 1 + index of a non-positive pivot of G (0 = fine)
+// gersh[0..1] = Gershgorin bounds of the spectrum of G
+cudaError_t launch_lsq_build(int d, int m, int W, int Wc, int b, const double* L, const int* rstart, double* rval,
+                             int* cidx, double* cval, double* lband, double* fw, double* bw, int* info, double* gersh,
+                             cudaStream_t st);
+cudaError_t launch_lsq_apply(const LsqPlanDev& P, ColBlocks eta, int64_t cols, double* xi, double* scratch, cudaStream_t st);
+// first K non-zeros of every row of a dense slab (column order), info[0] = atomicMax of the row counts
+cudaError_t launch_ell_from_dense(int nr, int m, int K, const double* P, int64_t ld, int* pidx, double* pval, int* info,
+                                  cudaStream_t st);
+cudaError_t launch_ell_spmm(int nr, int m, int K, const int* pidx, const double* pval, const double* X, int64_t N,
+                            double* Y, int64_t ldy, cudaStream_t st);
+
 // ---- canonical-frame HMC with dense constraints (lqg_hmc_canonical.cu) ------------------
 struct CanonParams {
   int d, c;

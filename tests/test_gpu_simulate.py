@@ -85,6 +85,44 @@ def test_pipeline_slabs_and_ragged_rows(lqg, oracle):
     assert np.abs(a["ymean"] - b["ymean"]).max() <= 1e-15 * max(1.0, np.abs(a["ymean"]).max())
 
 
+@pytest.mark.parametrize("lam_kind,phi_kind", [("banded2", "hat"), ("banded2", "dense"), ("dense", "hat"), ("blockdiag", "hat3")])
+def test_pipeline_structured_and_dense_products(lqg, lam_kind, phi_kind):
+    """xi = qr.solve(Lambda, eta) and ysim = Phi xi take structure-aware kernels when Lambda's rows have short
+    non-zero windows (banded normal equations + refinement) and Phi's rows few non-zeros (ELL product), and the
+    dense tensor-core products otherwise: every combination must agree with numpy's least squares / product."""
+    from lineqgpr_b200.simulate import simulate_pipeline
+    rng = np.random.default_rng(11)
+    m = 70
+    I = np.eye(m); D1 = np.diff(I, axis=0); D2 = np.diff(I, n=2, axis=0)
+    if lam_kind == "banded2":
+        Lam = np.vstack([I, 3.0 * D1, -0.5 * D2])            # bounded + monotone + convex rows: windows of 1, 2, 3 columns
+    elif lam_kind == "blockdiag":
+        blk = np.vstack([np.eye(10), np.diff(np.eye(10), axis=0)])
+        Lam = np.kron(np.eye(7), blk)                          # additive model: one block per input dimension
+    else:
+        Lam = rng.standard_normal((2 * m, m))                  # no structure: dense Lambda^+ product
+    d = Lam.shape[0]
+    B = rng.standard_normal((d, d)); S = B @ B.T / d + 0.5 * np.eye(d)
+    par = dict(mu=0.1 * rng.standard_normal(d), Sigma=S, lb=np.full(d, -2.0), ub=np.full(d, 2.5))
+    n_t = 53
+    if phi_kind == "dense":
+        Phi = rng.standard_normal((n_t, m))
+    else:
+        Phi = np.zeros((n_t, m))
+        for t in range(n_t):                                    # hat functions: 2 neighbours (hat3: a third entry further away)
+            j = rng.integers(0, m - 1); w = rng.uniform()
+            Phi[t, j], Phi[t, j + 1] = 1 - w, w
+            if phi_kind == "hat3":
+                Phi[t, (j + 17) % m] += 0.25
+    ctl = {"burn.in": 4, "n.chains": 12, "seed": 23, "burn.in.exact": True}
+    r = simulate_pipeline(par, 12 * 50, Lambda=Lam, Phi_test=Phi, control=ctl, return_eta=True, return_ysim=True)
+    xi_ref = np.linalg.lstsq(Lam, r["eta"], rcond=None)[0]
+    assert np.abs(r["xi.sim"] - xi_ref).max() <= 1e-11 * max(1.0, np.abs(xi_ref).max())
+    y_ref = Phi @ r["xi.sim"]
+    assert np.abs(r["ysim"] - y_ref).max() <= 1e-12 * max(1.0, np.abs(y_ref).max())
+    assert np.abs(r["ymean"] - r["ysim"].mean(1)).max() <= 1e-13 * max(1.0, np.abs(y_ref).max())
+
+
 def test_simulate_lineqGP_uses_the_pipeline(lqg):
     """simulate() (R/lineqGP.R:601-643) routes HMC models through lqg_simulate: one call, and its
     result is what the stage-by-stage path returns."""
