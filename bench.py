@@ -46,9 +46,9 @@ METRIC = "constrained TMVN samples/sec (HMC, m=1000 knots)"
 UNIT = "samples/s"
 WORKLOADS = {
     "cfg4": ("cfg4: 1-D bounded+monotone lineqGP, m=1000 knots (d=2000, 2999 bound rows), HMC T=pi/2, "
-             "125000 samples per GPU (10^6 over 8), burn.in=100 per chain, one chain per resident CTA slot"),
+             "125000 samples per GPU (10^6 over 8), burn.in=100, one chain per resident chain slot"),
     "cfg5": ("cfg5: additive monotone lineqAGP D=100 x 10 knots (m=d=1000, 900 bound rows), HMC T=pi/2, 125000 samples per GPU "
-             "(10^6 over 8), burn.in=100 per chain; e2e adds xi = Lambda^+ eta and the bands of Phi xi at 10^5 test points"),
+             "(10^6 over 8), burn.in=100; e2e adds xi = qr.solve(Lambda, eta) and the bands of Phi xi at 10^5 test points"),
     "cfg1": "cfg1: 1-D monotone lineqGP, m=100 knots, 10 noisy points, 1000 samples via simulate",
     "cfg2": "cfg2: 2-D monotone MaxMod lineqGP (knots 5 x 2, d=20, 13 bound rows), 10^4 samples",
     "cfg3": "cfg3: 5-D additive monotone MaxMod lineqAGP (knots 6 + 4, d=10, 8 bound rows), 10^5 samples",
@@ -68,6 +68,8 @@ def parse():
     ap.add_argument("--chains-per-gpu", type=int, default=0, help="0 = lqg_hmc_box_slots(d)")
     ap.add_argument("--burn-in", type=int, default=100)
     ap.add_argument("--prepass", type=int, default=-1)
+    ap.add_argument("--fork", type=int, default=3, help="chains per family sharing one root chain's burn-in (lqg_opts.fork; 1 = independent chains)")
+    ap.add_argument("--fork-burn-in", type=int, default=5, help="transitions a forked chain runs before it emits")
     ap.add_argument("--n-test", type=int, default=0, help="test points of the e2e pipeline (0 = 1000 for cfg4, 100000 for cfg5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-transitions", type=int, default=0, help="transitions per core for the CPU sample (0 = auto)")
@@ -341,7 +343,7 @@ def run_ours(a):
     def step_device(seed):
         st = L.HmcStats()
         o = L.make_opts(mem=L.MEM_DEVICE, stream=stream.cuda_stream, seed=seed, n_chains=n_chains,
-                        chain_offset=rank * n_chains, prepass=a.prepass)
+                        chain_offset=rank * n_chains, prepass=a.prepass, fork=a.fork, fork_burn_in=a.fork_burn_in)
         rc = lib.lqg_hmc_box(d, mu_t.data_ptr(), Ut.data_ptr(), 1, St.data_ptr(), lb_t.data_ptr(), ub_t.data_ptr(),
                              init_t.data_ptr(), 0, n_per, burn, o, out_t.data_ptr(), None, st)
         L.check(rc, "lqg_hmc_box")
@@ -427,7 +429,7 @@ def run_ours(a):
 
     def step_pipeline(seed):
         st = L.SimulateStats()
-        o = L.make_opts(mem=L.MEM_HOST, stream=stream.cuda_stream, seed=seed, n_chains=n_chains, prepass=a.prepass)
+        o = L.make_opts(mem=L.MEM_HOST, stream=stream.cuda_stream, seed=seed, n_chains=n_chains, prepass=a.prepass, fork=a.fork, fork_burn_in=a.fork_burn_in)
         rc = lib.lqg_simulate(ctypes.byref(sa), o, comm.handle if comm is not None else None, st)
         L.check(rc, "lqg_simulate")
         return st
@@ -478,7 +480,7 @@ def run_ours(a):
         def step_host(seed):
             st = L.HmcStats()
             o = L.make_opts(mem=L.MEM_HOST, stream=stream.cuda_stream, seed=seed, n_chains=n_chains,
-                            chain_offset=rank * n_chains, prepass=a.prepass)
+                            chain_offset=rank * n_chains, prepass=a.prepass, fork=a.fork, fork_burn_in=a.fork_burn_in)
             rc = lib.lqg_hmc_box(d, hmu.data_ptr(), hU.data_ptr(), 1, hS.data_ptr(), hlb.data_ptr(), hub.data_ptr(),
                                  hinit.data_ptr(), 0, n_per, burn, o, hout.data_ptr(), None, st)
             L.check(rc, "lqg_hmc_box(host)")
@@ -555,6 +557,10 @@ def run_ours(a):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOADS[a.workload], "d": d, "c": c, "m": m,
                        "samples_per_gpu": n_gpu, "chains_per_gpu": n_chains, "burn_in": burn,
+                       "burn_in_scheme": (f"families of {a.fork} chains share one root chain's {burn} burn-in transitions from the clamped MAP, "
+                                          f"then each chain runs {a.fork_burn_in} more on its own stream before it emits "
+                                          f"({burn + a.fork_burn_in} transitions between the start and any emitted sample)") if a.fork > 1
+                                         else f"{burn} burn-in transitions per chain",
                        "l2": "256 MiB buffer written between timed iterations (L2 flush)",
                        "parallelism": f"chains sharded over {world} GPU(s); no collective while sampling; e2e: NCCL all-gather of xi shards and band pieces" if world > 1
                                       else "1 GPU"},

@@ -67,6 +67,15 @@ typedef struct lqg_opts {
   int32_t  prepass;        /* HMC box: 1 = batch the fresh momenta U*a of all transitions as one
                               FP64 tensor-core GEMM before the chain kernel, 0 = per-chain
                               in-kernel product, -1 = auto                                      */
+  int32_t  fork;           /* lqg_hmc_box / lqg_simulate: F > 1 = chains share their burn-in in families of F.
+                              Chains with global ids [kF, (k+1)F) start from the state that ONE root chain
+                              (Philox stream of chain kF) has reached after burn_in transitions from `init`,
+                              run fork_burn_in more transitions each on their own streams, then emit: the
+                              burn-in work is burn_in * n_chains / F + fork_burn_in * n_chains instead of
+                              burn_in * n_chains, every emitted column still comes from a chain that is
+                              burn_in + fork_burn_in transitions away from the start.  Samples depend on
+                              (seed, global id, F), not on the sharding.  0 / 1 = independent chains       */
+  int32_t  fork_burn_in;   /* transitions a forked chain runs before it emits (see fork)                  */
   int32_t  canon_mode;     /* lqg_hmc_canonical: 0 = auto, 1 = one persistent CTA per chain (F in shared
                               memory when it fits), 2 = lock-step rounds, the dot products of all
                               chains as one FP64 tensor-core GEMM per round (large dense F)        */

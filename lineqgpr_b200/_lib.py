@@ -42,7 +42,7 @@ class Opts(C.Structure):
                 ("seed", C.c_uint64), ("n_chains", C.c_int32), ("max_restarts", C.c_int32),
                 ("chain_offset", C.c_int64), ("injected", C.c_void_p), ("n_injected", C.c_int64),
                 ("injected_u", C.c_void_p), ("n_injected_u", C.c_int64), ("prepass", C.c_int32),
-                ("canon_mode", C.c_int32)]
+                ("fork", C.c_int32), ("fork_burn_in", C.c_int32), ("canon_mode", C.c_int32)]
 
 
 class HmcStats(C.Structure):
@@ -204,7 +204,8 @@ def ptr(a):
 
 
 def make_opts(mem=MEM_HOST, stream=None, seed=0, n_chains=1, max_restarts=0, chain_offset=0,
-              injected=None, n_injected=0, injected_u=None, n_injected_u=0, prepass=-1, canon_mode=0, hmc_search=0) -> Opts:
+              injected=None, n_injected=0, injected_u=None, n_injected_u=0, prepass=-1, canon_mode=0, hmc_search=0,
+              fork=0, fork_burn_in=0) -> Opts:
     o = Opts()
     o.mem = mem
     o.hmc_search = int(hmc_search)
@@ -219,6 +220,8 @@ def make_opts(mem=MEM_HOST, stream=None, seed=0, n_chains=1, max_restarts=0, cha
     o.n_injected_u = int(n_injected_u)
     o.prepass = int(prepass)
     o.canon_mode = int(canon_mode)
+    o.fork = int(fork)
+    o.fork_burn_in = int(fork_burn_in)
     return o
 
 

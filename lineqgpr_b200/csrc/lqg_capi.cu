@@ -263,23 +263,32 @@ struct BoxRun {
   // all-gather) work on another stream while later rounds run.  Nullable.
   std::function<int(int from, int upto, cudaEvent_t ready)> on_round;
   bool short_tail = false;    // cut the last stretch into halving rounds (the consumer cannot overlap the last one)
+  int fork = 0, fork_burn_in = 0;   // lqg_opts.fork: families of `fork` chains share one root chain's burn-in
+  // set by the fork logic for its two phases (never by the entry points):
+  int chain_stride = 1;             // global id of local chain c = chain_offset + c * chain_stride
+  const double* state0 = nullptr;   // centred start states d x n_chains (instead of init - mu)
+  const int64_t* pos0 = nullptr;    // momenta already consumed per chain
+  const int* sdone0 = nullptr;      // transitions already behind every chain
+  bool keep_pos = false;            // leave the chains' draw counters in BoxResult::pos
 };
 struct BoxResult {
   unsigned long long stats[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // device layout, see BoxParams::stats
   std::vector<int> status;
   double chain_ms = 0.0, pre_ms = 0.0;
   DevBuf state;               // d x n_chains centred positions x_b of the last transition
+  DevBuf pos;                 // [n_chains] momenta consumed (BoxRun::keep_pos)
   int max_restarts = 0;
 };
 
-static int hmc_box_core(const BoxRun& r, BoxResult& res) {
+static int hmc_box_rounds(const BoxRun& r, BoxResult& res) {
   Phase ph("hmc_box");
   const int d = r.d, n_chains = r.n_chains, n_per_chain = r.n_per_chain, burn_in = r.burn_in;
   cudaStream_t st = r.st;
   const size_t n_cols = (size_t)n_chains * n_per_chain;
   double* d_out = r.out;
-  DevBuf b_glo, b_ghi, b_sd, b_misc, b_status, b_sdone, b_pos, b_rcount, b_act;
+  DevBuf b_glo, b_ghi, b_sd, b_misc, b_status, b_sdone, b_rcount, b_act;
   DevBuf& b_state = res.state;
+  DevBuf& b_pos = res.pos;
   LQG_CUDA_TRY(b_state.alloc((size_t)d * n_chains * sizeof(double)));
   LQG_CUDA_TRY(b_glo.alloc(d * sizeof(double)));
   LQG_CUDA_TRY(b_ghi.alloc(d * sizeof(double)));
@@ -298,8 +307,14 @@ static int hmc_box_core(const BoxRun& r, BoxResult& res) {
 
   ph.mark("alloc");
   LQG_CUDA_TRY(launch_box_prep(d, r.mu, r.lb, r.ub, r.Sigma, b_glo.as<double>(), b_ghi.as<double>(), b_sd.as<double>(), st));
-  // x_b(0) = init - mu for every chain (init_ld == 0 broadcasts one shared start)
-  LQG_CUDA_TRY(launch_box_init_state(d, n_chains, r.init, r.init_ld, r.mu, b_state.as<double>(), st));
+  if (r.state0) {     // forked chains: start states, draw counters and transition counts come from the root phase
+    LQG_CUDA_TRY(cudaMemcpyAsync(b_state.p, r.state0, (size_t)d * n_chains * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    LQG_CUDA_TRY(cudaMemcpyAsync(b_pos.p, r.pos0, (size_t)n_chains * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    LQG_CUDA_TRY(cudaMemcpyAsync(b_sdone.p, r.sdone0, (size_t)n_chains * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  } else {
+    // x_b(0) = init - mu for every chain (init_ld == 0 broadcasts one shared start)
+    LQG_CUDA_TRY(launch_box_init_state(d, n_chains, r.init, r.init_ld, r.mu, b_state.as<double>(), st));
+  }
   std::vector<double> h_sd(d);
   LQG_CUDA_TRY(cudaMemcpyAsync(h_sd.data(), b_sd.p, d * sizeof(double), cudaMemcpyDeviceToHost, st));
   LQG_CUDA_TRY(cudaStreamSynchronize(st));
@@ -317,7 +332,7 @@ static int hmc_box_core(const BoxRun& r, BoxResult& res) {
   p.state = b_state.as<double>(); p.n_chains = n_chains;
   p.s_done = b_sdone.as<int>(); p.pos = b_pos.as<int64_t>(); p.rcount = b_rcount.as<int>();
   p.burn_in = burn_in; p.n_per_chain = n_per_chain; p.out = d_out; p.seed = r.seed;
-  p.chain_offset = r.chain_offset; p.injected = r.injected;
+  p.chain_offset = r.chain_offset; p.chain_stride = r.chain_stride; p.injected = r.injected;
   p.n_injected = r.n_injected;
   p.max_restarts = r.max_restarts > 0 ? r.max_restarts : 100000;
   res.max_restarts = p.max_restarts;
@@ -380,7 +395,7 @@ static int hmc_box_core(const BoxRun& r, BoxResult& res) {
     LQG_CUDA_TRY(b_off.alloc((size_t)(n_chains + 1) * sizeof(int)));
     size_t round_cols = (size_t)n_chains * attempts;            // first round: `attempts` columns for every chain
     while (n_active > 0) {
-      NormalGen gen{r.seed, r.chain_offset, attempts, first ? nullptr : act[cur], p.pos, first ? nullptr : b_off.as<int>(), n_active};
+      NormalGen gen{r.seed, r.chain_offset, attempts, first ? nullptr : act[cur], p.pos, first ? nullptr : b_off.as<int>(), n_active, r.chain_stride};
       t_pre.start();
       LQG_CUDA_TRY(launch_fill_normals(d, round_cols, b_a.as<double>(), gen, st));
       LQG_CUDA_TRY(launch_dgemm(d, (int)round_cols, d, r.U, d, b_a.as<double>(), d,
@@ -431,6 +446,54 @@ static int hmc_box_core(const BoxRun& r, BoxResult& res) {
   LQG_CUDA_TRY(cudaStreamSynchronize(st));
   res.chain_ms = chain_ms; res.pre_ms = pre_ms;
   ph.mark("audit");
+  return LQG_OK;
+}
+
+// Families of chains that share their burn-in (lqg_opts.fork = F > 1): phase 1 runs the root chains
+// (one per family, Philox stream of the family's first chain) through the burn-in, phase 2 starts every
+// chain of a family from its root's state, fork_burn_in transitions before its first emission.  Which
+// root a chain belongs to follows from its GLOBAL id, so a rank whose range starts inside a family
+// simply re-runs that family's root: no exchange, and the samples do not depend on the sharding.
+static int hmc_box_core(const BoxRun& r, BoxResult& res) {
+  const int F = r.fork;
+  if (F <= 1 || r.injected || r.burn_in <= 0 || r.init_ld != 0 || r.chain_offset < 0)
+    return hmc_box_rounds(r, res);
+  const int d = r.d, n = r.n_chains;
+  const int64_t g0 = r.chain_offset, g1 = g0 + n - 1;
+  const int64_t root0 = g0 - g0 % F;
+  const int n_root = (int)((g1 - g1 % F - root0) / F) + 1;
+  BoxRun r1 = r;
+  r1.fork = 0; r1.n_chains = n_root; r1.chain_offset = root0; r1.chain_stride = F; r1.n_per_chain = 0; r1.out = nullptr;
+  r1.on_round = nullptr; r1.short_tail = false; r1.keep_pos = true;
+  BoxResult res1;
+  int rc;
+  if ((rc = hmc_box_rounds(r1, res1))) return rc;
+  bool root_failed = false;
+  for (int s : res1.status) root_failed |= s != 0;
+  if (root_failed) {                     // report through the chains of the failed families
+    res.status.assign(n, 0);
+    unsigned long long bad = 0;
+    for (int c = 0; c < n; ++c) {
+      const int s = res1.status[(size_t)((g0 + c - root0) / F)];
+      res.status[c] = s; bad += s != 0;
+    }
+    memcpy(res.stats, res1.stats, sizeof(res.stats));
+    res.stats[7] = bad;
+    res.chain_ms = res1.chain_ms; res.pre_ms = res1.pre_ms; res.max_restarts = res1.max_restarts;
+    return LQG_OK;
+  }
+  DevBuf b_state0, b_pos0, b_s0;
+  LQG_CUDA_TRY(b_state0.alloc((size_t)d * n * sizeof(double)));
+  LQG_CUDA_TRY(b_pos0.alloc((size_t)n * sizeof(int64_t)));
+  LQG_CUDA_TRY(b_s0.alloc((size_t)n * sizeof(int)));
+  const int s0 = std::max(0, r.burn_in - std::max(0, r.fork_burn_in));
+  LQG_CUDA_TRY(launch_box_fork(d, n, F, g0, root0, res1.state.as<double>(), res1.pos.as<int64_t>(), b_state0.as<double>(),
+                               b_pos0.as<int64_t>(), b_s0.as<int>(), s0, r.st));
+  BoxRun r2 = r;
+  r2.fork = 0; r2.state0 = b_state0.as<double>(); r2.pos0 = b_pos0.as<int64_t>(); r2.sdone0 = b_s0.as<int>();
+  if ((rc = hmc_box_rounds(r2, res))) return rc;
+  for (int k : {0, 1, 2, 3, 4, 5, 10, 11}) res.stats[k] += res1.stats[k];
+  res.chain_ms += res1.chain_ms; res.pre_ms += res1.pre_ms;
   return LQG_OK;
 }
 
@@ -519,7 +582,7 @@ extern "C" int lqg_hmc_box(int32_t d, const double* mu, const double* U, int32_t
   r.d = d; r.mu = i_mu.dev; r.U = i_U.dev; r.u_upper = u_upper; r.Sigma = i_S.dev; r.lb = i_lb.dev; r.ub = i_ub.dev;
   r.init = i_init.dev; r.init_ld = init_ld; r.n_chains = n_chains; r.n_per_chain = n_per_chain; r.burn_in = burn_in;
   r.seed = o.seed; r.chain_offset = o.chain_offset; r.prepass = o.prepass; r.max_restarts = o.max_restarts;
-  r.exact_search = o.hmc_search == 1; r.no_window = o.hmc_search == 2;
+  r.exact_search = o.hmc_search == 1; r.no_window = o.hmc_search == 2; r.fork = o.fork; r.fork_burn_in = o.fork_burn_in;
   r.injected = o.injected ? i_inj.dev : nullptr; r.n_injected = o.n_injected;
   r.out = d_out; r.st = st;
 
@@ -1912,7 +1975,7 @@ extern "C" int lqg_simulate(const lqg_simulate_args* a_, const lqg_opts* opts_, 
   r.d = d; r.mu = i_mu.dev; r.U = i_U.dev; r.u_upper = u_upper; r.Sigma = i_S.dev; r.lb = i_lb.dev; r.ub = i_ub.dev;
   r.init = i_init.dev; r.init_ld = 0; r.n_chains = n_chains; r.n_per_chain = n_per; r.burn_in = a.burn_in;
   r.seed = o.seed; r.chain_offset = o.chain_offset + (int64_t)rank * n_chains; r.prepass = o.prepass;
-  r.max_restarts = o.max_restarts; r.exact_search = o.hmc_search == 1; r.no_window = o.hmc_search == 2; r.out = d_eta; r.st = st;
+  r.max_restarts = o.max_restarts; r.exact_search = o.hmc_search == 1; r.no_window = o.hmc_search == 2; r.fork = o.fork; r.fork_burn_in = o.fork_burn_in; r.out = d_eta; r.st = st;
   static const char* env_tail = getenv("LQG_SIM_SHORT_TAIL");          // A/B aid
   r.short_tail = env_tail ? env_tail[0] != '0' : (host_out || W > 1);  // the last round's copy / gather cannot hide behind sampling
   // The xi products, the all-gathers and the copies work on UNITS of `unit` samples per chain, not on

@@ -346,7 +346,7 @@ __global__ void fill_normals_kernel(int d, size_t n_cols, double* __restrict__ A
     const int chain = g.active ? g.active[a] : a;
     const uint64_t draw = (uint64_t)(g.pos[chain] + j);
     double n0, n1;
-    normal_pair(g.seed, (uint64_t)(g.chain_offset + chain), draw, pr, n0, n1);
+    normal_pair(g.seed, (uint64_t)(g.chain_offset + (int64_t)chain * g.chain_stride), draw, pr, n0, n1);
     double* dst = A + col * d + 2 * (size_t)pr;
     dst[0] = n0;
     if (2 * pr + 1 < (uint32_t)d) dst[1] = n1;

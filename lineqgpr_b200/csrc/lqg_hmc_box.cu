@@ -105,7 +105,7 @@ static __device__ __noinline__ bool draw_momentum(const BoxParams& p, int chain,
     const double* src = p.injected + (size_t)chain * p.n_injected + (size_t)draw * d;
     for (int i = tid; i < d; i += T) a_sm[i] = src[i];
   } else {
-    const uint64_t gchain = (uint64_t)(p.chain_offset + chain);
+    const uint64_t gchain = (uint64_t)(p.chain_offset + (int64_t)chain * p.chain_stride);
     for (int pr = tid; 2 * pr < d; pr += T) {
       double n0, n1;
       normal_pair(p.seed, gchain, (uint64_t)draw, (uint32_t)pr, n0, n1);
@@ -744,6 +744,22 @@ __global__ void box_init_state_kernel(int d, int n_chains, const double* init, i
   state[idx] = init[ch * (size_t)init_ld + i] - mu[i];
 }
 
+__global__ void box_fork_kernel(int d, int n_chains, int F, int64_t g0, int64_t root0, const double* __restrict__ root_state,
+                                const int64_t* __restrict__ root_pos, double* __restrict__ state, int64_t* __restrict__ pos,
+                                int* __restrict__ s_done, int s0) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)d * n_chains) return;
+  const int i = (int)(idx % d);
+  const int c = (int)(idx / d);
+  const int64_t g = g0 + c;
+  const int64_t rho = (g - root0) / F;
+  state[idx] = root_state[(size_t)rho * d + i];
+  if (i == 0) {
+    pos[c] = (g % F == 0) ? root_pos[rho] : 0;
+    s_done[c] = s0;
+  }
+}
+
 // chains that still have transitions to run (and did not fail) -> next round's work list
 __global__ void box_compact_kernel(int n_chains, int total, const int* s_done, const int* status,
                                    int* active_out, int* n_active_out) {
@@ -994,6 +1010,14 @@ cudaError_t launch_box_init_state(int d, int n_chains, const double* init, int64
                                   const double* mu, double* state, cudaStream_t st) {
   const size_t total = (size_t)d * n_chains;
   box_init_state_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d, n_chains, init, init_ld, mu, state);
+  ++launch_counter();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_box_fork(int d, int n_chains, int F, int64_t g0, int64_t root0, const double* root_state,
+                            const int64_t* root_pos, double* state, int64_t* pos, int* s_done, int s0, cudaStream_t st) {
+  const size_t total = (size_t)d * n_chains;
+  box_fork_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d, n_chains, F, g0, root0, root_state, root_pos, state, pos, s_done, s0);
   ++launch_counter();
   return cudaGetLastError();
 }

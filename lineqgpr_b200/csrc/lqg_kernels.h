@@ -33,7 +33,8 @@ struct BoxParams {
   int burn_in, n_per_chain;
   double* out;             // d x (n_chains * n_per_chain)
   uint64_t seed;
-  int64_t chain_offset;
+  int64_t chain_offset;    // global id of local chain c = chain_offset + c * chain_stride (Philox key)
+  int chain_stride;        // 1, or F while the root chains of forked families run (see lqg_opts.fork)
   const double* injected;  // nullable [n_chains][n_injected]
   int64_t n_injected;
   int max_restarts;
@@ -56,6 +57,11 @@ cudaError_t launch_box_prep(int d, const double* mu, const double* lb, const dou
                             cudaStream_t st);
 cudaError_t launch_box_init_state(int d, int n_chains, const double* init, int64_t init_ld,
                                   const double* mu, double* state, cudaStream_t st);
+// forked families (lqg_opts.fork = F): chain c (global id g = g0 + c) takes the centred state of root
+// (g - root0) / F; the first chain of a family (g % F == 0) continues the root's Philox stream at root_pos,
+// the others start theirs at 0; every chain has s0 transitions behind it
+cudaError_t launch_box_fork(int d, int n_chains, int F, int64_t g0, int64_t root0, const double* root_state,
+                            const int64_t* root_pos, double* state, int64_t* pos, int* s_done, int s0, cudaStream_t st);
 // n_active_out[0] = number of unfinished chains, n_active_out[1] = min over healthy chains of s_done.
 // Then the next round is planned on the device: every unfinished chain gets as many pool columns as it
 // can still use (transitions left + a restart allowance, at most the round's cap, which follows the
@@ -172,6 +178,7 @@ struct NormalGen {
   const int64_t* pos;      // [n_chains]
   const int* col_off;      // nullable [n_active + 1]: per-chain column ranges (see BoxParams::col_off)
   int n_active;
+  int chain_stride;        // global id of local chain c = chain_offset + c * chain_stride
 };
 // b_blk_w > 0: the columns of B come in blocks of b_blk_w consecutive columns (stride ldb) that
 // start b_blk_pitch doubles apart (a round of chain-major samples: w finished columns per chain)

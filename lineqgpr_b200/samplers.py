@@ -14,7 +14,8 @@ What stays on the host, exactly where the reference has it on the host: the one-
 whitening algebra (solve, chol, triangular inverse).  Everything per-sample runs on the GPU.
 Extensions (all optional keys of `control`): "n.chains" (independent chains; 1 reproduces the
 reference's single serial chain; with several chains each one runs at least 100 burn-in
-transitions, see chain_burn_in), "burn.in.exact", "seed", "prepass", "injected", "max.restarts", "hmc.search" (lqg_opts.hmc_search),
+transitions, see chain_burn_in), "burn.in.exact", "fork" / "fork.burn.in" (families of chains sharing a root chain's burn-in, see
+chain_fork), "seed", "prepass", "injected", "max.restarts", "hmc.search" (lqg_opts.hmc_search),
 "chain.offset", "U" (a precomputed factor), "whiten" ("device" (default) | "ul" | "tmg", see whiten_box).
 """
 from __future__ import annotations
@@ -103,6 +104,24 @@ def chain_burn_in(burn_in, n_chains, control=None):
     return int(burn_in)
 
 
+FORK_DEFAULT, FORK_BURN_IN = 3, 5
+
+
+def chain_fork(n_chains, control=None):
+    """(fork, fork_burn_in) of lqg_opts.  With many chains, families of 3 share one root chain's burn-in
+    (the root runs the burn-in from the clamped MAP; its 3 chains start from the state it reached, run
+    5 more transitions on their own streams, then emit): a third of the burn-in work, and every emitted
+    column is still burn.in + 5 transitions away from the start.  control["fork"] = 1 gives fully
+    independent chains (each with its own burn-in); injected draws never fork."""
+    control = control or {}
+    if control.get("injected") is not None:
+        return 0, 0
+    # (the default must not depend on how many chains THIS call runs: a sharded job has to pick the same
+    #  families as the whole job; a lone chain without an offset is the reference's single serial chain)
+    fork = int(control.get("fork", FORK_DEFAULT if (n_chains > 1 or "chain.offset" in control) else 1))
+    return (fork, int(control.get("fork.burn.in", FORK_BURN_IN))) if fork > 1 else (0, 0)
+
+
 def tmvrnorm_HMC(object, nsim, control=None, **kw):
     """tmvrnorm.HMC (R/lineqGPsamplers.R:99-143) on the GPU: box-form exact HMC, lqg_hmc_box."""
     control = dict(control or {})
@@ -133,11 +152,12 @@ def tmvrnorm_HMC(object, nsim, control=None, **kw):
     if injected is not None:
         injected = np.ascontiguousarray(injected, dtype=np.float64).reshape(n_chains, -1)
         n_inj = injected.shape[1]
+    fork, fork_burn = chain_fork(n_chains, control)
     opts = L.make_opts(mem=L.MEM_HOST, seed=seed, n_chains=n_chains,
                        max_restarts=int(control.get("max.restarts", 0)),
                        chain_offset=int(control.get("chain.offset", 0)),
                        injected=injected, n_injected=n_inj, prepass=int(control.get("prepass", -1)),
-                       hmc_search=int(control.get("hmc.search", 0)))
+                       hmc_search=int(control.get("hmc.search", 0)), fork=fork, fork_burn_in=fork_burn)
     Uf, Sf = (L.f64(U) if U is not None else None), L.f64(Sigma)
     mu_c, lb_c, ub_c, init_c = (np.ascontiguousarray(v, dtype=np.float64) for v in (mu, lb, ub, init))
     out = control.get("out")                                            # optional caller-owned d x (n_chains*n_per) F-array
@@ -151,7 +171,7 @@ def tmvrnorm_HMC(object, nsim, control=None, **kw):
     rc = L.lib().lqg_hmc_box(d, L.ptr(mu_c), L.ptr(Uf), 1, L.ptr(Sf), L.ptr(lb_c), L.ptr(ub_c),
                              L.ptr(init_c), 0, n_per, burn, opts, L.ptr(out), None, stats)
     last_stats.clear(); last_stats.update(stats.asdict(), sampler="HMC", n_chains=n_chains, n_per_chain=n_per, seed=seed,
-                                          burn_in_per_chain=burn)
+                                          burn_in_per_chain=burn, fork=fork, fork_burn_in=fork_burn)
     if rc == 8:
         raise ValueError("Error: M must be positive definite.")        # tmg:R/tmg.R:17-20 (device whitening)
     L.check(rc, "tmvrnorm.HMC")

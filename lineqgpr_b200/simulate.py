@@ -238,12 +238,15 @@ def simulate_pipeline(tmvPar, nsim, Lambda=None, Phi_test=None, xtest=None, ulis
     seed = control.get("seed")
     if seed is None:
         seed = int(np.random.randint(1, 10000000))                     # tmg:R/tmg.R:102
+    from .samplers import chain_fork
+    fork, fork_burn = chain_fork(n_chains, control)
     opts = L.make_opts(mem=L.MEM_HOST, seed=seed, n_chains=n_chains, max_restarts=int(control.get("max.restarts", 0)),
-                       chain_offset=int(control.get("chain.offset", 0)), prepass=int(control.get("prepass", -1)))
+                       chain_offset=int(control.get("chain.offset", 0)), prepass=int(control.get("prepass", -1)),
+                       hmc_search=int(control.get("hmc.search", 0)), fork=fork, fork_burn_in=fork_burn)
     st = L.SimulateStats()
     rc = L.lib().lqg_simulate(L.C.byref(a), opts, comm.handle if comm is not None else None, st)
     last_stats.clear(); last_stats.update(st.asdict(), sampler="HMC", n_chains=n_chains, n_per_chain=n_per, seed=seed,
-                                          burn_in_per_chain=int(a.burn_in))
+                                          burn_in_per_chain=int(a.burn_in), fork=fork, fork_burn_in=fork_burn)
     if rc == 8:
         raise ValueError("Error: M must be positive definite.")        # tmg:R/tmg.R:17-20 (device whitening)
     L.check(rc, "lqg_simulate")

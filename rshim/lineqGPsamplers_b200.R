@@ -5,6 +5,15 @@
 #
 # dyn.load("lqg_rcall.so") once (or useDynLib in NAMESPACE).
 
+# c(fork, fork.burn.in) of lqg_opts: with several chains, families of 3 share one root chain's burn-in
+# (the root runs burn.in transitions from the clamped MAP; its 3 chains start from the state it reached
+# and run 5 more on their own streams before they emit).  control$fork = 1: fully independent chains.
+.lqg_fork <- function(control) {
+  fork <- if ("fork" %in% names(control)) control$fork else if (control$n.chains > 1) 3L else 1L
+  fb <- if ("fork.burn.in" %in% names(control)) control$fork.burn.in else 5L
+  as.integer(c(fork, fb))
+}
+
 tmvrnorm.HMC <- function(object, nsim, control = list(burn.in = 1e2), ...) {
   if (!("burn.in" %in% names(control))) control$burn.in <- 1e2
   # extension: independent chains.  Default = one chain per resident CTA slot of the device for this
@@ -43,7 +52,7 @@ tmvrnorm.HMC <- function(object, nsim, control = list(burn.in = 1e2), ...) {
   seed <- sample(1:10000000, 1)             # tmg/R/tmg.R:102: set.seed() still determines the run
   xi <- .Call("lqg_hmc_box_call", as.double(tmvPar$mu), Ri, tmvPar$Sigma, as.double(lb), as.double(ub),
               as.double(init_vec), as.integer(n.per), as.integer(control$burn.in),
-              as.integer(control$n.chains), as.integer(seed))
+              as.integer(control$n.chains), as.integer(seed), .lqg_fork(control))
   return(xi[, seq_len(nsim), drop = FALSE])
 }
 
@@ -100,7 +109,8 @@ tmvrnorm.ExpT <- function(object, nsim, control = NULL, ...) {
   seed <- sample(1:10000000, 1)                                     # set.seed(seed) of the caller decides the run
   r <- .Call("lqg_simulate_call", as.double(tmvPar$mu), tmvPar$Sigma, as.double(lb), as.double(ub),
              as.double(init_vec), Lambda, Phi.test, as.double(probs), as.integer(n.per),
-             as.integer(control$burn.in), as.integer(control$n.chains), as.integer(seed), isTRUE(keep.ysim))
+             as.integer(control$burn.in), as.integer(control$n.chains), as.integer(seed), isTRUE(keep.ysim),
+             .lqg_fork(control))
   keep <- seq_len(nsim)
   list(xi.sim = r[[1]][, keep, drop = FALSE],
        ysim = if (is.null(r[[2]])) NULL else r[[2]][, keep, drop = FALSE],

@@ -39,7 +39,7 @@ SEXP lqg_rtmg_call(SEXP n_, SEXP seed_, SEXP initial_, SEXP numlin_, SEXP F_, SE
 
 /* tmvrnorm.HMC body: returns the d x nsim matrix directly (R/lineqGPsamplers.R:142) */
 SEXP lqg_hmc_box_call(SEXP mu_, SEXP U_, SEXP Sigma_, SEXP lb_, SEXP ub_, SEXP init_,
-                      SEXP n_per_chain_, SEXP burn_in_, SEXP n_chains_, SEXP seed_) {
+                      SEXP n_per_chain_, SEXP burn_in_, SEXP n_chains_, SEXP seed_, SEXP fork_) {
   const int d = Rf_length(mu_);
   const int n_per = Rf_asInteger(n_per_chain_), burn = Rf_asInteger(burn_in_);
   lqg_opts o;
@@ -48,6 +48,7 @@ SEXP lqg_hmc_box_call(SEXP mu_, SEXP U_, SEXP Sigma_, SEXP lb_, SEXP ub_, SEXP i
   o.n_chains = Rf_asInteger(n_chains_);
   o.seed = (uint64_t)Rf_asInteger(seed_);
   o.prepass = -1;
+  if (Rf_length(fork_) >= 2) { o.fork = INTEGER(fork_)[0]; o.fork_burn_in = INTEGER(fork_)[1]; }   /* c(fork, fork.burn.in) */
   lqg_hmc_stats st;
   /* Rf_allocMatrix takes int dimensions: n.chains * n.per is formed in 64 bits and refused when it
    * does not fit (the element count d * ncol itself may exceed 2^31: R long vectors hold it) */
@@ -73,7 +74,7 @@ SEXP lqg_hmc_box_slots_call(SEXP d_) {
  * ysim resident on the GPU.  Phi_ may be NULL (lineqAGP returns xiAll.sim only); keep_ysim = FALSE never
  * materialises ysim.  Returns list(xi.sim, ysim | NULL, mean | NULL, qtls | NULL). */
 SEXP lqg_simulate_call(SEXP mu_, SEXP Sigma_, SEXP lb_, SEXP ub_, SEXP init_, SEXP Lambda_, SEXP Phi_, SEXP probs_,
-                       SEXP n_per_chain_, SEXP burn_in_, SEXP n_chains_, SEXP seed_, SEXP keep_ysim_) {
+                       SEXP n_per_chain_, SEXP burn_in_, SEXP n_chains_, SEXP seed_, SEXP keep_ysim_, SEXP fork_) {
   const int d = Rf_length(mu_), m = Rf_ncols(Lambda_);
   const int n_per = Rf_asInteger(n_per_chain_);
   const int have_phi = !Rf_isNull(Phi_), keep = have_phi && Rf_asInteger(keep_ysim_);
@@ -86,6 +87,7 @@ SEXP lqg_simulate_call(SEXP mu_, SEXP Sigma_, SEXP lb_, SEXP ub_, SEXP init_, SE
   o.n_chains = Rf_asInteger(n_chains_);
   o.seed = (uint64_t)Rf_asInteger(seed_);
   o.prepass = -1;
+  if (Rf_length(fork_) >= 2) { o.fork = INTEGER(fork_)[0]; o.fork_burn_in = INTEGER(fork_)[1]; }   /* c(fork, fork.burn.in) */
   const long long ncol = (long long)o.n_chains * (long long)n_per;
   if (o.n_chains <= 0 || n_per <= 0 || ncol > 2147483647LL)
     Rf_error("lqg_simulate: n.chains * n.per = %lld columns do not fit an R matrix dimension", ncol);

@@ -284,6 +284,43 @@ def test_box_sharding_invariance(lqg):
     assert np.array_equal(full, np.hstack([lo, hi]))
 
 
+def test_forked_families_share_a_root_chain(lqg):
+    """lqg_opts.fork = F: the chains of a family start from the state their root chain reached after the
+    burn-in.  (1) With fork.burn.in = 0 the first chain of every family IS the independent chain of the
+    same global id, bit for bit (it continues the root's stream); the other chains of the family differ
+    from their independent versions but start from the same point.  (2) Which root a chain has follows
+    from its global id: shards that cut through families give the columns of the whole job.
+    (3) Statistics of the forked job agree with independent chains."""
+    from lineqgpr_b200 import workloads as W
+    par, _ = W.cfg3()
+    obj = dict(par, **{"class": "HMC"})
+    n_ch, n_per = 12, 6
+    indep = lqg.tmvrnorm(obj, n_ch * n_per, {"burn.in": 7, "n.chains": n_ch, "seed": 3, "fork": 1, "burn.in.exact": True})
+    s_ind = dict(lqg.last_stats)
+    fork0 = lqg.tmvrnorm(obj, n_ch * n_per, {"burn.in": 7, "n.chains": n_ch, "seed": 3, "fork": 3, "fork.burn.in": 0, "burn.in.exact": True})
+    s_f = dict(lqg.last_stats)
+    for c in range(n_ch):
+        a, b = indep[:, c * n_per:(c + 1) * n_per], fork0[:, c * n_per:(c + 1) * n_per]
+        assert np.array_equal(a, b) == (c % 3 == 0), c
+    assert s_f["transitions"] == 4 * 7 + n_ch * n_per and s_ind["transitions"] == n_ch * (7 + n_per)
+    # (2) shards of 5 + 7 chains cut through the families {3,4,5} and nothing else lines up with 3
+    ctl = {"burn.in": 7, "seed": 3, "fork": 3, "fork.burn.in": 2, "burn.in.exact": True}
+    whole = lqg.tmvrnorm(obj, n_ch * n_per, dict(ctl, **{"n.chains": n_ch}))
+    lo = lqg.tmvrnorm(obj, 5 * n_per, dict(ctl, **{"n.chains": 5, "chain.offset": 0}))
+    hi = lqg.tmvrnorm(obj, 7 * n_per, dict(ctl, **{"n.chains": 7, "chain.offset": 5}))
+    assert np.array_equal(whole, np.hstack([lo, hi]))
+    one = lqg.tmvrnorm(obj, n_per, dict(ctl, **{"n.chains": 1, "chain.offset": 4}))
+    assert np.array_equal(one, whole[:, 4 * n_per:5 * n_per])
+    # (3) moments: 300 chains in families of 3 against 300 independent chains
+    x3 = lqg.tmvrnorm(obj, 6000, {"burn.in": 100, "n.chains": 300, "seed": 5})
+    assert lqg.last_stats["fork"] == 3
+    x1 = lqg.tmvrnorm(obj, 6000, {"burn.in": 100, "n.chains": 300, "seed": 6, "fork": 1})
+    se = np.sqrt((x3.var(1) + x1.var(1)) / 6000)
+    assert (np.abs(x3.mean(1) - x1.mean(1)) > 3.5 * se).sum() <= 1
+    pv = np.array([stats.ks_2samp(x3[i], x1[i]).pvalue for i in range(x3.shape[0])])
+    assert (pv < 0.01).sum() <= max(1, int(0.05 * x3.shape[0]))
+
+
 @pytest.mark.parametrize("cfg", ["cfg1", "cfg2", "cfg3"])
 def test_box_statistical_agreement_with_oracle(lqg, oracle, cfg):
     """L-stat: per-coordinate KS p > 0.01 and mean/variance within 3 Monte-Carlo standard errors
@@ -298,13 +335,48 @@ def test_box_statistical_agreement_with_oracle(lqg, oracle, cfg):
     xo_t, xg_t = xo[:, ::thin], xg[:, ::thin]
     d = xo.shape[0]
     pvals = np.array([stats.ks_2samp(xo_t[i], xg_t[i]).pvalue for i in range(d)])
-    # d simultaneous tests at level 0.01: allow the expected handful of chance rejections
-    assert (pvals < 0.01).sum() <= max(1, int(0.05 * d)), pvals.min()
+    # d simultaneous tests at level 0.01.  Neighbouring coordinates of a GP are correlated at 0.9 and more, so
+    # chance rejections come in runs of 5-15 coordinates (one unlucky stretch of either chain): the raw count
+    # gets room for one such run, and the same test on decorrelated coordinates (projections on the
+    # eigenvectors of Sigma, nearly independent tests) keeps the 5 % allowance.
+    assert (pvals < 0.01).sum() <= max(1, int(0.15 * d)), ((pvals < 0.01).sum(), pvals.min())
+    V = np.linalg.eigh(np.asarray(par["Sigma"], float))[1]
+    po, pg = V.T @ xo_t, V.T @ xg_t
+    pv_dec = np.array([stats.ks_2samp(po[i], pg[i]).pvalue for i in range(d)])
+    assert (pv_dec < 0.01).sum() <= max(1, int(0.05 * d)), ((pv_dec < 0.01).sum(), pv_dec.min())
     ne = xo_t.shape[1]
     se_mean = np.sqrt((xo_t.var(1) + xg_t.var(1)) / ne)
     assert (np.abs(xo_t.mean(1) - xg_t.mean(1)) > 3 * se_mean).sum() <= max(1, int(0.05 * d))
     se_var = np.sqrt(2.0 / (ne - 1)) * np.sqrt(xo_t.var(1) ** 2 + xg_t.var(1) ** 2) * 1.5   # kurtosis slack
     assert (np.abs(xo_t.var(1) - xg_t.var(1)) > 3 * se_var).sum() <= max(1, int(0.05 * d))
+
+
+def test_multi_chain_default_with_burn_in_one_matches_a_long_single_chain(lqg):
+    """simulate.* hands tmvrnorm burn.in = 1 (R/lineqGP.R:617): fine for the reference's ONE long chain,
+    but with many chains started at the same clamped MAP every column would sit two transitions from it.
+    The wrapper therefore runs at least 100 burn-in transitions per chain (chain_burn_in); on a tightly
+    constrained problem (MAP on the boundary of a narrow box) the default multi-chain output must have the
+    distribution of a single long chain.  (With T = pi/2 the exact HMC forgets its start within a few
+    transitions — lag-1 autocorrelations are below 0.1 at every BASELINE config — so the floor is a
+    safeguard, not something a KS test on a few hundred columns can see.)"""
+    rng = np.random.default_rng(5)
+    d = 24
+    B = rng.standard_normal((d, d)); S = B @ B.T / d + 0.2 * np.eye(d)
+    sd = np.sqrt(np.diag(S))
+    mu = np.zeros(d)
+    lb, ub = 0.25 * sd, 2.0 * sd                                    # the box sits in the upper tail: the mode is in its lb corner
+    par = dict(mu=mu, Sigma=S, lb=lb, ub=ub, map=lb + 0.02 * sd)
+    par["class"] = "HMC"
+    n = 4096
+    one = lqg.tmvrnorm(par, 4 * n, {"burn.in": 200, "n.chains": 1, "seed": 3})[:, ::4]
+    many = lqg.tmvrnorm(par, n, {"burn.in": 1, "n.chains": 512, "seed": 9})
+    assert lqg.last_stats["burn_in_per_chain"] == 100
+    pv = np.array([stats.ks_2samp(one[i], many[i]).pvalue for i in range(d)])
+    assert (pv < 0.01).sum() <= 1, pv.min()
+    se = np.sqrt((one.var(1) + many.var(1)) / n)
+    assert (np.abs(one.mean(1) - many.mean(1)) > 3.5 * se).sum() <= 1
+    lqg.tmvrnorm(par, 512, {"burn.in": 1, "n.chains": 512, "seed": 9, "burn.in.exact": True})
+    assert lqg.last_stats["burn_in_per_chain"] == 1                 # the caller's value stands when asked for
 
 
 def test_stacked_constraints_statistics_m150(lqg, oracle):
@@ -385,7 +457,8 @@ def test_full_size_m1000_properties(lqg):
         assert np.isfinite(x).all()
         assert np.all(x >= lb[:, None]) and np.all(x <= ub[:, None])
         assert st["violations"] == 0 and st["failed_chains"] == 0
-        assert st["transitions"] == n_chains * (3 + n // n_chains)
+        # families of 3 chains share a root chain's 3 burn-in transitions, then every chain runs min(5, 3) more
+        assert st["fork"] == 3 and st["transitions"] == -(-n_chains // 3) * 3 + n_chains * (3 + n // n_chains)
         assert st["hit_searches"] >= st["bounces"] + st["transitions"]
 
 
