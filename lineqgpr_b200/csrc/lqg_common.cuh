@@ -280,6 +280,35 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// Several chains may share one CTA (NCH > 1): a chain is then run by a GROUP of G warps with its own
+// named barrier (id 1 + group), its own state copy, queues and slots; what the groups share is the read-only
+// per-coordinate tables in shared memory.  With NCH == 1 the group is the CTA and the barrier is barrier 0.
+struct Grp {
+  int id;      // group (chain slot) inside the CTA
+  int tid;     // thread index inside the group
+};
+template <int NCH, int T>
+__device__ __forceinline__ void group_sync(int grp) {
+  if (NCH == 1) __syncthreads();
+  else asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(T) : "memory");
+}
+template <int NCH, int T>
+__device__ __forceinline__ bool group_and(int grp, bool v) {
+  if (NCH == 1) return __syncthreads_and(v) != 0;
+  unsigned r;
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      "setp.ne.u32 p, %1, 0;\n"
+      "bar.red.and.pred q, %2, %3, p;\n"
+      "selp.u32 %0, 1, 0, q;\n"
+      "}\n"
+      : "=r"(r)
+      : "r"((unsigned)v), "r"(grp + 1), "n"(T)
+      : "memory");
+  return r != 0;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);

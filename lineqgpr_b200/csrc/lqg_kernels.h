@@ -142,7 +142,7 @@ cudaError_t launch_canon_rownorms(int d, int c, const double* F, double* frow2, 
 cudaError_t launch_canon_violations(int d, int c, size_t n_cols, const double* F, const double* g,
                                     const double* fnorm, const double* out,
                                     unsigned long long* count, cudaStream_t st);
-size_t canon_smem_bytes(int d, int c, int f_in_smem);
+size_t canon_smem_bytes(int d, int c, int f_in_smem, int nch = 1);
 int canon_f_fits_smem(int d, int c);
 
 // ---- lock-step canonical HMC for large dense F (lqg_hmc_canonical_batched.cu) ----------------
