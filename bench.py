@@ -519,6 +519,19 @@ def run_ours(a):
     # is the pre-pass GEMM (d^2 each, triangular U halves the executed work)
     w_chain = 40.0 * c * se + 8.0 * d * bo + 3.0 * d * tr + float(d) * d * rs
     w_pre = float(d) * d * tr
+    # forked families: the root phase (one chain per family burning in, at most one chain per SM: latency-bound) and
+    # the sampling phase (every chain slot busy) of the same kernel, separately
+    phases = None
+    r_tr = sum(s.root_transitions for s in stats)
+    if r_tr > 0:
+        r_bo = sum(s.root_bounces for s in stats); r_se = sum(s.root_hit_searches for s in stats)
+        r_rs = sum(s.root_restarts for s in stats); r_ms = sum(s.root_chain_ms for s in stats)
+        w_root = 40.0 * c * r_se + 8.0 * d * r_bo + 3.0 * d * r_tr + float(d) * d * r_rs
+        phases = {"root": {"transitions_per_step": r_tr / len(stats), "chain_ms_per_step": r_ms / len(stats),
+                           "frac": w_root / (r_ms * 1e-3) / 1e12 / dfma.value},
+                  "sampling": {"transitions_per_step": (tr - r_tr) / len(stats), "chain_ms_per_step": (chain_ms - r_ms) / len(stats),
+                               "frac": (w_chain - w_root) / ((chain_ms - r_ms) * 1e-3) / 1e12 / dfma.value},
+                  "note": "roofline.frac is over both phases; the root phase runs n_chains / fork chains (one per SM)"}
     traffic = traffic_detail = None
     try:      # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of THIS workload
         allt = json.load(open(ROOT / "profiles" / "traffic.json"))
@@ -532,7 +545,7 @@ def run_ours(a):
             "peak": dfma.value, "peak_source": "lqg_measure_fp64_peaks DFMA micro-benchmark, this run (MEASURED_PEAKS.json has no FP64 entry)",
             "unit": "TFLOP/s", "frac": w_chain / (chain_ms * 1e-3) / 1e12 / dfma.value, "traffic": traffic,
             "launch_ms": chain_ms / len(stats), "share_of_step": chain_ms / sum(step_ms),
-            "traffic_detail": traffic_detail,
+            "traffic_detail": traffic_detail, "phases": phases,
             "note": "bound = FP64 CUDA-core pipe (SURVEY.md par.8d): state in registers, Sigma/U L2-resident; see roofline_hbm for the HBM view"}
     # the same kernel against the HBM roofline: algorithmic bytes = momentum columns read + samples written
     try:

@@ -94,6 +94,10 @@ typedef struct lqg_hmc_stats {
   double  prepass_ms;      /* device time of the momentum GEMM pre-pass (0 when off)           */
   int64_t slow_searches;   /* box kernel: hit searches that were re-run with tmg's exact arithmetic */
   int64_t window_retries;  /* box kernel: time windows without a hit, searched again 4 x wider          */
+  /* forked families (lqg_opts.fork > 1): the share of the totals above spent in the root phase (one chain per
+   * family burning in; at most one chain per SM runs then, so it is latency- rather than throughput-bound)   */
+  int64_t root_transitions, root_bounces, root_hit_searches, root_restarts;
+  double  root_chain_ms, root_prepass_ms;
 } lqg_hmc_stats;
 
 typedef struct lqg_rsm_stats {

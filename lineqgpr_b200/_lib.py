@@ -49,7 +49,9 @@ class HmcStats(C.Structure):
     _fields_ = [("transitions", C.c_int64), ("bounces", C.c_int64), ("hit_searches", C.c_int64),
                 ("vel_restarts", C.c_int64), ("chk_restarts", C.c_int64), ("exact_evals", C.c_int64),
                 ("violations", C.c_int64), ("failed_chains", C.c_int64), ("chain_ms", C.c_double),
-                ("prepass_ms", C.c_double), ("slow_searches", C.c_int64), ("window_retries", C.c_int64)]
+                ("prepass_ms", C.c_double), ("slow_searches", C.c_int64), ("window_retries", C.c_int64),
+                ("root_transitions", C.c_int64), ("root_bounces", C.c_int64), ("root_hit_searches", C.c_int64),
+                ("root_restarts", C.c_int64), ("root_chain_ms", C.c_double), ("root_prepass_ms", C.c_double)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -179,6 +179,11 @@ static int fetch_host(std::vector<double>& dst, const double* src, size_t n, int
   return LQG_OK;
 }
 
+static void fill_root_stats(lqg_hmc_stats* s, const unsigned long long* h, double chain_ms, double pre_ms) {
+  if (!s) return;
+  s->root_transitions = (int64_t)h[0]; s->root_bounces = (int64_t)h[1]; s->root_hit_searches = (int64_t)h[2];
+  s->root_restarts = (int64_t)(h[3] + h[4]); s->root_chain_ms = chain_ms; s->root_prepass_ms = pre_ms;
+}
 static void fill_stats(lqg_hmc_stats* s, const unsigned long long* h, double chain_ms, double pre_ms, unsigned long long slow = 0,
                        unsigned long long widen = 0) {
   if (!s) return;
@@ -278,6 +283,8 @@ struct BoxResult {
   DevBuf state;               // d x n_chains centred positions x_b of the last transition
   DevBuf pos;                 // [n_chains] momenta consumed (BoxRun::keep_pos)
   int max_restarts = 0;
+  unsigned long long root_stats[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // the root phase's share of stats (forked families)
+  double root_chain_ms = 0.0, root_pre_ms = 0.0;
 };
 
 static int hmc_box_rounds(const BoxRun& r, BoxResult& res) {
@@ -494,6 +501,8 @@ static int hmc_box_core(const BoxRun& r, BoxResult& res) {
   if ((rc = hmc_box_rounds(r2, res))) return rc;
   for (int k : {0, 1, 2, 3, 4, 5, 10, 11}) res.stats[k] += res1.stats[k];
   res.chain_ms += res1.chain_ms; res.pre_ms += res1.pre_ms;
+  memcpy(res.root_stats, res1.stats, sizeof(res.root_stats));
+  res.root_chain_ms = res1.chain_ms; res.root_pre_ms = res1.pre_ms;
   return LQG_OK;
 }
 
@@ -629,6 +638,7 @@ extern "C" int lqg_hmc_box(int32_t d, const double* mu, const double* U, int32_t
   ph.mark("copy out");
   rc = box_result_rc(res, "lqg_hmc_box");
   fill_stats(stats, res.stats, res.chain_ms, res.pre_ms, res.stats[10], res.stats[11]);
+  fill_root_stats(stats, res.root_stats, res.root_chain_ms, res.root_pre_ms);
   fold_launches();
   return rc;
   LQG_API_END("lqg_hmc_box")
@@ -2210,6 +2220,7 @@ extern "C" int lqg_simulate(const lqg_simulate_args* a_, const lqg_opts* opts_, 
   for (auto& pr : xi_timers) { float f = 0; if (cudaEventElapsedTime(&f, pr.first, pr.second) == cudaSuccess) xi_ms += f; }
   if (stats) {
     fill_stats(&stats->hmc, res.stats, res.chain_ms, res.pre_ms, res.stats[10], res.stats[11]);
+    fill_root_stats(&stats->hmc, res.root_stats, res.root_chain_ms, res.root_pre_ms);
     stats->xi_ms = xi_ms; stats->gemm_ms = t_gemm; stats->bands_ms = t_bands; stats->total_ms = t_total.ms();
     stats->n_local = N_local; stats->n_total = N_total; stats->row_begin = r0; stats->row_end = r1;
     stats->rank = rank; stats->world = W; stats->rounds = rounds;

@@ -23,6 +23,7 @@
 //     dimensions); partial k-tiles and odd row counts are staged by the threads themselves.
 //   * dgemm_dmma_kernel: LDG -> registers -> STS double buffering with one barrier per k-tile;
 //     kept for operands that are not 16-byte aligned (LQG_GEMM_RING=0 forces it).
+#include <cuda.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -325,6 +326,183 @@ dgemm_ring_kernel(int m, int n, int k, const double* __restrict__ A, int64_t lda
   }
 }
 
+
+// ---- tensor-map kernel -------------------------------------------------------------------
+// Same tile shape, ring and epilogue as dgemm_ring_kernel, but a k-tile arrives as 9 tiled TMA copies
+// (cp.async.bulk.tensor.2d, SASS UTMALDG) issued by ONE thread: 8 boxes of 16 rows x 16 k of A and one box
+// of 16 k x 64 columns of B, 128-byte swizzled.  Out-of-range rows, columns and k are zero-filled by the
+// copy engine, so there is no edge path.  Shared-memory layout of a stage (1024-byte aligned):
+//   A box b (rows 16 b .. 16 b + 15):  byte 2048 b + 128 k + 8 r, with address bits [4:6] ^= bits [7:9]
+//   B:                                 byte 16384 + 128 n + 8 k,  same swizzle
+// DMMA sums 4 values of k per instruction; which 4 is free as long as A and B agree.  Step k4 of a k-tile
+// takes k = 2 q + 4 (fk / 2) + (fk mod 2), q in {0, 1, 4, 5}: with that choice both fragment loads touch
+// every shared-memory bank pair exactly twice (2 wavefronts, the minimum for 32 x 8 bytes), whereas the
+// natural order k = 4 k4 + fk costs 4 wavefronts on the A side.
+constexpr int TST = 4, TPF = 2;
+constexpr int T_A_BYTES = BM * BK * 8, T_B_BYTES = BN * BK * 8, T_STAGE_BYTES = T_A_BYTES + T_B_BYTES;
+static_assert(T_STAGE_BYTES % 1024 == 0, "stages must keep the 1024-byte alignment of the swizzle pattern");
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+
+__global__ void __launch_bounds__(NT, 2)
+dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int m, int n, int k,
+                 double* __restrict__ C, int64_t ldc, double* __restrict__ row_sum, int a_upper, int tail_cb) {
+  extern __shared__ __align__(1024) unsigned char dg_tma[];
+  __shared__ __align__(8) uint64_t full_bar[TST], empty_bar[TST];
+  // dynamic shared memory is only guaranteed 16-byte aligned: round up (the launch asks for 1 KB more)
+  unsigned char* ring = dg_tma + ((1024u - (smem_u32(dg_tma) & 1023u)) & 1023u);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp & 3, wn = warp >> 2;
+  const int MB = (m + BM - 1) / BM, NB = (n + BN - 1) / BN;     // tile order: see dgemm_dmma_kernel
+  const int NBh = NB - tail_cb;
+  int bm, bn;
+  if ((int)blockIdx.x < MB * NBh) { bn = blockIdx.x / MB; bm = blockIdx.x - bn * MB; }
+  else { const int r = blockIdx.x - MB * NBh; bm = r / tail_cb; bn = NBh + (r - bm * tail_cb); }
+  const int row0 = bm * BM, col0 = bn * BN;
+  const int kt_end = (k + BK - 1) / BK;
+  const int kt_begin = a_upper ? min(row0 / BK, kt_end) : 0;
+  const int nkt = kt_end - kt_begin;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < TST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], NWARP); }
+  }
+  __syncthreads();
+
+  // k-tile `it` is issued by lane 0 of warp it % 8 (the job rotates so that no warp's DMMA stream pays for all of it)
+  auto issue = [&](int it) {
+    if (warp != (it & (NWARP - 1))) return;
+    const int s = it % TST;
+    if (it >= TST) mbar_wait(&empty_bar[s], (uint32_t)((it / TST) - 1) & 1u);
+    if (lane == 0) {
+      const int k0 = (kt_begin + it) * BK;
+      unsigned char* stage = ring + (size_t)s * T_STAGE_BYTES;
+      mbar_expect_tx(&full_bar[s], (uint32_t)T_STAGE_BYTES);
+#pragma unroll
+      for (int b = 0; b < BM / 16; ++b) tma_load_2d(stage + b * 2048, &mapA, row0 + 16 * b, k0, &full_bar[s]);
+      tma_load_2d(stage + T_A_BYTES, &mapB, k0, col0, &full_bar[s]);
+    }
+  };
+
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  for (int it = 0; it < TPF && it < nkt; ++it) issue(it);
+
+  const int fr = lane >> 2, fk = lane & 3;
+  // lane parts of the swizzled fragment addresses (bytes; see the layout above)
+  const int a_lane = wm * 4096 + (4 * (fk >> 1) + (fk & 1)) * 128 + 8 * (fr & 1);
+  const int a_c0 = (fr >> 1) ^ (fk & 1);
+  const int a_off[2][2] = {{64 * (fk >> 1) + 16 * a_c0, 64 * (fk >> 1) + 16 * (a_c0 ^ 2)},
+                           {64 * (1 - (fk >> 1)) + 16 * a_c0, 64 * (1 - (fk >> 1)) + 16 * (a_c0 ^ 2)}};   // [i & 1][k4 & 1]
+  const int b_lane = T_A_BYTES + (wn * 32 + fr) * 128 + 8 * (fk & 1);
+  const int b_l = ((fk >> 1) << 1) ^ fr;
+  const int b_off[4] = {16 * (0 ^ b_l), 16 * (1 ^ b_l), 16 * (4 ^ b_l), 16 * (5 ^ b_l)};                 // [k4]: q = 0, 1, 4, 5
+  const int wrow = row0 + wm * 32;
+  for (int it = 0; it < nkt; ++it) {
+    if (it + TPF < nkt) issue(it + TPF);
+    const int s = it % TST;
+    const int k0 = (kt_begin + it) * BK;
+    mbar_wait(&full_bar[s], (uint32_t)(it / TST) & 1u);
+    const unsigned char* stage = ring + (size_t)s * T_STAGE_BYTES;
+    constexpr int Q2[4] = {0, 2, 8, 10};
+    if (a_upper && k0 < wrow + 32) {
+      // diagonal block of an upper-triangular A: the largest k of step k4 is k0 + Q2[k4] + 5; a group of 8
+      // rows that starts below it contributes nothing
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4) {
+        const int kmax = k0 + Q2[k4] + 5;
+        if (wrow > kmax) continue;
+        double bf[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bf[j] = *reinterpret_cast<const double*>(stage + b_lane + j * 1024 + b_off[k4]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (wrow + i * 8 > kmax) continue;
+          const double af = *reinterpret_cast<const double*>(stage + a_lane + (i >> 1) * 2048 + Q2[k4] * 128 + a_off[i & 1][k4 & 1]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af, bf[j]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4) {
+        double af[4], bf[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          af[i] = *reinterpret_cast<const double*>(stage + a_lane + (i >> 1) * 2048 + Q2[k4] * 128 + a_off[i & 1][k4 & 1]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bf[j] = *reinterpret_cast<const double*>(stage + b_lane + j * 1024 + b_off[k4]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);
+  }
+
+  // ---- epilogue: C store and optional row sums (band mean numerator) ----
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = row0 + wm * 32 + i * 8 + fr;
+    double rs = 0.0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int cc = col0 + wn * 32 + j * 8 + 2 * fk;
+      if (r < m) {
+        if (cc < n)     { if (C) C[(size_t)cc * ldc + r] = acc[i][j][0];       rs += acc[i][j][0]; }
+        if (cc + 1 < n) { if (C) C[(size_t)(cc + 1) * ldc + r] = acc[i][j][1]; rs += acc[i][j][1]; }
+      }
+    }
+    if (row_sum) {
+      rs += __shfl_xor_sync(0xffffffffu, rs, 1);
+      rs += __shfl_xor_sync(0xffffffffu, rs, 2);
+      if (fk == 0 && r < m) atomicAdd(row_sum + r, rs);
+    }
+  }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      p = nullptr;
+    }
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+// 2-D column-major FP64 matrix (rows x cols, leading dimension ld) with a box of box_r x box_c, 128-byte swizzle
+static bool make_map(CUtensorMap* map, const double* base, int rows, int cols, int64_t ld, int box_r, int box_c) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)rows, (cuuint64_t)cols};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(double)};
+  const cuuint32_t box[2] = {(cuuint32_t)box_r, (cuuint32_t)box_c};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // A[kk, col] = N(0,1) draw of (chain = active[col / attempts], draw index = pos[chain] + col % attempts,
 // coordinate kk; with col_off the columns of active chain a are [col_off[a], col_off[a+1])) — the same Philox addressing the chain kernels use, so pool and in-kernel
 // draws agree.
@@ -357,33 +535,44 @@ cudaError_t launch_dgemm(int m, int n, int k, const double* A, int64_t lda, cons
                          int64_t ldb, double* C, int64_t ldc, double* row_sum, int a_upper,
                          cudaStream_t st, int b_blk_w, int64_t b_blk_pitch) {
   if (m <= 0 || n <= 0) return cudaSuccess;
-  // the ring kernel's bulk copies need 16-byte aligned operand columns
-  static const char* env_ring = getenv("LQG_GEMM_RING");             // A/B aid: 0 = register-staged kernel
+  // kernel choice (LQG_GEMM_RING: 2 = tensor-map TMA where possible (default), 1 = one-column bulk copies,
+  // 0 = register-staged kernel): bulk copies of either kind need 16-byte aligned operand columns; the
+  // tensor-map form also needs plain (not blocked) columns of B
+  static const char* env_ring = getenv("LQG_GEMM_RING");
+  const int want = env_ring ? atoi(env_ring) : 2;
   const bool aligned = ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && lda % 2 == 0 && ldb % 2 == 0 &&
                        (b_blk_w <= 0 || b_blk_pitch % 2 == 0);
-  const bool ring = aligned && !(env_ring && env_ring[0] == '0');
-  const size_t smem = ring ? (size_t)ST * STAGE * sizeof(double) : (size_t)(2 * BK * A_LD + 2 * BN * B_LD) * sizeof(double);
-  auto kern = ring ? dgemm_ring_kernel : dgemm_dmma_kernel;
+  int kind = !aligned ? 0 : std::min(want, b_blk_w > 0 ? 1 : 2);
+  CUtensorMap mapA, mapB;
+  if (kind == 2 && !(make_map(&mapA, A, m, k, lda, 16, BK) && make_map(&mapB, B, k, n, ldb, BK, BN))) kind = 1;
+  const size_t smem = kind == 2 ? (size_t)TST * T_STAGE_BYTES + 1024
+                    : kind == 1 ? (size_t)ST * STAGE * sizeof(double) : (size_t)(2 * BK * A_LD + 2 * BN * B_LD) * sizeof(double);
+  const void* kern = kind == 2 ? (const void*)dgemm_tma_kernel : kind == 1 ? (const void*)dgemm_ring_kernel : (const void*)dgemm_dmma_kernel;
   cudaError_t e0 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e0 != cudaSuccess) return e0;
   const long long tiles = (long long)((m + BM - 1) / BM) * ((n + BN - 1) / BN);
   if (tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
   int tail_cb = 0;
   if (a_upper) {                       // four waves of resident CTAs' worth of column blocks, longest tiles first
-    static int slots_of[2] = {0, 0};
-    if (slots_of[ring] == 0) {
+    static int slots_of[3] = {0, 0, 0};
+    if (slots_of[kind] == 0) {
       int dev = 0, sms = 148, per_sm = 2;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem);
-      slots_of[ring] = sms * (per_sm > 0 ? per_sm : 1);
+      slots_of[kind] = sms * (per_sm > 0 ? per_sm : 1);
     }
     static const char* env_tail = getenv("LQG_GEMM_TAIL");           // tuning aid: waves of column blocks reordered (default 4)
     const double waves = env_tail ? atof(env_tail) : 4.0;
     const int MBc = (m + BM - 1) / BM, NBc = (n + BN - 1) / BN;
-    tail_cb = std::min(NBc, (int)(waves * slots_of[ring] / MBc));
+    tail_cb = std::min(NBc, (int)(waves * slots_of[kind] / MBc));
   }
-  kern<<<(unsigned)tiles, NT, smem, st>>>(m, n, k, A, lda, B, ldb, C, ldc, row_sum, a_upper, b_blk_w, b_blk_pitch, tail_cb);
+  if (kind == 2)
+    dgemm_tma_kernel<<<(unsigned)tiles, NT, smem, st>>>(mapA, mapB, m, n, k, C, ldc, row_sum, a_upper, tail_cb);
+  else if (kind == 1)
+    dgemm_ring_kernel<<<(unsigned)tiles, NT, smem, st>>>(m, n, k, A, lda, B, ldb, C, ldc, row_sum, a_upper, b_blk_w, b_blk_pitch, tail_cb);
+  else
+    dgemm_dmma_kernel<<<(unsigned)tiles, NT, smem, st>>>(m, n, k, A, lda, B, ldb, C, ldc, row_sum, a_upper, b_blk_w, b_blk_pitch, tail_cb);
   ++launch_counter();
   return cudaGetLastError();
 }

@@ -23,7 +23,7 @@ def test_header_and_library_export_the_same_symbols(lqg):
 def test_struct_layouts_match_header(lqg):
     from lineqgpr_b200 import _lib
     assert ctypes.sizeof(_lib.Opts) == 88
-    assert ctypes.sizeof(_lib.HmcStats) == 96
+    assert ctypes.sizeof(_lib.HmcStats) == 144
     assert ctypes.sizeof(_lib.RsmStats) == 40
     assert ctypes.sizeof(_lib.ExptStats) == 32
 
