@@ -335,9 +335,13 @@ dgemm_ring_kernel(int m, int n, int k, const double* __restrict__ A, int64_t lda
 //   A box b (rows 16 b .. 16 b + 15):  byte 2048 b + 128 k + 8 r, with address bits [4:6] ^= bits [7:9]
 //   B:                                 byte 16384 + 128 n + 8 k,  same swizzle
 // DMMA sums 4 values of k per instruction; which 4 is free as long as A and B agree.  Step k4 of a k-tile
-// takes k = 2 q + 4 (fk / 2) + (fk mod 2), q in {0, 1, 4, 5}: with that choice both fragment loads touch
-// every shared-memory bank pair exactly twice (2 wavefronts, the minimum for 32 x 8 bytes), whereas the
-// natural order k = 4 k4 + fk costs 4 wavefronts on the A side.
+// takes k = 2 q + 4 (fk / 2) + (fk mod 2), q in {0, 1, 4, 5}.  A 64-bit shared-memory load is served half-warp
+// by half-warp; with this choice each half-warp of either fragment load covers 8 of the 16 bank pairs twice
+// (4 wavefronts per load, ncu: half of the wavefronts are conflicts), the balanced point: a k order that
+// makes the A loads conflict free (k bits 1,2 from fk) makes the B loads 4-way conflicting and vice versa,
+// because the swizzle XORs the row (A) / column (B) index into the same address bits.  The padded layout of
+// the bulk-copy ring needs 2 wavefronts per load, but TMA cannot write padding; at 47 % of the
+// shared-memory data pipe the loads are not what limits the kernel (DMMA sub-pipe 94 % active).
 constexpr int TST = 4, TPF = 2;
 constexpr int T_A_BYTES = BM * BK * 8, T_B_BYTES = BN * BK * 8, T_STAGE_BYTES = T_A_BYTES + T_B_BYTES;
 static_assert(T_STAGE_BYTES % 1024 == 0, "stages must keep the 1024-byte alignment of the swizzle pattern");
