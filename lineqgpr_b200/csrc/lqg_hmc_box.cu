@@ -371,6 +371,58 @@ __global__ void __launch_bounds__(32 * G * NCH, MINB) hmc_box_kernel(const BoxPa
         gsync();                                         // dl is reused by the next bounce
       };
 
+      // The fast search's filter result (two bits per coordinate of this thread) and the window it was
+      // computed for.  After a bounce the new (x_a, x_b) are in registers inside the update loop and the
+      // sine / cosine of the new remaining time are known, so the filter of the NEXT search is evaluated
+      // right there (one pass over the state per bounce instead of two); a separate filter pass only runs
+      // for the first search of an attempt and when a window held no hit.
+      using Mask = typename std::conditional<(CPT > 16), unsigned long long, unsigned>::type;
+      Mask mask = 0;
+      bool have_mask = false;
+      double ktt = 0.0, klim = 0.0, Sf = S, Cf = C;
+      bool win_full = true;
+      // window of the coming search (see c_winK): the smallest dyadic angle whose tan(tau/2) covers 4 x the
+      // running mean of the hit times; from the current (S, C) = sin / cos of the remaining time
+      auto select_window = [&]() {
+        ktt = S / (1.0 + C);                                     // tan(tt/2) of the remaining time
+        win_full = !p.window;
+        Sf = S; Cf = C;
+        klim = fma(ktt, 1e-9, ktt) + 1e-12;
+        if (!win_full) {
+          const double target = 4.0 * kavg;
+          while (wlvl + 1 < kNLV && c_winK[wlvl + 1] >= target) ++wlvl;
+          while (wlvl > 0 && c_winK[wlvl] < target) --wlvl;
+          const double kwin = c_winK[wlvl];
+          win_full = kwin >= 0.999 * ktt;                        // reaches the remaining time: search all of it
+          if (!win_full) { Sf = c_winS[wlvl]; Cf = c_winC[wlvl]; klim = kwin * (1.0 - 4e-6); }
+        }
+      };
+      // Filter of coordinate slot k (see may_hit in lqg_common.cuh).  With y = position at the end of the
+      // window, dy = velocity there, u^2 = a^2 + b^2 and the threshold h = g - margin:
+      //   lower row (f = +e_i):  safe iff min(b, y) > -h, unless the orbit dips in between
+      //                          (a < 0 and dy > 0) AND reaches the wall (u^2 >= h^2)
+      //   upper row (f = -e_i):  mirrored.
+      // h |h| compares like h^2 for h > 0 and is negative (always reachable) for h <= 0.  Straight-line
+      // predicates (bitwise & |: no short-circuit branches, no fmin/fmax NaN fix-ups).
+      auto filter_bits = [&](int k, double a_, double b_) -> Mask {
+        const int i = tid + k * T;
+        const double y = fma(a_, Sf, b_ * Cf);
+        const double dy = fma(a_, Cf, -b_ * Sf);
+        const double u2 = fma(a_, a_, b_ * b_);
+        double hl, hh;
+        if (THR == 0) { hl = hlo_r[THR == 0 ? k : 0]; hh = hhi_r[THR == 0 ? k : 0]; }
+        else if (THR == 1) { hl = hlo_s[i]; hh = hhi_s[i]; }
+        else { hl = thr(g_of(i < d ? i : 0)); hh = thr(g_of(i < d ? d + i : d)); if (i >= d) { hl = kBigG; hh = kBigG; } }
+        const double nhl = -hl;
+        const bool safe_lo = (b_ > nhl) & (y > nhl);
+        const bool safe_hi = (b_ < hh) & (y < hh);
+        const bool dip_lo = (a_ < 0.0) & (dy > 0.0) & (u2 >= hl * fabs(hl));
+        const bool dip_hi = (a_ > 0.0) & (dy < 0.0) & (u2 >= hh * fabs(hh));
+        const bool need_lo = !safe_lo | dip_lo;
+        const bool need_hi = !safe_hi | dip_hi;
+        return ((Mask)(need_lo ? 1u : 0u) << (2 * k)) | ((Mask)(need_hi ? 1u : 0u) << (2 * k + 1));
+      };
+
       for (;;) {                                                 // while(1), :64
         unsigned long long wtb = kNoHitBits; int wkey = INT_MAX;
         double wxa = 0.0, wxb = 0.0, wst = 0.0, wct = 0.0;
@@ -382,19 +434,7 @@ __global__ void __launch_bounds__(32 * G * NCH, MINB) hmc_box_kernel(const BoxPa
           double bxa = 0.0, bxb = 0.0, bst = 0.0, bct = 0.0;
           unsigned bhi2 = 0xffffffffu;
           bool bslow = false;
-          const double ktt = S / (1.0 + C);                      // tan(tt/2) of the remaining time
-          // window of this pass (see c_winK): the smallest dyadic angle whose tan(tau/2) covers 4 x the running mean
-          bool win_full = !p.window;
-          double Sf = S, Cf = C;
-          double klim = fma(ktt, 1e-9, ktt) + 1e-12;
-          if (!win_full) {
-            const double target = 4.0 * kavg;
-            while (wlvl + 1 < kNLV && c_winK[wlvl + 1] >= target) ++wlvl;
-            while (wlvl > 0 && c_winK[wlvl] < target) --wlvl;
-            const double kwin = c_winK[wlvl];
-            win_full = kwin >= 0.999 * ktt;                      // reaches the remaining time: search all of it
-            if (!win_full) { Sf = c_winS[wlvl]; Cf = c_winC[wlvl]; klim = kwin * (1.0 - 4e-6); }
-          }
+          if (!have_mask) select_window();                       // else: chosen when the mask was computed (bounce update)
           auto consider = [&](int key) {
             const int i = key < d ? key : key - d;
             const double sgn = key < d ? 1.0 : -1.0;             // wall row f = sgn e_i
@@ -421,40 +461,16 @@ __global__ void __launch_bounds__(32 * G * NCH, MINB) hmc_box_kernel(const BoxPa
             n_exact += (lane == 0) ? qn : 0;
             qn = 0;
           };
-          // Filter (see may_hit in lqg_common.cuh).  With y = position at time tt, dy = velocity
-          // at time tt, u^2 = a^2 + b^2 and the threshold h = g - margin:
-          //   lower row (f = +e_i):  safe iff min(b, y) > -h, unless the orbit dips in between
-          //                          (a < 0 and dy > 0) AND reaches the wall (u^2 >= h^2)
-          //   upper row (f = -e_i):  mirrored.
-          // h |h| compares like h^2 for h > 0 and is negative (always reachable) for h <= 0.
-          // Phase 1 is straight-line code over the thread's coordinates (no votes, no branches: the
-          // CPT coordinates overlap in the pipeline) and leaves one bit per wall in `mask`.
           LQG_TICK(0);                                           // 0: everything since the last bounce update
-          using Mask = typename std::conditional<(CPT > 16), unsigned long long, unsigned>::type;
-          Mask mask = 0;
-          // (with the state in shared memory nothing forces a full unroll: 8 coordinates in flight are enough)
+          if (!have_mask) {
+            // separate filter pass: straight-line code over the thread's coordinates (no votes, no branches: the
+            // coordinates overlap in the pipeline); with the state in shared memory nothing forces a full
+            // unroll: 8 coordinates in flight are enough
+            mask = 0;
 #pragma unroll (RS ? CPT : (CPT < 8 ? CPT : 8))
-          for (int k = 0; k < CPT; ++k) {
-            const int i = tid + k * T;
-            const double a_ = XA(k), b_ = XB(k);
-            const double y = fma(a_, Sf, b_ * Cf);
-            const double dy = fma(a_, Cf, -b_ * Sf);
-            const double u2 = fma(a_, a_, b_ * b_);
-            double hl, hh;
-            if (THR == 0) { hl = hlo_r[THR == 0 ? k : 0]; hh = hhi_r[THR == 0 ? k : 0]; }
-            else if (THR == 1) { hl = hlo_s[i]; hh = hhi_s[i]; }
-            else { hl = thr(g_of(i < d ? i : 0)); hh = thr(g_of(i < d ? d + i : d)); if (i >= d) { hl = kBigG; hh = kBigG; } }
-            // straight-line predicates (bitwise & |: no short-circuit branches, no fmin/fmax NaN fix-ups)
-            const double nhl = -hl;
-            const bool safe_lo = (b_ > nhl) & (y > nhl);
-            const bool safe_hi = (b_ < hh) & (y < hh);
-            const bool dip_lo = (a_ < 0.0) & (dy > 0.0) & (u2 >= hl * fabs(hl));
-            const bool dip_hi = (a_ > 0.0) & (dy < 0.0) & (u2 >= hh * fabs(hh));
-            const bool need_lo = !safe_lo | dip_lo;
-            const bool need_hi = !safe_hi | dip_hi;
-            mask |= (Mask)(need_lo ? 1u : 0u) << (2 * k);
-            mask |= (Mask)(need_hi ? 1u : 0u) << (2 * k + 1);
+            for (int k = 0; k < CPT; ++k) mask |= filter_bits(k, XA(k), XB(k));
           }
+          have_mask = false;
           LQG_TICK(1);                                           // 1: filter masks
           // Phase 2: the survivors' wall ids are compacted into the warp's queue: exclusive prefix sum of
           // the per-lane counts, then every lane walks its set bits (most lanes have none).
@@ -607,6 +623,10 @@ __global__ void __launch_bounds__(32 * G * NCH, MINB) hmc_box_kernel(const BoxPa
 #endif
         const double vj = __dsub_rn(__dmul_rn(ct, wxa), __dmul_rn(st, wxb));   // hit_vel[j]
         const double alpha2 = 2.0 * (vj / sjj);                  // 2*alpha, alpha = f.v / f.f
+        const double Sn = fma(S, ct, -C * st), Cn = fma(C, ct, S * st);   // sin/cos(tt - t)
+        S = Sn; C = Cn;
+        if (fast_on) select_window();                            // window of the next search: its filter runs in the loop below
+        mask = 0;
 #pragma unroll
         for (int k = 0; k < CPT; ++k) {
           const double a_ = XA(k), b_ = XB(k);
@@ -615,11 +635,11 @@ __global__ void __launch_bounds__(32 * G * NCH, MINB) hmc_box_kernel(const BoxPa
           const double na = fma(-alpha2, sc[k], v);              // reflected velocity (:109)
           if (RS) { xa[RS ? k : 0] = na; xb[RS ? k : 0] = nb; }
           xa_s[tid + k * T] = na; xb_s[tid + k * T] = nb;        // the copy the next search evaluates from
+          if (fast_on) mask |= filter_bits(k, na, nb);
         }
+        have_mask = fast_on;
         velsign = side * __dsub_rn(vj, __dmul_rn(alpha2, sjj));  // a.f (:110)
         if (velsign < 0.0) break;                                // :112
-        const double Sn = fma(S, ct, -C * st), Cn = fma(C, ct, S * st);   // sin/cos(tt - t)
-        S = Sn; C = Cn;
         LQG_TICK(9);                                             // 9: rotate + reflect
       }
       if (velsign < 0.0) {                                       // :117
