@@ -240,8 +240,8 @@ __global__ void __launch_bounds__(32 * G * NCH, MINB) hmc_box_kernel(const BoxPa
   double* hhi_s = hlo_s + NS;
   double* st_base = dyn_sm + (size_t)NS * ((GS ? 2 : 0) + (THR == 1 ? 2 : 0));
   // xa_s doubles as the staging area of a fresh draw (draw_momentum): x_a is being replaced then
-  double* xa_s = st_base + (size_t)gr.id * 2 * NS; // [NS] copy of x_a
-  double* xb_s = xa_s + NS;                        // [NS] copy of x_b
+  double* xa_s = st_base + (size_t)gr.id * 2 * NS; // [NS] copy of x_a   (the two copies swap roles when a transition
+  double* xb_s = xa_s + NS;                        // [NS] copy of x_b    is accepted, see the end of the attempt loop)
   __shared__ WinSlot red_[NCH][2][G];
   __shared__ Cand queue_[NCH][G];
   __shared__ int qcnt_[NCH][G];                    // PACK: candidates left in every warp's queue after the filter
@@ -653,36 +653,70 @@ __global__ void __launch_bounds__(32 * G * NCH, MINB) hmc_box_kernel(const BoxPa
       //      re-basing: ~1e-14); otherwise tt is exact and they are recomputed from it ----
       if (n_dl == 0) sincos(tt, &S, &C);
       bool fine = true;
-#pragma unroll
-      for (int k = 0; k < CPT; ++k) {
-        const int i = tid + k * T;
-        if (i < d) {
-          const double bb = fma(XA(k), S, XB(k) * C);
-          const double e = __ldg(p.mu + i) + bb;
-          const double gl = GS ? glo_s[i] : __ldg(p.glo + i), gh = GS ? ghi_s[i] : __ldg(p.ghi + i);
-          fine = fine && (bb + gl >= 0.0) && (gh - bb >= 0.0) && (e >= __ldg(p.lb + i)) && (e <= __ldg(p.ub + i));
-        }
-      }
-      fine = (G > 1) ? group_and<NCH, T>(gr.id, fine) : __all_sync(0xffffffffu, fine);
-      if (!fine) {                                               // :130
-        ++n_chk;
-        if (++rcount > p.max_restarts) status = LQG_ERR_RESTART_CAP;
-        continue;
-      }
-#pragma unroll
-      for (int k = 0; k < CPT; ++k) {
-        const double nb = fma(XA(k), S, XB(k) * C);              // lastSample = bb (:123)
-        if (RS) xb[RS ? k : 0] = nb;
-        xb_s[tid + k * T] = nb;
-      }
-      rcount = 0;
-      ++n_trans;
-      if (s >= p.burn_in) {                                      // tmg:R/tmg.R:105 drops burn-in
-        double* dst = p.out + ((size_t)chain * p.n_per_chain + (s - p.burn_in)) * d;
-#pragma unroll
+      if constexpr (!RS) {
+        // One pass: end point, both checks, and the sample itself.  The end point is parked in the x_a copy
+        // (x_a is consumed; a restart overwrites it with the next momentum and keeps x_b at the wall, as
+        // tmg does), the sample is written before the verdict is known — a rejected end point is simply
+        // overwritten when the transition is redone — and an accepted one becomes x_b by swapping the
+        // two copies.
+        const bool emit = s >= p.burn_in;                        // tmg:R/tmg.R:105 drops burn-in
+        double* dst = p.out + ((size_t)chain * p.n_per_chain + (emit ? s - p.burn_in : 0)) * d;
+#pragma unroll (CPT < 8 ? CPT : 8)
         for (int k = 0; k < CPT; ++k) {
           const int i = tid + k * T;
-          if (i < d) __stcs(dst + i, __ldg(p.mu + i) + XB(k));   // tmg:R/tmg.R:106; written once, read by later stages
+          const double bb = fma(xa_s[i], S, xb_s[i] * C);        // lastSample = bb (:119, :123)
+          xa_s[i] = bb;
+          if (i < d) {
+            // (loads first, bitwise &: a short-circuit && would chain the L2 latencies of mu, lb, ub one after another)
+            const double mu_i = __ldg(p.mu + i), lb_i = __ldg(p.lb + i), ub_i = __ldg(p.ub + i);
+            const double e = mu_i + bb;                          // tmg:R/tmg.R:106
+            const double gl = GS ? glo_s[i] : __ldg(p.glo + i), gh = GS ? ghi_s[i] : __ldg(p.ghi + i);
+            fine &= (bb + gl >= 0.0) & (gh - bb >= 0.0) & (e >= lb_i) & (e <= ub_i);
+            if (emit) __stcs(dst + i, e);                        // written once (again if redone), read by later stages
+          }
+        }
+        fine = (G > 1) ? group_and<NCH, T>(gr.id, fine) : __all_sync(0xffffffffu, fine);
+        if (!fine) {                                             // :130
+          ++n_chk;
+          if (++rcount > p.max_restarts) status = LQG_ERR_RESTART_CAP;
+          continue;
+        }
+        double* t_ = xa_s; xa_s = xb_s; xb_s = t_;
+        sh.xa_s = xa_s; sh.xb_s = xb_s;
+        rcount = 0;
+        ++n_trans;
+      } else {
+  #pragma unroll
+        for (int k = 0; k < CPT; ++k) {
+          const int i = tid + k * T;
+          if (i < d) {
+            const double bb = fma(XA(k), S, XB(k) * C);
+            const double e = __ldg(p.mu + i) + bb;
+            const double gl = GS ? glo_s[i] : __ldg(p.glo + i), gh = GS ? ghi_s[i] : __ldg(p.ghi + i);
+            fine = fine && (bb + gl >= 0.0) && (gh - bb >= 0.0) && (e >= __ldg(p.lb + i)) && (e <= __ldg(p.ub + i));
+          }
+        }
+        fine = (G > 1) ? group_and<NCH, T>(gr.id, fine) : __all_sync(0xffffffffu, fine);
+        if (!fine) {                                               // :130
+          ++n_chk;
+          if (++rcount > p.max_restarts) status = LQG_ERR_RESTART_CAP;
+          continue;
+        }
+  #pragma unroll
+        for (int k = 0; k < CPT; ++k) {
+          const double nb = fma(XA(k), S, XB(k) * C);              // lastSample = bb (:123)
+          if (RS) xb[RS ? k : 0] = nb;
+          xb_s[tid + k * T] = nb;
+        }
+        rcount = 0;
+        ++n_trans;
+        if (s >= p.burn_in) {                                      // tmg:R/tmg.R:105 drops burn-in
+          double* dst = p.out + ((size_t)chain * p.n_per_chain + (s - p.burn_in)) * d;
+  #pragma unroll
+          for (int k = 0; k < CPT; ++k) {
+            const int i = tid + k * T;
+            if (i < d) __stcs(dst + i, __ldg(p.mu + i) + XB(k));   // tmg:R/tmg.R:106; written once, read by later stages
+          }
         }
       }
       ++s;
