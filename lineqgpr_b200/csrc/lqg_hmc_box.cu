@@ -351,6 +351,7 @@ __global__ void __launch_bounds__(32 * G * NCH, MINB) hmc_box_kernel(const BoxPa
         for (int k = 0; k < CPT; ++k) if (RS) xa[RS ? k : 0] = xa_s[tid + k * T];
       }
       ++draw;
+      LQG_TICK(11);                                              // 11: a fresh momentum is in place (pool column or in-kernel draw)
       double tt = kHalfPi;                                       // :57; exact up to the hit times still owed (n_dl)
       double velsign = 0.0;                                      // :53
       // sin/cos of the remaining time, advanced by angle subtraction after every bounce.  They feed

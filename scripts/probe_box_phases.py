@@ -19,16 +19,16 @@ par = W.cfg4()[0] if cfg == "cfg4" else W.cfg5(n_test=10)[0]
 U = whiten_box(np.asarray(par["mu"]), np.asarray(par["Sigma"]))
 names = ["since last update (loop head)", "filter masks", "compaction", "barrier after pushes", "candidate evaluation",
          "warp arg-min + slot", "barrier of the slot exchange", "slot reduce + decision", "Sigma column (L2)", "rotate + reflect",
-         "end of transition"]
+         "end of transition", "fresh momentum in place"]
 buf = (ctypes.c_ulonglong * 16)()
 for rep in range(2):
     L.lib().lqg_debug_box_phases(buf)
     x = lqg.tmvrnorm(dict(par, **{"class": "HMC"}), chains * n_per, {"burn.in": 20, "n.chains": chains, "seed": 1, "U": U, "burn.in.exact": True})
     st = dict(lqg.last_stats)
     L.lib().lqg_debug_box_phases(buf)
-tot = sum(buf[i] for i in range(11))
+tot = sum(buf[i] for i in range(12))
 se = st["hit_searches"]
 out = {"cfg": cfg, "chains": chains, "searches": se, "chain_ms": st["chain_ms"], "cycles_per_search": tot / se,
-       "phases_cycles_per_search": {names[i]: buf[i] / se for i in range(11)},
-       "phases_share": {names[i]: buf[i] / tot for i in range(11)}}
+       "phases_cycles_per_search": {names[i]: buf[i] / se for i in range(12)},
+       "phases_share": {names[i]: buf[i] / tot for i in range(12)}}
 print(json.dumps(out, indent=1))
