@@ -13,7 +13,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
     U = whiten_box(np.asarray(par["mu"]), np.asarray(par["Sigma"]))
     best = None
     for rep in range(2):
-        x = lqg.tmvrnorm(dict(par, **{"class": "HMC"}), chains * n_per, {"burn.in": 100, "n.chains": chains, "seed": 1, "U": U, "prepass": 1})
+        x = lqg.tmvrnorm(dict(par, **{"class": "HMC"}), chains * n_per, {"burn.in": 100, "n.chains": chains, "seed": 1, "U": U, "prepass": 1, "fork": int(os.environ.get("LQG_FORK", "1"))})
         st = dict(lqg.last_stats)
         if best is None or st["chain_ms"] < best["chain_ms"]:
             best = st
