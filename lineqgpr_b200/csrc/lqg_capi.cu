@@ -1680,6 +1680,42 @@ static int bands_on_device(int n_t, int64_t N, const double* y_dev, int64_t ld, 
 }
 
 // ===========================================================================================
+static bool sparse_paths_enabled() {
+  static const char* env = getenv("LQG_SPARSE");                     // A/B aid: 0 = always the dense DMMA products
+  return !(env && env[0] == '0');
+}
+// Y (nr x N) = Phi_slab (nr x m) X (m x N).  A slab whose rows hold at most kEllMaxNnz non-zeros (1-D hat basis: 2)
+// is multiplied in ELL form — bound by writing Y instead of an nr x m x N GEMM; the first dense slab ends the probing.
+struct SlabProduct {
+  DevBuf pidx, pval, pinfo;
+  bool probe = sparse_paths_enabled();
+  int run(int nr, int m, int rows_cap, const double* phi, int64_t ld, const double* X, int64_t ldx, int64_t N, double* Y, int64_t ldy,
+          cudaStream_t st, double* ms) {
+    bool ell = false;
+    int ell_k = 0;
+    if (probe) {
+      if (!pidx.p) {
+        LQG_CUDA_TRY(pidx.alloc((size_t)kEllMaxNnz * rows_cap * sizeof(int)));
+        LQG_CUDA_TRY(pval.alloc((size_t)kEllMaxNnz * rows_cap * sizeof(double)));
+        LQG_CUDA_TRY(pinfo.alloc(sizeof(int)));
+      }
+      LQG_CUDA_TRY(cudaMemsetAsync(pinfo.p, 0, sizeof(int), st));
+      LQG_CUDA_TRY(launch_ell_from_dense(nr, m, kEllMaxNnz, phi, ld, pidx.as<int>(), pval.as<double>(), pinfo.as<int>(), st));
+      LQG_CUDA_TRY(cudaMemcpyAsync(&ell_k, pinfo.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+      LQG_CUDA_TRY(cudaStreamSynchronize(st));
+      ell = ell_k <= kEllMaxNnz;
+      if (!ell) probe = false;
+    }
+    Timer tg(st);
+    tg.start();
+    if (ell) LQG_CUDA_TRY(launch_ell_spmm(nr, m, std::max(1, ell_k), pidx.as<int>(), pval.as<double>(), X, ldx, N, Y, ldy, st));
+    else LQG_CUDA_TRY(launch_dgemm(nr, (int)N, m, phi, ld, X, ldx, Y, ldy, nullptr, 0, st));
+    tg.stop();
+    if (ms) *ms += tg.ms();
+    return LQG_OK;
+  }
+};
+
 extern "C" int lqg_paths(int32_t n_t, int32_t m, int64_t N, const double* Phi, int64_t ldphi,
                          const double* xi, int64_t ldxi, const double* probs, int32_t nprobs,
                          double* ysim, int64_t ldy, double* mean, double* qtls, int32_t slab_rows,
@@ -1714,16 +1750,14 @@ extern "C" int lqg_paths(int32_t n_t, int32_t m, int64_t N, const double* Phi, i
     LQG_CUDA_TRY(b_q.alloc((size_t)std::max(1, nprobs) * n_t * sizeof(double))); d_q = b_q.as<double>();
   }
   double t_gemm = 0.0, t_bands = 0.0;
+  SlabProduct slab;
   for (int r0 = 0; r0 < n_t; r0 += rows) {
     const int nr = std::min(rows, n_t - r0);
-    Timer tg(st);
-    tg.start();
-    LQG_CUDA_TRY(launch_dgemm(nr, (int)N, m, i_phi.dev + r0, ldphi, i_xi.dev, ldxi, b_y.as<double>(), nr, nullptr, 0, st));
-    tg.stop();
+    if ((rc = slab.run(nr, m, rows, i_phi.dev + r0, ldphi, i_xi.dev, ldxi, N, b_y.as<double>(), nr, st, &t_gemm))) return rc;
     double ms = 0.0;
     if ((rc = bands_on_device(nr, N, b_y.as<double>(), nr, h_probs, nprobs, d_mean + r0, d_q + (size_t)r0 * nprobs, b_scr, &ms, st)))
       return rc;
-    t_gemm += tg.ms(); t_bands += ms;
+    t_bands += ms;
     if (ysim) {
       if (mem == LQG_MEM_HOST) LQG_CUDA_TRY(d2h_result(ysim + r0, ldy * sizeof(double), b_y.p, (size_t)nr * sizeof(double), (size_t)nr * sizeof(double), N, st));
       else LQG_CUDA_TRY(cudaMemcpy2DAsync(ysim + r0, ldy * sizeof(double), b_y.p, (size_t)nr * sizeof(double), (size_t)nr * sizeof(double), N,
@@ -1807,10 +1841,6 @@ struct LsqPlan {
   LsqPlanDev dev{};
   DevBuf rstart, rval, cidx, cval, lband, fw, bw, info, gersh;
 };
-static bool sparse_paths_enabled() {
-  static const char* env = getenv("LQG_SPARSE");                     // A/B aid: 0 = always the dense DMMA products
-  return !(env && env[0] == '0');
-}
 static int lsq_plan_build(int d, int m, const double* L_dev, LsqPlan& P, cudaStream_t st) {
   P.ok = false;
   if (!sparse_paths_enabled()) return LQG_OK;
@@ -2120,9 +2150,7 @@ extern "C" int lqg_simulate(const lqg_simulate_args* a_, const lqg_opts* opts_, 
         LQG_CUDA_TRY(cudaStreamSynchronize(st));               // perm is a local
         if (mem == LQG_MEM_HOST) LQG_CUDA_TRY(b_yp.alloc((size_t)rows * N_total * sizeof(double)));
       }
-      DevBuf b_pidx, b_pval, b_pinfo;
-      bool phi_sparse_probe = sparse_paths_enabled();
-      int ell_k = 0;
+      SlabProduct slab;
       for (int s0 = 0; s0 < nr_local; s0 += rows) {
         const int nr = std::min(rows, nr_local - s0);
         const double* phi_slab; int64_t ld_slab;
@@ -2139,36 +2167,14 @@ extern "C" int lqg_simulate(const lqg_simulate_args* a_, const lqg_opts* opts_, 
           }
           phi_slab = b_phi.as<double>(); ld_slab = nr;
         }
-        // a slab whose rows hold at most kEllMaxNnz non-zeros (1-D hat basis: 2) is multiplied in ELL form:
-        // bound by writing ysim instead of an nr x m x N GEMM; the first dense slab ends the probing
-        bool ell = false;
-        if (phi_sparse_probe) {
-          if (!b_pidx.p) {
-            LQG_CUDA_TRY(b_pidx.alloc((size_t)kEllMaxNnz * rows * sizeof(int)));
-            LQG_CUDA_TRY(b_pval.alloc((size_t)kEllMaxNnz * rows * sizeof(double)));
-            LQG_CUDA_TRY(b_pinfo.alloc(sizeof(int)));
-          }
-          LQG_CUDA_TRY(cudaMemsetAsync(b_pinfo.p, 0, sizeof(int), st));
-          LQG_CUDA_TRY(launch_ell_from_dense(nr, m, kEllMaxNnz, phi_slab, ld_slab, b_pidx.as<int>(), b_pval.as<double>(), b_pinfo.as<int>(), st));
-          int mx = 0;
-          LQG_CUDA_TRY(cudaMemcpyAsync(&mx, b_pinfo.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-          LQG_CUDA_TRY(cudaStreamSynchronize(st));
-          ell = mx <= kEllMaxNnz;
-          ell_k = mx;
-          if (!ell) phi_sparse_probe = false;
-        }
-        Timer tg(st);
-        tg.start();
-        if (ell) LQG_CUDA_TRY(launch_ell_spmm(nr, m, std::max(1, ell_k), b_pidx.as<int>(), b_pval.as<double>(), xi_all, N_total, b_y.as<double>(), nr, st));
-        else LQG_CUDA_TRY(launch_dgemm(nr, (int)N_total, m, phi_slab, ld_slab, xi_all, m, b_y.as<double>(), nr, nullptr, 0, st));
-        tg.stop();
+        if ((rc = slab.run(nr, m, rows, phi_slab, ld_slab, xi_all, m, N_total, b_y.as<double>(), nr, st, &t_gemm))) return rc;
         double ms = 0.0;
         double* q_slab = nprobs > 0 ? band_mine + rows_per + (size_t)s0 * nprobs : nullptr;
         // the slab's quantiles land in a (nprobs x rows_per) column-major block: column = test point
         if ((rc = bands_on_device(nr, N_total, b_y.as<double>(), nr, h_probs, nprobs, band_mine + s0,
                                   nprobs > 0 ? q_slab : band_mine + rows_per, b_scr, &ms, st)))
           return rc;
-        t_gemm += tg.ms(); t_bands += ms;
+        t_bands += ms;
         if (a.ysim_out) {
           double* yp = mem == LQG_MEM_HOST ? b_yp.as<double>() : a.ysim_out + s0;
           const int64_t ldp = mem == LQG_MEM_HOST ? nr : a.ldy;

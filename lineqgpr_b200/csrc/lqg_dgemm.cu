@@ -510,28 +510,30 @@ static bool make_map(CUtensorMap* map, const double* base, int rows, int cols, i
 // A[kk, col] = N(0,1) draw of (chain = active[col / attempts], draw index = pos[chain] + col % attempts,
 // coordinate kk; with col_off the columns of active chain a are [col_off[a], col_off[a+1])) — the same Philox addressing the chain kernels use, so pool and in-kernel
 // draws agree.
-__global__ void fill_normals_kernel(int d, size_t n_cols, double* __restrict__ A, NormalGen g) {
+__global__ void __launch_bounds__(256) fill_normals_kernel(int d, size_t n_cols, double* __restrict__ A, NormalGen g) {
+  // one column per CTA at a time: which chain and draw a column belongs to is worked out once per column
+  // (no 64-bit divisions per element), the threads run over the coordinate pairs
   const int pairs = (d + 1) / 2;
-  const size_t total = (size_t)pairs * n_cols;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (size_t)gridDim.x * blockDim.x) {
-    const uint32_t pr = (uint32_t)(idx % pairs);
-    const size_t col = idx / pairs;
+  const bool d_even = (d & 1) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0;
+  for (size_t col = blockIdx.x; col < n_cols; col += gridDim.x) {
     int a; int64_t j;
     if (g.col_off) {                                   // per-chain column ranges: last a with col_off[a] <= col
       int lo = 0, hi = g.n_active;
       while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if ((size_t)g.col_off[mid] <= col) lo = mid; else hi = mid; }
       a = lo; j = (int64_t)(col - (size_t)g.col_off[lo]);
     } else {
-      a = (int)(col / g.attempts); j = (int64_t)(col % g.attempts);
+      a = (int)(col / (size_t)g.attempts); j = (int64_t)(col - (size_t)a * g.attempts);
     }
     const int chain = g.active ? g.active[a] : a;
     const uint64_t draw = (uint64_t)(g.pos[chain] + j);
-    double n0, n1;
-    normal_pair(g.seed, (uint64_t)(g.chain_offset + (int64_t)chain * g.chain_stride), draw, pr, n0, n1);
-    double* dst = A + col * d + 2 * (size_t)pr;
-    dst[0] = n0;
-    if (2 * pr + 1 < (uint32_t)d) dst[1] = n1;
+    const uint64_t gchain = (uint64_t)(g.chain_offset + (int64_t)chain * g.chain_stride);
+    double* dst = A + col * d;
+    for (int pr = threadIdx.x; pr < pairs; pr += blockDim.x) {
+      double n0, n1;
+      normal_pair(g.seed, gchain, draw, (uint32_t)pr, n0, n1);
+      if (d_even) *reinterpret_cast<double2*>(dst + 2 * pr) = make_double2(n0, n1);   // col * d + 2 pr is even: 16-byte aligned
+      else { dst[2 * pr] = n0; if (2 * pr + 1 < d) dst[2 * pr + 1] = n1; }
+    }
   }
 }
 
@@ -582,7 +584,7 @@ cudaError_t launch_dgemm(int m, int n, int k, const double* A, int64_t lda, cons
 }
 
 cudaError_t launch_fill_normals(int d, size_t n_cols, double* A, const NormalGen& g, cudaStream_t st) {
-  fill_normals_kernel<<<148 * 8, 256, 0, st>>>(d, n_cols, A, g);
+  fill_normals_kernel<<<(unsigned)std::min<size_t>(n_cols, 148 * 16), 256, 0, st>>>(d, n_cols, A, g);
   ++launch_counter();
   return cudaGetLastError();
 }

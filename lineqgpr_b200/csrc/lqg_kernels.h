@@ -109,7 +109,7 @@ cudaError_t launch_lsq_apply(const LsqPlanDev& P, ColBlocks eta, int64_t cols, d
 // first K non-zeros of every row of a dense slab (column order), info[0] = atomicMax of the row counts
 cudaError_t launch_ell_from_dense(int nr, int m, int K, const double* P, int64_t ld, int* pidx, double* pval, int* info,
                                   cudaStream_t st);
-cudaError_t launch_ell_spmm(int nr, int m, int K, const int* pidx, const double* pval, const double* X, int64_t N,
+cudaError_t launch_ell_spmm(int nr, int m, int K, const int* pidx, const double* pval, const double* X, int64_t ldx, int64_t N,
                             double* Y, int64_t ldy, cudaStream_t st);
 
 // ---- canonical-frame HMC with dense constraints (lqg_hmc_canonical.cu) ------------------

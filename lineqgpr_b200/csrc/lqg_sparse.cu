@@ -242,7 +242,7 @@ __global__ void ell_from_dense_kernel(int nr, int m, int K, const double* __rest
 // Y[t, s] = sum_k pval[k, t] X[pidx[k, t], s]
 template <int K>
 __global__ void __launch_bounds__(256) ell_spmm_kernel(int nr, int m, const int* __restrict__ pidx, const double* __restrict__ pval,
-                                                       const double* __restrict__ X, int64_t N, double* __restrict__ Y, int64_t ldy) {
+                                                       const double* __restrict__ X, int64_t ldx, int64_t N, double* __restrict__ Y, int64_t ldy) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   int idx[K]; double val[K];
 #pragma unroll
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(256) ell_spmm_kernel(int nr, int m, const int*
     val[k] = t < nr ? pval[(size_t)k * nr + t] : 0.0;
   }
   for (int64_t s = blockIdx.y; s < N; s += gridDim.y) {
-    const double* x = X + (size_t)s * m;
+    const double* x = X + (size_t)s * ldx;
     double acc = 0.0;
 #pragma unroll
     for (int k = 0; k < K; ++k) acc = fma(val[k], __ldg(x + idx[k]), acc);
@@ -323,13 +323,13 @@ cudaError_t launch_ell_from_dense(int nr, int m, int K, const double* P, int64_t
   return cudaGetLastError();
 }
 
-cudaError_t launch_ell_spmm(int nr, int m, int K, const int* pidx, const double* pval, const double* X, int64_t N,
+cudaError_t launch_ell_spmm(int nr, int m, int K, const int* pidx, const double* pval, const double* X, int64_t ldx, int64_t N,
                             double* Y, int64_t ldy, cudaStream_t st) {
   if (nr <= 0 || N <= 0) return cudaSuccess;
   const dim3 grid((nr + 255) / 256, (unsigned)std::min<int64_t>(N, 32768));
-  if (K <= 2) ell_spmm_kernel<2><<<grid, 256, 0, st>>>(nr, m, pidx, pval, X, N, Y, ldy);
-  else if (K <= 4) ell_spmm_kernel<4><<<grid, 256, 0, st>>>(nr, m, pidx, pval, X, N, Y, ldy);
-  else if (K <= 8) ell_spmm_kernel<8><<<grid, 256, 0, st>>>(nr, m, pidx, pval, X, N, Y, ldy);
+  if (K <= 2) ell_spmm_kernel<2><<<grid, 256, 0, st>>>(nr, m, pidx, pval, X, ldx, N, Y, ldy);
+  else if (K <= 4) ell_spmm_kernel<4><<<grid, 256, 0, st>>>(nr, m, pidx, pval, X, ldx, N, Y, ldy);
+  else if (K <= 8) ell_spmm_kernel<8><<<grid, 256, 0, st>>>(nr, m, pidx, pval, X, ldx, N, Y, ldy);
   else return cudaErrorInvalidValue;
   ++launch_counter();
   return cudaGetLastError();
