@@ -216,6 +216,19 @@ int lqg_expt(int32_t d, const double* L0, const double* l, const double* u, cons
              double psistar, int64_t nsim, int64_t max_proposals, const lqg_opts* opts,
              double* Z_out, lqg_expt_stats* stats);
 
+/* Set-up of tmvrnorm.ExpT on the device: what TruncatedNormal::mvrandn (reached from
+ * R/lineqGPsamplers.R:179-185) does before its accept-reject loop — the variable-reordered Cholesky
+ * factor of Sigma (Gibson, Glasbey & Elston) and the Newton solve for the minimax tilt (Botev 2017,
+ * eq. 11).  l, u = lb - mu, ub - mu [d].  Outputs (each [d] unless noted): L0 d x d (row-scaled factor,
+ * zero diagonal), l_out / u_out (permuted, scaled), mu_out (tilt, last entry 0), x_out (last entry 0),
+ * *psistar, perm (int32: variable perm[j] comes j-th), Lfull d x d (unscaled factor) — the arguments of
+ * lqg_expt and of the back-transformation  x = Lfull[order, ] %*% Z.  *iters = Newton iterations.
+ * LQG_ERR_NOT_PD: Sigma is not positive semi-definite; LQG_ERR_INVALID: the Newton iteration failed
+ * ("Covariance matrix is ill-conditioned and method failed").  d <= 2048.                          */
+int lqg_expt_setup(int32_t d, const double* Sigma, const double* l, const double* u, const lqg_opts* opts,
+                   double* L0, double* l_out, double* u_out, double* mu_out, double* x_out, double* psistar,
+                   int32_t* perm, double* Lfull, int32_t* iters);
+
 /* ---- sample paths and bands --------------------------------------------------------- */
 
 /* C (m x n) = A (m x k) * B (k x n), all column-major FP64, on the FP64 tensor cores.

@@ -21,7 +21,7 @@ STATUS = {0: "LQG_OK", 1: "LQG_ERR_INVALID", 2: "LQG_ERR_UNSUPPORTED", 3: "LQG_E
 MEM_HOST, MEM_DEVICE = 0, 1
 
 # every symbol include/lineqgpr_b200.h declares
-SYMBOLS = ["lqg_rtmg", "lqg_hmc_canonical", "lqg_hmc_canonical_trace", "lqg_hmc_box", "lqg_hmc_box_slots", "lqg_rsm", "lqg_expt", "lqg_dgemm", "lqg_bands",
+SYMBOLS = ["lqg_rtmg", "lqg_hmc_canonical", "lqg_hmc_canonical_trace", "lqg_hmc_box", "lqg_hmc_box_slots", "lqg_rsm", "lqg_expt", "lqg_expt_setup", "lqg_dgemm", "lqg_bands",
            "lqg_alloc_host", "lqg_free_host", "lqg_version", "lqg_last_error", "lqg_device_count", "lqg_measure_fp64_peaks",
            "lqg_launch_count", "lqg_guard_violations",
            "lqg_whiten_box", "lqg_chol", "lqg_solve_spd", "lqg_eta_params", "lqg_lambda_pinv", "lqg_solve_qp", "lqg_basis", "lqg_paths",
@@ -127,6 +127,8 @@ def lib():
     L.lqg_rsm.argtypes = [i32, vp, vp, vp, vp, vp, i64, i64, C.POINTER(Opts), vp, C.POINTER(RsmStats)]
     L.lqg_expt.restype = C.c_int
     L.lqg_expt.argtypes = [i32, vp, vp, vp, vp, C.c_double, i64, i64, C.POINTER(Opts), vp, C.POINTER(ExptStats)]
+    L.lqg_expt_setup.restype = C.c_int
+    L.lqg_expt_setup.argtypes = [i32, vp, vp, vp, C.POINTER(Opts), vp, vp, vp, vp, vp, _dp, vp, vp, C.POINTER(C.c_int32)]
     L.lqg_dgemm.restype = C.c_int
     L.lqg_dgemm.argtypes = [i32, i32, i32, vp, i64, vp, i64, vp, i64, vp, C.POINTER(Opts), _dp]
     L.lqg_bands.restype = C.c_int

@@ -10,7 +10,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "liblineqgpr_b200.so"
 SOURCES = ["lqg_capi.cu", "lqg_hmc_box.cu", "lqg_hmc_canonical.cu", "lqg_dgemm.cu", "lqg_rsm.cu", "lqg_expt.cu",
-           "lqg_bands.cu", "lqg_peaks.cu", "lqg_linalg.cu", "lqg_qp.cu", "lqg_basis.cu", "lqg_hostcopy.cu", "lqg_hmc_canonical_batched.cu", "lqg_comm.cu", "lqg_sparse.cu"]
+           "lqg_bands.cu", "lqg_peaks.cu", "lqg_linalg.cu", "lqg_qp.cu", "lqg_basis.cu", "lqg_hostcopy.cu", "lqg_hmc_canonical_batched.cu", "lqg_comm.cu", "lqg_sparse.cu", "lqg_expt_setup.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -1375,6 +1375,69 @@ extern "C" int lqg_lambda_pinv(int32_t d, int32_t m, const double* Lambda, const
   LQG_API_END("lqg_lambda_pinv")
 }
 
+extern "C" int lqg_expt_setup(int32_t d, const double* Sigma, const double* l, const double* u, const lqg_opts* opts_,
+                              double* L0, double* l_out, double* u_out, double* mu_out, double* x_out, double* psistar,
+                              int32_t* perm, double* Lfull, int32_t* iters) {
+  LQG_API_BEGIN
+  if (!have_device()) return LQG_ERR_CUDA;
+  const lqg_opts o = opts_ ? *opts_ : default_opts();
+  if (d <= 0 || d > 2048 || !Sigma || !l || !u || !L0 || !l_out || !u_out || !mu_out || !psistar || !perm) {
+    set_error("lqg_expt_setup: invalid argument (d=%d; needs 1 <= d <= 2048)", d);
+    return LQG_ERR_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)o.stream;
+  DevBuf::cur_stream = st;
+  const int mem = o.mem;
+  const size_t dd = (size_t)d * d;
+  int rc;
+  std::vector<double> h_l, h_u;
+  if ((rc = fetch_host(h_l, l, d, mem, st)) || (rc = fetch_host(h_u, u, d, mem, st))) return rc;
+  for (int i = 0; i < d; ++i)
+    if (!(h_l[i] < h_u[i])) { set_error("l, u, and Sig have to match in dimension with u>l"); return LQG_ERR_INVALID; }
+  DevBuf b_S, b_l, b_u, b_Lf, b_L0, b_perm, b_y, b_work, b_info;
+  LQG_CUDA_TRY(b_S.alloc(dd * sizeof(double)));
+  LQG_CUDA_TRY(b_l.alloc(d * sizeof(double)));
+  LQG_CUDA_TRY(b_u.alloc(d * sizeof(double)));
+  LQG_CUDA_TRY(b_Lf.alloc(dd * sizeof(double)));
+  LQG_CUDA_TRY(b_L0.alloc(dd * sizeof(double)));
+  LQG_CUDA_TRY(b_perm.alloc(d * sizeof(int)));
+  LQG_CUDA_TRY(b_y.alloc((size_t)2 * d * sizeof(double)));
+  LQG_CUDA_TRY(b_work.alloc((3 * dd + 32 * (size_t)d + 64) * sizeof(double)));
+  LQG_CUDA_TRY(b_info.alloc(2 * sizeof(int)));
+  const cudaMemcpyKind in_kind = mem == LQG_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  LQG_CUDA_TRY(cudaMemcpyAsync(b_S.p, Sigma, dd * sizeof(double), in_kind, st));
+  LQG_CUDA_TRY(cudaMemcpyAsync(b_l.p, l, d * sizeof(double), in_kind, st));
+  LQG_CUDA_TRY(cudaMemcpyAsync(b_u.p, u, d * sizeof(double), in_kind, st));
+  LQG_CUDA_TRY(cudaMemsetAsync(b_y.p, 0, b_y.bytes, st));
+  double ps = 0.0; int its = 0;
+  const int r = expt_setup_device(d, b_S.as<double>(), b_l.as<double>(), b_u.as<double>(), b_Lf.as<double>(), b_L0.as<double>(),
+                                  b_perm.as<int>(), b_y.as<double>(), b_work.as<double>(), b_info.as<int>(), &ps, &its, st);
+  fold_launches();
+  if (r < 0) { set_error("lqg_expt_setup: %s", cudaGetErrorString((cudaError_t)(-r))); return LQG_ERR_CUDA; }
+  if (r == 1) { set_error("Sigma is not positive semi-definite"); return LQG_ERR_NOT_PD; }
+  if (r == 2 || r == 3) { set_error("Covariance matrix is ill-conditioned and method failed"); return LQG_ERR_INVALID; }
+  // tilt: y = [x (d-1) | mu (d-1)], both padded with a final zero
+  std::vector<double> h_y((size_t)2 * d, 0.0), h_x(d, 0.0), h_mu(d, 0.0);
+  if (d > 1) LQG_CUDA_TRY(cudaMemcpyAsync(h_y.data(), b_y.p, (size_t)2 * (d - 1) * sizeof(double), cudaMemcpyDeviceToHost, st));
+  LQG_CUDA_TRY(cudaStreamSynchronize(st));
+  for (int i = 0; i + 1 < d; ++i) { h_x[i] = h_y[i]; h_mu[i] = h_y[d - 1 + i]; }
+  std::vector<int> h_perm(d);
+  LQG_CUDA_TRY(cudaMemcpyAsync(h_perm.data(), b_perm.p, d * sizeof(int), cudaMemcpyDeviceToHost, st));
+  LQG_CUDA_TRY(cudaStreamSynchronize(st));
+  const cudaMemcpyKind hk = mem == LQG_MEM_DEVICE ? cudaMemcpyHostToDevice : cudaMemcpyHostToHost;
+  LQG_CUDA_TRY(cudaMemcpyAsync(mu_out, h_mu.data(), d * sizeof(double), hk, st));
+  if (x_out) LQG_CUDA_TRY(cudaMemcpyAsync(x_out, h_x.data(), d * sizeof(double), hk, st));
+  LQG_CUDA_TRY(cudaMemcpyAsync(perm, h_perm.data(), d * sizeof(int), hk, st));
+  if ((rc = deliver(L0, b_L0.as<double>(), dd, mem, st)) || (rc = deliver(l_out, b_l.as<double>(), d, mem, st)) ||
+      (rc = deliver(u_out, b_u.as<double>(), d, mem, st)) || (Lfull && (rc = deliver(Lfull, b_Lf.as<double>(), dd, mem, st))))
+    return rc;
+  LQG_CUDA_TRY(cudaStreamSynchronize(st));
+  *psistar = ps;
+  if (iters) *iters = its;
+  return LQG_OK;
+  LQG_API_END("lqg_expt_setup")
+}
+
 extern "C" int lqg_basis(int32_t n_t, int32_t D, const int32_t* m_k, const double* x, int64_t ldx, const double* u,
                          const lqg_opts* opts_, double* Phi, int64_t ld) {
   LQG_API_BEGIN

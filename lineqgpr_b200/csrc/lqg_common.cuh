@@ -280,6 +280,26 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// ---------------------------------------------------------------------------------------
+// log of the N(0,1) mass of [a, b], stable in both tails (ExpT: proposals and set-up)
+constexpr double kInvSqrt2 = 0.7071067811865476;
+// log of the upper tail of N(0,1), stable for large a:  log(erfcx(a/sqrt2)/2) - a^2/2
+__device__ __forceinline__ double log_upper(double a) {
+  if (a > 0.0) return log(0.5 * erfcx(a * kInvSqrt2)) - 0.5 * a * a;
+  return log(0.5 * erfc(a * kInvSqrt2));
+}
+static __device__ double lnNpr(double a, double b) {
+  if (a > 0.0) {                                   // 0 < a < b
+    const double pa = log_upper(a), pb = log_upper(b);
+    return pa + log1p(-exp(pb - pa));
+  }
+  if (b < 0.0) {                                   // a < b < 0
+    const double pa = log_upper(-a), pb = log_upper(-b);
+    return pb + log1p(-exp(pa - pb));
+  }
+  return log1p(-0.5 * erfc(-a * kInvSqrt2) - 0.5 * erfc(b * kInvSqrt2));   // a <= 0 <= b
+}
+
 // Several chains may share one CTA (NCH > 1): a chain is then run by a GROUP of G warps with its own
 // named barrier (id 1 + group), its own state copy, queues and slots; what the groups share is the read-only
 // per-coordinate tables in shared memory.  With NCH == 1 the group is the CTA and the barrier is barrier 0.

@@ -22,7 +22,7 @@ namespace lqg {
 namespace {
 
 constexpr uint32_t TAG_EXPT = 0x45585054u;
-constexpr double kSqrt2 = 1.4142135623730951, kInvSqrt2 = 0.7071067811865476;
+constexpr double kSqrt2 = 1.4142135623730951;
 
 struct Draws {                 // uniform stream of one (proposal, coordinate)
   uint64_t seed, p; uint32_t k, j;
@@ -32,23 +32,6 @@ struct Draws {                 // uniform stream of one (proposal, coordinate)
     ua = u01(r[0], r[1]); ub = u01(r[2], r[3]);
   }
 };
-
-// log of the upper tail of N(0,1), stable for large a:  log(erfcx(a/sqrt2)/2) - a^2/2
-__device__ __forceinline__ double log_upper(double a) {
-  if (a > 0.0) return log(0.5 * erfcx(a * kInvSqrt2)) - 0.5 * a * a;
-  return log(0.5 * erfc(a * kInvSqrt2));
-}
-__device__ double lnNpr(double a, double b) {
-  if (a > 0.0) {                                   // 0 < a < b
-    const double pa = log_upper(a), pb = log_upper(b);
-    return pa + log1p(-exp(pb - pa));
-  }
-  if (b < 0.0) {                                   // a < b < 0
-    const double pa = log_upper(-a), pb = log_upper(-b);
-    return pb + log1p(-exp(pa - pb));
-  }
-  return log1p(-0.5 * erfc(-a * kInvSqrt2) - 0.5 * erfc(b * kInvSqrt2));   // a <= 0 <= b
-}
 
 // N(0,1) conditional on l < Z < u with l > 0: Rayleigh-proposal rejection (Botev's ntail)
 __device__ double ntail(double l, double u, Draws& g) {

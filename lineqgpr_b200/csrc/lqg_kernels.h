@@ -205,6 +205,10 @@ cudaError_t launch_transpose(int rows, int cols, const double* in, int64_t ldi, 
                              cudaStream_t st);
 cudaError_t launch_axpy(size_t n, double alpha, const double* x, double* y, cudaStream_t st);
 
+// ---- ExpT set-up (lqg_expt_setup.cu): permuted Cholesky + Newton tilt, see the file header --------
+int expt_setup_device(int d, double* Sigma, double* l, double* u, double* Lfull, double* L0, int* perm, double* y,
+                      double* work, int* info_dev, double* psistar, int* iters, cudaStream_t st);
+
 // ---- interior-point QP vector kernels (lqg_qp.cu); scal = 6 doubles -------------------------
 cudaError_t launch_qp_init(int mc, const double* Ax, const double* b, double* s, double* lam, cudaStream_t st);
 cudaError_t launch_qp_neg_copy(int n, const double* src, double* dst, cudaStream_t st);

@@ -138,3 +138,28 @@ def setup(l, u, Sig):
     psistar = psy(x, L0, lp, up, mu)
     order = np.argsort(perm)
     return dict(L0=L0, l=lp, u=up, mu=mu, psistar=psistar, Lfull=Lfull, order=order, perm=perm, x=x)
+
+
+def setup_device(l, u, Sig):
+    """expt.setup on the GPU (lqg_expt_setup: permuted Cholesky in one CTA, Newton tilt through the SPD Schur
+    complement on the FP64 tensor cores).  Same dict as setup()."""
+    from . import _lib as L
+    l = np.ascontiguousarray(np.asarray(l, float).ravel()); u = np.ascontiguousarray(np.asarray(u, float).ravel())
+    d = l.size
+    if np.any(l >= u):
+        raise ValueError("l, u, and Sig have to match in dimension with u>l")
+    Sf = L.f64(np.asarray(Sig, float))
+    L0 = np.empty((d, d), order="F"); Lfull = np.empty((d, d), order="F")
+    lo = np.empty(d); uo = np.empty(d); mu = np.empty(d); x = np.empty(d)
+    perm = np.empty(d, dtype=np.int32)
+    ps = L.C.c_double(0.0); it = L.C.c_int32(0)
+    rc = L.lib().lqg_expt_setup(d, L.ptr(Sf), L.ptr(l), L.ptr(u), L.make_opts(mem=L.MEM_HOST), L.ptr(L0), L.ptr(lo), L.ptr(uo),
+                                L.ptr(mu), L.ptr(x), L.C.byref(ps), perm.ctypes.data, L.ptr(Lfull), L.C.byref(it))
+    if rc == 8:
+        raise ValueError("Sigma is not positive semi-definite")
+    if rc == 1:
+        raise ValueError("Covariance matrix is ill-conditioned and method failed")
+    L.check(rc, "lqg_expt_setup")
+    perm = perm.astype(np.int64)
+    return dict(L0=L0, l=lo, u=uo, mu=mu, psistar=float(ps.value), Lfull=Lfull, order=np.argsort(perm), perm=perm,
+                x=x[:d - 1], newton_iterations=int(it.value))

@@ -233,7 +233,9 @@ def tmvrnorm_ExpT(object, nsim, control=None, **kw):
     mu, Sigma, lb, ub = tmvPar["mu"], tmvPar["Sigma"], tmvPar["lb"], tmvPar["ub"]
     d = mu.size
     nsim = int(nsim)
-    su = control.get("setup") or expt.setup(lb - mu, ub - mu, Sigma)
+    su = control.get("setup")
+    if su is None or isinstance(su, str):              # "device": lqg_expt_setup; default: the host restatement
+        su = expt.setup_device(lb - mu, ub - mu, Sigma) if su == "device" else expt.setup(lb - mu, ub - mu, Sigma)
     seed = control.get("seed")
     if seed is None:
         seed = int(np.random.randint(1, 2 ** 31 - 1))

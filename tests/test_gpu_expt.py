@@ -90,3 +90,60 @@ def test_simulate_with_the_package_default_sampler(lqg):
     sim = lqg.simulate(mdl, nsim=500, seed=3, xtest=aux["xtest"])
     assert sim["xi.sim"].shape == (30, 500) and np.diff(sim["xi.sim"], axis=0).min() > -1e-9
     assert sim["stats"]["sampler"] == "ExpT"
+
+
+@pytest.mark.parametrize("case", ["cfg1", "cfg2", "random60", "d1"])
+def test_expt_setup_on_the_device_matches_the_host_restatement(lqg, case):
+    """lqg_expt_setup (permuted Cholesky + Newton tilt on the GPU) against expt.setup: same permutation, factor,
+    scaled bounds, tilt and psi* (1e-9), and tmvrnorm.ExpT with control["setup"] = "device" draws the same samples."""
+    from lineqgpr_b200 import expt, workloads as W
+    if case in ("cfg1", "cfg2"):
+        par, _ = W.CONFIGS[case](sampler="ExpT")
+        mu, S = np.asarray(par["mu"], float), np.asarray(par["Sigma"], float)
+        l, u = np.asarray(par["lb"], float) - mu, np.asarray(par["ub"], float) - mu
+    else:
+        rng = np.random.default_rng(4)
+        d = 60 if case == "random60" else 1
+        B = rng.standard_normal((d, d)); S = B @ B.T / d + 0.3 * np.eye(d)
+        mu = np.zeros(d); l = -0.5 - rng.uniform(size=d); u = 0.7 + rng.uniform(size=d)
+        l[::7] = -np.inf
+        par = dict(mu=mu, Sigma=S, lb=l, ub=u)
+    h = expt.setup(l, u, S)
+    g = expt.setup_device(l, u, S)
+    d = l.size
+    ph, pg = h["perm"], g["perm"]
+    assert np.array_equal(np.sort(pg), np.arange(d))
+    # the factor belongs to the permutation the device chose
+    Sp = S[np.ix_(pg, pg)]
+    assert np.abs(g["Lfull"] @ g["Lfull"].T - Sp).max() <= 1e-12 * np.abs(S).max() * d
+    assert np.abs(g["L0"] - (g["Lfull"] / np.diag(g["Lfull"])[:, None] - np.eye(d))).max() <= 1e-13
+    # Late in the order the remaining variables are all but unconstrained given the earlier ones: their
+    # conditional log-masses are zero to rounding and the arg-min between them is decided by the last bit of
+    # differently ordered sums, so the two permutations may part ways there (any order is a valid
+    # factorization; it only matters for efficiency where the masses differ).  They must agree while the
+    # pivot choice is decisive, and wherever they agree the factors agree.
+    same = int(np.argmax(ph != pg)) if np.any(ph != pg) else d
+    assert same >= min(d, 8)
+    assert np.abs(h["Lfull"][:same, :same] - g["Lfull"][:same, :same]).max() <= 1e-11 * max(1.0, np.abs(h["Lfull"]).max())
+    fin = np.isfinite(h["l"][:same])
+    if fin.any():
+        assert np.abs(h["l"][:same][fin] - g["l"][:same][fin]).max() <= 1e-10 * max(1.0, np.abs(h["l"][:same][fin]).max())
+    # the tilt, compared variable by variable, and psi*
+    mh = np.zeros(d); mg = np.zeros(d); mh[ph] = h["mu"]; mg[pg] = g["mu"]
+    assert np.abs(mh - mg).max() <= 1e-8 * max(1.0, np.abs(mh).max())
+    assert abs(h["psistar"] - g["psistar"]) <= 1e-9 * max(1.0, abs(h["psistar"]))
+    obj = dict(par, **{"class": "ExpT"})
+    xa = lqg.tmvrnorm(obj, 4000, {"seed": 3, "setup": g})
+    sa = dict(lqg.last_stats)
+    xb = lqg.tmvrnorm(obj, 4000, {"seed": 3, "setup": h})
+    sb = dict(lqg.last_stats)
+    lbv, ubv = np.asarray(par["lb"], float), np.asarray(par["ub"], float)
+    assert np.all(xa >= lbv[:, None]) and np.all(xa <= ubv[:, None])
+    se = np.sqrt((xa.var(1) + xb.var(1)) / 4000)
+    assert (np.abs(xa.mean(1) - xb.mean(1)) > 4 * se + 1e-12).sum() <= max(1, d // 50)
+    ra, rb = sa["accepted"] / sa["proposals"], sb["accepted"] / sb["proposals"]
+    assert abs(ra - rb) <= 0.05 * max(ra, rb) + 0.01                  # same acceptance rate: the same psi*
+    if same == d:
+        assert np.abs(xa - xb).max() <= 1e-8 * max(1.0, np.abs(xb).max())
+    xc = lqg.tmvrnorm(obj, 64, {"seed": 3, "setup": "device"})
+    assert np.array_equal(xa[:, :64], lqg.tmvrnorm(obj, 64, {"seed": 3, "setup": g})) and np.array_equal(xc, xa[:, :64])
