@@ -73,13 +73,19 @@ tmvrnorm.ExpT <- function(object, nsim, control = NULL, ...) {
   tmvPar <- object
   d <- length(tmvPar$mu)
   l <- tmvPar$lb - tmvPar$mu; u <- tmvPar$ub - tmvPar$mu
-  # set-up exactly as TruncatedNormal::mvrandn does it (its internal helpers)
-  out <- TruncatedNormal:::cholperm(tmvPar$Sigma, l, u)
-  Lfull <- out$L; D <- diag(Lfull); perm <- out$perm
-  L0 <- Lfull / D - diag(d); l <- out$l / D; u <- out$u / D
-  xmu <- TruncatedNormal:::nleq(l, u, L0)
-  x <- xmu[1:(d - 1)]; mu <- c(xmu[d:(2 * d - 2)], 0)
-  psistar <- TruncatedNormal:::psy(x, L0, l, u, mu)
+  if (identical(control$setup, "host")) {
+    # set-up exactly as TruncatedNormal::mvrandn does it (its internal helpers)
+    out <- TruncatedNormal:::cholperm(tmvPar$Sigma, l, u)
+    Lfull <- out$L; D <- diag(Lfull); perm <- out$perm
+    L0 <- Lfull / D - diag(d); l <- out$l / D; u <- out$u / D
+    xmu <- TruncatedNormal:::nleq(l, u, L0)
+    x <- xmu[1:(d - 1)]; mu <- c(xmu[d:(2 * d - 2)], 0)
+    psistar <- TruncatedNormal:::psy(x, L0, l, u, mu)
+  } else {
+    # the same three steps on the device (permuted Cholesky, Newton tilt, psi*)
+    su <- .Call("lqg_expt_setup_call", tmvPar$Sigma, as.double(l), as.double(u))
+    L0 <- su[[1]]; l <- su[[2]]; u <- su[[3]]; mu <- su[[4]]; psistar <- su[[5]]; perm <- su[[6]]; Lfull <- su[[7]]
+  }
   seed <- sample(1:10000000, 1)
   Z <- .Call("lqg_expt_call", L0, as.double(l), as.double(u), as.double(mu), as.double(psistar),
              as.integer(nsim), as.integer(seed))

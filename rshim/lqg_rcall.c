@@ -150,6 +150,33 @@ SEXP lqg_expt_call(SEXP L0_, SEXP l_, SEXP u_, SEXP mu_, SEXP psistar_, SEXP nsi
   return out;
 }
 
+/* set-up of TruncatedNormal::mvrandn on the device (cholperm, nleq, psy):
+ * list(L0, l, u, mu, psistar, perm (1-based), Lfull) */
+SEXP lqg_expt_setup_call(SEXP Sigma_, SEXP l_, SEXP u_) {
+  const int d = Rf_length(l_);
+  if (Rf_nrows(Sigma_) != d || Rf_ncols(Sigma_) != d || Rf_length(u_) != d) Rf_error("l, u, and Sig have to match in dimension with u>l");
+  lqg_opts o;
+  memset(&o, 0, sizeof(o));
+  o.mem = LQG_MEM_HOST;
+  SEXP L0 = PROTECT(Rf_allocMatrix(REALSXP, d, d));
+  SEXP lo = PROTECT(Rf_allocVector(REALSXP, d));
+  SEXP uo = PROTECT(Rf_allocVector(REALSXP, d));
+  SEXP mu = PROTECT(Rf_allocVector(REALSXP, d));
+  SEXP ps = PROTECT(Rf_allocVector(REALSXP, 1));
+  SEXP perm = PROTECT(Rf_allocVector(INTSXP, d));
+  SEXP Lf = PROTECT(Rf_allocMatrix(REALSXP, d, d));
+  int32_t iters = 0;
+  int rc = lqg_expt_setup(d, REAL(Sigma_), REAL(l_), REAL(u_), &o, REAL(L0), REAL(lo), REAL(uo), REAL(mu), NULL, REAL(ps),
+                          INTEGER(perm), REAL(Lf), &iters);
+  for (int i = 0; i < d; ++i) INTEGER(perm)[i] += 1;           /* R indices */
+  SEXP res = PROTECT(Rf_allocVector(VECSXP, 7));
+  SET_VECTOR_ELT(res, 0, L0); SET_VECTOR_ELT(res, 1, lo); SET_VECTOR_ELT(res, 2, uo); SET_VECTOR_ELT(res, 3, mu);
+  SET_VECTOR_ELT(res, 4, ps); SET_VECTOR_ELT(res, 5, perm); SET_VECTOR_ELT(res, 6, Lf);
+  UNPROTECT(8);
+  lqg_check(rc, "lqg_expt_setup");
+  return res;
+}
+
 /* A %*% B on the FP64 tensor cores: xi.sim = Lambda^+ eta, ysim = Phi.test %*% xi.sim */
 SEXP lqg_dgemm_call(SEXP A_, SEXP B_) {
   const int m = Rf_nrows(A_), k = Rf_ncols(A_), n = Rf_ncols(B_);
