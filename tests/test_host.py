@@ -223,3 +223,18 @@ def test_r_shim_type_checks_against_the_header():
     rfile = (ROOT / "rshim" / "lineqGPsamplers_b200.R").read_text()
     for name in set(re.findall(r'\.Call\("(lqg_[a-z_]+)"', rfile)):
         assert re.search(r"\bSEXP %s\(" % name, shim), name
+
+
+def test_fork_defaults_do_not_depend_on_the_shard():
+    """Families of chains sharing a root chain's burn-in (lqg_opts.fork): the wrapper's default must be the same
+    for a whole job and for any shard of it (a shard is recognisable by its chain.offset), a lone chain without
+    an offset is the reference's single serial chain, and injected draws never fork."""
+    from lineqgpr_b200.samplers import chain_fork, chain_burn_in, FORK_DEFAULT, FORK_BURN_IN
+    assert chain_fork(444) == (FORK_DEFAULT, FORK_BURN_IN)
+    assert chain_fork(2) == (FORK_DEFAULT, FORK_BURN_IN)
+    assert chain_fork(1) == (0, 0)
+    assert chain_fork(1, {"chain.offset": 7}) == (FORK_DEFAULT, FORK_BURN_IN)      # one chain of a larger job
+    assert chain_fork(444, {"fork": 1}) == (0, 0)
+    assert chain_fork(444, {"fork": 6, "fork.burn.in": 2}) == (6, 2)
+    assert chain_fork(444, {"injected": object()}) == (0, 0)
+    assert chain_burn_in(1, 444) == 100 and chain_burn_in(1, 1) == 1 and chain_burn_in(1, 444, {"burn.in.exact": True}) == 1
