@@ -68,7 +68,7 @@ def parse():
     ap.add_argument("--chains-per-gpu", type=int, default=0, help="0 = lqg_hmc_box_slots(d)")
     ap.add_argument("--burn-in", type=int, default=100)
     ap.add_argument("--prepass", type=int, default=-1)
-    ap.add_argument("--fork", type=int, default=3, help="chains per family sharing one root chain's burn-in (lqg_opts.fork; 1 = independent chains)")
+    ap.add_argument("--fork", type=int, default=6, help="chains per family sharing one root chain's burn-in (lqg_opts.fork; 1 = independent chains)")
     ap.add_argument("--fork-burn-in", type=int, default=5, help="transitions a forked chain runs before it emits")
     ap.add_argument("--n-test", type=int, default=0, help="test points of the e2e pipeline (0 = 1000 for cfg4, 100000 for cfg5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -104,13 +104,13 @@ def chain_burn_in(burn_in, n_chains, control=None):
     return int(burn_in)
 
 
-FORK_DEFAULT, FORK_BURN_IN = 3, 5
+FORK_DEFAULT, FORK_BURN_IN = 6, 5
 
 
 def chain_fork(n_chains, control=None):
-    """(fork, fork_burn_in) of lqg_opts.  With many chains, families of 3 share one root chain's burn-in
-    (the root runs the burn-in from the clamped MAP; its 3 chains start from the state it reached, run
-    5 more transitions on their own streams, then emit): a third of the burn-in work, and every emitted
+    """(fork, fork_burn_in) of lqg_opts.  With many chains, families of 6 share one root chain's burn-in
+    (the root runs the burn-in from the clamped MAP; its 6 chains start from the state it reached, run
+    5 more transitions on their own streams, then emit): a sixth of the burn-in work, and every emitted
     column is still burn.in + 5 transitions away from the start.  control["fork"] = 1 gives fully
     independent chains (each with its own burn-in); injected draws never fork."""
     control = control or {}

@@ -5,11 +5,11 @@
 #
 # dyn.load("lqg_rcall.so") once (or useDynLib in NAMESPACE).
 
-# c(fork, fork.burn.in) of lqg_opts: with several chains, families of 3 share one root chain's burn-in
+# c(fork, fork.burn.in) of lqg_opts: with several chains, families of 6 share one root chain's burn-in
 # (the root runs burn.in transitions from the clamped MAP; its 3 chains start from the state it reached
 # and run 5 more on their own streams before they emit).  control$fork = 1: fully independent chains.
 .lqg_fork <- function(control) {
-  fork <- if ("fork" %in% names(control)) control$fork else if (control$n.chains > 1) 3L else 1L
+  fork <- if ("fork" %in% names(control)) control$fork else if (control$n.chains > 1) 6L else 1L
   fb <- if ("fork.burn.in" %in% names(control)) control$fork.burn.in else 5L
   as.integer(c(fork, fb))
 }

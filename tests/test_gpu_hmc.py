@@ -311,9 +311,9 @@ def test_forked_families_share_a_root_chain(lqg):
     assert np.array_equal(whole, np.hstack([lo, hi]))
     one = lqg.tmvrnorm(obj, n_per, dict(ctl, **{"n.chains": 1, "chain.offset": 4}))
     assert np.array_equal(one, whole[:, 4 * n_per:5 * n_per])
-    # (3) moments: 300 chains in families of 3 against 300 independent chains
+    # (3) moments: 300 chains in families (the wrapper's default) against 300 independent chains
     x3 = lqg.tmvrnorm(obj, 6000, {"burn.in": 100, "n.chains": 300, "seed": 5})
-    assert lqg.last_stats["fork"] == 3
+    assert lqg.last_stats["fork"] == 6
     x1 = lqg.tmvrnorm(obj, 6000, {"burn.in": 100, "n.chains": 300, "seed": 6, "fork": 1})
     se = np.sqrt((x3.var(1) + x1.var(1)) / 6000)
     assert (np.abs(x3.mean(1) - x1.mean(1)) > 3.5 * se).sum() <= 1
@@ -457,8 +457,8 @@ def test_full_size_m1000_properties(lqg):
         assert np.isfinite(x).all()
         assert np.all(x >= lb[:, None]) and np.all(x <= ub[:, None])
         assert st["violations"] == 0 and st["failed_chains"] == 0
-        # families of 3 chains share a root chain's 3 burn-in transitions, then every chain runs min(5, 3) more
-        assert st["fork"] == 3 and st["transitions"] == -(-n_chains // 3) * 3 + n_chains * (3 + n // n_chains)
+        # families of 6 chains share a root chain's 3 burn-in transitions, then every chain runs min(5, 3) more
+        assert st["fork"] == 6 and st["transitions"] == -(-n_chains // 6) * 3 + n_chains * (3 + n // n_chains)
         assert st["hit_searches"] >= st["bounces"] + st["transitions"]
 
 
