@@ -462,6 +462,28 @@ def test_full_size_m1000_properties(lqg):
         assert st["hit_searches"] >= st["bounces"] + st["transitions"]
 
 
+@pytest.mark.parametrize("d", [2500, 5000])
+def test_kernel_shapes_beyond_2048_coordinates(lqg, d):
+    """d in (2048, 4096] and (4096, 8192] run other shapes of the box kernel (8 and 16 warps per chain, 16
+    coordinates per thread, register or recomputed thresholds): every emitted value inside the box, the
+    three hit-search modes (tan(t/2) ranking with windows, without, tmg's arithmetic throughout) decide
+    the same events — identical with and without windows, 1e-9 against the exact search."""
+    rng = np.random.default_rng(1)
+    B = rng.standard_normal((d, 64)); S = B @ B.T / 64 + np.eye(d)
+    sd = np.sqrt(np.diag(S))
+    par = dict(mu=np.zeros(d), Sigma=S, lb=-2.2 * sd, ub=2.6 * sd)
+    par["class"] = "HMC"
+    out = {}
+    for mode in (0, 2, 1):
+        out[mode] = lqg.tmvrnorm(par, 16, {"burn.in": 3, "n.chains": 8, "seed": 5, "burn.in.exact": True, "hmc.search": mode})
+        st = dict(lqg.last_stats)
+        assert st["violations"] == 0 and st["failed_chains"] == 0 and st["bounces"] > 10 * st["transitions"]
+        assert np.all(out[mode] >= par["lb"][:, None]) and np.all(out[mode] <= par["ub"][:, None])
+    assert np.array_equal(out[0], out[2])
+    first = [out[m].reshape(d, 8, 2, order="F")[:, :, 0] for m in (2, 1)]
+    assert np.abs(first[0] - first[1]).max() <= 1e-9 * np.abs(first[1]).max()
+
+
 # ------------------------------------------------------------------------------------- edge cases
 def test_edge_cases_shapes_and_bounds(lqg):
     """d = 1, one-sided and unbounded coordinates, more chains than samples, a single long chain."""
