@@ -405,7 +405,7 @@ typedef struct lqg_simulate_stats {
  * eta_out equals what lqg_hmc_box returns for the same opts).  While later sampling rounds run, the
  * samples every chain has finished are multiplied by Lambda^+ on a second stream, copied to xi_out
  * and — with a communicator — all-gathered, so that after the last round every rank holds the xi of
- * the whole job (m x N_total; the work proceeds in units of 16 samples per chain, the same on every
+ * the whole job (m x N_total; the work proceeds in units of 16 (one GPU) or 32 (several) samples per chain, the same on every
  * rank, and the gathered columns are ordered unit, rank, chain, sample).  Rank r then
  * summarises rows [r ceil(n_t/world), (r+1) ceil(n_t/world)) of Phi over all N_total samples (exact
  * mean and type-7 quantiles) and the band pieces are all-gathered: every rank returns the full

@@ -2089,7 +2089,10 @@ extern "C" int lqg_simulate(const lqg_simulate_args* a_, const lqg_opts* opts_, 
   // each of them gets there.  The column order of the gathered xi is therefore fixed: unit, rank,
   // chain, sample.
   static const char* env_unit = getenv("LQG_GATHER_UNIT");            // tuning aid
-  const int unit = std::max(1, env_unit ? atoi(env_unit) : 16);       // 16: the part of the last unit's copy that no compute hides stays small (32: +2 % step time, 8: launch-bound)
+  // one GPU: 16 — the part of the last unit's copy that no compute hides stays small (32: +2 % step time, 8:
+  // launch-bound); several GPUs: 32 — the host's copy bandwidth is shared and fewer, larger copies and
+  // all-gathers do better (8 GPUs: 8.9 vs 8.3 M samples/s end to end)
+  const int unit = std::max(1, env_unit ? atoi(env_unit) : (W > 1 ? 32 : 16));
   const int n_units = (n_per + unit - 1) / unit;
   int next_unit = 0;
   DevBuf b_lsq_scr;                          // refinement right-hand sides of one unit (banded path)
