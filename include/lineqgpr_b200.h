@@ -254,6 +254,9 @@ int lqg_bands(int32_t n_t, int64_t N, const double* ysim, int64_t ld,
  * matrix is produced slab by slab on the device (row slabs of Phi of at most slab_rows rows,
  * 0 = as many as fit ~4 GB), summarised exactly and dropped, so it never has to exist anywhere
  * (config 5: 10^5 x 10^6 doubles); when ysim (ldy >= n_t) is given the slabs are also copied out.
+ * Without ysim, a dense slab with N >= 8192 is not even stored on the device: the product's epilogue
+ * counts, collects and sums for the bands (same exact order statistics; ldphi and m even, else the
+ * slab is stored and read again).
  * mean[n_t]; qtls nprobs x n_t (nullable when nprobs = 0).  gemm_ms / bands_ms nullable.          */
 int lqg_paths(int32_t n_t, int32_t m, int64_t N, const double* Phi, int64_t ldphi,
               const double* xi, int64_t ldxi, const double* probs, int32_t nprobs,

@@ -326,6 +326,11 @@ bands_select_kernel(int n_t, int64_t N, BandPlan pl, BandTargets tg, const doubl
   bool failed = false;
   // applies f(key) to every collected value of (row, k): warps take segments, lanes stride inside
   auto for_each_key = [&](const double* seg0, auto&& f) {
+    if (ns == 1) {                                             // one segment (fused product): the whole CTA strides over it
+      const unsigned cs = c[0];
+      for (unsigned j = tid; j < cs; j += BT) f(ordered_key(seg0[j]));
+      return;
+    }
     for (int sp = warp; sp < ns; sp += BT / 32) {
       const double* seg = seg0 + (size_t)sp * pl.cap_split;
       const unsigned cs = c[sp];
@@ -599,6 +604,129 @@ cudaError_t launch_bands_bracketed(int n_t, int64_t N, const double* ysim, int64
   }
 #undef LQG_COLLECT
   bands_select_kernel<<<n_t, BT, 0, st>>>(n_t, N, pl, tg, part_sum, below_g, cnt_g, buf, mean, qtls, fail);
+  launch_counter() += 2;
+  *fail_dev = fail;
+  return cudaGetLastError();
+}
+
+// ---- fused form: the product's epilogue collects (dgemm_tma_kernel<true>, lqg_dgemm.cu) ----------------------
+// Xs[:, e] = X[:, floor(e N / SAMP)]: the sample columns the brackets are drawn from
+__global__ void __launch_bounds__(256)
+gather_sample_cols_kernel(int m, int64_t N, const double* __restrict__ X, int64_t ldx, double* __restrict__ Xs, int64_t ldxs) {
+  const int e = blockIdx.x;
+  const int64_t n = ((int64_t)e * N) / SAMP;
+  for (int i = threadIdx.x; i < ldxs; i += blockDim.x) Xs[(size_t)e * ldxs + i] = i < m ? X[(size_t)n * ldx + i] : 0.0;
+}
+
+// part_sum[row] = compensated sum of the partial row sums the product left, in a fixed order: a CTA takes 32 test
+// points (lane = test point: 256-byte loads), warp w the parts w, w + 8, ...; warp 0 then adds the eight slices in order
+__global__ void __launch_bounds__(256)
+bands_tile_sum_kernel(int n_t, int parts, const double* __restrict__ tile_sum, double* __restrict__ part_sum) {
+  __shared__ double s_sum[8][32], s_comp[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = blockIdx.x * 32 + lane;
+  double sum = 0.0, comp = 0.0;
+  auto add = [&](double x) {
+    const double t = __dadd_rn(sum, x);
+    comp = __dadd_rn(comp, fabs(sum) >= fabs(x) ? __dadd_rn(__dsub_rn(sum, t), x) : __dadd_rn(__dsub_rn(x, t), sum));
+    sum = t;
+  };
+  if (row < n_t) {
+    const double* src = tile_sum + row;
+    int p = warp;
+    for (; p + 8 * (UNR - 1) < parts; p += 8 * UNR) {
+      double v[UNR];
+#pragma unroll
+      for (int q = 0; q < UNR; ++q) v[q] = __ldg(src + (size_t)(p + 8 * q) * n_t);
+#pragma unroll
+      for (int q = 0; q < UNR; ++q) add(v[q]);
+    }
+    for (; p < parts; p += 8) add(__ldg(src + (size_t)p * n_t));
+  }
+  s_sum[warp][lane] = sum; s_comp[warp][lane] = comp;
+  __syncthreads();
+  if (warp == 0 && row < n_t) {
+    sum = 0.0; comp = 0.0;
+    for (int w = 0; w < 8; ++w) { add(s_sum[w][lane]); add(s_comp[w][lane]); }
+    part_sum[(size_t)row * 2] = sum;
+    part_sum[(size_t)row * 2 + 1] = comp;
+  }
+}
+
+namespace {
+struct FusedLayout {
+  size_t xs, ys, brackets, part_sum, counts, fail, tile_sum, buf, total;
+  int64_t ldxs;
+  int parts;
+  long long cap;
+};
+FusedLayout fused_layout(int n_t, int m, int64_t N, int nprobs) {
+  FusedLayout L;
+  const int npz = nprobs > 0 ? nprobs : 1;
+  L.ldxs = m + (m & 1);                                   // even leading dimension: 16-byte aligned columns for the tensor map
+  L.parts = dgemm_bands_parts((int)N);
+  L.cap = (long long)(0.15 * 1.25 * (double)N) + 256;     // as make_plan: brackets hold <= 10 % of a row
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t at = off; off = (off + bytes + 255) & ~(size_t)255; return at; };
+  L.xs = take((size_t)L.ldxs * SAMP * sizeof(double));
+  L.ys = take((size_t)n_t * SAMP * sizeof(double));
+  L.brackets = take((size_t)n_t * npz * 2 * sizeof(uint64_t));
+  L.part_sum = take((size_t)n_t * 2 * sizeof(double));
+  L.counts = take(2 * (size_t)n_t * npz * sizeof(unsigned));        // below | cursor
+  L.fail = take((size_t)n_t * sizeof(int));
+  L.tile_sum = take((size_t)L.parts * n_t * sizeof(double));
+  L.buf = take((size_t)n_t * nprobs * (size_t)L.cap * sizeof(double) + 512);
+  L.total = off;
+  return L;
+}
+}  // namespace
+
+size_t paths_bands_fused_scratch_bytes(int n_t, int m, int64_t N, int nprobs, const double* phi, int64_t ldphi,
+                                       const double* X, int64_t ldx) {
+  if (N < 4 * SAMP || N >= ((int64_t)1 << 31) || nprobs > MAXP || nprobs < 0 || n_t <= 0 || m <= 0) return 0;
+  if (!dgemm_bands_usable(phi, ldphi, X, ldx)) return 0;
+  return fused_layout(n_t, m, N, nprobs).total;
+}
+
+cudaError_t launch_paths_bands_fused(int n_t, int m, int64_t N, const double* phi, int64_t ldphi, const double* X, int64_t ldx,
+                                     const double* probs_host, int nprobs, double* mean, double* qtls, void* scratch,
+                                     int** fail_dev, cudaStream_t st, cudaEvent_t ev_product_done) {
+  if (paths_bands_fused_scratch_bytes(n_t, m, N, nprobs, phi, ldphi, X, ldx) == 0) return cudaErrorNotSupported;
+  const FusedLayout L = fused_layout(n_t, m, N, nprobs);
+  const BandTargets tg = make_targets(N, probs_host, nprobs);
+  BandPlan pl = make_plan(n_t, N, probs_host, nprobs);      // bracket positions; one segment per (test point, probability)
+  pl.splits = 1;
+  pl.cap_split = L.cap;
+  const int npz = nprobs > 0 ? nprobs : 1;
+  unsigned char* w = static_cast<unsigned char*>(scratch);
+  double* xs = reinterpret_cast<double*>(w + L.xs);
+  double* ys = reinterpret_cast<double*>(w + L.ys);
+  uint64_t* brackets = reinterpret_cast<uint64_t*>(w + L.brackets);
+  double* part_sum = reinterpret_cast<double*>(w + L.part_sum);
+  unsigned* below = reinterpret_cast<unsigned*>(w + L.counts);
+  unsigned* cursor = below + (size_t)n_t * npz;
+  int* fail = reinterpret_cast<int*>(w + L.fail);
+  cudaError_t e;
+  if (nprobs > 0) {
+    // pilot: the 2048 sampled columns of the product, sorted per test point -> brackets
+    gather_sample_cols_kernel<<<SAMP, 256, 0, st>>>(m, N, X, ldx, xs, L.ldxs);
+    ++launch_counter();
+    if ((e = launch_dgemm(n_t, SAMP, m, phi, ldphi, xs, L.ldxs, ys, n_t, nullptr, 0, st)) != cudaSuccess) return e;
+    bands_sample_kernel<<<n_t, SAMP / 2, 0, st>>>(n_t, SAMP, ys, n_t, pl, brackets);
+    ++launch_counter();
+  }
+  if ((e = cudaMemsetAsync(below, 0, 2 * (size_t)n_t * npz * sizeof(unsigned), st)) != cudaSuccess) return e;
+  BandFuse f;
+  f.brackets = reinterpret_cast<const unsigned long long*>(brackets);
+  f.below = below; f.cursor = cursor;
+  f.buf = reinterpret_cast<double*>(w + L.buf);
+  f.tile_sum = reinterpret_cast<double*>(w + L.tile_sum);
+  f.cap = (unsigned)L.cap;
+  f.nprobs = nprobs;
+  if ((e = launch_dgemm_bands(n_t, (int)N, m, phi, ldphi, X, ldx, f, st)) != cudaSuccess) return e;
+  if (ev_product_done && (e = cudaEventRecord(ev_product_done, st)) != cudaSuccess) return e;
+  bands_tile_sum_kernel<<<(n_t + 31) / 32, 256, 0, st>>>(n_t, L.parts, f.tile_sum, part_sum);
+  bands_select_kernel<<<n_t, BT, 0, st>>>(n_t, N, pl, tg, part_sum, below, cursor, f.buf, mean, qtls, fail);
   launch_counter() += 2;
   *fail_dev = fail;
   return cudaGetLastError();

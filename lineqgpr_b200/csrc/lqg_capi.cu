@@ -1752,23 +1752,27 @@ static bool sparse_paths_enabled() {
 struct SlabProduct {
   DevBuf pidx, pval, pinfo;
   bool probe = sparse_paths_enabled();
-  int run(int nr, int m, int rows_cap, const double* phi, int64_t ld, const double* X, int64_t ldx, int64_t N, double* Y, int64_t ldy,
-          cudaStream_t st, double* ms) {
-    bool ell = false;
-    int ell_k = 0;
-    if (probe) {
-      if (!pidx.p) {
-        LQG_CUDA_TRY(pidx.alloc((size_t)kEllMaxNnz * rows_cap * sizeof(int)));
-        LQG_CUDA_TRY(pval.alloc((size_t)kEllMaxNnz * rows_cap * sizeof(double)));
-        LQG_CUDA_TRY(pinfo.alloc(sizeof(int)));
-      }
-      LQG_CUDA_TRY(cudaMemsetAsync(pinfo.p, 0, sizeof(int), st));
-      LQG_CUDA_TRY(launch_ell_from_dense(nr, m, kEllMaxNnz, phi, ld, pidx.as<int>(), pval.as<double>(), pinfo.as<int>(), st));
-      LQG_CUDA_TRY(cudaMemcpyAsync(&ell_k, pinfo.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-      LQG_CUDA_TRY(cudaStreamSynchronize(st));
-      ell = ell_k <= kEllMaxNnz;
-      if (!ell) probe = false;
+  bool ell = false;                                                // of the slab classified last
+  int ell_k = 0;
+  int classify(int nr, int m, int rows_cap, const double* phi, int64_t ld, cudaStream_t st) {
+    ell = false;
+    ell_k = 0;
+    if (!probe) return LQG_OK;
+    if (!pidx.p) {
+      LQG_CUDA_TRY(pidx.alloc((size_t)kEllMaxNnz * rows_cap * sizeof(int)));
+      LQG_CUDA_TRY(pval.alloc((size_t)kEllMaxNnz * rows_cap * sizeof(double)));
+      LQG_CUDA_TRY(pinfo.alloc(sizeof(int)));
     }
+    LQG_CUDA_TRY(cudaMemsetAsync(pinfo.p, 0, sizeof(int), st));
+    LQG_CUDA_TRY(launch_ell_from_dense(nr, m, kEllMaxNnz, phi, ld, pidx.as<int>(), pval.as<double>(), pinfo.as<int>(), st));
+    LQG_CUDA_TRY(cudaMemcpyAsync(&ell_k, pinfo.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    LQG_CUDA_TRY(cudaStreamSynchronize(st));
+    ell = ell_k <= kEllMaxNnz;
+    if (!ell) probe = false;
+    return LQG_OK;
+  }
+  int product(int nr, int m, const double* phi, int64_t ld, const double* X, int64_t ldx, int64_t N, double* Y, int64_t ldy,
+              cudaStream_t st, double* ms) {
     Timer tg(st);
     tg.start();
     if (ell) LQG_CUDA_TRY(launch_ell_spmm(nr, m, std::max(1, ell_k), pidx.as<int>(), pval.as<double>(), X, ldx, N, Y, ldy, st));
@@ -1778,6 +1782,70 @@ struct SlabProduct {
     return LQG_OK;
   }
 };
+
+static bool bands_fused_enabled() {
+  static const char* env = getenv("LQG_BANDS_FUSED");                // A/B aid: 0 = always product, then bands of the stored slab
+  return !(env && env[0] == '0');
+}
+
+// One row slab of the path stage: the bands of Phi_slab X.  When the caller does not want the paths themselves and
+// the slab is dense, the product is summarised in its own epilogue (launch_paths_bands_fused) and never stored;
+// otherwise it goes into y (allocated on first use: rows_cap x N) and lqg_bands' kernels read it from there.
+// *stored tells whether y holds the slab afterwards.
+static int slab_paths_bands(SlabProduct& sp, int nr, int m, int rows_cap, const double* phi, int64_t ld, const double* X, int64_t ldx,
+                            int64_t N, const std::vector<double>& h_probs, int nprobs, double* d_mean, double* d_q, DevBuf& b_y,
+                            bool want_y, DevBuf& b_scr, DevBuf& b_row, double* t_gemm, double* t_bands, bool* stored, cudaStream_t st) {
+  int rc;
+  if ((rc = sp.classify(nr, m, rows_cap, phi, ld, st))) return rc;
+  auto need_y = [&]() -> cudaError_t { return b_y.p ? cudaSuccess : b_y.alloc((size_t)rows_cap * N * sizeof(double)); };
+  *stored = false;
+  const size_t fused_bytes = (want_y || sp.ell || !bands_fused_enabled()) ? 0 : paths_bands_fused_scratch_bytes(nr, m, N, nprobs, phi, ld, X, ldx);
+  if (!fused_bytes) {
+    LQG_CUDA_TRY(need_y());
+    if ((rc = sp.product(nr, m, phi, ld, X, ldx, N, b_y.as<double>(), nr, st, t_gemm))) return rc;
+    *stored = true;
+    double ms = 0.0;
+    if ((rc = bands_on_device(nr, N, b_y.as<double>(), nr, h_probs, nprobs, d_mean, d_q, b_scr, &ms, st))) return rc;
+    *t_bands += ms;
+    return LQG_OK;
+  }
+  if (!b_scr.p || b_scr.bytes < fused_bytes) LQG_CUDA_TRY(b_scr.alloc(fused_bytes));
+  Timer tg(st), tb(st);
+  tg.start();
+  int* fail_dev = nullptr;
+  LQG_CUDA_TRY(launch_paths_bands_fused(nr, m, N, phi, ld, X, ldx, h_probs.data(), nprobs, d_mean, d_q, b_scr.p, &fail_dev, st, tg.b));
+  std::vector<int> h_fail(nr);
+  LQG_CUDA_TRY(cudaMemcpyAsync(h_fail.data(), fail_dev, nr * sizeof(int), cudaMemcpyDeviceToHost, st));
+  LQG_CUDA_TRY(cudaStreamSynchronize(st));
+  std::vector<int> rows;
+  for (int r = 0; r < nr; ++r) if (h_fail[r]) rows.push_back(r);
+  if (getenv("LQG_TRACE")) fprintf(stderr, "[lqg bands] fused product: %zu of %d test points go to the exact path (first %d)\n",
+                                   rows.size(), nr, rows.empty() ? -1 : rows[0]);
+  if (rows.size() > 64) {
+    // the whole slab after all: same kernel arithmetic, stored this time
+    LQG_CUDA_TRY(need_y());
+    LQG_CUDA_TRY(launch_dgemm(nr, (int)N, m, phi, ld, X, ldx, b_y.as<double>(), nr, nullptr, 0, st));
+    *stored = true;
+    if (b_scr.bytes < (size_t)nr * N * sizeof(double)) LQG_CUDA_TRY(b_scr.alloc((size_t)nr * N * sizeof(double)));
+    LQG_CUDA_TRY(launch_bands_exact(nr, N, b_y.as<double>(), nr, h_probs.data(), nprobs, d_mean, d_q, b_scr.as<double>(), st));
+  } else if (!rows.empty()) {
+    // single test points: their row of the product again (from an even row, so that the operand stays 16-byte
+    // aligned and the same tensor-map kernel — the same rounding — produces it), then the exact selection
+    if (!b_row.p || b_row.bytes < (size_t)3 * N * sizeof(double)) LQG_CUDA_TRY(b_row.alloc((size_t)3 * N * sizeof(double)));
+    for (int r : rows) {
+      const int rb = r & ~1, nrow = std::min(2, nr - rb);
+      LQG_CUDA_TRY(launch_dgemm(nrow, (int)N, m, phi + rb, ld, X, ldx, b_row.as<double>(), nrow, nullptr, 0, st));
+      LQG_CUDA_TRY(launch_bands_exact(1, N, b_row.as<double>() + (r - rb), nrow, h_probs.data(), nprobs, d_mean + r,
+                                      d_q + (size_t)r * nprobs, b_row.as<double>() + (size_t)2 * N, st));
+    }
+  }
+  tb.stop();
+  float f = 0.f;
+  *t_gemm += tg.ms();
+  LQG_CUDA_TRY(cudaEventSynchronize(tb.b));
+  if (cudaEventElapsedTime(&f, tg.b, tb.b) == cudaSuccess) *t_bands += f;
+  return LQG_OK;
+}
 
 extern "C" int lqg_paths(int32_t n_t, int32_t m, int64_t N, const double* Phi, int64_t ldphi,
                          const double* xi, int64_t ldxi, const double* probs, int32_t nprobs,
@@ -1805,8 +1873,7 @@ extern "C" int lqg_paths(int32_t n_t, int32_t m, int64_t N, const double* Phi, i
   int rows = slab_rows > 0 ? slab_rows : (int)std::max<int64_t>(1, std::min<int64_t>(n_t, ((int64_t)4 << 30) / (8 * N)));
   if (rows >= 128 && rows < n_t) rows -= rows % 128;              // whole 128-row GEMM tiles
   if (rows > n_t) rows = n_t;
-  DevBuf b_y, b_scr, b_mean, b_q;
-  LQG_CUDA_TRY(b_y.alloc((size_t)rows * N * sizeof(double)));
+  DevBuf b_y, b_scr, b_row, b_mean, b_q;
   double* d_mean = mean; double* d_q = qtls;
   if (mem == LQG_MEM_HOST) {
     LQG_CUDA_TRY(b_mean.alloc(n_t * sizeof(double))); d_mean = b_mean.as<double>();
@@ -1816,11 +1883,10 @@ extern "C" int lqg_paths(int32_t n_t, int32_t m, int64_t N, const double* Phi, i
   SlabProduct slab;
   for (int r0 = 0; r0 < n_t; r0 += rows) {
     const int nr = std::min(rows, n_t - r0);
-    if ((rc = slab.run(nr, m, rows, i_phi.dev + r0, ldphi, i_xi.dev, ldxi, N, b_y.as<double>(), nr, st, &t_gemm))) return rc;
-    double ms = 0.0;
-    if ((rc = bands_on_device(nr, N, b_y.as<double>(), nr, h_probs, nprobs, d_mean + r0, d_q + (size_t)r0 * nprobs, b_scr, &ms, st)))
+    bool stored = false;
+    if ((rc = slab_paths_bands(slab, nr, m, rows, i_phi.dev + r0, ldphi, i_xi.dev, ldxi, N, h_probs, nprobs, d_mean + r0,
+                               d_q + (size_t)r0 * nprobs, b_y, ysim != nullptr, b_scr, b_row, &t_gemm, &t_bands, &stored, st)))
       return rc;
-    t_bands += ms;
     if (ysim) {
       if (mem == LQG_MEM_HOST) LQG_CUDA_TRY(d2h_result(ysim + r0, ldy * sizeof(double), b_y.p, (size_t)nr * sizeof(double), (size_t)nr * sizeof(double), N, st));
       else LQG_CUDA_TRY(cudaMemcpy2DAsync(ysim + r0, ldy * sizeof(double), b_y.p, (size_t)nr * sizeof(double), (size_t)nr * sizeof(double), N,
@@ -2165,7 +2231,7 @@ extern "C" int lqg_simulate(const lqg_simulate_args* a_, const lqg_opts* opts_, 
   const int nr_local = r1 - r0;
   if (n_t > 0) {
     const int bw = 1 + nprobs;                                   // per test point: mean + nprobs quantiles
-    DevBuf b_band, b_y, b_scr, b_phi, b_x, b_u;
+    DevBuf b_band, b_y, b_scr, b_row, b_phi, b_x, b_u;
     LQG_CUDA_TRY(b_band.alloc((size_t)W * rows_per * bw * sizeof(double)));
     LQG_CUDA_TRY(cudaMemsetAsync(b_band.p, 0, b_band.bytes, st));
     double* band_mine = b_band.as<double>() + (size_t)rank * rows_per * bw;   // [mean (rows_per) | qtls (nprobs x rows_per)]
@@ -2173,7 +2239,6 @@ extern "C" int lqg_simulate(const lqg_simulate_args* a_, const lqg_opts* opts_, 
       int rows = a.slab_rows > 0 ? a.slab_rows : (int)std::max<int64_t>(1, std::min<int64_t>(nr_local, ((int64_t)4 << 30) / (8 * N_total)));
       if (rows >= 128 && rows < nr_local) rows -= rows % 128;    // whole 128-row GEMM tiles
       if (rows > nr_local) rows = nr_local;
-      LQG_CUDA_TRY(b_y.alloc((size_t)rows * N_total * sizeof(double)));
       // this rank's rows of Phi: staged from the host (rows r0..r1 only), used in place on the device,
       // or built slab by slab from the test points
       const double* phi_dev = nullptr; int64_t phi_ld = 0;
@@ -2233,14 +2298,13 @@ extern "C" int lqg_simulate(const lqg_simulate_args* a_, const lqg_opts* opts_, 
           }
           phi_slab = b_phi.as<double>(); ld_slab = nr;
         }
-        if ((rc = slab.run(nr, m, rows, phi_slab, ld_slab, xi_all, m, N_total, b_y.as<double>(), nr, st, &t_gemm))) return rc;
-        double ms = 0.0;
         double* q_slab = nprobs > 0 ? band_mine + rows_per + (size_t)s0 * nprobs : nullptr;
         // the slab's quantiles land in a (nprobs x rows_per) column-major block: column = test point
-        if ((rc = bands_on_device(nr, N_total, b_y.as<double>(), nr, h_probs, nprobs, band_mine + s0,
-                                  nprobs > 0 ? q_slab : band_mine + rows_per, b_scr, &ms, st)))
+        bool stored = false;
+        if ((rc = slab_paths_bands(slab, nr, m, rows, phi_slab, ld_slab, xi_all, m, N_total, h_probs, nprobs, band_mine + s0,
+                                   nprobs > 0 ? q_slab : band_mine + rows_per, b_y, a.ysim_out != nullptr, b_scr, b_row, &t_gemm,
+                                   &t_bands, &stored, st)))
           return rc;
-        t_bands += ms;
         if (a.ysim_out) {
           double* yp = mem == LQG_MEM_HOST ? b_yp.as<double>() : a.ysim_out + s0;
           const int64_t ldp = mem == LQG_MEM_HOST ? nr : a.ldy;

@@ -354,9 +354,27 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
       : "memory");
 }
 
+// bracket end (order-preserving key, lqg_bands.cu ordered_key) back to the double it came from; the open ends
+// (key 0 / ~0) become -inf / +inf.  The epilogue compares doubles, not keys: one DSETP instead of a key
+// construction and a 64-bit integer compare per value.  The two orders differ only on -0.0 < +0.0, where the
+// double comparison makes the bracket one zero wider at that end — still a contiguous range of the key order with
+// everything "below" in front of it, which is all the selection relies on.
+__device__ __forceinline__ double band_bound(unsigned long long key) {
+  if (key == 0ull) return __longlong_as_double(0xfff0000000000000ll);
+  if (key == ~0ull) return __longlong_as_double(0x7ff0000000000000ll);
+  const unsigned long long b = (key & 0x8000000000000000ull) ? (key & 0x7fffffffffffffffull) : ~key;
+  return __longlong_as_double((long long)b);
+}
+
+// FUSE: the tile is summarised for the band statistics instead of being stored (BandFuse, lqg_kernels.h) — per
+// test point (row) and column half-tile a partial sum, per (row, probability) the count of values below the
+// bracket and the values inside it, appended at a cursor.  Integer atomics only: the counts and the SET of
+// collected values do not depend on the order the tiles retire in, so the selected order statistics are
+// reproducible bit for bit; the sums are reduced afterwards in tile order.
+template <bool FUSE>
 __global__ void __launch_bounds__(NT, 2)
 dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int m, int n, int k,
-                 double* __restrict__ C, int64_t ldc, double* __restrict__ row_sum, int a_upper, int tail_cb) {
+                 double* __restrict__ C, int64_t ldc, double* __restrict__ row_sum, int a_upper, int tail_cb, BandFuse bf) {
   extern __shared__ __align__(1024) unsigned char dg_tma[];
   __shared__ __align__(8) uint64_t full_bar[TST], empty_bar[TST];
   // dynamic shared memory is only guaranteed 16-byte aligned: round up (the launch asks for 1 KB more)
@@ -457,6 +475,85 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     if (lane == 0) mbar_arrive(&empty_bar[s]);
   }
 
+  if constexpr (FUSE) {
+    // a thread holds, for each of 4 rows (i), 8 values: columns wn 32 + 8 j + 2 fk + {0, 1}; the 64 columns of a
+    // row sit in the 4 lanes of a quad (fk) of two warps (wn)
+    const int quad0 = lane & ~3;
+    bool okc[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int cc = col0 + wn * 32 + j * 8 + 2 * fk;
+      okc[2 * j] = cc < n; okc[2 * j + 1] = cc + 1 < n;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = row0 + wm * 32 + i * 8 + fr;
+      double rs = 0.0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (okc[2 * j]) rs += acc[i][j][0];
+        if (okc[2 * j + 1]) rs += acc[i][j][1];
+      }
+      rs += __shfl_xor_sync(0xffffffffu, rs, 1);
+      rs += __shfl_xor_sync(0xffffffffu, rs, 2);
+      if (fk == 0 && r < m) bf.tile_sum[(size_t)(2 * bn + wn) * m + r] = rs;
+    }
+    const int np = bf.nprobs;
+    for (int kq = 0; kq < np; ++kq) {
+      unsigned inm[4], off[4], tot[4], nbq[4], base[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {                       // masks and counts of the four rows
+        const int r = row0 + wm * 32 + i * 8 + fr;
+        const bool rv = r < m;
+        double lo = 0.0, hi = 0.0;
+        if (rv) {
+          const ulonglong2 br = __ldg(reinterpret_cast<const ulonglong2*>(bf.brackets) + (size_t)r * np + kq);
+          lo = band_bound(br.x); hi = band_bound(br.y);
+        }
+        unsigned nb = 0u, mk = 0u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const double x = acc[i][j][e];
+            const bool ok = okc[2 * j + e] && rv;          // rows and columns past the end: nothing below, nothing inside
+            nb += (ok && x < lo) ? 1u : 0u;
+            mk |= (ok && x >= lo && x <= hi) ? (1u << (2 * j + e)) : 0u;
+          }
+        nb += __shfl_xor_sync(0xffffffffu, nb, 1);
+        nb += __shfl_xor_sync(0xffffffffu, nb, 2);
+        const unsigned c = __popc(mk);
+        const unsigned c0 = __shfl_sync(0xffffffffu, c, quad0), c1 = __shfl_sync(0xffffffffu, c, quad0 + 1),
+                       c2 = __shfl_sync(0xffffffffu, c, quad0 + 2), c3 = __shfl_sync(0xffffffffu, c, quad0 + 3);
+        inm[i] = mk; nbq[i] = nb;
+        tot[i] = c0 + c1 + c2 + c3;
+        off[i] = (fk > 0 ? c0 : 0u) + (fk > 1 ? c1 : 0u) + (fk > 2 ? c2 : 0u);
+      }
+      // the four cursor atomics of this probability go out back to back: one round trip to L2, not four
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = row0 + wm * 32 + i * 8 + fr;
+        base[i] = 0u;
+        if (fk == 0 && r < m) {
+          if (nbq[i]) atomicAdd(bf.below + (size_t)r * np + kq, nbq[i]);
+          if (tot[i]) base[i] = atomicAdd(bf.cursor + (size_t)r * np + kq, tot[i]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        unsigned p = __shfl_sync(0xffffffffu, base[i], quad0) + off[i];
+        if (inm[i] == 0u) continue;
+        const int r = row0 + wm * 32 + i * 8 + fr;
+        double* seg = bf.buf + ((size_t)r * np + kq) * bf.cap;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+            if (inm[i] >> (2 * j + e) & 1u) { if (p < bf.cap) seg[p] = acc[i][j][e]; ++p; }   // an overflowing row is flagged by the selection
+      }
+    }
+    return;
+  }
   // ---- epilogue: C store and optional row sums (band mean numerator) ----
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -553,7 +650,7 @@ cudaError_t launch_dgemm(int m, int n, int k, const double* A, int64_t lda, cons
   if (kind == 2 && !(make_map(&mapA, A, m, k, lda, 16, BK) && make_map(&mapB, B, k, n, ldb, BK, BN))) kind = 1;
   const size_t smem = kind == 2 ? (size_t)TST * T_STAGE_BYTES + 1024
                     : kind == 1 ? (size_t)ST * STAGE * sizeof(double) : (size_t)(2 * BK * A_LD + 2 * BN * B_LD) * sizeof(double);
-  const void* kern = kind == 2 ? (const void*)dgemm_tma_kernel : kind == 1 ? (const void*)dgemm_ring_kernel : (const void*)dgemm_dmma_kernel;
+  const void* kern = kind == 2 ? (const void*)dgemm_tma_kernel<false> : kind == 1 ? (const void*)dgemm_ring_kernel : (const void*)dgemm_dmma_kernel;
   cudaError_t e0 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e0 != cudaSuccess) return e0;
   const long long tiles = (long long)((m + BM - 1) / BM) * ((n + BN - 1) / BN);
@@ -574,11 +671,37 @@ cudaError_t launch_dgemm(int m, int n, int k, const double* A, int64_t lda, cons
     tail_cb = std::min(NBc, (int)(waves * slots_of[kind] / MBc));
   }
   if (kind == 2)
-    dgemm_tma_kernel<<<(unsigned)tiles, NT, smem, st>>>(mapA, mapB, m, n, k, C, ldc, row_sum, a_upper, tail_cb);
+    dgemm_tma_kernel<false><<<(unsigned)tiles, NT, smem, st>>>(mapA, mapB, m, n, k, C, ldc, row_sum, a_upper, tail_cb, BandFuse{});
   else if (kind == 1)
     dgemm_ring_kernel<<<(unsigned)tiles, NT, smem, st>>>(m, n, k, A, lda, B, ldb, C, ldc, row_sum, a_upper, b_blk_w, b_blk_pitch, tail_cb);
   else
     dgemm_dmma_kernel<<<(unsigned)tiles, NT, smem, st>>>(m, n, k, A, lda, B, ldb, C, ldc, row_sum, a_upper, b_blk_w, b_blk_pitch, tail_cb);
+  ++launch_counter();
+  return cudaGetLastError();
+}
+
+// the tensor-map kernel needs 16-byte aligned operand columns
+bool dgemm_bands_usable(const double* A, int64_t lda, const double* B, int64_t ldb) {
+  static const char* env_ring = getenv("LQG_GEMM_RING");
+  if (env_ring && atoi(env_ring) != 2) return false;
+  return ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && lda % 2 == 0 && ldb % 2 == 0 && encode_tiled_fn() != nullptr;
+}
+
+int dgemm_bands_parts(int n) { return 2 * ((n + BN - 1) / BN); }
+
+// A (m x k) B (k x n) summarised for the bands, nothing stored (dgemm_tma_kernel<true>)
+cudaError_t launch_dgemm_bands(int m, int n, int k, const double* A, int64_t lda, const double* B, int64_t ldb,
+                               const BandFuse& f, cudaStream_t st) {
+  if (m <= 0 || n <= 0) return cudaSuccess;
+  CUtensorMap mapA, mapB;
+  if (!dgemm_bands_usable(A, lda, B, ldb) || !(make_map(&mapA, A, m, k, lda, 16, BK) && make_map(&mapB, B, k, n, ldb, BK, BN)))
+    return cudaErrorNotSupported;
+  const size_t smem = (size_t)TST * T_STAGE_BYTES + 1024;
+  cudaError_t e0 = cudaFuncSetAttribute(dgemm_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e0 != cudaSuccess) return e0;
+  const long long tiles = (long long)((m + BM - 1) / BM) * ((n + BN - 1) / BN);
+  if (tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
+  dgemm_tma_kernel<true><<<(unsigned)tiles, NT, smem, st>>>(mapA, mapB, m, n, k, nullptr, 0, nullptr, 0, 0, f);
   ++launch_counter();
   return cudaGetLastError();
 }

@@ -186,6 +186,21 @@ cudaError_t launch_dgemm(int m, int n, int k, const double* A, int64_t lda, cons
                          int64_t ldb, double* C, int64_t ldc, double* row_sum, int a_upper,
                          cudaStream_t st, int b_blk_w = 0, int64_t b_blk_pitch = 0);
 cudaError_t launch_fill_normals(int d, size_t n_cols, double* A, const NormalGen& g, cudaStream_t st);
+// Product summarised for the band statistics in the GEMM epilogue (rows = test points, columns = samples); see
+// launch_paths_bands_fused (lqg_bands.cu), which owns the buffers
+struct BandFuse {
+  const unsigned long long* brackets = nullptr;   // [row][nprobs][2] order-preserving keys bracketing the wanted ranks
+  unsigned* below = nullptr;                      // [row][nprobs] values below the bracket
+  unsigned* cursor = nullptr;                     // [row][nprobs] values inside it (append cursor; may exceed cap)
+  double* buf = nullptr;                          // [row][nprobs][cap] the values inside
+  double* tile_sum = nullptr;                     // [dgemm_bands_parts(n)][rows] partial row sums, one per 32 columns
+  unsigned cap = 0;
+  int nprobs = 0;
+};
+bool dgemm_bands_usable(const double* A, int64_t lda, const double* B, int64_t ldb);
+int dgemm_bands_parts(int n);
+cudaError_t launch_dgemm_bands(int m, int n, int k, const double* A, int64_t lda, const double* B, int64_t ldb,
+                               const BandFuse& f, cudaStream_t st);
 
 // ---- dense set-up algebra (lqg_linalg.cu) ---------------------------------------------------
 // C = alpha op(A) op(B) + beta C on the FP64 tensor cores; tri = 1: lower tiles only
@@ -280,6 +295,15 @@ size_t bands_bracket_scratch_bytes(int n_t, int64_t N, int nprobs);
 cudaError_t launch_bands_bracketed(int n_t, int64_t N, const double* ysim, int64_t ld, const double* probs_host,
                                    int nprobs, double* mean, double* qtls, void* scratch, int** fail_dev,
                                    cudaStream_t st);
+
+// fused form: Phi_slab (n_t x m) X (m x N) is summarised inside the product's epilogue and never stored; brackets
+// from a pilot product on the 2048 sampled columns.  scratch of paths_bands_fused_scratch_bytes() bytes
+// (0: not applicable — few samples, operands the tensor-map kernel cannot take); *fail_dev as above
+size_t paths_bands_fused_scratch_bytes(int n_t, int m, int64_t N, int nprobs, const double* phi, int64_t ldphi,
+                                       const double* X, int64_t ldx);
+cudaError_t launch_paths_bands_fused(int n_t, int m, int64_t N, const double* phi, int64_t ldphi, const double* X, int64_t ldx,
+                                     const double* probs_host, int nprobs, double* mean, double* qtls, void* scratch,
+                                     int** fail_dev, cudaStream_t st, cudaEvent_t ev_product_done);
 
 // ---- peaks (lqg_peaks.cu) ---------------------------------------------------------------
 cudaError_t measure_fp64_peaks(double* dfma_tflops, double* dmma_tflops, cudaStream_t st);

@@ -196,3 +196,78 @@ def test_lqg_paths_one_call_matches_gemm_plus_bands(lqg, oracle):
     assert np.array_equal(q, q2) and np.allclose(mean, m2, rtol=1e-14)
     mean0, q0, _ = lqg.paths(Phi, xi, np.zeros(0))
     assert q0.shape == (0, 301) and np.allclose(mean0, mo, rtol=1e-12, atol=1e-13)
+
+
+def test_lqg_paths_identity_slabs_take_every_fallback_route(lqg, oracle):
+    """Several slabs of a sparse Phi (ELL product, bands of the stored slab): slabs whose test points go through the
+    per-row exact path, a slab that goes through the whole-slab exact path and clean slabs, interleaved, against the
+    oracle bit for bit (Phi = I, so ysim is the crafted matrix itself)."""
+    rng = np.random.default_rng(5)
+    n_t, N = 400, 9001
+    y = rng.standard_normal((n_t, N)) * 10.0 ** rng.integers(-2, 3, size=(n_t, 1))
+    y[85:160] = 3.25                                               # slab 1 (rows 80..159): 75 constant rows -> whole slab
+    y[170, : N // 2] = y[170, 0]                                   # slab 2: two rows with heavy ties -> single-row launches
+    y[200] = np.round(y[200])
+    y[399] = np.round(y[399])                                      # last slab
+    probs = np.array([0.025, 0.5, 0.975])
+    mo, qo = oracle.bands(y, probs)
+    mean, q, info = lqg.paths(np.eye(n_t), y, probs, slab_rows=80)
+    assert np.array_equal(q, qo)
+    assert np.allclose(mean, mo, rtol=1e-12, atol=1e-300)
+    mean1, q1, _ = lqg.paths(np.eye(n_t), y, probs, slab_rows=n_t)
+    assert np.array_equal(q, q1) and np.allclose(mean, mean1, rtol=1e-14, atol=1e-300)   # split count follows the slab size
+
+
+def _dense_case(seed, n_t=300, m=40, N=20011):
+    rng = np.random.default_rng(seed)
+    return rng.uniform(size=(n_t, m)), rng.standard_normal((m, N)), np.array([0.025, 0.5, 0.975])
+
+
+@pytest.mark.parametrize("slab", [0, 128, 76, 75])
+def test_fused_product_bands_equal_bands_of_the_stored_product(lqg, oracle, slab):
+    """Dense Phi, >= 8192 samples, paths not requested: the product is summarised in its own epilogue and never
+    stored.  The order statistics must be those of the very same product (same kernel, stored this time) bit for
+    bit, and agree with numpy's product within GEMM rounding; slabs of 75 rows start on odd rows every other
+    time, which the tensor-map kernel cannot take: those go through the stored form."""
+    Phi, xi, probs = _dense_case(31)
+    mean, q, info = lqg.paths(Phi, xi, probs, slab_rows=slab)
+    mean_s, q_s, ysim, _ = lqg.paths(Phi, xi, probs, return_ysim=True, slab_rows=slab)
+    mo, qo = oracle.bands(ysim, probs)
+    assert np.array_equal(q_s, qo)
+    assert np.array_equal(q, qo)
+    tol = 1e-14 * np.abs(ysim).max()                                       # rows cancel: compare on the scale of the values summed
+    assert np.abs(mean - mo).max() <= tol and np.abs(mean_s - mo).max() <= tol
+    m2, q2 = oracle.bands(Phi @ xi, probs)
+    assert np.allclose(q, q2, rtol=1e-12, atol=1e-12) and np.allclose(mean, m2, rtol=1e-12, atol=1e-13)
+    assert info["gemm_ms"] > 0 and info["bands_ms"] > 0
+    pe = np.array([0.0, 0.0001, 0.2, 0.9999, 1.0])                          # open-ended brackets
+    _, qe, _ = lqg.paths(Phi, xi, pe, slab_rows=slab)
+    assert np.array_equal(qe, oracle.bands(ysim, pe)[1])
+    mean0, q0, _ = lqg.paths(Phi, xi, np.zeros(0), slab_rows=slab)          # means only
+    assert q0.shape == (0, Phi.shape[0]) and np.abs(mean0 - mo).max() <= tol
+
+
+def test_fused_product_bands_fallback_routes(lqg, oracle):
+    """Test points the bracketed statistics cannot settle inside the fused product: a few rows with massive ties
+    (their row of the product is formed again by the same kernel, odd and even rows, first and last of a slab)
+    and slabs where every row is tied (the slab is stored after all) — bit for bit against the oracle on the
+    stored product."""
+    Phi, xi, probs = _dense_case(32)
+    n_t = Phi.shape[0]
+    xi[7] = np.round(xi[7])                                        # rows of Phi that pick coordinate 7 see few distinct values
+    for r in (0, 3, 10, 149, 150, 224, 298, 299):
+        Phi[r] = 0.0; Phi[r, 7] = 1.0
+    for slab in (0, 75, 150):
+        mean, q, _ = lqg.paths(Phi, xi, probs, slab_rows=slab)
+        mean_s, q_s, ysim, _ = lqg.paths(Phi, xi, probs, return_ysim=True, slab_rows=slab)
+        mo, qo = oracle.bands(ysim, probs)
+        assert np.array_equal(q, qo), slab
+        assert np.abs(mean - mo).max() <= 1e-14 * np.abs(ysim).max()
+    xi2 = xi.copy()
+    xi2[:, : xi.shape[1] // 2] = xi2[:, [0]]                       # half of the samples identical: every row is half tied
+    mean, q, _ = lqg.paths(Phi, xi2, probs, slab_rows=150)
+    _, _, ysim, _ = lqg.paths(Phi, xi2, probs, return_ysim=True, slab_rows=150)
+    _, qo = oracle.bands(ysim, probs)
+    mo = np.asarray(ysim, np.longdouble).mean(axis=1).astype(float)   # 10 005 equal terms: a plain running sum drifts by 1e-12
+    assert np.array_equal(q, qo)
+    assert np.abs(mean - mo).max() <= 1e-14 * np.abs(ysim).max()
