@@ -1783,9 +1783,15 @@ struct SlabProduct {
   }
 };
 
-static bool bands_fused_enabled() {
-  static const char* env = getenv("LQG_BANDS_FUSED");                // A/B aid: 0 = always product, then bands of the stored slab
-  return !(env && env[0] == '0');
+// Fusing pays when the band pass over a stored slab (HBM-bound: 8 N bytes per row at ~2 TB/s) costs more than what the
+// fused form adds to the product (DMMA-bound: 2 m N flop per row at ~36 Tflop/s): the pilot product on 2048 of the N
+// columns plus ~2.5 % for the epilogue and the bracket sort.  Measured on one B200 at N = 125 208: m = 1000 the stored
+// form's bands are 13 % of the product (fused: +6 %), m = 2000 3.2 % (fused: +3.9 %).
+static bool bands_fused_enabled(int m, int64_t N) {
+  static const char* env = getenv("LQG_BANDS_FUSED");                // A/B aid: 0 = always store the slab, 1 = fuse whenever possible
+  if (env && env[0] == '0') return false;
+  if (env && env[0] == '1') return true;
+  return 72.0 / (double)m > 2048.0 / (double)N + 0.025;
 }
 
 // One row slab of the path stage: the bands of Phi_slab X.  When the caller does not want the paths themselves and
@@ -1799,7 +1805,7 @@ static int slab_paths_bands(SlabProduct& sp, int nr, int m, int rows_cap, const 
   if ((rc = sp.classify(nr, m, rows_cap, phi, ld, st))) return rc;
   auto need_y = [&]() -> cudaError_t { return b_y.p ? cudaSuccess : b_y.alloc((size_t)rows_cap * N * sizeof(double)); };
   *stored = false;
-  const size_t fused_bytes = (want_y || sp.ell || !bands_fused_enabled()) ? 0 : paths_bands_fused_scratch_bytes(nr, m, N, nprobs, phi, ld, X, ldx);
+  const size_t fused_bytes = (want_y || sp.ell || !bands_fused_enabled(m, N)) ? 0 : paths_bands_fused_scratch_bytes(nr, m, N, nprobs, phi, ld, X, ldx);
   if (!fused_bytes) {
     LQG_CUDA_TRY(need_y());
     if ((rc = sp.product(nr, m, phi, ld, X, ldx, N, b_y.as<double>(), nr, st, t_gemm))) return rc;
