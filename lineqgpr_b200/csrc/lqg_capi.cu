@@ -1783,15 +1783,16 @@ struct SlabProduct {
   }
 };
 
-// Fusing pays when the band pass over a stored slab (HBM-bound: 8 N bytes per row at ~2 TB/s) costs more than what the
-// fused form adds to the product (DMMA-bound: 2 m N flop per row at ~36 Tflop/s): the pilot product on 2048 of the N
-// columns plus ~2.5 % for the epilogue and the bracket sort.  Measured on one B200 at N = 125 208: m = 1000 the stored
-// form's bands are 13 % of the product (fused: +6 %), m = 2000 3.2 % (fused: +3.9 %).
+// Fusing pays when the band pass over a stored slab costs more than what the fused form adds to the product.  Per
+// 4 224 x 125 208 slab on one B200: the band pass 1.9 ms (Gaussian values; 3.9 ms in the cfg5 pipeline), the fused
+// epilogue + bracket sort 1.25 ms — both per value of the product, whatever m — and the pilot product 2048 / N of
+// the product, which itself is 29.6 ms x m / 1000.  Hence: fuse iff (1.9 - 1.25) ms > (2048 / N) x 29.6 ms x m / 1000,
+// i.e. 22 / m > 2048 / N (m = 1000: N > 93 000; measured break-even at N = 125 208: m between 1000 and 2000).
 static bool bands_fused_enabled(int m, int64_t N) {
   static const char* env = getenv("LQG_BANDS_FUSED");                // A/B aid: 0 = always store the slab, 1 = fuse whenever possible
   if (env && env[0] == '0') return false;
   if (env && env[0] == '1') return true;
-  return 72.0 / (double)m > 2048.0 / (double)N + 0.025;
+  return 22.0 / (double)m > 2048.0 / (double)N;
 }
 
 // One row slab of the path stage: the bands of Phi_slab X.  When the caller does not want the paths themselves and

@@ -86,17 +86,18 @@ def test_pipeline_slabs_and_ragged_rows(lqg, oracle):
 
 
 def test_pipeline_fused_bands_equal_bands_of_stored_paths(lqg, oracle):
-    """Dense Phi and >= 8192 samples: without ysim_out the product is summarised in its epilogue and never stored;
-    with it the slab is stored and read again.  Same order statistics bit for bit, also slab by slab."""
+    """Dense Phi and enough samples for the pilot product to pay (N > 2048 m / 22): without ysim_out the product is
+    summarised in its epilogue and never stored; with it the slab is stored and read again.  Same order statistics
+    bit for bit, also slab by slab."""
     from lineqgpr_b200.simulate import simulate_pipeline
     par, Lam, _ = _cfg("cfg4small")
     rng = np.random.default_rng(8)
     Phi = rng.uniform(size=(130, Lam.shape[1]))
     ctl = {"burn.in": 5, "n.chains": 24, "seed": 3, "burn.in.exact": True}
     probs = (0.025, 0.5, 0.975)
-    a = simulate_pipeline(par, 24 * 400, Lambda=Lam, Phi_test=Phi, probs=probs, control=ctl)
-    b = simulate_pipeline(par, 24 * 400, Lambda=Lam, Phi_test=Phi, probs=probs, control=ctl, return_ysim=True)
-    c = simulate_pipeline(par, 24 * 400, Lambda=Lam, Phi_test=Phi, probs=probs, control=ctl, slab_rows=48)
+    a = simulate_pipeline(par, 24 * 600, Lambda=Lam, Phi_test=Phi, probs=probs, control=ctl)
+    b = simulate_pipeline(par, 24 * 600, Lambda=Lam, Phi_test=Phi, probs=probs, control=ctl, return_ysim=True)
+    c = simulate_pipeline(par, 24 * 600, Lambda=Lam, Phi_test=Phi, probs=probs, control=ctl, slab_rows=48)
     assert np.array_equal(a["xi.sim"], b["xi.sim"])
     mo, qo = oracle.bands(b["ysim"], probs)
     assert np.array_equal(b["qtls"], qo)
